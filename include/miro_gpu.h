@@ -1,0 +1,256 @@
+/* miro_gpu.h — C ABI of the B200-native ray-casting core for the Miro ray tracer.
+ *
+ * This is the drop-in boundary.  The reference (bitfrozen/rendering-algorithms-raytracer)
+ * has no FFI: its seams are three C++ member functions.  Each entry point below names the
+ * reference interface it replaces (file:line relative to the reference tree):
+ *
+ *   Scene::preCalc()                 src/Scene.cpp:63-79  (-> BVH::build, src/BVH.h:130)
+ *        after it has run, the host flattens what it built and calls miro_gpu_upload_scene
+ *   Scene::trace(tid, hit, ray, tMin) src/Scene.h:32, src/Scene.cpp:295-298 (-> BVH::intersect,
+ *        src/BVH.h:147, src/BVH.cpp:1112-1178; intersect4, src/BVH.cpp:1298-1459)
+ *        -> miro_gpu_trace_closest / miro_gpu_trace_any (batched)
+ *   Scene::raytraceImage(cam, img)    src/Scene.h:31, src/Scene.cpp:86-217
+ *        -> miro_gpu_render (float radiance, before Image::Map, src/Image.cpp:71-87)
+ *
+ * Conventions: plain C, POD structs, host pointers unless a *_device variant says otherwise,
+ * no torch / C++ types.  Every call returns 0 (MIRO_GPU_OK) or a negative MIRO_GPU_E* code;
+ * the message is available through miro_gpu_last_error().  No exceptions cross the boundary.
+ * Buffers passed in are borrowed for the duration of the call only; device memory is owned
+ * by the context.  A context is not re-entrant (one host thread at a time); calls are
+ * synchronous unless stated.  There is NO CPU fallback: without a CUDA device every compute
+ * entry point fails with MIRO_GPU_ENODEVICE.
+ */
+#ifndef MIRO_GPU_H
+#define MIRO_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIRO_GPU_ABI_VERSION 1
+
+enum {
+    MIRO_GPU_OK = 0,
+    MIRO_GPU_EINVAL = -1,       /* bad argument / malformed scene description */
+    MIRO_GPU_ENODEVICE = -2,    /* no CUDA device, or device is not sm_100 */
+    MIRO_GPU_ECUDA = -3,        /* CUDA runtime error (message has the details) */
+    MIRO_GPU_ENOSCENE = -4,     /* trace/render before upload_scene */
+    MIRO_GPU_EUNSUPPORTED = -5, /* scene uses a feature outside the hot-path scope */
+    MIRO_GPU_ENOMEM = -6
+};
+
+/* ---- constants shared with the reference (src/Miro.h:35-68) ------------------------- */
+#define MIRO_GPU_TMAX 1e12f      /* MIRO_TMAX */
+#define MIRO_GPU_EPSILON 0.001f  /* epsilon   */
+
+/* ---- rays and hits (reference: Ray, src/Ray.h:27-178; HitInfo, src/Ray.h:185-200) ---- */
+typedef struct miro_gpu_ray {   /* 48 bytes, 16-byte aligned: three 16-byte vector loads */
+    float ox, oy, oz, tmin;
+    float dx, dy, dz, tmax;
+    float time;                 /* motion-blur lerp weight, Ray::time */
+    uint32_t flags;             /* reserved, 0 */
+    uint32_t user0, user1;      /* opaque to the tracer */
+} miro_gpu_ray;
+
+typedef struct miro_gpu_hit {   /* 20 bytes */
+    float t, a, b;              /* distance; barycentric weights of vertex 1 and vertex 2 (HitInfo::a,b) */
+    int32_t prim;               /* index into miro_gpu_scene_desc::prims, -1 = miss */
+    int32_t inst;               /* index into ::instances (HitInfo::m_proxy), -1 = none */
+} miro_gpu_hit;
+
+/* ---- acceleration structure ------------------------------------------------------------
+ * 4-wide BVH node, 128 bytes, 128-byte aligned (one L1/L2 line), SoA bounds as in the
+ * reference's QBVH_Node (src/BVH.h:89-96) so its tree flattens 1:1.  All BVHs of a scene
+ * (the top level and every instanced bottom level) live in ONE node array.
+ * child[i]:  >= 0            index of an inner node
+ *            MIRO_GPU_CHILD_EMPTY  unused slot (flagsIsValid[i] == false)
+ *            otherwise (bit 31 set) a leaf reference, see MIRO_GPU_LEAF().             */
+#define MIRO_GPU_CHILD_EMPTY ((int32_t)0x7fffffff)
+#define MIRO_GPU_KIND_TRI 0u    /* static triangle      (reference: Object,      objectType OBJECT) */
+#define MIRO_GPU_KIND_MBTRI 1u  /* motion-blur triangle (reference: MBObject,    MB_OBJECT)         */
+#define MIRO_GPU_KIND_INST 2u   /* instance             (reference: ProxyObject, PROXY_OBJECT)      */
+#define MIRO_GPU_MAX_LEAF 4u    /* MAX_LEAF_SIZE, src/Miro.h:38 */
+#define MIRO_GPU_LEAF_INDEX_BITS 26
+/* leaf reference: bit31 | kind<<29 | (count-1)<<26 | first ; `first` indexes tris / mbtris / instances */
+#define MIRO_GPU_LEAF(kind, first, count) \
+    ((int32_t)(0x80000000u | ((uint32_t)(kind) << 29) | (((uint32_t)(count) - 1u) << 26) | (uint32_t)(first)))
+
+typedef struct miro_gpu_node {
+    float lo_x[4], lo_y[4], lo_z[4];
+    float hi_x[4], hi_y[4], hi_z[4];
+    int32_t child[4];
+    uint32_t reserved[4];
+} miro_gpu_node;
+
+typedef struct miro_gpu_tri {       /* 48 bytes: three vertices, padded to float4 */
+    float v0[3]; uint32_t pad0;
+    float v1[3]; uint32_t pad1;
+    float v2[3]; uint32_t pad2;
+} miro_gpu_tri;
+
+typedef struct miro_gpu_mbtri {     /* 96 bytes: pose 1 (time 0) and pose 2 (time 1), src/BVH.cpp:1316-1335 */
+    miro_gpu_tri pose[2];
+} miro_gpu_mbtri;
+
+typedef struct miro_gpu_instance {  /* 64 bytes: what traversal needs of a ProxyObject */
+    float inv[12];                  /* rows 0..2 of M^-1 (row-major 3x4), src/ProxyObject.cpp:78-79 */
+    int32_t blas_root;              /* node index of the instanced BVH's root */
+    uint32_t reserved[3];
+} miro_gpu_instance;
+
+/* Shading record of one primitive; prims[0..n_tris) describe tris[], prims[n_tris..n_tris+n_mbtris)
+ * describe mbtris[].  (reference: Object{m_material,m_mesh,m_index}, src/Object.h:73-76)        */
+typedef struct miro_gpu_prim {      /* 48 bytes */
+    uint32_t n[3];                  /* indices into normals[]  (TriangleMesh::m_normalIndices)   */
+    uint32_t uv[3];                 /* indices into uvs[], or 0xffffffff: (u,v) = (a,b), src/Ray.cpp:42-48 */
+    uint32_t material;
+    uint32_t mesh;                  /* caller's mesh ordinal (reported back, not interpreted)     */
+    uint32_t tri;                   /* Object::m_index                                             */
+    uint32_t reserved[3];
+} miro_gpu_prim;
+
+/* ---- materials (reference: Lambert src/Lambert.cpp:19-53, Blinn src/Blinn.cpp:39-236,335) ---- */
+#define MIRO_GPU_MAT_LAMBERT 0u
+#define MIRO_GPU_MAT_BLINN 1u
+typedef struct miro_gpu_material {  /* 96 bytes */
+    uint32_t kind;
+    float kd[3];
+    float ka[3];
+    float ks[3];
+    float spec_exp, spec_amt;
+    float emit_intensity;           /* Blinn::m_lightEmitted */
+    float le[3];                    /* Blinn::m_Le           */
+    int32_t color_map;              /* texture index or -1   */
+    int32_t alpha_map;              /* -1 (alpha cut-outs are outside the round-1 scope: EUNSUPPORTED) */
+    float reflect_amt, refract_amt; /* must be 0 (specular transport is outside the scope: EUNSUPPORTED) */
+    float spec_gloss;               /* must be 1 */
+    float translucency;             /* must be <= 0.01 */
+    uint32_t sample_env;            /* Material::m_sampleEnv */
+    uint32_t reserved[2];
+} miro_gpu_material;
+
+/* ---- lights (reference: src/PointLight.cpp:8-82, src/RectangleLight.cpp:14-137, src/DomeLight.cpp:8-161) */
+#define MIRO_GPU_LIGHT_POINT 0u
+#define MIRO_GPU_LIGHT_RECT 1u
+#define MIRO_GPU_LIGHT_DOME 2u
+#define MIRO_GPU_MAX_LIGHTS 8u
+typedef struct miro_gpu_light {     /* 64 bytes */
+    uint32_t kind;
+    float p0[3];                    /* point: position; rect: v1 */
+    float p1[3];                    /* rect: v2 */
+    float p2[3];                    /* rect: v3 */
+    float power;                    /* point: m_power; rect: m_power AFTER setPower's 1/area (RectangleLight.cpp:39); dome: gain */
+    int32_t num_samples;            /* Light::m_numSamples */
+    float noise_threshold;          /* Light::m_noiseThreshold */
+    uint32_t cast_shadows;
+    int32_t texture;                /* dome: light map texture index */
+    uint32_t reserved;
+} miro_gpu_light;
+
+/* ---- textures (reference: src/Texture.cpp:12-125; float texels, row-major, already linearised) */
+typedef struct miro_gpu_texture {
+    const float* texels;            /* width*height*channels floats */
+    int32_t width, height, channels; /* channels: 1 (GRAYSCALE), 3 (RGB / HDR), 4 (RGBA) */
+    int32_t reserved;
+} miro_gpu_texture;
+
+typedef struct miro_gpu_scene_desc {
+    uint32_t abi_version;           /* MIRO_GPU_ABI_VERSION */
+    /* acceleration structure */
+    const miro_gpu_node* nodes;       uint32_t n_nodes;
+    int32_t root;                   /* child-style reference to the top-level root: a node index, or a leaf reference
+                                       when the whole scene is a single leaf (src/BVH.cpp:118-132) */
+    const miro_gpu_tri* tris;         uint32_t n_tris;
+    const miro_gpu_mbtri* mbtris;     uint32_t n_mbtris;
+    const miro_gpu_instance* instances; uint32_t n_instances;
+    /* shading data */
+    const miro_gpu_prim* prims;       /* n_tris + n_mbtris records */
+    const float* normals;             uint32_t n_normals;   /* xyz triples */
+    const float* uvs;                 uint32_t n_uvs;       /* uv pairs (may be NULL/0) */
+    const float* inst_normal_xform;   /* n_instances x 9: rows 0..2 of (M^-1)^T, src/Ray.cpp:27-31 */
+    const miro_gpu_material* materials; uint32_t n_materials;
+    const miro_gpu_light* lights;       uint32_t n_lights;
+    const miro_gpu_texture* textures;   uint32_t n_textures;
+    int32_t env_map;                /* Scene::m_envMap texture index or -1 */
+    float env_exposure;             /* Scene::m_envExposure */
+    float bg_color[3];              /* Scene::m_BGColor */
+} miro_gpu_scene_desc;
+
+/* ---- camera and render parameters (reference: Camera src/Camera.h:26-69; Scene src/Scene.h:40-64) */
+typedef struct miro_gpu_camera {
+    float eye[3];
+    float view_dir[3];              /* normalised, Camera::m_viewDir */
+    float up[3];                    /* normalised, Camera::m_up      */
+    float fov_deg;
+    float focus_plane, aperture, shutter_speed;
+} miro_gpu_camera;
+
+typedef struct miro_gpu_render_params {
+    int32_t width, height;
+    int32_t min_subdivs, max_subdivs;   /* Scene::m_minSubdivs / m_maxSubdivs (src/Scene.cpp:252-293) */
+    float noise_threshold;              /* Scene::m_noiseThreshold */
+    int32_t num_paths;                  /* Scene::m_numPaths   */
+    int32_t max_bounces;                /* Scene::m_maxBounces */
+    uint32_t path_trace;                /* Scene::m_pathTrace  */
+    uint32_t sample_env;                /* Scene::m_sampleLightFromEnv */
+    uint64_t seed;                      /* counter-based RNG seed (replaces the global MT19937, src/Scene.cpp:26-47) */
+    /* work sharding (multi-GPU): this call renders the 32x32 buckets b with b % shard_count == shard_index
+       (bucket order of src/Scene.cpp:160-175).  shard_count <= 1 renders everything.  Pixels outside the
+       shard are left untouched in rgb_out. */
+    int32_t shard_index, shard_count;
+    uint32_t reserved[4];
+} miro_gpu_render_params;
+
+typedef struct miro_gpu_counters {
+    uint64_t rays_closest;      /* closest-hit queries since the last reset (one Scene::trace call = one ray) */
+    uint64_t rays_any;          /* any-hit (shadow) queries */
+    uint64_t nodes_fetched;     /* 128-byte nodes fetched (only counted when counting is enabled) */
+    uint64_t tris_tested;       /* triangles tested */
+    uint64_t insts_entered;     /* instance transforms fetched */
+    double trace_ms;            /* device time of the traversal kernels (CUDA events) */
+    double total_ms;            /* device time of everything the last trace/render call launched */
+    uint64_t kernel_launches;   /* kernels launched by this context since the last reset */
+} miro_gpu_counters;
+
+typedef struct miro_gpu_ctx miro_gpu_ctx;
+
+/* Create a context on one CUDA device (device_id as in cudaSetDevice).  One context per GPU; a
+ * multi-GPU job is one process per GPU (torch.distributed / NCCL combine the frame buffers). */
+int miro_gpu_create(miro_gpu_ctx** out, int device_id);
+void miro_gpu_destroy(miro_gpu_ctx* ctx);
+const char* miro_gpu_last_error(const miro_gpu_ctx* ctx);   /* ctx may be NULL: last create() error */
+int miro_gpu_abi_version(void);
+
+/* Use an existing CUDA stream (cudaStream_t passed as void*) for all work of this context;
+ * NULL restores the context's own stream.  Lets the caller order work against torch streams. */
+int miro_gpu_set_stream(miro_gpu_ctx* ctx, void* cuda_stream);
+
+/* Copy a flattened scene to the device (replaces any previous scene of this context). */
+int miro_gpu_upload_scene(miro_gpu_ctx* ctx, const miro_gpu_scene_desc* desc);
+
+/* Batched Scene::trace.  Host buffers: copied in, traced, copied out (timed end to end by callers). */
+int miro_gpu_trace_closest(miro_gpu_ctx* ctx, const miro_gpu_ray* rays, size_t n, miro_gpu_hit* hits);
+/* occluded_bits: (n+31)/32 words, bit i set iff ray i hits anything in [tmin, tmax). */
+int miro_gpu_trace_any(miro_gpu_ctx* ctx, const miro_gpu_ray* rays, size_t n, uint32_t* occluded_bits);
+/* Same, buffers already resident in device memory (e.g. torch CUDA tensors); asynchronous on the
+ * context's stream — the caller synchronises. */
+int miro_gpu_trace_closest_device(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, miro_gpu_hit* d_hits);
+int miro_gpu_trace_any_device(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, uint32_t* d_occluded_bits);
+
+/* Scene::raytraceImage.  rgb_out: width*height*3 floats, row 0 = bottom row (src/Image.cpp:150-151),
+ * linear radiance before Image::Map.  rgb_out may be a host or a device pointer. */
+int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, const miro_gpu_render_params* params, float* rgb_out);
+
+/* Counters.  enable != 0 switches the traversal kernels to their instrumented variant (node / triangle
+ * / instance fetch counts, used for the roofline's algorithmic bytes); ray counts and times are always kept. */
+int miro_gpu_enable_counting(miro_gpu_ctx* ctx, int enable);
+int miro_gpu_get_counters(miro_gpu_ctx* ctx, miro_gpu_counters* out);
+int miro_gpu_reset_counters(miro_gpu_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIRO_GPU_H */

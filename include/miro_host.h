@@ -1,0 +1,43 @@
+/* miro_host.h — C view of the product's C++ host layer (rendering-algorithms-raytracer_b200/host),
+ * for bindings (the Python tests/bench use it through ctypes).  The host layer mirrors the
+ * reference's scene API (Scene/Camera/Image/TriangleMesh/Material/Light, src/ headers); a scene is
+ * described by a ".miro" script (one reference API call per line, see host/miro_script.cpp).
+ * All GPU work goes through include/miro_gpu.h; nothing here renders on the CPU.               */
+#ifndef MIRO_HOST_H
+#define MIRO_HOST_H
+#include <stddef.h>
+#include <stdint.h>
+#include "miro_gpu.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct miro_host_scene miro_host_scene;
+
+/* Begin a scene; meshes / images registered before load_script replace the files named in the script
+ * (arrays are copied).  nidx/normals and tidx/uvs may be NULL. */
+miro_host_scene* miro_host_new(void);
+void miro_host_free(miro_host_scene* s);
+const char* miro_host_error(const miro_host_scene* s);
+int miro_host_preload_mesh(miro_host_scene* s, const char* name, const float* vertices, uint32_t nv, const uint32_t* vidx, uint32_t nf,
+                           const float* normals, uint32_t nn, const uint32_t* nidx, const float* uvs, uint32_t nt, const uint32_t* tidx);
+int miro_host_preload_image(miro_host_scene* s, const char* name, const float* texels, int width, int height, int channels, int is_hdr);
+/* Parse the script, run Scene::preCalc (BVH build + flatten).  Host only — works without a GPU. */
+int miro_host_load_script(miro_host_scene* s, const char* script_path, const char* asset_root);
+/* The flattened scene (valid until the scene is freed / reloaded) and the derived call arguments. */
+int miro_host_get_desc(const miro_host_scene* s, miro_gpu_scene_desc* out);
+int miro_host_get_camera(const miro_host_scene* s, miro_gpu_camera* out);
+int miro_host_get_render_params(const miro_host_scene* s, miro_gpu_render_params* out);
+int miro_host_bvh_stats(const miro_host_scene* s, uint32_t* nodes, uint32_t* leaves, uint32_t* max_depth, double* sah_cost);
+/* Scene::attach: create the GPU context on `device` and upload.  Fails loudly without a GPU. */
+int miro_host_attach(miro_host_scene* s, int device);
+miro_gpu_ctx* miro_host_ctx(miro_host_scene* s);
+/* Scene::raytraceImage: rgb = width*height*3 floats (row 0 = bottom); rgb8 (optional) = Image::Map'ed bytes. */
+int miro_host_raytrace_image(miro_host_scene* s, float* rgb, unsigned char* rgb8, int shard_index, int shard_count);
+/* Standalone BVH build over triangle soup (testing the builder): returns node count, fills order (n entries). */
+int miro_host_write_ppm(miro_host_scene* s, const char* path);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

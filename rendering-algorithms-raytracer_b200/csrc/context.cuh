@@ -1,0 +1,110 @@
+// context.cuh — the device context behind miro_gpu_ctx (shared by the API and the renderer).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/miro_gpu.h"
+#include "traverse.cuh"
+
+namespace miro {
+
+// Device-side view of everything shading needs (the traversal subset is DeviceScene).
+struct DeviceTexture {
+    const float* texels;
+    int32_t width, height, channels, pad;
+};
+
+struct DeviceDome {            // per DomeLight: alias table over the nu x nv cells (DomeLight.cpp:8-78)
+    const float2* alias;       // {acceptance threshold, alias index as float bits}
+    const float4* cell_E;      // per cell: gain-free  L(dir)/pdf  (rgb), w = 1 if usable else 0
+    const float* cos_u; const float* sin_u;   // nu+1 entries (DomeLight.cpp:59-66)
+    const float* cos_v; const float* sin_v;   // nv+1 entries (DomeLight.cpp:68-76)
+    int32_t nu, nv;
+};
+
+struct DeviceShading {
+    const miro_gpu_prim* prims;
+    const float* normals;
+    const float* uvs;
+    const float* inst_nxf;     // n_instances x 9
+    const miro_gpu_material* materials;
+    const miro_gpu_light* lights;
+    const DeviceTexture* textures;
+    const DeviceDome* domes;   // indexed by light ordinal (unused slots zero)
+    uint32_t n_lights, n_materials, n_textures, n_prims;
+    int32_t env_map;
+    float env_exposure;
+    float bg[3];
+};
+
+template <class T>
+struct DeviceBuffer {
+    T* ptr = nullptr;
+    size_t cap = 0;   // elements
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr; cap = 0;
+        size_t want = n + n / 4;
+        cudaError_t e = cudaMalloc((void**)&ptr, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+};
+
+struct EventPair { cudaEvent_t a, b; bool trace; };
+
+}  // namespace miro
+
+struct miro_gpu_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    bool has_scene = false;
+    bool counting = false;
+
+    // scene storage (device)
+    std::vector<void*> scene_allocs;
+    miro::DeviceScene scene{};
+    miro::DeviceShading shading{};
+    uint32_t n_nodes = 0, n_tris = 0, n_mbtris = 0, n_insts = 0;
+    std::vector<miro_gpu_light> host_lights;
+    std::vector<miro_gpu_material> host_materials;
+
+    // counters
+    miro::TraceCounters* d_counters = nullptr;
+    std::vector<miro::EventPair> events;        // pending (not yet summed) timing pairs
+    std::vector<miro::EventPair> event_pool;
+    double trace_ms = 0.0, total_ms = 0.0;
+    uint64_t launches = 0;
+
+    // scratch for the host-pointer trace entry points
+    miro::DeviceBuffer<miro_gpu_ray> d_rays;
+    miro::DeviceBuffer<miro_gpu_hit> d_hits;
+    miro::DeviceBuffer<uint32_t> d_bits;
+
+    // renderer state (render.cu)
+    void* render_state = nullptr;
+};
+
+namespace miro {
+
+int set_error(miro_gpu_ctx* ctx, int code, const std::string& msg);
+int cuda_fail(miro_gpu_ctx* ctx, cudaError_t e, const char* what);
+#define MIRO_CUDA(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return miro::cuda_fail(ctx, e__, #call); } while (0)
+
+// timing helpers: bracket a group of launches with events on ctx->stream
+EventPair begin_timing(miro_gpu_ctx* ctx, bool trace);
+void end_timing(miro_gpu_ctx* ctx, EventPair p);
+void drain_timing(miro_gpu_ctx* ctx);
+
+// launches the traversal kernel over device buffers (count either n, or *d_count when non-null)
+void launch_trace_closest(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, const uint32_t* d_count, miro_gpu_hit* d_hits);
+void launch_trace_any(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, const uint32_t* d_count, uint32_t* d_bits);
+
+void render_state_free(miro_gpu_ctx* ctx);
+
+}  // namespace miro

@@ -1,0 +1,414 @@
+// miro_gpu_api.cu — C ABI implementation: context, scene upload, batched Scene::trace, counters.
+// See include/miro_gpu.h for the reference interfaces each entry point replaces.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+#include "context.cuh"
+#include "dome.cuh"
+
+using namespace miro;
+
+static std::string g_create_error;
+
+namespace miro {
+
+int set_error(miro_gpu_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->error = msg; else g_create_error = msg;
+    return code;
+}
+int cuda_fail(miro_gpu_ctx* ctx, cudaError_t e, const char* what) {
+    return set_error(ctx, MIRO_GPU_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+EventPair begin_timing(miro_gpu_ctx* ctx, bool trace) {
+    EventPair p;
+    if (!ctx->event_pool.empty()) { p = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
+    else { cudaEventCreate(&p.a); cudaEventCreate(&p.b); }
+    p.trace = trace;
+    cudaEventRecord(p.a, ctx->stream);
+    return p;
+}
+void end_timing(miro_gpu_ctx* ctx, EventPair p) {
+    cudaEventRecord(p.b, ctx->stream);
+    ctx->events.push_back(p);
+    if (ctx->events.size() > 4096) drain_timing(ctx);
+}
+void drain_timing(miro_gpu_ctx* ctx) {
+    for (EventPair& p : ctx->events) {
+        if (cudaEventSynchronize(p.b) == cudaSuccess) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+                if (p.trace) ctx->trace_ms += ms; else ctx->total_ms += ms;
+            }
+        }
+        ctx->event_pool.push_back(p);
+    }
+    ctx->events.clear();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Traversal kernels.  One thread per ray; a warp covers 32 consecutive rays, so the any-hit variant
+// can emit one packed word per warp.  Rays / hits are streamed (ld.cs / st.cs) so they do not
+// displace BVH nodes from L1/L2.
+template <bool ANY, bool COUNT>
+__global__ void __launch_bounds__(TRACE_BLOCK)
+k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const uint32_t* __restrict__ d_count,
+        miro_gpu_hit* __restrict__ hits, uint32_t* __restrict__ bits, TraceCounters* __restrict__ ctr) {
+    __shared__ unsigned long long stack[SMEM_STACK * TRACE_BLOCK];
+    const uint32_t n = d_count ? *d_count : n_static;
+    const uint32_t stride = gridDim.x * TRACE_BLOCK;
+    uint32_t c_nodes = 0, c_tris = 0, c_insts = 0, c_rays = 0;
+    // warp-uniform loop bound: every lane of a warp iterates the same number of times
+    for (uint32_t base = blockIdx.x * TRACE_BLOCK + (threadIdx.x & ~31u); base < n; base += stride) {
+        const uint32_t i = base + (threadIdx.x & 31u);
+        bool occluded = false;
+        if (i < n) {
+            const float4* rp = rays + (size_t)i * 3;
+            const float4 r0 = __ldcs(rp), r1 = __ldcs(rp + 1), r2 = __ldcs(rp + 2);
+            HitRec h; h.t = r1.w;
+            traverse<ANY, COUNT>(s, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r0.w, r2.x, stack + threadIdx.x, h, c_nodes, c_tris, c_insts);
+            ++c_rays;
+            if (ANY) occluded = h.prim >= 0;
+            else {
+                float* o = reinterpret_cast<float*>(hits + i);
+                const bool hit = h.prim >= 0;
+                __stcs(o + 0, hit ? h.t : -1.0f); __stcs(o + 1, hit ? h.a : 0.f); __stcs(o + 2, hit ? h.b : 0.f);
+                __stcs(reinterpret_cast<int*>(o) + 3, h.prim); __stcs(reinterpret_cast<int*>(o) + 4, hit ? h.inst : -1);
+            }
+        }
+        if (ANY) {
+            const uint32_t w = __ballot_sync(0xffffffffu, occluded);
+            if ((threadIdx.x & 31u) == 0) bits[base >> 5] = w;
+        }
+    }
+    // counters: warp-reduce then one atomic per warp
+    unsigned long long v_rays = c_rays, v_nodes = c_nodes, v_tris = c_tris, v_insts = c_insts;
+    for (int o = 16; o > 0; o >>= 1) {
+        v_rays += __shfl_down_sync(0xffffffffu, v_rays, o);
+        if (COUNT) {
+            v_nodes += __shfl_down_sync(0xffffffffu, v_nodes, o);
+            v_tris += __shfl_down_sync(0xffffffffu, v_tris, o);
+            v_insts += __shfl_down_sync(0xffffffffu, v_insts, o);
+        }
+    }
+    if ((threadIdx.x & 31u) == 0 && v_rays) {
+        atomicAdd(ANY ? &ctr->rays_any : &ctr->rays_closest, v_rays);
+        if (COUNT) { atomicAdd(&ctr->nodes, v_nodes); atomicAdd(&ctr->tris, v_tris); atomicAdd(&ctr->insts, v_insts); }
+    }
+}
+
+static int trace_grid(miro_gpu_ctx* ctx, size_t n, bool device_count) {
+    size_t blocks = (n + TRACE_BLOCK - 1) / TRACE_BLOCK;
+    if (blocks < 1) blocks = 1;
+    // device-side counts (wavefront queues): persistent-style grid, 148 SMs x 16 resident blocks
+    const size_t persistent = 148 * 16;
+    if (device_count) blocks = std::min(blocks, persistent);
+    return (int)std::min<size_t>(blocks, 0x7fffffff);
+}
+
+void launch_trace_closest(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, const uint32_t* d_count, miro_gpu_hit* d_hits) {
+    if (n == 0) return;
+    const int grid = trace_grid(ctx, n, d_count != nullptr);
+    const float4* r = reinterpret_cast<const float4*>(d_rays);
+    if (ctx->counting) k_trace<false, true><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(ctx->scene, r, (uint32_t)n, d_count, d_hits, nullptr, ctx->d_counters);
+    else k_trace<false, false><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(ctx->scene, r, (uint32_t)n, d_count, d_hits, nullptr, ctx->d_counters);
+    ctx->launches++;
+}
+void launch_trace_any(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, const uint32_t* d_count, uint32_t* d_bits) {
+    if (n == 0) return;
+    const int grid = trace_grid(ctx, n, d_count != nullptr);
+    const float4* r = reinterpret_cast<const float4*>(d_rays);
+    if (ctx->counting) k_trace<true, true><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(ctx->scene, r, (uint32_t)n, d_count, nullptr, d_bits, ctx->d_counters);
+    else k_trace<true, false><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(ctx->scene, r, (uint32_t)n, d_count, nullptr, d_bits, ctx->d_counters);
+    ctx->launches++;
+}
+
+}  // namespace miro
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int miro_gpu_abi_version(void) { return MIRO_GPU_ABI_VERSION; }
+
+const char* miro_gpu_last_error(const miro_gpu_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int miro_gpu_create(miro_gpu_ctx** out, int device_id) {
+    if (!out) return set_error(nullptr, MIRO_GPU_EINVAL, "miro_gpu_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return set_error(nullptr, MIRO_GPU_ENODEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                         " (this library has no CPU fallback)");
+    if (device_id < 0 || device_id >= n) return set_error(nullptr, MIRO_GPU_EINVAL, "miro_gpu_create: bad device id");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+    if (prop.major != 10)
+        return set_error(nullptr, MIRO_GPU_ENODEVICE, std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                         "; this build contains sm_100a code only");
+    if ((e = cudaSetDevice(device_id)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+    miro_gpu_ctx* ctx = new miro_gpu_ctx();
+    ctx->device = device_id;
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaStreamCreate"); }
+    ctx->stream = ctx->own_stream;
+    if ((e = cudaMalloc((void**)&ctx->d_counters, sizeof(TraceCounters))) != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaMalloc(counters)"); }
+    cudaMemset(ctx->d_counters, 0, sizeof(TraceCounters));
+    // the traversal kernels keep their stacks in shared memory and want the rest of the 256 KB as L1
+    cudaFuncSetAttribute(k_trace<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutDefault);
+    *out = ctx;
+    return MIRO_GPU_OK;
+}
+
+static void free_scene(miro_gpu_ctx* ctx) {
+    for (void* p : ctx->scene_allocs) cudaFree(p);
+    ctx->scene_allocs.clear();
+    ctx->has_scene = false;
+}
+
+void miro_gpu_destroy(miro_gpu_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    drain_timing(ctx);
+    for (EventPair& p : ctx->event_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    render_state_free(ctx);
+    free_scene(ctx);
+    ctx->d_rays.release(); ctx->d_hits.release(); ctx->d_bits.release();
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int miro_gpu_set_stream(miro_gpu_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return MIRO_GPU_EINVAL;
+    cudaStreamSynchronize(ctx->stream);
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return MIRO_GPU_OK;
+}
+
+}  // extern "C"
+
+template <class T>
+static int upload_array(miro_gpu_ctx* ctx, const T* host, size_t n, const T** dev, size_t min_elems = 1) {
+    size_t bytes = std::max(n, min_elems) * sizeof(T);
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(scene)");
+    ctx->scene_allocs.push_back(p);
+    if (n == 0 || !host) cudaMemsetAsync(p, 0, bytes, ctx->stream);
+    else if ((e = cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return cuda_fail(ctx, e, "cudaMemcpy(scene)");
+    *dev = (const T*)p;
+    return MIRO_GPU_OK;
+}
+
+// depth of the (sub)tree behind a child-style reference; -1 on a malformed tree
+static int tree_depth(const miro_gpu_scene_desc* d, int32_t ref, int level, std::string& err) {
+    if (ref == MIRO_GPU_CHILD_EMPTY) return 0;
+    if (ref < 0) {
+        uint32_t u = (uint32_t)ref, kind = (u >> 29) & 3u, count = ((u >> MIRO_GPU_LEAF_INDEX_BITS) & 7u) + 1u, first = u & ((1u << MIRO_GPU_LEAF_INDEX_BITS) - 1u);
+        uint32_t limit = kind == MIRO_GPU_KIND_TRI ? d->n_tris : kind == MIRO_GPU_KIND_MBTRI ? d->n_mbtris : kind == MIRO_GPU_KIND_INST ? d->n_instances : 0;
+        if (kind > 2 || first + count > limit) { err = "leaf reference out of range"; return -1; }
+        return 0;
+    }
+    if ((uint32_t)ref >= d->n_nodes) { err = "child node index out of range"; return -1; }
+    if (level > 64) { err = "BVH deeper than 64 levels (cycle?)"; return -1; }
+    int best = 0;
+    for (int i = 0; i < 4; ++i) {
+        int c = tree_depth(d, d->nodes[ref].child[i], level + 1, err);
+        if (c < 0) return -1;
+        best = std::max(best, c);
+    }
+    return best + 1;
+}
+
+extern "C" {
+
+int miro_gpu_upload_scene(miro_gpu_ctx* ctx, const miro_gpu_scene_desc* d) {
+    if (!ctx || !d) return MIRO_GPU_EINVAL;
+    if (d->abi_version != MIRO_GPU_ABI_VERSION) return set_error(ctx, MIRO_GPU_EINVAL, "scene desc abi_version mismatch");
+    if ((d->n_nodes && !d->nodes) || (d->n_tris && !d->tris) || (d->n_mbtris && !d->mbtris) || (d->n_instances && !d->instances))
+        return set_error(ctx, MIRO_GPU_EINVAL, "scene desc: NULL array with non-zero count");
+    if (d->n_tris >= (1u << MIRO_GPU_LEAF_INDEX_BITS) || d->n_mbtris >= (1u << MIRO_GPU_LEAF_INDEX_BITS) || d->n_instances >= (1u << MIRO_GPU_LEAF_INDEX_BITS))
+        return set_error(ctx, MIRO_GPU_EUNSUPPORTED, "scene desc: more than 2^26 primitives of one kind");
+    if (d->n_lights > MIRO_GPU_MAX_LIGHTS) return set_error(ctx, MIRO_GPU_EUNSUPPORTED, "more than MIRO_GPU_MAX_LIGHTS lights");
+    // validate the trees and bound the traversal stack: <= 3 pushes per level, + 2 for an instance hop
+    std::string err;
+    int top = tree_depth(d, d->root, 0, err);
+    if (top < 0) return set_error(ctx, MIRO_GPU_EINVAL, "scene desc: " + err);
+    int blas = 0;
+    for (uint32_t i = 0; i < d->n_instances; ++i) {
+        int b = tree_depth(d, d->instances[i].blas_root, 0, err);
+        if (b < 0) return set_error(ctx, MIRO_GPU_EINVAL, "scene desc: instance " + std::to_string(i) + ": " + err);
+        blas = std::max(blas, b);
+    }
+    if (3 * top + 2 + 3 * blas > SMEM_STACK + LMEM_STACK)
+        return set_error(ctx, MIRO_GPU_EUNSUPPORTED, "BVH too deep for the traversal stack (top " + std::to_string(top) + ", instanced " + std::to_string(blas) + " levels)");
+    for (uint32_t i = 0; i < d->n_materials; ++i) {
+        const miro_gpu_material& m = d->materials[i];
+        if (m.kind > MIRO_GPU_MAT_BLINN) return set_error(ctx, MIRO_GPU_EINVAL, "unknown material kind");
+        if (m.reflect_amt != 0.f || m.refract_amt != 0.f || m.translucency > 0.01f || (m.kind == MIRO_GPU_MAT_BLINN && m.spec_gloss < 1.f) || m.alpha_map >= 0)
+            return set_error(ctx, MIRO_GPU_EUNSUPPORTED, "material " + std::to_string(i) + " uses reflection/refraction/gloss/translucency/alpha cut-outs (outside the hot-path scope, SURVEY 8f)");
+        if (m.color_map >= (int32_t)d->n_textures) return set_error(ctx, MIRO_GPU_EINVAL, "material color_map out of range");
+    }
+    for (uint32_t i = 0; i < d->n_tris + d->n_mbtris && d->prims; ++i)
+        if (d->prims[i].material >= d->n_materials) return set_error(ctx, MIRO_GPU_EINVAL, "prim material out of range");
+
+    MIRO_CUDA(ctx, cudaSetDevice(ctx->device));
+    MIRO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    free_scene(ctx);
+    int rc;
+    const miro_gpu_node* dn; const miro_gpu_tri* dt; const miro_gpu_mbtri* dm; const miro_gpu_instance* di;
+    if ((rc = upload_array(ctx, d->nodes, d->n_nodes, &dn))) return rc;
+    if ((rc = upload_array(ctx, d->tris, d->n_tris, &dt))) return rc;
+    if ((rc = upload_array(ctx, d->mbtris, d->n_mbtris, &dm))) return rc;
+    if ((rc = upload_array(ctx, d->instances, d->n_instances, &di))) return rc;
+    ctx->scene.nodes = reinterpret_cast<const float4*>(dn);
+    ctx->scene.tris = reinterpret_cast<const float4*>(dt);
+    ctx->scene.mbtris = reinterpret_cast<const float4*>(dm);
+    ctx->scene.insts = reinterpret_cast<const float4*>(di);
+    ctx->scene.root = d->root;
+    ctx->scene.n_tris = d->n_tris;
+    ctx->n_nodes = d->n_nodes; ctx->n_tris = d->n_tris; ctx->n_mbtris = d->n_mbtris; ctx->n_insts = d->n_instances;
+
+    DeviceShading& sh = ctx->shading;
+    memset(&sh, 0, sizeof(sh));
+    const uint32_t n_prims = d->prims ? d->n_tris + d->n_mbtris : 0;
+    if ((rc = upload_array(ctx, d->prims, n_prims, &sh.prims))) return rc;
+    if ((rc = upload_array(ctx, d->normals, (size_t)d->n_normals * 3, &sh.normals))) return rc;
+    if ((rc = upload_array(ctx, d->uvs, (size_t)d->n_uvs * 2, &sh.uvs))) return rc;
+    if ((rc = upload_array(ctx, d->inst_normal_xform, d->inst_normal_xform ? (size_t)d->n_instances * 9 : 0, &sh.inst_nxf))) return rc;
+    if ((rc = upload_array(ctx, d->materials, d->n_materials, &sh.materials))) return rc;
+    if ((rc = upload_array(ctx, d->lights, d->n_lights, &sh.lights))) return rc;
+    sh.n_lights = d->n_lights; sh.n_materials = d->n_materials; sh.n_textures = d->n_textures; sh.n_prims = n_prims;
+    sh.env_map = d->env_map; sh.env_exposure = d->env_exposure;
+    sh.bg[0] = d->bg_color[0]; sh.bg[1] = d->bg_color[1]; sh.bg[2] = d->bg_color[2];
+    ctx->host_lights.assign(d->lights, d->lights + d->n_lights);
+    ctx->host_materials.assign(d->materials, d->materials + d->n_materials);
+    if (d->env_map >= (int32_t)d->n_textures) return set_error(ctx, MIRO_GPU_EINVAL, "env_map out of range");
+    // textures
+    std::vector<DeviceTexture> tex(d->n_textures);
+    for (uint32_t i = 0; i < d->n_textures; ++i) {
+        const miro_gpu_texture& t = d->textures[i];
+        if (!t.texels || t.width <= 0 || t.height <= 0 || (t.channels != 1 && t.channels != 3 && t.channels != 4))
+            return set_error(ctx, MIRO_GPU_EINVAL, "bad texture " + std::to_string(i));
+        const float* p;
+        if ((rc = upload_array(ctx, t.texels, (size_t)t.width * t.height * t.channels, &p))) return rc;
+        tex[i].texels = p; tex[i].width = t.width; tex[i].height = t.height; tex[i].channels = t.channels; tex[i].pad = 0;
+    }
+    if ((rc = upload_array(ctx, tex.data(), tex.size(), &sh.textures))) return rc;
+    // dome lights: importance tables (DomeLight::setTexture, src/DomeLight.cpp:8-78)
+    std::vector<DeviceDome> domes(std::max<uint32_t>(d->n_lights, 1));
+    memset(domes.data(), 0, domes.size() * sizeof(DeviceDome));
+    for (uint32_t i = 0; i < d->n_lights; ++i) {
+        const miro_gpu_light& l = d->lights[i];
+        if (l.kind > MIRO_GPU_LIGHT_DOME) return set_error(ctx, MIRO_GPU_EINVAL, "unknown light kind");
+        if (l.kind != MIRO_GPU_LIGHT_DOME) continue;
+        if (l.texture < 0 || l.texture >= (int32_t)d->n_textures) return set_error(ctx, MIRO_GPU_EINVAL, "dome light without a texture");
+        if ((rc = build_dome_tables(ctx, d->textures[l.texture], &domes[i]))) return rc;
+    }
+    if ((rc = upload_array(ctx, domes.data(), domes.size(), &sh.domes))) return rc;
+    MIRO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->has_scene = true;
+    return MIRO_GPU_OK;
+}
+
+int miro_gpu_trace_closest_device(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, miro_gpu_hit* d_hits) {
+    if (!ctx) return MIRO_GPU_EINVAL;
+    if (!ctx->has_scene) return set_error(ctx, MIRO_GPU_ENOSCENE, "trace before upload_scene");
+    if (n > 0xffffffffull) return set_error(ctx, MIRO_GPU_EINVAL, "more than 2^32-1 rays in one call");
+    if (n == 0) return MIRO_GPU_OK;
+    if (!d_rays || !d_hits) return set_error(ctx, MIRO_GPU_EINVAL, "NULL ray/hit buffer");
+    MIRO_CUDA(ctx, cudaSetDevice(ctx->device));
+    EventPair p = begin_timing(ctx, true);
+    launch_trace_closest(ctx, d_rays, n, nullptr, d_hits);
+    end_timing(ctx, p);
+    MIRO_CUDA(ctx, cudaGetLastError());
+    return MIRO_GPU_OK;
+}
+
+int miro_gpu_trace_any_device(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, uint32_t* d_bits) {
+    if (!ctx) return MIRO_GPU_EINVAL;
+    if (!ctx->has_scene) return set_error(ctx, MIRO_GPU_ENOSCENE, "trace before upload_scene");
+    if (n > 0xffffffffull) return set_error(ctx, MIRO_GPU_EINVAL, "more than 2^32-1 rays in one call");
+    if (n == 0) return MIRO_GPU_OK;
+    if (!d_rays || !d_bits) return set_error(ctx, MIRO_GPU_EINVAL, "NULL ray/bit buffer");
+    MIRO_CUDA(ctx, cudaSetDevice(ctx->device));
+    EventPair p = begin_timing(ctx, true);
+    launch_trace_any(ctx, d_rays, n, nullptr, d_bits);
+    end_timing(ctx, p);
+    MIRO_CUDA(ctx, cudaGetLastError());
+    return MIRO_GPU_OK;
+}
+
+int miro_gpu_trace_closest(miro_gpu_ctx* ctx, const miro_gpu_ray* rays, size_t n, miro_gpu_hit* hits) {
+    if (!ctx) return MIRO_GPU_EINVAL;
+    if (!ctx->has_scene) return set_error(ctx, MIRO_GPU_ENOSCENE, "trace before upload_scene");
+    if (n == 0) return MIRO_GPU_OK;
+    if (!rays || !hits) return set_error(ctx, MIRO_GPU_EINVAL, "NULL ray/hit buffer");
+    MIRO_CUDA(ctx, cudaSetDevice(ctx->device));
+    MIRO_CUDA(ctx, ctx->d_rays.reserve(n));
+    MIRO_CUDA(ctx, ctx->d_hits.reserve(n));
+    EventPair tot = begin_timing(ctx, false);
+    MIRO_CUDA(ctx, cudaMemcpyAsync(ctx->d_rays.ptr, rays, n * sizeof(miro_gpu_ray), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = miro_gpu_trace_closest_device(ctx, ctx->d_rays.ptr, n, ctx->d_hits.ptr);
+    if (rc) return rc;
+    MIRO_CUDA(ctx, cudaMemcpyAsync(hits, ctx->d_hits.ptr, n * sizeof(miro_gpu_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    end_timing(ctx, tot);
+    MIRO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MIRO_GPU_OK;
+}
+
+int miro_gpu_trace_any(miro_gpu_ctx* ctx, const miro_gpu_ray* rays, size_t n, uint32_t* occluded_bits) {
+    if (!ctx) return MIRO_GPU_EINVAL;
+    if (!ctx->has_scene) return set_error(ctx, MIRO_GPU_ENOSCENE, "trace before upload_scene");
+    if (n == 0) return MIRO_GPU_OK;
+    if (!rays || !occluded_bits) return set_error(ctx, MIRO_GPU_EINVAL, "NULL ray/bit buffer");
+    MIRO_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t words = (n + 31) / 32;
+    MIRO_CUDA(ctx, ctx->d_rays.reserve(n));
+    MIRO_CUDA(ctx, ctx->d_bits.reserve(words));
+    EventPair tot = begin_timing(ctx, false);
+    MIRO_CUDA(ctx, cudaMemcpyAsync(ctx->d_rays.ptr, rays, n * sizeof(miro_gpu_ray), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = miro_gpu_trace_any_device(ctx, ctx->d_rays.ptr, n, ctx->d_bits.ptr);
+    if (rc) return rc;
+    MIRO_CUDA(ctx, cudaMemcpyAsync(occluded_bits, ctx->d_bits.ptr, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    end_timing(ctx, tot);
+    MIRO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MIRO_GPU_OK;
+}
+
+int miro_gpu_enable_counting(miro_gpu_ctx* ctx, int enable) {
+    if (!ctx) return MIRO_GPU_EINVAL;
+    ctx->counting = enable != 0;
+    return MIRO_GPU_OK;
+}
+
+int miro_gpu_get_counters(miro_gpu_ctx* ctx, miro_gpu_counters* out) {
+    if (!ctx || !out) return MIRO_GPU_EINVAL;
+    MIRO_CUDA(ctx, cudaSetDevice(ctx->device));
+    MIRO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    drain_timing(ctx);
+    TraceCounters h;
+    MIRO_CUDA(ctx, cudaMemcpy(&h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+    out->rays_closest = h.rays_closest; out->rays_any = h.rays_any;
+    out->nodes_fetched = h.nodes; out->tris_tested = h.tris; out->insts_entered = h.insts;
+    out->trace_ms = ctx->trace_ms; out->total_ms = ctx->total_ms;
+    out->kernel_launches = ctx->launches;
+    return MIRO_GPU_OK;
+}
+
+int miro_gpu_reset_counters(miro_gpu_ctx* ctx) {
+    if (!ctx) return MIRO_GPU_EINVAL;
+    MIRO_CUDA(ctx, cudaSetDevice(ctx->device));
+    MIRO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    drain_timing(ctx);
+    MIRO_CUDA(ctx, cudaMemset(ctx->d_counters, 0, sizeof(TraceCounters)));
+    ctx->trace_ms = ctx->total_ms = 0.0; ctx->launches = 0;
+    return MIRO_GPU_OK;
+}
+
+}  // extern "C"

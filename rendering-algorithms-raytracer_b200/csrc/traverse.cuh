@@ -1,0 +1,260 @@
+// traverse.cuh — wide-BVH traversal and watertight ray/triangle intersection (device code, sm_100a).
+//
+// Replaces, on the GPU:
+//   BVH::intersect (QBVH branch)   reference src/BVH.cpp:1128-1178
+//   QBVH_Node::intersect           reference src/BVH.cpp:391-414   (4-wide slab test)
+//   intersect4                     reference src/BVH.cpp:1298-1459 (Moller-Trumbore, 4 triangles)
+//   ProxyObject::intersect         reference src/ProxyObject.cpp:76-95 (instancing, t shared)
+//   MB lanes of intersect4         reference src/BVH.cpp:1316-1335 (two-pose lerp at ray.time)
+//
+// Design (B200-first, not a translation):
+//   * one thread per ray, while-while traversal of 128-byte BVH4 nodes fetched with seven
+//     16-byte vector loads through the read-only path (the whole tree lives in the 126 MB L2;
+//     hot top levels in L1);
+//   * children are visited nearest-first (4-element sorting network) and the deferred ones go
+//     to a per-thread stack in SHARED memory laid out [entry][lane] (conflict-free, "warp
+//     coherent"); entries carry their entry distance so popped sub-trees behind the current
+//     hit are culled without a fetch.  The reference visits children unordered (0..3);
+//     closest-hit results are order independent except for exact-t ties;
+//   * the triangle test is a watertight edge-function test in ray space (shear + scale as in
+//     Woop/Benthin/Wald 2013) evaluated in FP32 with error-free products (Kahan) so the SIGN of
+//     every edge function is exact: neighbouring triangles agree on shared edges and no ray
+//     slips between them (the reference's test is not watertight — crack pixels in its Cornell
+//     render).  Same acceptance set as the reference: two-sided, edges inclusive,
+//     tMin <= t < current hit.t; barycentrics a,b are the weights of vertex 1 and vertex 2;
+//   * instances: one level (as the reference), ray transformed by the 3x4 inverse, direction NOT
+//     renormalised so t is shared with the parent space; a sentinel on the stack restores the
+//     world-space ray;
+//   * zero direction components use the reference's +-1e12 reciprocal (src/Ray.h:79-90) to
+//     avoid 0*inf NaNs in the slab test.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/miro_gpu.h"
+
+namespace miro {
+
+constexpr int TRACE_BLOCK = 128;        // threads per block of the traversal kernels
+constexpr int SMEM_STACK = 24;          // per-thread stack entries kept in shared memory
+constexpr int LMEM_STACK = 72;          // overflow entries (local memory, touched only by very deep trees)
+constexpr int32_t STACK_SENTINEL = 0x7ffffffe;   // "leave instance" marker
+
+struct DeviceScene {
+    const float4* nodes;     // 8 x float4 per node
+    const float4* tris;      // 3 x float4 per triangle
+    const float4* mbtris;    // 6 x float4 per motion-blur triangle
+    const float4* insts;     // 4 x float4 per instance
+    int32_t root;
+    uint32_t n_tris;
+};
+
+struct TraceCounters {
+    unsigned long long rays_closest, rays_any, nodes, tris, insts;
+};
+
+struct HitRec {
+    float t, a, b;
+    int32_t prim, inst;
+};
+
+__device__ __forceinline__ float safe_rcp_dir(float d) {
+    // src/Ray.h:79-90: 1/d, with d == 0 mapped to +-MIRO_TMAX by the sign of the IEEE quotient
+    if (d == 0.0f) return (__float_as_uint(d) >> 31) ? -MIRO_GPU_TMAX : MIRO_GPU_TMAX;
+    return 1.0f / d;
+}
+
+__device__ __forceinline__ float sel3(float x, float y, float z, int k) { return k == 0 ? x : (k == 1 ? y : z); }
+
+// error-free a*b - c*d (Kahan): relative error <= 1.5 ulp, sign always exact, exactly 0 when the true value is 0
+__device__ __forceinline__ float diff_of_products(float a, float b, float c, float d) {
+    float w = __fmul_rn(c, d);
+    float e = __fmaf_rn(-c, d, w);
+    float f = __fmaf_rn(a, b, -w);
+    return __fadd_rn(f, e);
+}
+
+struct RaySpace {
+    float ox, oy, oz;
+    float dx, dy, dz;
+    float ix, iy, iz;      // reciprocal direction (slab test)
+    float Sx, Sy, Sz;      // shear / scale of the watertight test
+    int kx, ky, kz;
+
+    __device__ __forceinline__ void set(float ox_, float oy_, float oz_, float dx_, float dy_, float dz_) {
+        ox = ox_; oy = oy_; oz = oz_; dx = dx_; dy = dy_; dz = dz_;
+        ix = safe_rcp_dir(dx); iy = safe_rcp_dir(dy); iz = safe_rcp_dir(dz);
+        float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+        kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
+        kx = kz + 1; if (kx == 3) kx = 0;
+        ky = kx + 1; if (ky == 3) ky = 0;
+        float dkz = sel3(dx, dy, dz, kz);
+        if (dkz < 0.0f) { int t = kx; kx = ky; ky = t; }
+        float rz = 1.0f / dkz;
+        Sx = sel3(dx, dy, dz, kx) * rz;
+        Sy = sel3(dx, dy, dz, ky) * rz;
+        Sz = rz;
+    }
+};
+
+// Watertight two-sided ray/triangle test.  Returns true and updates (t,a,b) when tmin <= t < tmax.
+__device__ __forceinline__ bool intersect_tri(const RaySpace& r, float tmin, float tmax,
+                                              float4 p0, float4 p1, float4 p2, float& t_out, float& a_out, float& b_out) {
+    const float Ax_ = p0.x - r.ox, Ay_ = p0.y - r.oy, Az_ = p0.z - r.oz;
+    const float Bx_ = p1.x - r.ox, By_ = p1.y - r.oy, Bz_ = p1.z - r.oz;
+    const float Cx_ = p2.x - r.ox, Cy_ = p2.y - r.oy, Cz_ = p2.z - r.oz;
+    const float Akz = sel3(Ax_, Ay_, Az_, r.kz), Bkz = sel3(Bx_, By_, Bz_, r.kz), Ckz = sel3(Cx_, Cy_, Cz_, r.kz);
+    const float Ax = __fmaf_rn(-r.Sx, Akz, sel3(Ax_, Ay_, Az_, r.kx));
+    const float Ay = __fmaf_rn(-r.Sy, Akz, sel3(Ax_, Ay_, Az_, r.ky));
+    const float Bx = __fmaf_rn(-r.Sx, Bkz, sel3(Bx_, By_, Bz_, r.kx));
+    const float By = __fmaf_rn(-r.Sy, Bkz, sel3(Bx_, By_, Bz_, r.ky));
+    const float Cx = __fmaf_rn(-r.Sx, Ckz, sel3(Cx_, Cy_, Cz_, r.kx));
+    const float Cy = __fmaf_rn(-r.Sy, Ckz, sel3(Cx_, Cy_, Cz_, r.ky));
+    const float U = diff_of_products(Cx, By, Cy, Bx);
+    const float V = diff_of_products(Ax, Cy, Ay, Cx);
+    const float W = diff_of_products(Bx, Ay, By, Ax);
+    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+    const float det = U + V + W;
+    if (det == 0.0f) return false;
+    const float Az = r.Sz * Akz, Bz = r.Sz * Bkz, Cz = r.Sz * Ckz;
+    const float T = U * Az + V * Bz + W * Cz;
+    const float rdet = 1.0f / det;
+    const float t = T * rdet;
+    if (!(t >= tmin && t < tmax)) return false;
+    t_out = t; a_out = V * rdet; b_out = W * rdet;
+    return true;
+}
+
+struct StackEntry { int32_t ref; float t; };
+
+// Per-thread traversal stack: first SMEM_STACK entries in shared memory ([entry][lane] layout),
+// the rest in local memory.
+struct TraversalStack {
+    unsigned long long* smem;   // base + threadIdx.x, stride = blockDim.x
+    unsigned long long lmem[LMEM_STACK];
+    int sp;
+    __device__ __forceinline__ void push(int32_t ref, float t) {
+        unsigned long long v = ((unsigned long long)__float_as_uint(t) << 32) | (uint32_t)ref;
+        if (sp < SMEM_STACK) smem[sp * TRACE_BLOCK] = v;
+        else if (sp - SMEM_STACK < LMEM_STACK) lmem[sp - SMEM_STACK] = v;
+        ++sp;    // entries beyond both stacks are dropped by the guard above (trees that deep are rejected at upload)
+    }
+    __device__ __forceinline__ StackEntry pop() {
+        --sp;
+        StackEntry e;
+        if (sp >= SMEM_STACK + LMEM_STACK) { e.ref = MIRO_GPU_CHILD_EMPTY; e.t = 0.f; return e; }
+        unsigned long long v = (sp < SMEM_STACK) ? smem[sp * TRACE_BLOCK] : lmem[sp - SMEM_STACK]; e.ref = (int32_t)(uint32_t)v; e.t = __uint_as_float((uint32_t)(v >> 32));
+        return e;
+    }
+};
+
+#define MIRO_CSWAP(ta, ca, tb, cb) { if (tb < ta) { float tt = ta; ta = tb; tb = tt; int32_t cc = ca; ca = cb; cb = cc; } }
+
+// Closest-hit (ANY=false) or any-hit (ANY=true) traversal of one ray.  `hit.t` must hold tmax on
+// entry; on return hit.prim >= 0 iff something was hit in [tmin, tmax).
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ void traverse(const DeviceScene& s, float ox, float oy, float oz, float dx, float dy, float dz,
+                                         float tmin, float time, unsigned long long* smem_stack, HitRec& hit,
+                                         uint32_t& n_nodes, uint32_t& n_tris, uint32_t& n_insts) {
+    RaySpace r;
+    r.set(ox, oy, oz, dx, dy, dz);
+    TraversalStack st;
+    st.smem = smem_stack; st.sp = 0;
+    int32_t cur = s.root;
+    int32_t cur_inst = -1;
+    hit.prim = -1; hit.inst = -1; hit.a = 0.f; hit.b = 0.f;
+
+    while (true) {
+        // ---- inner nodes: descend nearest-first until a leaf (or nothing) is reached
+        while (cur >= 0 && cur != MIRO_GPU_CHILD_EMPTY && cur != STACK_SENTINEL) {
+            const float4* n = s.nodes + (size_t)cur * 8;
+            const float4 lox = __ldg(n + 0), loy = __ldg(n + 1), loz = __ldg(n + 2);
+            const float4 hix = __ldg(n + 3), hiy = __ldg(n + 4), hiz = __ldg(n + 5);
+            const int4 ch = __ldg(reinterpret_cast<const int4*>(n + 6));
+            if (COUNT) ++n_nodes;
+            float tn0, tn1, tn2, tn3;
+#define MIRO_SLAB(LX, LY, LZ, HX, HY, HZ, CH, TN) { \
+            float ax = (LX - r.ox) * r.ix, bx = (HX - r.ox) * r.ix; \
+            float ay = (LY - r.oy) * r.iy, by = (HY - r.oy) * r.iy; \
+            float az = (LZ - r.oz) * r.iz, bz = (HZ - r.oz) * r.iz; \
+            float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin)); \
+            float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), hit.t)); \
+            TN = (tn <= tf && CH != MIRO_GPU_CHILD_EMPTY) ? tn : __int_as_float(0x7f800000); }
+            int32_t c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
+            MIRO_SLAB(lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, c0, tn0)
+            MIRO_SLAB(lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, c1, tn1)
+            MIRO_SLAB(lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, c2, tn2)
+            MIRO_SLAB(lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, c3, tn3)
+#undef MIRO_SLAB
+            MIRO_CSWAP(tn0, c0, tn1, c1) MIRO_CSWAP(tn2, c2, tn3, c3)
+            MIRO_CSWAP(tn0, c0, tn2, c2) MIRO_CSWAP(tn1, c1, tn3, c3)
+            MIRO_CSWAP(tn1, c1, tn2, c2)
+            const float inf = __int_as_float(0x7f800000);
+            if (tn3 < inf) st.push(c3, tn3);
+            if (tn2 < inf) st.push(c2, tn2);
+            if (tn1 < inf) st.push(c1, tn1);
+            if (tn0 < inf) cur = c0;
+            else cur = MIRO_GPU_CHILD_EMPTY;
+        }
+        // ---- leaf
+        if (cur < 0) {
+            const uint32_t u = (uint32_t)cur;
+            const uint32_t kind = (u >> 29) & 3u;
+            const uint32_t count = ((u >> MIRO_GPU_LEAF_INDEX_BITS) & 7u) + 1u;
+            const uint32_t first = u & ((1u << MIRO_GPU_LEAF_INDEX_BITS) - 1u);
+            if (kind == MIRO_GPU_KIND_TRI) {
+                for (uint32_t i = 0; i < count; ++i) {
+                    const float4* t = s.tris + (size_t)(first + i) * 3;
+                    const float4 p0 = __ldg(t), p1 = __ldg(t + 1), p2 = __ldg(t + 2);
+                    if (COUNT) ++n_tris;
+                    if (intersect_tri(r, tmin, hit.t, p0, p1, p2, hit.t, hit.a, hit.b)) {
+                        hit.prim = (int32_t)(first + i); hit.inst = cur_inst;
+                        if (ANY) return;
+                    }
+                }
+            } else if (kind == MIRO_GPU_KIND_MBTRI) {
+                const float w1 = time, w0 = 1.0f - time;    // src/BVH.cpp:1323-1334
+                for (uint32_t i = 0; i < count; ++i) {
+                    const float4* t = s.mbtris + (size_t)(first + i) * 6;
+                    const float4 a0 = __ldg(t), a1 = __ldg(t + 1), a2 = __ldg(t + 2);
+                    const float4 b0 = __ldg(t + 3), b1 = __ldg(t + 4), b2 = __ldg(t + 5);
+                    if (COUNT) ++n_tris;
+                    float4 p0, p1, p2;
+                    p0.x = w1 * b0.x + w0 * a0.x; p0.y = w1 * b0.y + w0 * a0.y; p0.z = w1 * b0.z + w0 * a0.z;
+                    p1.x = w1 * b1.x + w0 * a1.x; p1.y = w1 * b1.y + w0 * a1.y; p1.z = w1 * b1.z + w0 * a1.z;
+                    p2.x = w1 * b2.x + w0 * a2.x; p2.y = w1 * b2.y + w0 * a2.y; p2.z = w1 * b2.z + w0 * a2.z;
+                    if (intersect_tri(r, tmin, hit.t, p0, p1, p2, hit.t, hit.a, hit.b)) {
+                        hit.prim = (int32_t)(s.n_tris + first + i); hit.inst = cur_inst;
+                        if (ANY) return;
+                    }
+                }
+            } else {   // MIRO_GPU_KIND_INST: enter the first instance, defer the others
+                if (count > 1u) st.push(MIRO_GPU_LEAF(MIRO_GPU_KIND_INST, first + 1u, count - 1u), -__int_as_float(0x7f800000));
+                st.push(STACK_SENTINEL, -__int_as_float(0x7f800000));
+                const float4* m = s.insts + (size_t)first * 4;
+                const float4 r0 = __ldg(m), r1 = __ldg(m + 1), r2 = __ldg(m + 2);
+                const int4 meta = __ldg(reinterpret_cast<const int4*>(m + 3));
+                if (COUNT) ++n_insts;
+                // o' = M^-1 [o 1], d' = M^-1 [d 0]  (src/ProxyObject.cpp:78-79; affine, so w = 1)
+                const float nox = r0.x * ox + r0.y * oy + r0.z * oz + r0.w;
+                const float noy = r1.x * ox + r1.y * oy + r1.z * oz + r1.w;
+                const float noz = r2.x * ox + r2.y * oy + r2.z * oz + r2.w;
+                const float ndx = r0.x * dx + r0.y * dy + r0.z * dz;
+                const float ndy = r1.x * dx + r1.y * dy + r1.z * dz;
+                const float ndz = r2.x * dx + r2.y * dy + r2.z * dz;
+                r.set(nox, noy, noz, ndx, ndy, ndz);
+                cur_inst = (int32_t)first;
+                cur = meta.x;
+                continue;
+            }
+        }
+        // ---- pop
+        while (true) {
+            if (st.sp == 0) return;
+            StackEntry e = st.pop();
+            if (e.ref == STACK_SENTINEL) { r.set(ox, oy, oz, dx, dy, dz); cur_inst = -1; continue; }
+            if (e.t < hit.t) { cur = e.ref; break; }
+        }
+    }
+}
+
+}  // namespace miro

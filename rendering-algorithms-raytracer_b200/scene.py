@@ -1,0 +1,184 @@
+"""Thin Python handle on the native host layer (include/miro_host.h) and the GPU ABI (include/miro_gpu.h).
+
+Used by tests/ and bench.py.  All geometry processing, BVH construction, flattening and every ray
+is handled by libmiro_gpu.so; this file only marshals numpy / torch buffers into C pointers.
+"""
+import ctypes as C
+import numpy as np
+
+from . import capi
+
+RAY_DTYPE = np.dtype([("o", np.float32, 3), ("tmin", np.float32), ("d", np.float32, 3), ("tmax", np.float32),
+                      ("time", np.float32), ("flags", np.uint32), ("user", np.uint32, 2)])
+HIT_DTYPE = np.dtype([("t", np.float32), ("a", np.float32), ("b", np.float32), ("prim", np.int32), ("inst", np.int32)])
+assert RAY_DTYPE.itemsize == 48 and HIT_DTYPE.itemsize == 20
+
+
+class MiroError(RuntimeError):
+    pass
+
+
+def make_rays(origins, directions, tmin=capi.EPSILON, tmax=capi.TMAX, time=0.0):
+    """Pack (n,3) origins / directions into the 48-byte miro_gpu_ray layout."""
+    o = np.asarray(origins, np.float32); d = np.asarray(directions, np.float32)
+    r = np.zeros(o.shape[0], RAY_DTYPE)
+    r["o"] = o; r["d"] = d; r["tmin"] = tmin; r["tmax"] = tmax; r["time"] = time
+    return r
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class MiroScene:
+    """Scene described by a .miro script, pre-processed on the host, traced / rendered on the GPU."""
+
+    def __init__(self):
+        self.L = capi.lib()
+        self.h = self.L.miro_host_new()
+        self._keep = []
+        self.loaded = False
+        self.attached = False
+
+    def close(self):
+        if self.h:
+            self.L.miro_host_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self.L.miro_host_error(self.h).decode()
+            ctx = self.L.miro_host_ctx(self.h) if self.loaded else None
+            if ctx:
+                gm = self.L.miro_gpu_last_error(ctx).decode()
+                if gm:
+                    msg = f"{msg} | {gm}"
+            raise MiroError(f"{what} failed (rc={rc}): {msg}")
+
+    # ---- host side -------------------------------------------------------------------------
+    def preload_mesh(self, name, vertices, vidx, normals=None, nidx=None, uvs=None, tidx=None):
+        v = np.ascontiguousarray(vertices, np.float32).reshape(-1, 3)
+        vi = np.ascontiguousarray(vidx, np.uint32).reshape(-1, 3)
+        n = np.ascontiguousarray(normals, np.float32).reshape(-1, 3) if normals is not None and nidx is not None else None
+        ni = np.ascontiguousarray(nidx, np.uint32).reshape(-1, 3) if n is not None else None
+        t = np.ascontiguousarray(uvs, np.float32).reshape(-1, 2) if uvs is not None and tidx is not None else None
+        ti = np.ascontiguousarray(tidx, np.uint32).reshape(-1, 3) if t is not None else None
+        rc = self.L.miro_host_preload_mesh(self.h, name.encode(), _ptr(v), len(v), _ptr(vi), len(vi),
+                                           _ptr(n), 0 if n is None else len(n), _ptr(ni),
+                                           _ptr(t), 0 if t is None else len(t), _ptr(ti))
+        self._check(rc, "preload_mesh")
+
+    def preload_image(self, name, texels, hdr=True):
+        a = np.ascontiguousarray(texels, np.float32)
+        if a.ndim == 2:
+            a = a[:, :, None]
+        h, w, c = a.shape
+        self._check(self.L.miro_host_preload_image(self.h, name.encode(), _ptr(a), w, h, c, 1 if hdr else 0), "preload_image")
+
+    def load_script(self, path, asset_root="."):
+        self._check(self.L.miro_host_load_script(self.h, str(path).encode(), str(asset_root).encode()), "load_script")
+        self.loaded = True
+        return self
+
+    def desc(self):
+        d = capi.SceneDesc()
+        self._check(self.L.miro_host_get_desc(self.h, C.byref(d)), "get_desc")
+        return d
+
+    def camera(self):
+        c = capi.Camera()
+        self._check(self.L.miro_host_get_camera(self.h, C.byref(c)), "get_camera")
+        return c
+
+    def render_params(self):
+        p = capi.RenderParams()
+        self._check(self.L.miro_host_get_render_params(self.h, C.byref(p)), "get_render_params")
+        return p
+
+    def bvh_stats(self):
+        n, l, d, s = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_double()
+        self._check(self.L.miro_host_bvh_stats(self.h, C.byref(n), C.byref(l), C.byref(d), C.byref(s)), "bvh_stats")
+        return {"nodes": n.value, "leaves": l.value, "max_depth": d.value, "sah_cost": s.value}
+
+    def prim_table(self):
+        """(n_prims, 2) int array: (mesh ordinal, triangle index) per primitive id, and instance ordinals."""
+        d = self.desc()
+        n = d.n_tris + d.n_mbtris
+        prims = np.ctypeslib.as_array(C.cast(d.prims, C.POINTER(C.c_uint32)), shape=(n, 12)) if n else np.zeros((0, 12), np.uint32)
+        inst = (np.ctypeslib.as_array(C.cast(d.instances, C.POINTER(C.c_uint32)), shape=(d.n_instances, 16))[:, 13].copy()
+                if d.n_instances else np.zeros(0, np.uint32))
+        return prims[:, 7].astype(np.int64), prims[:, 8].astype(np.int64), inst.astype(np.int64)
+
+    def resolve_hits(self, hits):
+        """Map GPU hit records to the reference's identity (mesh ordinal, triangle index, proxy ordinal)."""
+        mesh_of, tri_of, inst_ord = self.prim_table()
+        prim = hits["prim"]; ok = prim >= 0
+        mesh = np.full(len(hits), -1, np.int64); tri = np.full(len(hits), -1, np.int64); proxy = np.full(len(hits), -1, np.int64)
+        mesh[ok] = mesh_of[prim[ok]]; tri[ok] = tri_of[prim[ok]]
+        hi = ok & (hits["inst"] >= 0)
+        proxy[hi] = inst_ord[hits["inst"][hi]]
+        return mesh, tri, proxy
+
+    # ---- GPU side --------------------------------------------------------------------------
+    def attach(self, device=0):
+        self._check(self.L.miro_host_attach(self.h, device), "attach")
+        self.attached = True
+        return self
+
+    @property
+    def ctx(self):
+        return self.L.miro_host_ctx(self.h)
+
+    def _gpu_check(self, rc, what):
+        if rc != 0:
+            raise MiroError(f"{what} failed (rc={rc}): {self.L.miro_gpu_last_error(self.ctx).decode()}")
+
+    def trace_closest(self, rays):
+        """Host buffers in, host buffers out (H2D + kernel + D2H inside the call)."""
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        hits = np.empty(len(rays), HIT_DTYPE)
+        self._gpu_check(self.L.miro_gpu_trace_closest(self.ctx, _ptr(rays), len(rays), _ptr(hits)), "trace_closest")
+        return hits
+
+    def trace_any(self, rays):
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        bits = np.zeros((len(rays) + 31) // 32, np.uint32)
+        self._gpu_check(self.L.miro_gpu_trace_any(self.ctx, _ptr(rays), len(rays), _ptr(bits)), "trace_any")
+        return np.unpackbits(bits.view(np.uint8), bitorder="little")[:len(rays)].astype(bool)
+
+    def trace_closest_device(self, d_rays_ptr, n, d_hits_ptr):
+        self._gpu_check(self.L.miro_gpu_trace_closest_device(self.ctx, d_rays_ptr, n, d_hits_ptr), "trace_closest_device")
+
+    def trace_any_device(self, d_rays_ptr, n, d_bits_ptr):
+        self._gpu_check(self.L.miro_gpu_trace_any_device(self.ctx, d_rays_ptr, n, d_bits_ptr), "trace_any_device")
+
+    def set_stream(self, cuda_stream_ptr):
+        self._gpu_check(self.L.miro_gpu_set_stream(self.ctx, cuda_stream_ptr), "set_stream")
+
+    def render(self, shard_index=0, shard_count=1, want_bytes=False):
+        p = self.render_params()
+        rgb = np.zeros((p.height, p.width, 3), np.float32)
+        rgb8 = np.zeros((p.height, p.width, 3), np.uint8) if want_bytes else None
+        self._check(self.L.miro_host_raytrace_image(self.h, _ptr(rgb), _ptr(rgb8), shard_index, shard_count), "raytrace_image")
+        return (rgb, rgb8) if want_bytes else rgb
+
+    def render_device(self, d_rgb_ptr, params=None, camera=None):
+        p = params or self.render_params(); c = camera or self.camera()
+        self._gpu_check(self.L.miro_gpu_render(self.ctx, C.byref(c), C.byref(p), d_rgb_ptr), "render")
+
+    def enable_counting(self, on=True):
+        self._gpu_check(self.L.miro_gpu_enable_counting(self.ctx, 1 if on else 0), "enable_counting")
+
+    def reset_counters(self):
+        self._gpu_check(self.L.miro_gpu_reset_counters(self.ctx), "reset_counters")
+
+    def counters(self):
+        c = capi.Counters()
+        self._gpu_check(self.L.miro_gpu_get_counters(self.ctx, C.byref(c)), "get_counters")
+        return {k: getattr(c, k) for k, _ in capi.Counters._fields_}

@@ -1,0 +1,113 @@
+"""Shared test plumbing: golden fixtures -> scenes, the oracle library, comparison helpers."""
+import ctypes as C
+import os
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+FULL = os.path.join(ROOT, "oracle", "_ref", "fixtures")
+ORACLE_LIB = os.path.join(ROOT, "oracle", "_build", "libmiro_oracle.so")
+
+import miro_b200 as mb  # noqa: E402
+from miro_b200 import capi  # noqa: E402
+
+REFHIT = np.dtype([("t", "f4"), ("a", "f4"), ("b", "f4"), ("mesh", "i4"), ("tri", "i4"), ("proxy", "i4")])
+
+
+def fixture_path(scene, full=False):
+    p = os.path.join(FULL if full else GOLDEN, scene + ".npz")
+    return p if os.path.exists(p) else None
+
+
+class Fixture:
+    """A golden file: the reference's geometry, rays, hits and images for one scene script."""
+
+    def __init__(self, path):
+        z = np.load(path, allow_pickle=False)
+        self.z = z
+        self.names = [str(n) for n in z["mesh_names"]]
+        self.script = str(z["script"])
+        self.rays = z["rays"]; self.hits = z["hits"]; self.ray_index = z["ray_index"]
+        self.radiance = z["radiance"].astype(np.float32) if "radiance" in z.files else None
+        self.image8 = z["image8"] if "image8" in z.files else None
+
+    def mesh(self, k):
+        g = lambda key: self.z[f"m{k}_{key}"]
+        ti = g("ti")
+        return dict(vertices=g("v"), vidx=g("vi").astype(np.uint32), normals=g("n"), nidx=g("ni").astype(np.uint32),
+                    uvs=g("t") if len(ti) else None, tidx=ti.astype(np.uint32) if len(ti) else None)
+
+    def scene(self, script_override=None, images=None):
+        """Build a MiroScene from the fixture: the reference's own geometry, the same scene script."""
+        sc = mb.MiroScene()
+        for k, name in enumerate(self.names):
+            sc.preload_mesh(name, **self.mesh(k))
+        for name, tex in (images or {}).items():
+            sc.preload_image(name, tex)
+        with tempfile.NamedTemporaryFile("w", suffix=".miro", delete=False) as f:
+            f.write(script_override or self.script)
+            path = f.name
+        try:
+            sc.load_script(path, "/nonexistent-asset-root")
+        finally:
+            os.unlink(path)
+        return sc
+
+
+_oracle = None
+
+
+def oracle():
+    """The CPU restatement (oracle/miro_oracle.c), compiled by __graft_entry__.build()."""
+    global _oracle
+    if _oracle is None:
+        L = C.CDLL(ORACLE_LIB)
+        L.oracle_trace_closest.argtypes = [C.POINTER(capi.SceneDesc), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.oracle_trace_closest.restype = C.c_int
+        L.oracle_trace_any.argtypes = [C.POINTER(capi.SceneDesc), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.oracle_trace_any.restype = C.c_int
+        _oracle = L
+    return _oracle
+
+
+def oracle_trace_closest(scene, rays):
+    rays = np.ascontiguousarray(rays, mb.RAY_DTYPE)
+    hits = np.empty(len(rays), mb.HIT_DTYPE)
+    ctr = np.zeros(2, np.uint64)
+    d = scene.desc()
+    oracle().oracle_trace_closest(C.byref(d), rays.ctypes.data, len(rays), hits.ctypes.data, ctr.ctypes.data)
+    return hits, ctr
+
+
+def oracle_trace_any(scene, rays):
+    rays = np.ascontiguousarray(rays, mb.RAY_DTYPE)
+    bits = np.zeros((len(rays) + 31) // 32, np.uint32)
+    ctr = np.zeros(2, np.uint64)
+    d = scene.desc()
+    oracle().oracle_trace_any(C.byref(d), rays.ctypes.data, len(rays), bits.ctypes.data, ctr.ctypes.data)
+    return np.unpackbits(bits.view(np.uint8), bitorder="little")[:len(rays)].astype(bool)
+
+
+def compare_hits(scene, hits, ref, t_rel=1e-5):
+    """Compare product hits with reference-identity hits (mesh, tri, proxy, t).
+
+    Returns a dict of statistics.  A mismatch is a *tie* when both sides report a hit at the same
+    distance (|dt| <= t_rel * t): an edge / vertex shared by two triangles, where the winner depends on
+    visiting order.  Everything else is a *hard* mismatch.
+    """
+    mesh, tri, proxy = scene.resolve_hits(hits) if hits.dtype == mb.HIT_DTYPE else (hits["mesh"], hits["tri"], hits["proxy"])
+    r_hit = ref["mesh"] >= 0; g_hit = mesh >= 0
+    same = (mesh == ref["mesh"]) & (tri == ref["tri"]) & (proxy == ref["proxy"])
+    both = r_hit & g_hit
+    dt = np.abs(hits["t"] - ref["t"]) / np.maximum(np.abs(ref["t"]), 1e-30)
+    tie = ~same & both & (dt <= t_rel)
+    hard = ~same & ~tie
+    ok = same & both
+    return dict(n=len(ref), id_match=float(same.mean()), ties=int(tie.sum()), hard=int(hard.sum()),
+                hard_idx=np.nonzero(hard)[0], max_rel_t=float(dt[ok].max()) if ok.any() else 0.0,
+                frac_t_within=float((dt[ok] <= t_rel).mean()) if ok.any() else 1.0,
+                max_abs_a=float(np.abs(hits["a"] - ref["a"])[ok].max()) if ok.any() else 0.0,
+                max_abs_b=float(np.abs(hits["b"] - ref["b"])[ok].max()) if ok.any() else 0.0,
+                closer=int((hard & g_hit & ((hits["t"] < ref["t"]) | ~r_hit)).sum()))
