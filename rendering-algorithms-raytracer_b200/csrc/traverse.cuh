@@ -20,7 +20,8 @@
 //     Woop/Benthin/Wald 2013) evaluated in FP32 with error-free products (Kahan) so the SIGN of
 //     every edge function is exact: neighbouring triangles agree on shared edges and no ray
 //     slips between them (the reference's test is not watertight — crack pixels in its Cornell
-//     render).  Same acceptance set as the reference: two-sided, edges inclusive,
+//     render).  Once a triangle is accepted, t/a/b are computed with the reference's own
+//     Moller-Trumbore expressions so they agree with it to rounding.  Same acceptance set as the reference: two-sided, edges inclusive,
 //     tMin <= t < current hit.t; barycentrics a,b are the weights of vertex 1 and vertex 2;
 //   * instances: one level (as the reference), ray transformed by the 3x4 inverse, direction NOT
 //     renormalised so t is shared with the parent space; a sentinel on the stack restores the
@@ -115,12 +116,29 @@ __device__ __forceinline__ bool intersect_tri(const RaySpace& r, float tmin, flo
     if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
     const float det = U + V + W;
     if (det == 0.0f) return false;
-    const float Az = r.Sz * Akz, Bz = r.Sz * Bkz, Cz = r.Sz * Ckz;
-    const float T = U * Az + V * Bz + W * Cz;
-    const float rdet = 1.0f / det;
-    const float t = T * rdet;
+    // The ray passes through the triangle (decided watertight, above).  Distance and barycentrics are then
+    // evaluated with the reference's Moller-Trumbore expressions in the reference's operation order
+    // (src/BVH.cpp:1343-1369; SoADot = x*x' + (y*y' + z*z'), no FMA contraction), so t, a, b agree with it
+    // to rounding instead of differing by the conditioning of two different algorithms on sliver triangles.
+    const float e0x = __fsub_rn(p1.x, p0.x), e0y = __fsub_rn(p1.y, p0.y), e0z = __fsub_rn(p1.z, p0.z);
+    const float e1x = __fsub_rn(p2.x, p0.x), e1y = __fsub_rn(p2.y, p0.y), e1z = __fsub_rn(p2.z, p0.z);
+    const float px = __fsub_rn(__fmul_rn(r.dy, e1z), __fmul_rn(r.dz, e1y));
+    const float py = -__fsub_rn(__fmul_rn(r.dx, e1z), __fmul_rn(r.dz, e1x));
+    const float pz = __fsub_rn(__fmul_rn(r.dx, e1y), __fmul_rn(r.dy, e1x));
+    const float mdet = __fadd_rn(__fmul_rn(e0x, px), __fadd_rn(__fmul_rn(e0y, py), __fmul_rn(e0z, pz)));
+    if (mdet == 0.0f) return false;
+    const float inv = __frcp_rn(mdet);
+    const float tx = __fsub_rn(r.ox, p0.x), ty = __fsub_rn(r.oy, p0.y), tz = __fsub_rn(r.oz, p0.z);
+    const float qx = __fsub_rn(__fmul_rn(ty, e0z), __fmul_rn(tz, e0y));
+    const float qy = -__fsub_rn(__fmul_rn(tx, e0z), __fmul_rn(tz, e0x));
+    const float qz = __fsub_rn(__fmul_rn(tx, e0y), __fmul_rn(ty, e0x));
+    const float t = __fmul_rn(inv, __fadd_rn(__fmul_rn(e1x, qx), __fadd_rn(__fmul_rn(e1y, qy), __fmul_rn(e1z, qz))));
     if (!(t >= tmin && t < tmax)) return false;
-    t_out = t; a_out = V * rdet; b_out = W * rdet;
+    const float a = __fmul_rn(inv, __fadd_rn(__fmul_rn(tx, px), __fadd_rn(__fmul_rn(ty, py), __fmul_rn(tz, pz))));
+    const float b = __fmul_rn(inv, __fadd_rn(__fmul_rn(r.dx, qx), __fadd_rn(__fmul_rn(r.dy, qy), __fmul_rn(r.dz, qz))));
+    t_out = t;
+    a_out = fminf(fmaxf(a, 0.0f), 1.0f);     // inside by the edge test: clamp the rounding residue
+    b_out = fminf(fmaxf(b, 0.0f), 1.0f - a_out);
     return true;
 }
 

@@ -25,26 +25,27 @@ def test_closest_hit_matches_reference(loaded):
     hits = sc.trace_closest(fx.rays)
     st = helpers.compare_hits(sc, hits, fx.hits, t_rel=1e-5)
     print(name, {k: v for k, v in st.items() if k != "hard_idx"})
-    # a hard mismatch is allowed only where the (non-watertight) reference missed a closer triangle
-    assert st["hard"] - st["closer"] == 0, st
-    assert st["hard"] <= 1e-4 * st["n"], st
-    assert (st["id_match"] >= 0.9999) or (st["ties"] + st["hard"] == round((1 - st["id_match"]) * st["n"])), st
-    assert st["frac_t_within"] >= 0.9999, st
-    assert st["max_abs_a"] < 2e-3 and st["max_abs_b"] < 2e-3, st
+    # every id mismatch must be an edge/vertex case; C1's symmetric camera puts a whole pixel diagonal exactly on
+    # the shared diagonal of the back wall's two triangles, so its tie count alone exceeds 0.01 % of the rays
+    assert st["hard"] == 0, st
+    assert st["id_match"] >= 0.9999 or name == "c1_cornell", st
+    assert st["id_match"] >= 0.999, st
+    assert st["frac_t_within"] == 1.0, st          # hit t within 1e-5 relative wherever the ids agree
+    assert st["max_abs_a"] < 1e-4 and st["max_abs_b"] < 1e-4, st
 
 
 def test_closest_hit_matches_oracle(loaded):
+    """Same rays through the CPU restatement (reference traversal order + Moller-Trumbore) on the same flattened scene."""
     name, fx, sc = loaded
     hits = sc.trace_closest(fx.rays)
     ohits, _ = helpers.oracle_trace_closest(sc, fx.rays)
-    same = hits["prim"] == ohits["prim"]
-    both = same & (hits["prim"] >= 0)
-    dt = np.abs(hits["t"] - ohits["t"]) / np.maximum(np.abs(ohits["t"]), 1e-30)
-    tie = ~same & (hits["prim"] >= 0) & (ohits["prim"] >= 0) & (dt <= 1e-5)
-    hard = ~same & ~tie
-    print(name, "oracle id match", same.mean(), "ties", tie.sum(), "hard", hard.sum())
-    assert hard.sum() <= 1e-4 * len(hits)
-    assert (dt[both] <= 1e-5).mean() >= 0.9999
+    omesh, otri, oproxy = sc.resolve_hits(ohits)
+    oref = np.zeros(len(ohits), helpers.REFHIT)
+    oref["t"], oref["a"], oref["b"], oref["mesh"], oref["tri"], oref["proxy"] = ohits["t"], ohits["a"], ohits["b"], omesh, otri, oproxy
+    st = helpers.compare_hits(sc, hits, oref)
+    print(name, {k: v for k, v in st.items() if k != "hard_idx"})
+    assert st["hard"] == 0, st
+    assert st["id_match"] >= 0.999 and st["frac_t_within"] == 1.0, st
 
 
 def test_any_hit_matches_closest(loaded):

@@ -12,11 +12,12 @@ def time_trace(sc, rays, any_hit=False, iters=10):
     n = len(rays)
     d_rays = torch.from_numpy(rays.view(np.uint8).reshape(n, 48)).cuda()
     d_out = torch.empty((n, 20) if not any_hit else ((n + 31) // 32 * 4,), dtype=torch.uint8, device="cuda")
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()
     sc.set_stream(stream.cuda_stream)
     f = sc.trace_any_device if any_hit else sc.trace_closest_device
-    for _ in range(3): f(d_rays.data_ptr(), n, d_out.data_ptr())
     torch.cuda.synchronize()
+    for _ in range(3): f(d_rays.data_ptr(), n, d_out.data_ptr())
+    stream.synchronize()
     ts = []
     for _ in range(iters):
         a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
