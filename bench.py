@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s of the ray-casting hot path on B200 (BASELINE.json metric), with roofline and CPU baseline.
+
+Workload (BASELINE config C2, stand-in geometry because bunny/dragon are missing from the reference mount):
+Models/Final/explosion01.obj (86 914 triangles, geometry as the reference's loader left it, carried by the
+fixture files), 1920x1080.  One STEP = one pass of the hot path over one batch of rays:
+    (i)   2 073 600 coherent primary rays at pixel centres      -> closest-hit  (Scene::trace)
+    (ii)  2 073 600 seeded incoherent rays (origins ~U(AABB), directions ~U(S^2))  -> closest-hit
+    (iii) 2 073 600 shadow rays (from the incoherent hits towards the point light)  -> any-hit
+A "ray" is one Scene::trace query.  `value` is device throughput with the ray buffers resident in HBM;
+`e2e` is the same step through the host-pointer C ABI (miro_gpu_trace_closest / _any) from PINNED host
+buffers, H2D + kernels + D2H inside the timed region.  Under torchrun each rank traces its own batch
+(weak scaling, no data-path collective; the scene is replicated).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WIDTH, HEIGHT = 1920, 1080
+N_BATCH = WIDTH * HEIGHT
+LIGHT_POS = np.array([-2.0, 4.0, 3.0], np.float32)
+SCENE = "c2_explosion"
+WORKLOAD = ("C2 stand-in: explosion01.obj 86914 tris, 1920x1080: 2073600 primary + 2073600 incoherent closest-hit "
+            "+ 2073600 shadow any-hit rays per step")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def primary_rays(cam, w, h):
+    """Pinhole rays at pixel centres (Camera::eyeRayAdaptive with 0.5 offsets, src/Camera.cpp:116-158), row 0 = bottom."""
+    from miro_b200 import RAY_DTYPE
+    eye = np.array(cam.eye[:], np.float32); vd = np.array(cam.view_dir[:], np.float32); up = np.array(cam.up[:], np.float32)
+    wv = -vd / np.linalg.norm(vd); u = np.cross(up, wv); u /= np.linalg.norm(u); v = np.cross(wv, u)
+    top = np.tan(np.float32(cam.fov_deg) * np.float32(3.1415926 / 360.0)); right = top * w / h
+    xs = (-right + 2 * right * (np.arange(w, dtype=np.float32) + 0.5) / w)[None, :, None]
+    ys = (-top + 2 * top * (np.arange(h, dtype=np.float32) + 0.5) / h)[:, None, None]
+    d = xs * u[None, None, :] + ys * v[None, None, :] - wv[None, None, :]
+    d = (d / np.linalg.norm(d, axis=2, keepdims=True)).reshape(-1, 3).astype(np.float32)
+    r = np.zeros(w * h, RAY_DTYPE)
+    r["o"] = eye; r["d"] = d; r["tmin"] = 1e-3; r["tmax"] = 1e12
+    return r
+
+
+def incoherent_rays(lo, hi, n, seed):
+    from miro_b200 import RAY_DTYPE
+    rng = np.random.default_rng(seed)
+    c, e = 0.5 * (lo + hi), 0.55 * (hi - lo) + 1e-3
+    r = np.zeros(n, RAY_DTYPE)
+    r["o"] = (c + e * rng.uniform(-1, 1, (n, 3))).astype(np.float32)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    r["d"] = d.astype(np.float32); r["tmin"] = 1e-3; r["tmax"] = 1e12
+    return r
+
+
+def shadow_rays(src, hits, light):
+    """Shadow rays as PointLight::sampleLight casts them (src/PointLight.cpp:20-48): from the hit point (or, for a
+    miss, from the ray origin) towards the light, tmin 1e-3, tmax = distance."""
+    from miro_b200 import RAY_DTYPE
+    t = np.where(hits["prim"] >= 0, hits["t"], 0.0).astype(np.float32)
+    p = src["o"] + t[:, None] * src["d"]
+    L = light[None, :] - p
+    dist = np.linalg.norm(L, axis=1).astype(np.float32)
+    r = np.zeros(len(src), RAY_DTYPE)
+    r["o"] = p; r["d"] = (L / np.maximum(dist, 1e-20)[:, None]).astype(np.float32); r["tmin"] = 1e-3; r["tmax"] = dist
+    return r
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index; self.rows = []; self.stop_flag = False; self.proc = None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def write_obj_scene(fx, tmp):
+    """Materialise the fixture's geometry as OBJ + script so the reference binary can load it with its own loader."""
+    script = fx.script
+    for k, name in enumerate(fx.names):
+        m = fx.mesh(k)
+        path = os.path.join(tmp, name + ".obj")
+        with open(path, "w") as f:
+            for v in m["vertices"]:
+                f.write("v %.9g %.9g %.9g\n" % tuple(v))
+            for t in m["vidx"]:
+                f.write("f %d %d %d\n" % (t[0] + 1, t[1] + 1, t[2] + 1))
+        lines = []
+        for line in script.splitlines():
+            tok = line.split()
+            if len(tok) >= 3 and tok[0] == "mesh" and tok[1] == name:
+                line = "mesh %s %s" % (name, path)
+            lines.append(line)
+        script = "\n".join(lines) + "\n"
+    sp = os.path.join(tmp, "scene.miro")
+    open(sp, "w").write(script)
+    return sp
+
+
+def reference_trace(fx, batches, threads, repeat):
+    """Time the reference's own Scene::trace (oracle/_ref/miro_ref) on the host cores; falls back to the oracle port."""
+    import helpers
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "miro_ref")
+    rays = np.concatenate(batches)
+    if os.path.exists(ref_bin):
+        with tempfile.TemporaryDirectory() as tmp:
+            sp = write_obj_scene(fx, tmp)
+            rp = os.path.join(tmp, "rays.bin"); rays.tofile(rp)
+            p = subprocess.run([ref_bin, "--scene", sp, "--assets", tmp, "--threads", str(threads), "--repeat", str(repeat), "--trace", rp],
+                               stderr=subprocess.PIPE, text=True)
+            ev = [json.loads(l) for l in p.stderr.splitlines() if l.startswith("{")]
+            tr = [e for e in ev if e.get("event") == "trace"]
+            if p.returncode == 0 and tr:
+                return tr[0]["seconds"], len(rays), "reference", tr[0]["threads"]
+    sc = fx.scene()
+    t0 = time.time(); helpers.oracle_trace_closest(sc, rays); t1 = time.time()
+    return t1 - t0, len(rays), "port", 1
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="miro_gpu", choices=["miro_gpu", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "miro_gpu" else args.warmup
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import __graft_entry__ as g
+    import helpers
+    path = helpers.fixture_path(SCENE, full=True) or helpers.fixture_path(SCENE)
+    fx = helpers.Fixture(path)
+    allv = np.concatenate([fx.mesh(k)["vertices"] for k in range(len(fx.names))])
+    lo, hi = allv.min(0), allv.max(0)
+    hbm_peak, peak_src = peaks()
+    config = {"workload": WORKLOAD, "scene": SCENE, "triangles": int(sum(len(fx.mesh(k)["vidx"]) for k in range(len(fx.names)))),
+              "rays_per_step_per_gpu": 3 * N_BATCH, "l2_policy": "inputs_larger_than_L2 (298 MB of rays per step; the 6 MB BVH stays L2-resident by nature of the workload)",
+              "sharding": "rays per rank, scene replicated, no collective"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        threads = min(os.cpu_count() or 1, 16)
+        sc_cpu = fx.scene()
+        cam = sc_cpu.camera()
+        prim = primary_rays(cam, WIDTH, HEIGHT)
+        inco = incoherent_rays(lo, hi, N_BATCH, 0x5EED)
+        # bounded sample of the step: 1/8 of each batch (strided, keeps the coherence pattern of the rows)
+        stride = 8
+        sample = [prim.reshape(HEIGHT, WIDTH)[::2, ::4].reshape(-1).copy(), inco[::stride].copy()]
+        ohits, _ = helpers.oracle_trace_closest(sc_cpu, sample[1])
+        sample.append(shadow_rays(sample[1], ohits, LIGHT_POS))
+        for _ in range(args.warmup):
+            reference_trace(fx, sample, threads, 1)
+        ts = []
+        for _ in range(args.steps):
+            sec, n, kind, used = reference_trace(fx, sample, threads, 1)
+            ts.append(sec)
+        sec = float(np.mean(ts)); n = sum(len(b) for b in sample)
+        val = n / sec * 1e-6
+        line = {"impl": "reference", "metric": "Mrays/s", "value": val, "unit": "Mrays/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config, "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": used, "kind": kind,
+                                                   "sample": "1/8 of each of the 3 ray batches of one step (%d rays) per step" % n},
+                "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ GPU arm
+    import torch
+    import miro_b200 as mb
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this framework has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sc = fx.scene().attach(local)
+    cam = sc.camera()
+    prim = primary_rays(cam, WIDTH, HEIGHT)
+    inco = incoherent_rays(lo, hi, N_BATCH, 0x5EED + rank)
+    inco_hits = sc.trace_closest(inco)
+    shad = shadow_rays(inco, inco_hits, LIGHT_POS)
+    batches = [prim, inco, shad]
+    stream = torch.cuda.Stream()
+    sc.set_stream(stream.cuda_stream)
+
+    def dev(a):
+        return torch.from_numpy(a.view(np.uint8).reshape(len(a), -1)).cuda()
+    d_rays = [dev(b) for b in batches]
+    d_hits = [torch.empty((N_BATCH, 20), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    d_bits = torch.empty(((N_BATCH + 31) // 32,), dtype=torch.int32, device="cuda")
+
+    def step():
+        sc.trace_closest_device(d_rays[0].data_ptr(), N_BATCH, d_hits[0].data_ptr())
+        sc.trace_closest_device(d_rays[1].data_ptr(), N_BATCH, d_hits[1].data_ptr())
+        sc.trace_any_device(d_rays[2].data_ptr(), N_BATCH, d_bits.data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # algorithmic bytes: device counters of the shipped layout (128 B nodes, 48 B triangles, 48 B ray in, 20 B hit / 1 bit out)
+    sc.enable_counting(True)
+    per_launch = []
+    for i, f in enumerate((sc.trace_closest_device, sc.trace_closest_device, sc.trace_any_device)):
+        sc.reset_counters()
+        f(d_rays[i].data_ptr(), N_BATCH, (d_hits[min(i, 1)] if i < 2 else d_bits).data_ptr())
+        c = sc.counters()
+        out_bytes = 20 * N_BATCH if i < 2 else 4 * ((N_BATCH + 31) // 32)
+        per_launch.append({"nodes": c["nodes_fetched"], "tris": c["tris_tested"],
+                           "bytes": c["nodes_fetched"] * 128 + c["tris_tested"] * 48 + c["insts_entered"] * 64 + 48 * N_BATCH + out_bytes})
+    sc.enable_counting(False)
+
+    sampler = ClockSampler(local); sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    t_wall0 = time.time()
+    for k in range(args.steps):
+        ev[k][0].record(stream)
+        sc.trace_closest_device(d_rays[0].data_ptr(), N_BATCH, d_hits[0].data_ptr()); ev[k][1].record(stream)
+        sc.trace_closest_device(d_rays[1].data_ptr(), N_BATCH, d_hits[1].data_ptr()); ev[k][2].record(stream)
+        sc.trace_any_device(d_rays[2].data_ptr(), N_BATCH, d_bits.data_ptr()); ev[k][3].record(stream)
+    stream.synchronize()
+    barrier()
+    clocks = sampler.finish()
+    total_ms = ev[0][0].elapsed_time(ev[-1][3])
+    launch_ms = [float(np.mean([ev[k][i].elapsed_time(ev[k][i + 1]) for k in range(args.steps)])) for i in range(3)]
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    rays_total = 3 * N_BATCH * args.steps * world
+    value = rays_total / total_ms * 1e-3
+
+    # end to end through the host-pointer ABI, pinned host buffers
+    pinned = [torch.from_numpy(b.view(np.uint8).reshape(len(b), -1).copy()).pin_memory() for b in batches]
+    out_hits = [torch.empty((N_BATCH, 20), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    out_bits = torch.empty(((N_BATCH + 31) // 32,), dtype=torch.int32).pin_memory()
+    L = sc.L
+
+    def e2e_step():
+        L.miro_gpu_trace_closest(sc.ctx, pinned[0].data_ptr(), N_BATCH, out_hits[0].data_ptr())
+        L.miro_gpu_trace_closest(sc.ctx, pinned[1].data_ptr(), N_BATCH, out_hits[1].data_ptr())
+        L.miro_gpu_trace_any(sc.ctx, pinned[2].data_ptr(), N_BATCH, out_bits.data_ptr())
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.time()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.time() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = 3 * N_BATCH * e2e_steps * world / e2e_s * 1e-6
+    assert np.array_equal(out_hits[1].numpy().view(mb.HIT_DTYPE).reshape(-1)["prim"], inco_hits["prim"])
+
+    if rank == 0:
+        dom = int(np.argmax(launch_ms))
+        kernel_names = ["k_trace<closest> primary", "k_trace<closest> incoherent", "k_trace<any> shadow"]
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):      # dram__bytes_read+write per launch from the committed ncu --set full capture
+            traffic = json.load(open(tp)).get("per_launch_dram_bytes", {}).get(kernel_names[dom])
+        achieved = per_launch[dom]["bytes"] / (launch_ms[dom] * 1e-3) * 1e-9
+        line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
+                "gpu_launches": 3 * args.steps,
+                "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": 3 * N_BATCH * 48,
+                        "d2h_bytes_per_step": 2 * N_BATCH * 20 + 4 * ((N_BATCH + 31) // 32), "steps": e2e_steps},
+                "roofline": {"bound": "hbm", "kernel": kernel_names[dom],
+                             "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": peak_src,
+                             "traffic": traffic, "algorithmic_bytes_per_launch": per_launch[dom]["bytes"],
+                             "nodes_per_ray": per_launch[dom]["nodes"] / N_BATCH, "tris_per_ray": per_launch[dom]["tris"] / N_BATCH,
+                             "launch_ms": launch_ms[dom], "share_of_step": launch_ms[dom] / sum(launch_ms),
+                             "all_launches": [{"ms": launch_ms[i], "Mrays_per_s": N_BATCH / launch_ms[i] * 1e-3,
+                                               "GBps": per_launch[i]["bytes"] / launch_ms[i] * 1e-6} for i in range(3)]}}
+        if world == 1:
+            threads = min(os.cpu_count() or 1, 16)
+            sample = [prim.reshape(HEIGHT, WIDTH)[::2, ::4].reshape(-1).copy(), inco[::8].copy(), shad[::8].copy()]
+            sec, n, kind, used = reference_trace(fx, sample, threads, 3)
+            line["cpu_baseline"] = {"value": n / sec * 1e-6, "unit": "Mrays/s", "cores": used, "kind": kind,
+                                    "sample": "1/8 of each of the 3 ray batches of one step (%d rays), best of 3" % n}
+        print(json.dumps(line))
+    sc.set_stream(None)
+    sc.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
