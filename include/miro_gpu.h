@@ -115,7 +115,7 @@ typedef struct miro_gpu_prim {      /* 48 bytes */
 /* ---- materials (reference: Lambert src/Lambert.cpp:19-53, Blinn src/Blinn.cpp:39-236,335) ---- */
 #define MIRO_GPU_MAT_LAMBERT 0u
 #define MIRO_GPU_MAT_BLINN 1u
-typedef struct miro_gpu_material {  /* 96 bytes */
+typedef struct miro_gpu_material {  /* 128 bytes */
     uint32_t kind;
     float kd[3];
     float ka[3];
@@ -129,7 +129,7 @@ typedef struct miro_gpu_material {  /* 96 bytes */
     float spec_gloss;               /* must be 1 */
     float translucency;             /* must be <= 0.01 */
     uint32_t sample_env;            /* Material::m_sampleEnv */
-    uint32_t reserved[2];
+    uint32_t reserved[9];
 } miro_gpu_material;
 
 /* ---- lights (reference: src/PointLight.cpp:8-82, src/RectangleLight.cpp:14-137, src/DomeLight.cpp:8-161) */
@@ -223,6 +223,10 @@ int miro_gpu_create(miro_gpu_ctx** out, int device_id);
 void miro_gpu_destroy(miro_gpu_ctx* ctx);
 const char* miro_gpu_last_error(const miro_gpu_ctx* ctx);   /* ctx may be NULL: last create() error */
 int miro_gpu_abi_version(void);
+/* sizeof() of the k-th struct of this header, in declaration order (ray, hit, node, tri, mbtri, instance, prim,
+ * material, light, texture, scene_desc, camera, render_params, counters); 0 for k out of range.  Lets a binding
+ * verify its mirror of the layouts at load time. */
+size_t miro_gpu_sizeof(int k);
 
 /* Use an existing CUDA stream (cudaStream_t passed as void*) for all work of this context;
  * NULL restores the context's own stream.  Lets the caller order work against torch streams. */

@@ -56,7 +56,7 @@ class Material(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("kd", C.c_float * 3), ("ka", C.c_float * 3), ("ks", C.c_float * 3),
                 ("spec_exp", C.c_float), ("spec_amt", C.c_float), ("emit_intensity", C.c_float), ("le", C.c_float * 3),
                 ("color_map", C.c_int32), ("alpha_map", C.c_int32), ("reflect_amt", C.c_float), ("refract_amt", C.c_float),
-                ("spec_gloss", C.c_float), ("translucency", C.c_float), ("sample_env", C.c_uint32), ("reserved", C.c_uint32 * 2)]
+                ("spec_gloss", C.c_float), ("translucency", C.c_float), ("sample_env", C.c_uint32), ("reserved", C.c_uint32 * 9)]
 
 
 class Light(C.Structure):
@@ -105,7 +105,7 @@ class Counters(C.Structure):
 
 
 # every symbol include/miro_gpu.h and include/miro_host.h declare (checked by tests/test_abi.py)
-GPU_SYMBOLS = ["miro_gpu_create", "miro_gpu_destroy", "miro_gpu_last_error", "miro_gpu_abi_version", "miro_gpu_set_stream",
+GPU_SYMBOLS = ["miro_gpu_create", "miro_gpu_destroy", "miro_gpu_last_error", "miro_gpu_abi_version", "miro_gpu_sizeof", "miro_gpu_set_stream",
                "miro_gpu_upload_scene", "miro_gpu_trace_closest", "miro_gpu_trace_any", "miro_gpu_trace_closest_device",
                "miro_gpu_trace_any_device", "miro_gpu_render", "miro_gpu_enable_counting", "miro_gpu_get_counters",
                "miro_gpu_reset_counters"]

@@ -134,6 +134,17 @@ extern "C" {
 
 int miro_gpu_abi_version(void) { return MIRO_GPU_ABI_VERSION; }
 
+static_assert(sizeof(miro_gpu_ray) == 48 && sizeof(miro_gpu_hit) == 20 && sizeof(miro_gpu_node) == 128 && sizeof(miro_gpu_tri) == 48 &&
+              sizeof(miro_gpu_mbtri) == 96 && sizeof(miro_gpu_instance) == 64 && sizeof(miro_gpu_prim) == 48 &&
+              sizeof(miro_gpu_material) == 128 && sizeof(miro_gpu_light) == 64, "include/miro_gpu.h layout changed");
+size_t miro_gpu_sizeof(int k) {
+    static const size_t sizes[] = {sizeof(miro_gpu_ray), sizeof(miro_gpu_hit), sizeof(miro_gpu_node), sizeof(miro_gpu_tri), sizeof(miro_gpu_mbtri),
+                                   sizeof(miro_gpu_instance), sizeof(miro_gpu_prim), sizeof(miro_gpu_material), sizeof(miro_gpu_light),
+                                   sizeof(miro_gpu_texture), sizeof(miro_gpu_scene_desc), sizeof(miro_gpu_camera), sizeof(miro_gpu_render_params),
+                                   sizeof(miro_gpu_counters)};
+    return (k >= 0 && k < (int)(sizeof(sizes) / sizeof(sizes[0]))) ? sizes[k] : 0;
+}
+
 const char* miro_gpu_last_error(const miro_gpu_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
 
 int miro_gpu_create(miro_gpu_ctx** out, int device_id) {

@@ -1,0 +1,158 @@
+"""Host layer (C++): BVH build + flatten invariants, scene scripts, loaders, Image::Map.  CPU only."""
+import ctypes as C
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import helpers
+import miro_b200 as mb
+from miro_b200 import capi
+
+
+def flat(sc):
+    d = sc.desc()
+    nodes = np.ctypeslib.as_array(C.cast(d.nodes, C.POINTER(C.c_float)), shape=(d.n_nodes, 32)).copy() if d.n_nodes else np.zeros((0, 32), np.float32)
+    child = nodes[:, 24:28].view(np.int32)
+    tris = np.ctypeslib.as_array(C.cast(d.tris, C.POINTER(C.c_float)), shape=(d.n_tris, 12)).copy() if d.n_tris else np.zeros((0, 12), np.float32)
+    return d, nodes, child, tris
+
+
+def leaf_fields(ref):
+    u = int(ref) & 0xffffffff
+    return (u >> 29) & 3, ((u >> 26) & 7) + 1, u & ((1 << 26) - 1)
+
+
+def walk(d, nodes, child, tris, ref, lo, hi, seen, depth=0):
+    """Every leaf range is inside its parent's box; every triangle is referenced exactly once."""
+    if ref == capi.CHILD_EMPTY:
+        return 0
+    if ref < 0:
+        kind, count, first = leaf_fields(ref)
+        assert 1 <= count <= 4
+        if kind == capi.KIND_TRI:
+            for i in range(first, first + count):
+                seen[i] += 1
+                v = tris[i].reshape(3, 4)[:, :3]
+                assert (v.min(0) >= lo - 1e-6).all() and (v.max(0) <= hi + 1e-6).all()
+        return depth
+    n = nodes[ref]
+    best = depth
+    for i in range(4):
+        c = int(child[ref, i])
+        if c == capi.CHILD_EMPTY:
+            continue
+        clo = np.array([n[0 + i], n[4 + i], n[8 + i]]); chi = np.array([n[12 + i], n[16 + i], n[20 + i]])
+        assert (clo <= chi).all()
+        assert (clo >= lo - 1e-6).all() and (chi <= hi + 1e-6).all()
+        best = max(best, walk(d, nodes, child, tris, c, clo, chi, seen, depth + 1))
+    return best
+
+
+@pytest.mark.parametrize("scene", ["c1_cornell", "c2_explosion"])
+def test_flatten_invariants(scene):
+    fx = helpers.Fixture(helpers.fixture_path(scene))
+    sc = fx.scene()
+    d, nodes, child, tris = flat(sc)
+    assert d.n_tris == sum(len(fx.mesh(k)["vidx"]) for k in range(len(fx.names)))
+    seen = np.zeros(d.n_tris, np.int64)
+    big = np.float32(3e38)
+    depth = walk(d, nodes, child, tris, d.root, -np.full(3, big), np.full(3, big), seen)
+    assert (seen == 1).all()          # flattening round trip: every triangle appears in exactly one leaf
+    st = sc.bvh_stats()
+    assert st["nodes"] == d.n_nodes and st["max_depth"] >= depth >= 1
+    # (mesh, tri) identity is a bijection onto the source triangles
+    mesh_of, tri_of, _ = sc.prim_table()
+    assert len(set(zip(mesh_of.tolist(), tri_of.tolist()))) == d.n_tris
+    # leaf-ordered vertices equal the source mesh's vertices
+    m = fx.mesh(0)
+    k = np.nonzero(mesh_of == 0)[0][:500]
+    src = m["vertices"][m["vidx"][tri_of[k]]]
+    assert np.array_equal(tris[k].reshape(-1, 3, 4)[:, :, :3], src)
+    sc.close()
+
+
+def _script_scene(text, meshes=None):
+    sc = mb.MiroScene()
+    for name, (v, f) in (meshes or {}).items():
+        sc.preload_mesh(name, v, f)
+    with tempfile.NamedTemporaryFile("w", suffix=".miro", delete=False) as fh:
+        fh.write(text)
+    try:
+        sc.load_script(fh.name, "/nonexistent")
+    finally:
+        os.unlink(fh.name)
+    return sc
+
+
+QUAD = (np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]], np.float32), np.array([[0, 1, 2], [0, 2, 3]], np.uint32))
+
+
+def test_script_errors_are_reported():
+    for bad, frag in [("bogus 1 2 3\n", "unknown command"), ("object nomesh nomat\n", "unknown mesh"),
+                      ("material m phong\n", "unknown material kind"), ("light dome power 1\n", "without tex")]:
+        with pytest.raises(mb.MiroError) as e:
+            _script_scene(bad)
+        assert frag in str(e.value)
+
+
+def test_single_leaf_scene_and_camera_defaults():
+    sc = _script_scene("image 64 32\ncamera eye 0 0 3 lookat 0 0 0 fov 40\nmaterial m lambert kd 1 0 0\nmesh q q.obj\nobject q m\n", {"q": QUAD})
+    d, nodes, child, tris = flat(sc)
+    assert d.n_nodes == 0 and d.root < 0           # whole scene is one leaf (src/BVH.cpp:118-132)
+    assert leaf_fields(d.root) == (capi.KIND_TRI, 2, 0)
+    cam = sc.camera(); p = sc.render_params()
+    assert (p.width, p.height) == (64, 32) and p.num_paths == 1 and p.max_bounces == 10 and p.seed == 3163513
+    assert np.allclose(cam.view_dir[:], [0, 0, -1]) and abs(cam.fov_deg - 40) < 1e-6
+    assert abs(cam.shutter_speed - 1e-3) < 1e-9 and cam.aperture == 0.0
+    sc.close()
+
+
+def test_motion_blur_and_instances_flatten():
+    v2 = QUAD[0] + np.float32([0, 0, 1])
+    ident = "1 0 0 0  0 1 0 0  0 0 1 0  0 0 0 1"
+    shifted = "2 0 0 5  0 2 0 0  0 0 2 0  0 0 0 1"
+    sc = _script_scene("material m blinn kd .5 .5 .5\nmesh a a.obj\nmesh b b.obj\nmbobject a b m\nblas g a m\n"
+                       f"instance g {ident}\ninstance g {shifted}\n", {"a": QUAD, "b": (v2, QUAD[1])})
+    d = sc.desc()
+    assert d.n_mbtris == 2 and d.n_instances == 2 and d.n_tris == 2
+    inst = np.ctypeslib.as_array(C.cast(d.instances, C.POINTER(C.c_float)), shape=(2, 16)).copy()
+    ords = inst[:, 13].view(np.int32) if False else np.ctypeslib.as_array(C.cast(d.instances, C.POINTER(C.c_uint32)), shape=(2, 16))[:, 13]
+    k = int(np.nonzero(ords == 1)[0][0])
+    assert np.allclose(inst[k, :12].reshape(3, 4), [[.5, 0, 0, -2.5], [0, .5, 0, 0], [0, 0, .5, 0]])   # rows of M^-1
+    nx = np.ctypeslib.as_array(d.inst_normal_xform, shape=(2, 9))[k].reshape(3, 3)
+    assert np.allclose(nx, np.eye(3) * .5)                                                                 # (M^-1)^T
+    mb_ = np.ctypeslib.as_array(C.cast(d.mbtris, C.POINTER(C.c_float)), shape=(2, 24))
+    assert np.allclose(mb_[:, 12:].reshape(2, 3, 4)[:, :, 2], 1.0) and np.allclose(mb_[:, :12].reshape(2, 3, 4)[:, :, 2], 0.0)
+    sc.close()
+
+
+def test_unsupported_features_fail_loudly():
+    # specular transport is outside the hot-path scope: the upload refuses it rather than rendering it wrong
+    sc = _script_scene("material m blinn kd .5 .5 .5 reflect 0.5\nmesh a a.obj\nobject a m\n", {"a": QUAD})
+    d = sc.desc()
+    mats = np.ctypeslib.as_array(C.cast(d.materials, C.POINTER(C.c_float)), shape=(1, 32))
+    assert abs(mats[0, 18] - 0.5) < 1e-7       # reflect_amt travels in the desc; miro_gpu_upload_scene rejects it (GPU test)
+    sc.close()
+
+
+def test_obj_loader_and_ppm_writer(tmp_path):
+    obj = tmp_path / "t.obj"
+    obj.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nv 1 1 0\nvt 0 0\nvt 1 0\nvt 0 1\nvn 0 0 1\nf 1/1/1 2/2/1 3/3/1\nf 2/2/1 4/3/1 3/3/1\n")
+    script = tmp_path / "s.miro"
+    script.write_text("image 8 4\nmaterial m lambert\nmesh t t.obj\nobject t m\n")
+    sc = mb.MiroScene(); sc.load_script(script, tmp_path)
+    d = sc.desc()
+    assert d.n_tris == 2 and d.n_normals == 1 and d.n_uvs == 3
+    prims = np.ctypeslib.as_array(C.cast(d.prims, C.POINTER(C.c_uint32)), shape=(2, 12))
+    assert (prims[:, 0:3] == 0).all() and prims[:, 3:6].max() == 2
+    sc.close()
+    # flat normals when the file has none (src/TriangleMeshLoad.cpp:194-206)
+    obj.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n")
+    sc = mb.MiroScene(); sc.load_script(script, tmp_path)
+    d = sc.desc()
+    assert np.allclose(np.ctypeslib.as_array(d.normals, shape=(3,)), [0, 0, 1])
+    prims = np.ctypeslib.as_array(C.cast(d.prims, C.POINTER(C.c_uint32)), shape=(1, 12))
+    assert (prims[0, 3:6] == 0xffffffff).all()
+    sc.close()

@@ -1,0 +1,58 @@
+"""Pins the oracle (oracle/miro_oracle.c, the CPU restatement) against hit dumps of the UNMODIFIED reference
+(tests/golden/*.npz, made by tools/make_fixtures.py with oracle/_ref/miro_ref).  CPU only."""
+import numpy as np
+import pytest
+
+import helpers
+
+SCENES = ["c1_cornell", "c2_explosion", "c5_mb_instances"]
+
+
+@pytest.fixture(scope="module", params=SCENES)
+def loaded(request):
+    path = helpers.fixture_path(request.param)
+    if path is None:
+        pytest.skip("fixture %s not generated" % request.param)
+    fx = helpers.Fixture(path)
+    sc = fx.scene()
+    yield request.param, fx, sc
+    sc.close()
+
+
+def as_ref(sc, ohits):
+    m, t, p = sc.resolve_hits(ohits)
+    r = np.zeros(len(ohits), helpers.REFHIT)
+    r["t"], r["a"], r["b"], r["mesh"], r["tri"], r["proxy"] = ohits["t"], ohits["a"], ohits["b"], m, t, p
+    return r
+
+
+def test_oracle_reproduces_reference_hits(loaded):
+    name, fx, sc = loaded
+    ohits, ctr = helpers.oracle_trace_closest(sc, fx.rays)
+    st = helpers.compare_hits(sc, ohits, fx.hits, t_rel=1e-5)
+    print(name, {k: v for k, v in st.items() if k != "hard_idx"}, "nodes/ray %.2f tris/ray %.2f" % (ctr[0] / len(fx.rays), ctr[1] / len(fx.rays)))
+    assert st["hard"] == 0, st
+    assert st["id_match"] >= 0.9995, st            # the rest: exact-t ties resolved by a different (but legal) visiting order
+    assert st["frac_t_within"] >= 0.9999, st
+    assert st["max_abs_a"] < 1e-3 and st["max_abs_b"] < 1e-3, st
+
+
+def test_oracle_any_is_closest_as_boolean(loaded):
+    """The reference's shadow query is a closest-hit query used as a boolean (src/PointLight.cpp:44, BVH.cpp:1156-1160)."""
+    name, fx, sc = loaded
+    r = fx.rays[:4096]
+    occ = helpers.oracle_trace_any(sc, r)
+    assert (occ == (fx.hits["mesh"][:4096] >= 0)).mean() >= 0.999
+
+
+def test_fixture_is_self_consistent(loaded):
+    name, fx, sc = loaded
+    h = fx.hits
+    hit = h["mesh"] >= 0
+    assert hit.any() and (~hit).any() or name == "c1_cornell"
+    assert (h["t"][hit] >= fx.rays["tmin"][hit]).all() and (h["t"][hit] < fx.rays["tmax"][hit]).all()
+    assert (h["a"][hit] >= 0).all() and (h["b"][hit] >= 0).all() and (h["a"][hit] + h["b"][hit] <= 1 + 1e-6).all()
+    # the recorded hit point lies on the recorded triangle (reference geometry carried by the fixture)
+    mesh_of, tri_of, _ = sc.prim_table()
+    d = sc.desc()
+    assert d.n_tris + d.n_mbtris == len(mesh_of)
