@@ -180,3 +180,14 @@ int oracle_trace_any(const miro_gpu_scene_desc* s, const miro_gpu_ray* rays, siz
     if (counters) { counters[0] += nn; counters[1] += nt; }
     return 0;
 }
+
+/* Scene::trace for one ray (used by oracle/miro_oracle_shade.c).  Returns 1 on a hit in [tmin, tmax). */
+int oracle_trace_one(const miro_gpu_scene_desc* s, const float o[3], const float d[3], float time, float tmin, float tmax, miro_gpu_hit* out) {
+    uint64_t nn = 0, nt = 0;
+    oray r; ray_set(&r, o, d, time);
+    ohit h; h.t = tmax; h.a = h.b = 0.f; h.prim = -1; h.inst = -1;
+    const int hit = traverse(s, s->root, &r, tmin, &h, -1, &nn, &nt);
+    if (hit && h.prim >= 0) { out->t = h.t; out->a = h.a; out->b = h.b; out->prim = h.prim; out->inst = h.inst; return 1; }
+    out->t = -1.f; out->a = out->b = 0.f; out->prim = -1; out->inst = -1;
+    return 0;
+}

@@ -387,6 +387,19 @@ void dumpMeshes(const std::string& dir) {
     }
 }
 
+// --dump-textures DIR: every texture as the reference's loaders left it (RawImage.cpp / hdrloader.cpp): float texels.
+void dumpTextures(const std::string& dir) {
+    for (std::map<std::string, Texture*>::iterator it = g_textures.begin(); it != g_textures.end(); ++it) {
+        RawImage* im = it->second->m_image;
+        int ch = im->m_imageType == GRAYSCALE ? 1 : (im->m_imageType == RGBA ? 4 : 3);
+        std::string path = dir + "/" + it->first + ".tex";
+        FILE* f = fopen(path.c_str(), "wb"); if (!f) die("cannot write " + path);
+        int32_t hdr[4] = {im->m_width, im->m_height, ch, (int32_t)im->m_imageType}; fwrite(hdr, 4, 4, f);
+        fwrite(im->m_rawData, 4, (size_t)im->m_width * im->m_height * ch, f);
+        fclose(f);
+    }
+}
+
 // --dump-qbvh FILE: the reference's own QBVH (BVH.cpp:100-389) walked and flattened — the data a
 // maintainer's flatten() would hand to miro_gpu_upload_scene.  Format:
 //   int32 nNodes, nLeaves; nodes: 24 float bounds (minX[4] minY[4] minZ[4] maxX[4] maxY[4] maxZ[4]),
@@ -429,7 +442,7 @@ void dumpQBVH(const std::string& path) {
 }  // namespace
 
 int main(int argc, char** argv) {
-    std::string scene, dumpPrim, traceIn, traceOut, floatOut, ppmOut, meshDir, qbvhOut;
+    std::string scene, dumpPrim, traceIn, traceOut, floatOut, ppmOut, meshDir, qbvhOut, texDir;
     int threads = 1, repeat = 1; bool stock = false, doFloat = false;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -445,6 +458,7 @@ int main(int argc, char** argv) {
         else if (a == "--render-stock") { stock = true; ppmOut = NEXT(); }
         else if (a == "--dump-meshes") meshDir = NEXT();
         else if (a == "--dump-qbvh") qbvhOut = NEXT();
+        else if (a == "--dump-textures") texDir = NEXT();
         else die("unknown argument " + a);
     }
     if (scene.empty()) die("usage: miro_ref --scene S.miro [--assets DIR] [--threads N] [--dump-primary F] [--trace RAYS --hits F] [--render-float F] [--render-stock F.ppm] [--dump-meshes DIR] [--dump-qbvh F]");
@@ -459,6 +473,7 @@ int main(int argc, char** argv) {
             g_scene->objects()->size(), QBVH_Node::nodeCount, QBVH_Node::leafCount, tb1 - tb0);
     if (!meshDir.empty()) dumpMeshes(meshDir);
     if (!qbvhOut.empty()) dumpQBVH(qbvhOut);
+    if (!texDir.empty()) dumpTextures(texDir);
     if (!dumpPrim.empty()) dumpPrimary(dumpPrim);
     if (!traceIn.empty()) {
         resetTraceCalls();

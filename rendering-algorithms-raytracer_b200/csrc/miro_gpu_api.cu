@@ -54,12 +54,18 @@ void drain_timing(miro_gpu_ctx* ctx) {
 // Traversal kernels.  One thread per ray; a warp covers 32 consecutive rays, so the any-hit variant
 // can emit one packed word per warp.  Rays / hits are streamed (ld.cs / st.cs) so they do not
 // displace BVH nodes from L1/L2.
-template <bool ANY, bool COUNT>
+// MODE: 0 closest hit -> hit records; 1 any hit -> one bit per ray; 2 any hit -> the unoccluded ray's light sample
+// (sample_E[i] = E.rgb, specular input) is added to the accumulator of its light loop (slot index in ray.user0).
+enum { TRACE_CLOSEST = 0, TRACE_ANY_BITS = 1, TRACE_ANY_ACCUM = 2 };
+
+template <int MODE, bool COUNT>
 __global__ void __launch_bounds__(TRACE_BLOCK)
 k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const uint32_t* __restrict__ d_count,
-        miro_gpu_hit* __restrict__ hits, uint32_t* __restrict__ bits, TraceCounters* __restrict__ ctr) {
+        miro_gpu_hit* __restrict__ hits, uint32_t* __restrict__ bits, const float4* __restrict__ sample_E, float4* __restrict__ slots,
+        TraceCounters* __restrict__ ctr) {
+    constexpr bool ANY = MODE != TRACE_CLOSEST;
     __shared__ unsigned long long stack[SMEM_STACK * TRACE_BLOCK];
-    const uint32_t n = d_count ? *d_count : n_static;
+    const uint32_t n = d_count ? min(*d_count, n_static) : n_static;
     const uint32_t stride = gridDim.x * TRACE_BLOCK;
     uint32_t c_nodes = 0, c_tris = 0, c_insts = 0, c_rays = 0;
     // warp-uniform loop bound: every lane of a warp iterates the same number of times
@@ -72,15 +78,17 @@ k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const
             HitRec h; h.t = r1.w;
             traverse<ANY, COUNT>(s, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r0.w, r2.x, stack + threadIdx.x, h, c_nodes, c_tris, c_insts);
             ++c_rays;
-            if (ANY) occluded = h.prim >= 0;
-            else {
+            if (MODE == TRACE_ANY_BITS) occluded = h.prim >= 0;
+            else if (MODE == TRACE_ANY_ACCUM) {
+                if (h.prim < 0) atomicAdd(slots + (size_t)__float_as_uint(r2.z) * 4, __ldcs(sample_E + i));
+            } else {
                 float* o = reinterpret_cast<float*>(hits + i);
                 const bool hit = h.prim >= 0;
                 __stcs(o + 0, hit ? h.t : -1.0f); __stcs(o + 1, hit ? h.a : 0.f); __stcs(o + 2, hit ? h.b : 0.f);
                 __stcs(reinterpret_cast<int*>(o) + 3, h.prim); __stcs(reinterpret_cast<int*>(o) + 4, hit ? h.inst : -1);
             }
         }
-        if (ANY) {
+        if (MODE == TRACE_ANY_BITS) {
             const uint32_t w = __ballot_sync(0xffffffffu, occluded);
             if ((threadIdx.x & 31u) == 0) bits[base >> 5] = w;
         }
@@ -110,21 +118,24 @@ static int trace_grid(miro_gpu_ctx* ctx, size_t n, bool device_count) {
     return (int)std::min<size_t>(blocks, 0x7fffffff);
 }
 
-void launch_trace_closest(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, const uint32_t* d_count, miro_gpu_hit* d_hits) {
+template <int MODE>
+static void launch_trace(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, const uint32_t* d_count, miro_gpu_hit* d_hits, uint32_t* d_bits,
+                         const float4* d_E, float4* d_slots) {
     if (n == 0) return;
     const int grid = trace_grid(ctx, n, d_count != nullptr);
     const float4* r = reinterpret_cast<const float4*>(d_rays);
-    if (ctx->counting) k_trace<false, true><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(ctx->scene, r, (uint32_t)n, d_count, d_hits, nullptr, ctx->d_counters);
-    else k_trace<false, false><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(ctx->scene, r, (uint32_t)n, d_count, d_hits, nullptr, ctx->d_counters);
+    if (ctx->counting) k_trace<MODE, true><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(ctx->scene, r, (uint32_t)n, d_count, d_hits, d_bits, d_E, d_slots, ctx->d_counters);
+    else k_trace<MODE, false><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(ctx->scene, r, (uint32_t)n, d_count, d_hits, d_bits, d_E, d_slots, ctx->d_counters);
     ctx->launches++;
 }
+void launch_trace_closest(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, const uint32_t* d_count, miro_gpu_hit* d_hits) {
+    launch_trace<TRACE_CLOSEST>(ctx, d_rays, n, d_count, d_hits, nullptr, nullptr, nullptr);
+}
 void launch_trace_any(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, const uint32_t* d_count, uint32_t* d_bits) {
-    if (n == 0) return;
-    const int grid = trace_grid(ctx, n, d_count != nullptr);
-    const float4* r = reinterpret_cast<const float4*>(d_rays);
-    if (ctx->counting) k_trace<true, true><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(ctx->scene, r, (uint32_t)n, d_count, nullptr, d_bits, ctx->d_counters);
-    else k_trace<true, false><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(ctx->scene, r, (uint32_t)n, d_count, nullptr, d_bits, ctx->d_counters);
-    ctx->launches++;
+    launch_trace<TRACE_ANY_BITS>(ctx, d_rays, n, d_count, nullptr, d_bits, nullptr, nullptr);
+}
+void launch_trace_shadow(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, const uint32_t* d_count, const float4* d_E, float4* d_slots) {
+    launch_trace<TRACE_ANY_ACCUM>(ctx, d_rays, n, d_count, nullptr, nullptr, d_E, d_slots);
 }
 
 }  // namespace miro
@@ -169,7 +180,6 @@ int miro_gpu_create(miro_gpu_ctx** out, int device_id) {
     if ((e = cudaMalloc((void**)&ctx->d_counters, sizeof(TraceCounters))) != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaMalloc(counters)"); }
     cudaMemset(ctx->d_counters, 0, sizeof(TraceCounters));
     // the traversal kernels keep their stacks in shared memory and want the rest of the 256 KB as L1
-    cudaFuncSetAttribute(k_trace<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutDefault);
     *out = ctx;
     return MIRO_GPU_OK;
 }

@@ -1,6 +1,543 @@
-// render.cu — Scene::raytraceImage on the GPU (wavefront path tracer).  (stub: filled in next)
-#include "context.cuh"
-namespace miro { void render_state_free(miro_gpu_ctx*) {} }
-extern "C" int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera*, const miro_gpu_render_params*, float*) {
-    return miro::set_error(ctx, MIRO_GPU_EUNSUPPORTED, "miro_gpu_render: not built yet");
+// render.cu — Scene::raytraceImage on the GPU: a wavefront renderer over device-resident ray queues.
+//
+// Replaces (reference, file:line relative to src/):
+//   Scene::raytraceImage          Scene.cpp:86-217    pixel loop over 32x32 buckets
+//   Scene::adaptiveSampleScene    Scene.cpp:252-293   level-k stratified supersampling with a gamma-space cut-off
+//   Scene::sampleScene            Scene.cpp:219-243   trace the camera ray, mean of numPaths shade() calls, miss -> env / BG
+//   Camera::eyeRayAdaptive        Camera.cpp:116-174
+//   Lambert::shade                Lambert.cpp:19-53
+//   Blinn::shade (diffuse + specular highlight part), Blinn::calculatePathTracing   Blinn.cpp:39-236,335
+//   Point/Rectangle/DomeLight::sampleLight   PointLight.cpp:8-82, RectangleLight.cpp:42-137, DomeLight.cpp:80-161
+//
+// The reference's shade() <-> trace() recursion becomes a loop over path depth; all state lives in queues in HBM:
+//
+//   per subdivision level k (host loop, one 4-byte read-back per level for the number of still-active pixels):
+//     per wave of <= W camera samples (W * numPaths <= wave capacity):
+//       k_raygen        camera samples of the active pixels                      -> camera-sample queue (48 B rays)
+//       k_trace closest                                                          -> 20 B hits
+//       k_shade<PRIMARY> one thread per (camera sample, path): the numPaths shade() calls of sampleScene share the hit
+//       for depth = 0 .. maxBounces-1:
+//         (k_shade emitted) shadow rays -> k_trace shadow: any-hit traversal whose epilogue adds the unoccluded
+//                           sample's irradiance / specular input into the accumulator of its light loop ("slot")
+//         k_resolve_slots   per light loop: mean over its samples, kd / ks*pow(spec, specExp) weighting -> pixel sum
+//         (k_shade emitted) bounce rays -> k_trace closest -> k_shade<BOUNCE>
+//     k_level_resolve   running mean over levels, gamma-space cut-off, compaction of the pixels that go on to level k+1
+//
+// Queue slots are claimed with warp-aggregated atomics (one atomicAdd per warp per queue): every thread first COUNTS
+// what it will emit (the light loops are pure functions of the counter-based RNG), the warp scans the counts, then
+// every thread EMITS at its offset.  Pixel sums are float atomics (red.global.add.f32).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+#include "shading.cuh"
+
+namespace miro {
+
+constexpr int SHADE_BLOCK = 128;
+constexpr uint32_t FLAG_SAMPLE_ENV = 0x80000000u;      // ray.flags bit 31: the spawning material samples the environment on a miss
+constexpr size_t WAVE_PATHS_MAX = (size_t)1 << 22;     // paths in flight per wave
+constexpr size_t WAVE_BYTES_BUDGET = (size_t)6 << 30;  // queue memory per context
+
+struct Slot {            // one light loop (one Light::sampleLight call of the reference): 64 bytes
+    float4 acc;          // sum over unoccluded samples: E.rgb, specular input
+    float4 tkd;          // throughput * diffuse colour (rgb); w = pixel index (bits)
+    float4 tks;          // throughput * ks * specAmt (rgb); w = specExp
+    float4 misc;         // x = 1 / samplesDone
+};
+
+struct RenderParamsDev {
+    int width, height;
+    int num_paths, max_bounces;
+    uint32_t path_trace, sample_env;
+    uint64_t seed;
+    float inv_paths;
+};
+
+struct Queues {
+    // camera samples of the wave
+    miro_gpu_ray* cs_rays; miro_gpu_hit* cs_hits;
+    // bounce queues (ping-pong): rays, throughput, hits
+    miro_gpu_ray* q_rays[2]; float4* q_thr[2]; miro_gpu_hit* q_hits;
+    // shadow queue and light-loop slots
+    miro_gpu_ray* sh_rays; float4* sh_E; Slot* slots;
+    // device counters: [0] next bounce count, [1] shadow count, [2] slot count, [3] next active-pixel count, [4..7] spare
+    uint32_t* counts;
+    size_t cap_cs, cap_paths, cap_shadow, cap_slots;
+};
+
+struct RenderState {
+    Queues q{};
+    std::vector<void*> allocs;
+    size_t key_paths = 0, key_shadow_per_path = 0, key_slots_per_path = 0;
+    // frame buffers
+    float4* level_sum = nullptr; float4* result = nullptr; uint32_t* active[2] = {nullptr, nullptr};
+    float* rgb_dev = nullptr; size_t frame_pixels = 0;
+    float* gamma_lut = nullptr;
+    uint32_t* h_count = nullptr;       // pinned
+};
+
+__device__ __forceinline__ void add_rgb(float4* buf, uint32_t pixel, float3x c) {
+    float* p = reinterpret_cast<float*>(buf + pixel);
+    if (c.x != 0.f) atomicAdd(p, c.x);
+    if (c.y != 0.f) atomicAdd(p + 1, c.y);
+    if (c.z != 0.f) atomicAdd(p + 2, c.z);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Camera samples.  Sample s of level k in pixel p: sub-cell (i, j) = (s / k, s % k), ordinal = getSum(k-1) + s.
+__global__ void __launch_bounds__(SHADE_BLOCK)
+k_raygen(DeviceCamera cam, RenderParamsDev P, const uint32_t* __restrict__ active, uint32_t first_cs, uint32_t n_cs, int level, uint32_t ordinal_base,
+         miro_gpu_ray* __restrict__ rays) {
+    const uint32_t i = blockIdx.x * SHADE_BLOCK + threadIdx.x;
+    if (i >= n_cs) return;
+    const uint32_t cs = first_cs + i;
+    const uint32_t k2 = (uint32_t)(level * level);
+    const uint32_t a = cs / k2, s = cs - a * k2;
+    const uint32_t pixel = __ldg(active + a);
+    const int x = (int)(pixel % (uint32_t)P.width), y = (int)(pixel / (uint32_t)P.width);
+    float minX = 0.5f, maxX = 0.5f, minY = 0.5f, maxY = 0.5f;         // level 1: the pixel centre (Scene.cpp:254)
+    if (level > 1) {
+        const int si = (int)(s / (uint32_t)level), sj = (int)(s - (uint32_t)si * (uint32_t)level);
+        const float offset = 1.0f / (float)level;                     // Scene.cpp:267-268
+        minX = si * offset; maxX = (si + 1) * offset; minY = sj * offset; maxY = (sj + 1) * offset;
+    }
+    RandAddr addr; addr.pixel = pixel; addr.sample = ordinal_base + s; addr.path_depth = 0; addr.seed = P.seed;
+    const CameraSample c = camera_ray(cam, x, y, minX, maxX, minY, maxY, P.width, P.height, addr);
+    float4* o = reinterpret_cast<float4*>(rays + i);
+    o[0] = make_float4(c.o.x, c.o.y, c.o.z, kEps);
+    o[1] = make_float4(c.d.x, c.d.y, c.d.z, MIRO_GPU_TMAX);
+    o[2] = make_float4(c.time, 0.f, __uint_as_float(pixel), __uint_as_float(ordinal_base + s));
+}
+
+// ---------------------------------------------------------------------------------------------
+// What one shading event emits.
+struct LoopPlan { int n_shadow; int n_slots; };
+
+struct ShadeCtx {
+    float3x P, N, rVec, kd, tks;      // hit point, shading normal, reflection vector, diffuse colour, throughput*ks*specAmt
+    float spec_exp;
+    float time;
+    bool is_secondary;
+};
+
+// Runs every light loop of one shading event; F(light, pass, normal, rVec, is_secondary, with_spec) is called once per loop.
+template <class F>
+__device__ __forceinline__ void for_each_light_loop(const DeviceShading& sh, bool pt_last_bounce, bool blinn, bool secondary, F&& f) {
+    if (pt_last_bounce)                                  // Blinn::calculatePathTracing, last bounce (Blinn.cpp:76-87): rVec = 0, isSecondary = true
+        for (uint32_t li = 0; li < sh.n_lights; ++li) f(li, 1u, true, false);
+    for (uint32_t li = 0; li < sh.n_lights; ++li)        // Lambert.cpp:41-46 (isSecondary defaults to false) / Blinn.cpp:212-221
+        f(li, 0u, blinn ? secondary : false, blinn);
+}
+
+template <bool PRIMARY>
+__global__ void __launch_bounds__(SHADE_BLOCK)
+k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q, uint32_t n_static, const uint32_t* __restrict__ d_count,
+        float4* __restrict__ level_sum, uint32_t shadow_cap, uint32_t slot_cap) {
+    const uint32_t n = PRIMARY ? n_static : *d_count;
+    const uint32_t stride = gridDim.x * SHADE_BLOCK;
+    for (uint32_t base = blockIdx.x * SHADE_BLOCK + (threadIdx.x & ~31u); base < n; base += stride) {
+        const uint32_t idx = base + (threadIdx.x & 31u);
+        // ------------------------------------------------------------------ phase 1: evaluate, count
+        bool active = idx < n;
+        uint32_t pixel = 0, sample = 0, path = 0, depth = 0;
+        float3x thr = f3(0, 0, 0), o = f3(0, 0, 0), d = f3(0, 0, 1), bounce_dir = f3(0, 0, 0), bounce_thr = f3(0, 0, 0);
+        float time = 0.f;
+        bool emit_bounce = false, pt_last = false, blinn = false, bounce_env = false;
+        ShadeCtx c{};
+        int n_shadow = 0, n_slots = 0;
+        RandAddr addr{};
+        if (active) {
+            const uint32_t ri = PRIMARY ? idx / (uint32_t)P.num_paths : idx;
+            const float4* rp = reinterpret_cast<const float4*>((PRIMARY ? q.cs_rays : q.q_rays[in_q]) + ri);
+            const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
+            const miro_gpu_hit* hp = (PRIMARY ? q.cs_hits : q.q_hits) + ri;
+            const float ht = __ldg(&hp->t), ha = __ldg(&hp->a), hb = __ldg(&hp->b);
+            const int hprim = __ldg(&hp->prim), hinst = __ldg(&hp->inst);
+            o = f3(r0.x, r0.y, r0.z); d = f3(r1.x, r1.y, r1.z); time = r2.x;
+            pixel = __float_as_uint(r2.z); sample = __float_as_uint(r2.w);
+            const uint32_t flags = __float_as_uint(r2.y);
+            if (PRIMARY) { path = idx - ri * (uint32_t)P.num_paths; depth = 0; thr = f3(P.inv_paths, P.inv_paths, P.inv_paths); }
+            else {
+                path = flags & 0xffffu; depth = (flags >> 16) & 0x7fffu;
+                const float4 t4 = __ldg(q.q_thr[in_q] + idx); thr = f3(t4.x, t4.y, t4.z);
+            }
+            addr.pixel = pixel; addr.sample = sample; addr.path_depth = path | (depth << 16); addr.seed = P.seed;
+            if (hprim < 0) {
+                // Scene::sampleScene miss (Scene.cpp:234-240): env / BG once per camera sample; bounce miss (Blinn.cpp:70-73)
+                if (PRIMARY) { if (path == 0) add_rgb(level_sum, pixel, environment(sh, d)); }
+                else if ((flags & FLAG_SAMPLE_ENV) && P.sample_env) add_rgb(level_sum, pixel, thr * environment(sh, d));
+                active = false;
+            } else {
+                const Surface s = surface_at(sc, sh, o, d, ht, ha, hb, hprim, hinst);
+                const miro_gpu_material* m = sh.materials + s.material;
+                float3x kd = f3(m->kd[0], m->kd[1], m->kd[2]);
+                if (m->color_map >= 0) { const float4 t = tex_lookup(sh.textures[m->color_map], s.u, s.v); kd = f3(t.x, t.y, t.z); }
+                float3x constant = f3(m->ka[0], m->ka[1], m->ka[2]);
+                c.P = s.P; c.kd = kd; c.time = time; c.is_secondary = depth > 0; c.spec_exp = m->spec_exp;
+                blinn = m->kind == MIRO_GPU_MAT_BLINN;
+                if (!blinn) { c.N = s.N; c.rVec = f3(0, 0, 0); c.tks = f3(0, 0, 0); }
+                else {
+                    // normal selection / flip towards the viewer (Blinn.cpp:144-155)
+                    const float3x viewDir = -d;
+                    float vDotN = dot3(viewDir, s.N);
+                    const float vDotGeoN = dot3(viewDir, s.geoN);
+                    const bool nEqGeoN = (vDotN * vDotGeoN >= 0.0f);
+                    float3x theNormal = nEqGeoN ? s.N : s.geoN;
+                    vDotN = nEqGeoN ? vDotN : vDotGeoN;
+                    if (vDotN < 0.0f) { vDotN = -vDotN; theNormal = -theNormal; }
+                    c.N = theNormal;
+                    c.rVec = d + (2.f * vDotN) * theNormal;                                      // Blinn.cpp:158
+                    c.tks = thr * f3(m->ks[0], m->ks[1], m->ks[2]) * m->spec_amt;
+                    const float3x Le = f3(m->le[0], m->le[1], m->le[2]);
+                    constant = constant + Le;                                                    // "+ m_Le", Blinn.cpp:335
+                    if (P.path_trace) {                                                          // Blinn::calculatePathTracing
+                        if (m->emit_intensity > 0.0f || (Le.x + Le.y + Le.z) > 0.0f) constant = constant + m->emit_intensity * Le;
+                        else if ((int)depth < P.max_bounces - 1) {
+                            const Rand4 r = rand4(addr, RP_COSINE, 0, 0, 0, 0);
+                            bounce_dir = cosine_sample(theNormal, r.x, r.y);
+                            bounce_thr = thr * kd; bounce_env = m->sample_env != 0;
+                            emit_bounce = true;
+                        } else pt_last = true;
+                    }
+                }
+                add_rgb(level_sum, pixel, thr * constant);
+                for_each_light_loop(sh, pt_last, blinn, c.is_secondary, [&](uint32_t li, uint32_t pass, bool secondary, bool with_spec) {
+                    int lit = 0;
+                    light_loop(sh, li, c.P, c.N, with_spec ? c.rVec : f3(0, 0, 0), secondary, pass, addr, [&](const LightSample&) { ++lit; });
+                    if (lit) { n_shadow += lit; ++n_slots; }
+                });
+            }
+        }
+        // ------------------------------------------------------------------ phase 2: claim queue space (warp aggregated)
+        const uint32_t lane = threadIdx.x & 31u;
+        uint32_t s_shadow = (uint32_t)n_shadow, s_slots = (uint32_t)n_slots, s_next = emit_bounce ? 1u : 0u;
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xffffffffu, s_shadow, off), b = __shfl_up_sync(0xffffffffu, s_slots, off), e = __shfl_up_sync(0xffffffffu, s_next, off);
+            if ((int)lane >= off) { s_shadow += a; s_slots += b; s_next += e; }
+        }
+        uint32_t b_shadow = 0, b_slots = 0, b_next = 0;
+        if (lane == 31) {
+            if (s_next) b_next = atomicAdd(q.counts + 0, s_next);
+            if (s_shadow) b_shadow = atomicAdd(q.counts + 1, s_shadow);
+            if (s_slots) b_slots = atomicAdd(q.counts + 2, s_slots);
+        }
+        b_shadow = __shfl_sync(0xffffffffu, b_shadow, 31) + s_shadow - (uint32_t)n_shadow;
+        b_slots = __shfl_sync(0xffffffffu, b_slots, 31) + s_slots - (uint32_t)n_slots;
+        b_next = __shfl_sync(0xffffffffu, b_next, 31) + s_next - (emit_bounce ? 1u : 0u);
+        if (!active) continue;
+        // ------------------------------------------------------------------ phase 3: emit
+        if (emit_bounce) {
+            float4* o4 = reinterpret_cast<float4*>(q.q_rays[in_q ^ 1] + b_next);
+            o4[0] = make_float4(c.P.x, c.P.y, c.P.z, kEps);
+            o4[1] = make_float4(bounce_dir.x, bounce_dir.y, bounce_dir.z, MIRO_GPU_TMAX);
+            o4[2] = make_float4(time, __uint_as_float(path | ((depth + 1u) << 16) | (bounce_env ? FLAG_SAMPLE_ENV : 0u)), __uint_as_float(pixel), __uint_as_float(sample));
+            q.q_thr[in_q ^ 1][b_next] = make_float4(bounce_thr.x, bounce_thr.y, bounce_thr.z, 0.f);
+        }
+        if (n_slots == 0) continue;
+        if (b_shadow + (uint32_t)n_shadow > shadow_cap || b_slots + (uint32_t)n_slots > slot_cap) continue;   // cannot happen: capacities are worst case
+        uint32_t w_shadow = b_shadow, w_slot = b_slots;
+        for_each_light_loop(sh, pt_last, blinn, c.is_secondary, [&](uint32_t li, uint32_t pass, bool secondary, bool with_spec) {
+            const uint32_t slot = w_slot;
+            int lit = 0;
+            const bool shadows = sh.lights[li].cast_shadows != 0;
+            const int done = light_loop(sh, li, c.P, c.N, with_spec ? c.rVec : f3(0, 0, 0), secondary, pass, addr, [&](const LightSample& ls) {
+                float4* o4 = reinterpret_cast<float4*>(q.sh_rays + w_shadow);
+                // a light that casts no shadows gets an empty interval: never occluded
+                __stcs(o4 + 0, make_float4(c.P.x, c.P.y, c.P.z, shadows ? ls.tmin : 1.f));
+                __stcs(o4 + 1, make_float4(ls.dir.x, ls.dir.y, ls.dir.z, shadows ? ls.tmax : 0.f));
+                __stcs(o4 + 2, make_float4(c.time, 0.f, __uint_as_float(slot), 0.f));
+                __stcs(q.sh_E + w_shadow, make_float4(ls.E.x, ls.E.y, ls.E.z, ls.spec));
+                ++w_shadow; ++lit;
+            });
+            if (lit) {
+                Slot* sp = q.slots + slot;
+                const float3x tkd = thr * c.kd;
+                sp->acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                sp->tkd = make_float4(tkd.x, tkd.y, tkd.z, __uint_as_float(pixel));
+                sp->tks = with_spec ? make_float4(c.tks.x, c.tks.y, c.tks.z, c.spec_exp) : make_float4(0.f, 0.f, 0.f, 1.f);
+                sp->misc = make_float4(1.0f / (float)done, 0.f, 0.f, 0.f);
+                ++w_slot;
+            }
+        });
+    }
+}
+
+// One light loop's contribution (tail of the sampleLight functions + Blinn.cpp:217-220 / Lambert.cpp:45)
+__global__ void __launch_bounds__(SHADE_BLOCK)
+k_resolve_slots(const Slot* __restrict__ slots, const uint32_t* __restrict__ d_count, float4* __restrict__ level_sum) {
+    const uint32_t n = *d_count;
+    for (uint32_t i = blockIdx.x * SHADE_BLOCK + threadIdx.x; i < n; i += gridDim.x * SHADE_BLOCK) {
+        const float4* s = reinterpret_cast<const float4*>(slots + i);
+        const float4 acc = s[0], tkd = s[1], tks = s[2], misc = s[3];
+        const float3x E = f3(acc.x, acc.y, acc.z) * misc.x;
+        float3x out = E * f3(tkd.x, tkd.y, tkd.z);
+        if (tks.x != 0.f || tks.y != 0.f || tks.z != 0.f) {
+            const float spec = powf(acc.w * misc.x, tks.w);
+            out = out + E * f3(tks.x, tks.y, tks.z) * spec;
+        }
+        add_rgb(level_sum, __float_as_uint(tkd.w), out);
+    }
+}
+
+// Scene::adaptiveSampleScene's level bookkeeping (Scene.cpp:259-290) for the pixels that were sampled at `level`.
+__global__ void __launch_bounds__(SHADE_BLOCK)
+k_level_resolve(const uint32_t* __restrict__ active, uint32_t n_active, int level, int min_subdivs, int max_subdivs, float noise,
+                const float* __restrict__ gamma_lut, float4* __restrict__ level_sum, float4* __restrict__ result,
+                uint32_t* __restrict__ next_active, uint32_t* __restrict__ next_count) {
+    const uint32_t i = blockIdx.x * SHADE_BLOCK + threadIdx.x;
+    bool go_on = false;
+    uint32_t pixel = 0;
+    if (i < n_active) {
+        pixel = active[i];
+        const float4 cur = level_sum[pixel];
+        level_sum[pixel] = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool cutOff = false;
+        float4 nr;
+        if (level == 1) nr = cur;
+        else {
+            const float4 old = result[pixel];
+            const int km1 = level - 1;
+            const float pre = (float)(int)(km1 * (km1 + 1) * (2 * km1 + 1) * 0.16666667f);     // getSum, Scene.cpp:245-248
+            const float now = (float)(level * level);
+            const float w = 1.0f / (pre + now);
+            nr = make_float4((old.x * pre + cur.x) * w, (old.y * pre + cur.y) * w, (old.z * pre + cur.z) * w, 0.f);
+            auto g = [&](float v) { return __ldg(gamma_lut + (int)(((v > 1.f) ? 1.f : (v < 0.f ? 0.f : v)) * 32767.f)); };
+            const float tx = fabsf(g(old.x) - g(nr.x)), ty = fabsf(g(old.y) - g(nr.y)), tz = fabsf(g(old.z) - g(nr.z));
+            cutOff = fmaxf(tx, fmaxf(ty, tz)) < noise;
+        }
+        result[pixel] = nr;
+        const int next = level + 1;
+        go_on = (next <= max_subdivs && !cutOff) || next <= min_subdivs;                         // Scene.cpp:259
+    }
+    const uint32_t ballot = __ballot_sync(0xffffffffu, go_on);
+    if (ballot) {
+        const uint32_t lane = threadIdx.x & 31u;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(next_count, __popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (go_on) next_active[base + __popc(ballot & ((1u << lane) - 1u))] = pixel;
+    }
+}
+
+__global__ void k_write_rgb(const uint32_t* __restrict__ pixels, uint32_t n, const float4* __restrict__ result, float* __restrict__ rgb) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t p = pixels[i];
+    const float4 r = result[p];
+    rgb[(size_t)p * 3 + 0] = r.x; rgb[(size_t)p * 3 + 1] = r.y; rgb[(size_t)p * 3 + 2] = r.z;
+}
+
+// ---------------------------------------------------------------------------------------------
+static RenderState* state_of(miro_gpu_ctx* ctx) {
+    if (!ctx->render_state) ctx->render_state = new RenderState();
+    return static_cast<RenderState*>(ctx->render_state);
+}
+
+static void free_queues(RenderState* st) {
+    for (void* p : st->allocs) cudaFree(p);
+    st->allocs.clear();
+    st->q = Queues{};
+    st->key_paths = 0;
+}
+
+void render_state_free(miro_gpu_ctx* ctx) {
+    if (!ctx->render_state) return;
+    RenderState* st = static_cast<RenderState*>(ctx->render_state);
+    free_queues(st);
+    cudaFree(st->level_sum); cudaFree(st->result); cudaFree(st->active[0]); cudaFree(st->active[1]); cudaFree(st->rgb_dev); cudaFree(st->gamma_lut);
+    if (st->h_count) cudaFreeHost(st->h_count);
+    delete st;
+    ctx->render_state = nullptr;
+}
+
+template <class T>
+static cudaError_t qalloc(RenderState* st, T** p, size_t n) {
+    void* v = nullptr;
+    cudaError_t e = cudaMalloc(&v, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) { st->allocs.push_back(v); *p = static_cast<T*>(v); }
+    return e;
+}
+
+static int ensure_queues(miro_gpu_ctx* ctx, RenderState* st, size_t paths, size_t cs, size_t shadow_per_path, size_t slots_per_path) {
+    if (st->key_paths == paths && st->q.cap_cs >= cs && st->key_shadow_per_path == shadow_per_path && st->key_slots_per_path == slots_per_path) return MIRO_GPU_OK;
+    free_queues(st);
+    Queues& q = st->q;
+    q.cap_cs = cs; q.cap_paths = paths; q.cap_shadow = paths * shadow_per_path; q.cap_slots = paths * slots_per_path;
+    MIRO_CUDA(ctx, qalloc(st, &q.cs_rays, q.cap_cs));
+    MIRO_CUDA(ctx, qalloc(st, &q.cs_hits, q.cap_cs));
+    for (int i = 0; i < 2; ++i) { MIRO_CUDA(ctx, qalloc(st, &q.q_rays[i], paths)); MIRO_CUDA(ctx, qalloc(st, &q.q_thr[i], paths)); }
+    MIRO_CUDA(ctx, qalloc(st, &q.q_hits, paths));
+    MIRO_CUDA(ctx, qalloc(st, &q.sh_rays, q.cap_shadow));
+    MIRO_CUDA(ctx, qalloc(st, &q.sh_E, q.cap_shadow));
+    MIRO_CUDA(ctx, qalloc(st, &q.slots, q.cap_slots));
+    MIRO_CUDA(ctx, qalloc(st, &q.counts, (size_t)8));
+    st->key_paths = paths; st->key_shadow_per_path = shadow_per_path; st->key_slots_per_path = slots_per_path;
+    return MIRO_GPU_OK;
+}
+
+static int ensure_frame(miro_gpu_ctx* ctx, RenderState* st, size_t pixels) {
+    if (!st->gamma_lut) {
+        // Image::generateGammaTables, Image.cpp:19-35: linear_to_gammaF[i] = pow(i/32768, 1/2.2) * 255 + 0.5
+        std::vector<float> lut(32769);
+        const float GAMMA = 2.2f;
+        for (int i = 0; i < 32769; i++) lut[i] = (float)(powf(i / 32768.0f, 1 / GAMMA) * 255.0 + 0.5);
+        MIRO_CUDA(ctx, cudaMalloc((void**)&st->gamma_lut, lut.size() * sizeof(float)));
+        MIRO_CUDA(ctx, cudaMemcpy(st->gamma_lut, lut.data(), lut.size() * sizeof(float), cudaMemcpyHostToDevice));
+        MIRO_CUDA(ctx, cudaMallocHost((void**)&st->h_count, 8 * sizeof(uint32_t)));
+    }
+    if (st->frame_pixels >= pixels) return MIRO_GPU_OK;
+    cudaFree(st->level_sum); cudaFree(st->result); cudaFree(st->active[0]); cudaFree(st->active[1]); cudaFree(st->rgb_dev);
+    st->level_sum = st->result = nullptr; st->active[0] = st->active[1] = nullptr; st->rgb_dev = nullptr; st->frame_pixels = 0;
+    MIRO_CUDA(ctx, cudaMalloc((void**)&st->level_sum, pixels * sizeof(float4)));
+    MIRO_CUDA(ctx, cudaMalloc((void**)&st->result, pixels * sizeof(float4)));
+    MIRO_CUDA(ctx, cudaMalloc((void**)&st->active[0], pixels * sizeof(uint32_t)));
+    MIRO_CUDA(ctx, cudaMalloc((void**)&st->active[1], pixels * sizeof(uint32_t)));
+    MIRO_CUDA(ctx, cudaMalloc((void**)&st->rgb_dev, pixels * 3 * sizeof(float)));
+    st->frame_pixels = pixels;
+    return MIRO_GPU_OK;
+}
+
+static inline int grid_for(size_t n, int block) { return (int)std::min<size_t>((n + block - 1) / block, 0x7fffffff); }
+static const int kPersistentGrid = 148 * 8;
+
+}  // namespace miro
+
+using namespace miro;
+
+extern "C" int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, const miro_gpu_render_params* rp, float* rgb_out) {
+    if (!ctx) return MIRO_GPU_EINVAL;
+    if (!cam || !rp || !rgb_out) return set_error(ctx, MIRO_GPU_EINVAL, "miro_gpu_render: NULL argument");
+    if (!ctx->has_scene) return set_error(ctx, MIRO_GPU_ENOSCENE, "render before upload_scene");
+    if (rp->width <= 0 || rp->height <= 0 || (size_t)rp->width * rp->height > 0x7fffffffu) return set_error(ctx, MIRO_GPU_EINVAL, "bad image size");
+    if (rp->num_paths < 1 || rp->num_paths > 0xffff) return set_error(ctx, MIRO_GPU_EINVAL, "num_paths must be in 1..65535");
+    if (rp->max_bounces > 0x7fff) return set_error(ctx, MIRO_GPU_EINVAL, "max_bounces too large");
+    const int max_sub = std::max(1, std::max(rp->max_subdivs, rp->min_subdivs));
+    if (max_sub > 32) return set_error(ctx, MIRO_GPU_EINVAL, "more than 32 subdivision levels");
+    if (ctx->shading.n_prims == 0 && (ctx->n_tris || ctx->n_mbtris)) return set_error(ctx, MIRO_GPU_EINVAL, "scene has no shading records (prims)");
+    MIRO_CUDA(ctx, cudaSetDevice(ctx->device));
+    RenderState* st = state_of(ctx);
+    const int W = rp->width, H = rp->height;
+    const size_t pixels = (size_t)W * H;
+    int rc;
+    if ((rc = ensure_frame(ctx, st, pixels))) return rc;
+
+    // ---- camera basis (Camera.cpp:123-137) — computed on the host once per frame
+    DeviceCamera dc;
+    {
+        auto norm = [](float3x a) { const float l = 1.0f / sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); return f3(a.x * l, a.y * l, a.z * l); };
+        const float3x vd = f3(cam->view_dir[0], cam->view_dir[1], cam->view_dir[2]), up = f3(cam->up[0], cam->up[1], cam->up[2]);
+        dc.w = norm(f3(-vd.x, -vd.y, -vd.z));
+        dc.u = norm(cross3(up, dc.w));
+        dc.v = cross3(dc.w, dc.u);
+        dc.eye = f3(cam->eye[0], cam->eye[1], cam->eye[2]);
+        dc.top = tanf(cam->fov_deg * (3.1415926f / 360.0f));
+        dc.right = ((float)W / (float)H) * dc.top;
+        dc.focus_plane = cam->focus_plane; dc.aperture = cam->aperture; dc.shutter = cam->shutter_speed;
+    }
+    RenderParamsDev P;
+    P.width = W; P.height = H; P.num_paths = rp->num_paths; P.max_bounces = rp->max_bounces;
+    P.path_trace = rp->path_trace; P.sample_env = rp->sample_env; P.seed = rp->seed; P.inv_paths = 1.0f / (float)rp->num_paths;
+
+    // ---- queue capacities: worst case per path
+    size_t light_samples = 0;
+    for (const miro_gpu_light& l : ctx->host_lights) light_samples += (size_t)std::max(1, l.num_samples);
+    const size_t loops = rp->path_trace ? 2 : 1;
+    const size_t shadow_per_path = std::max<size_t>(1, loops * light_samples), slots_per_path = std::max<size_t>(1, loops * ctx->host_lights.size());
+    const size_t bytes_per_path = 2 * (48 + 16) + 20 + shadow_per_path * 64 + slots_per_path * 64 + (48 + 20);
+    size_t paths = std::min<size_t>(WAVE_PATHS_MAX, std::max<size_t>(WAVE_BYTES_BUDGET / bytes_per_path, (size_t)rp->num_paths));
+    paths = std::min(paths, pixels * (size_t)max_sub * max_sub * rp->num_paths);
+    paths = std::max<size_t>((paths / rp->num_paths) * rp->num_paths, (size_t)rp->num_paths);
+    const size_t wave_cs = paths / rp->num_paths;
+    if ((rc = ensure_queues(ctx, st, paths, wave_cs, shadow_per_path, slots_per_path))) return rc;
+    Queues& q = st->q;
+    cudaStream_t s = ctx->stream;
+
+    // ---- pixels of this shard: 32x32 buckets in the order of Scene.cpp:160-175, bucket b owned when b % shard_count == shard_index
+    std::vector<uint32_t> own;
+    {
+        const int sc = std::max(1, rp->shard_count), si = rp->shard_index;
+        if (si < 0 || si >= sc) return set_error(ctx, MIRO_GPU_EINVAL, "shard_index out of range");
+        const int nbx = (W + 31) / 32, nby = (H + 31) / 32;
+        own.reserve(pixels / sc + 1024);
+        for (int b = si; b < nbx * nby; b += sc) {
+            const int bx = b % nbx, by = b / nbx;
+            for (int y = by * 32; y < std::min((by + 1) * 32, H); ++y)
+                for (int x = bx * 32; x < std::min((bx + 1) * 32, W); ++x) own.push_back((uint32_t)(y * W + x));
+        }
+    }
+    uint32_t n_active = (uint32_t)own.size();
+    EventPair tot = begin_timing(ctx, false);
+    MIRO_CUDA(ctx, cudaMemcpyAsync(st->active[0], own.data(), own.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    MIRO_CUDA(ctx, cudaMemsetAsync(st->level_sum, 0, pixels * sizeof(float4), s));
+    int cur = 0;
+    const int last_depth = rp->path_trace ? std::max(0, rp->max_bounces - 1) : 0;
+    for (int level = 1; level <= max_sub && n_active > 0; ++level) {
+        const uint32_t k2 = (uint32_t)(level * level);
+        const int km1 = level - 1;
+        const uint32_t ordinal_base = (uint32_t)(km1 * (km1 + 1) * (2 * km1 + 1) / 6);
+        const uint64_t total_cs = (uint64_t)n_active * k2;
+        for (uint64_t first = 0; first < total_cs; first += wave_cs) {
+            const uint32_t n_cs = (uint32_t)std::min<uint64_t>(wave_cs, total_cs - first);
+            k_raygen<<<grid_for(n_cs, SHADE_BLOCK), SHADE_BLOCK, 0, s>>>(dc, P, st->active[cur], (uint32_t)first, n_cs, level, ordinal_base, q.cs_rays);
+            ctx->launches++;
+            launch_trace_closest(ctx, q.cs_rays, n_cs, nullptr, q.cs_hits);
+            MIRO_CUDA(ctx, cudaMemsetAsync(q.counts, 0, 3 * sizeof(uint32_t), s));
+            const size_t n_threads = (size_t)n_cs * rp->num_paths;
+            k_shade<true><<<std::min(grid_for(n_threads, SHADE_BLOCK), kPersistentGrid * 4), SHADE_BLOCK, 0, s>>>(
+                ctx->scene, ctx->shading, P, q, 0, (uint32_t)n_threads, nullptr, st->level_sum, (uint32_t)q.cap_shadow, (uint32_t)q.cap_slots);
+            ctx->launches++;
+            int in_q = 1;      // k_shade<PRIMARY> wrote its bounce rays to q_rays[0 ^ 1]
+            for (int depth = 0; depth <= last_depth; ++depth) {
+                // shadow rays of the vertices at `depth`, then the per-loop resolve
+                launch_trace_shadow(ctx, q.sh_rays, q.cap_shadow, q.counts + 1, q.sh_E, reinterpret_cast<float4*>(q.slots));
+                k_resolve_slots<<<kPersistentGrid, SHADE_BLOCK, 0, s>>>(q.slots, q.counts + 2, st->level_sum);
+                ctx->launches++;
+                if (depth == last_depth) break;
+                // bounce rays spawned at `depth` -> vertices at depth + 1
+                MIRO_CUDA(ctx, cudaMemcpyAsync(q.counts + 4, q.counts + 0, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+                MIRO_CUDA(ctx, cudaMemsetAsync(q.counts, 0, 3 * sizeof(uint32_t), s));
+                launch_trace_closest(ctx, q.q_rays[in_q], q.cap_paths, q.counts + 4, q.q_hits);
+                k_shade<false><<<kPersistentGrid * 4, SHADE_BLOCK, 0, s>>>(ctx->scene, ctx->shading, P, q, in_q, 0, q.counts + 4, st->level_sum,
+                                                                           (uint32_t)q.cap_shadow, (uint32_t)q.cap_slots);
+                ctx->launches++;
+                in_q ^= 1;
+            }
+        }
+        MIRO_CUDA(ctx, cudaMemsetAsync(q.counts + 3, 0, sizeof(uint32_t), s));
+        k_level_resolve<<<grid_for(n_active, SHADE_BLOCK), SHADE_BLOCK, 0, s>>>(st->active[cur], n_active, level, rp->min_subdivs, rp->max_subdivs, rp->noise_threshold,
+                                                                               st->gamma_lut, st->level_sum, st->result, st->active[cur ^ 1], q.counts + 3);
+        ctx->launches++;
+        if (level < max_sub) {
+            MIRO_CUDA(ctx, cudaMemcpyAsync(st->h_count, q.counts + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            MIRO_CUDA(ctx, cudaStreamSynchronize(s));
+            n_active = st->h_count[0];
+            cur ^= 1;
+        }
+    }
+    // ---- hand the shard's pixels back (row 0 = bottom); pixels of other shards are left untouched
+    cudaPointerAttributes attr;
+    const bool out_is_device = cudaPointerGetAttributes(&attr, rgb_out) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    MIRO_CUDA(ctx, cudaMemcpyAsync(st->active[cur], own.data(), own.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    float* target = out_is_device ? rgb_out : st->rgb_dev;
+    if (!own.empty()) {
+        k_write_rgb<<<grid_for(own.size(), 256), 256, 0, s>>>(st->active[cur], (uint32_t)own.size(), st->result, target);
+        ctx->launches++;
+    }
+    MIRO_CUDA(ctx, cudaGetLastError());
+    if (!out_is_device) {
+        const bool whole = own.size() == pixels;
+        if (whole) MIRO_CUDA(ctx, cudaMemcpyAsync(rgb_out, st->rgb_dev, pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+        else {
+            std::vector<float> tmp(pixels * 3);
+            MIRO_CUDA(ctx, cudaMemcpyAsync(tmp.data(), st->rgb_dev, pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+            MIRO_CUDA(ctx, cudaStreamSynchronize(s));
+            for (uint32_t p : own) { rgb_out[(size_t)p * 3] = tmp[(size_t)p * 3]; rgb_out[(size_t)p * 3 + 1] = tmp[(size_t)p * 3 + 1]; rgb_out[(size_t)p * 3 + 2] = tmp[(size_t)p * 3 + 2]; }
+        }
+    }
+    end_timing(ctx, tot);
+    MIRO_CUDA(ctx, cudaStreamSynchronize(s));
+    return MIRO_GPU_OK;
 }

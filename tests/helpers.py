@@ -32,6 +32,7 @@ class Fixture:
         self.rays = z["rays"]; self.hits = z["hits"]; self.ray_index = z["ray_index"]
         self.radiance = z["radiance"].astype(np.float32) if "radiance" in z.files else None
         self.image8 = z["image8"] if "image8" in z.files else None
+        self.radiance_converged = z["radiance_converged"].astype(np.float32) if "radiance_converged" in z.files else None
 
     def mesh(self, k):
         g = lambda key: self.z[f"m{k}_{key}"]
@@ -44,6 +45,13 @@ class Fixture:
         sc = mb.MiroScene()
         for k, name in enumerate(self.names):
             sc.preload_mesh(name, **self.mesh(k))
+        for key in self.z.files:                       # textures exactly as the reference's loaders decoded them
+            if key.startswith("tex_"):
+                sc.preload_image(key[4:], self.z[key], hdr=int(self.z["texkind_" + key[4:]]) == 3)
+            elif key.startswith("texrgbe_"):
+                b = self.z[key]; e = b[..., 3].astype(np.int32)
+                tex = (b[..., :3].astype(np.float32) * np.ldexp(1.0, e - 136).astype(np.float32)[..., None]) * (e > 0)[..., None]
+                sc.preload_image(key[8:], tex.astype(np.float32), hdr=True)
         for name, tex in (images or {}).items():
             sc.preload_image(name, tex)
         with tempfile.NamedTemporaryFile("w", suffix=".miro", delete=False) as f:
@@ -119,3 +127,15 @@ def compare_hits(scene, hits, ref, t_rel=1e-5, edge_eps=1e-4):
                 max_abs_a=float(np.abs(hits["a"] - ref["a"])[ok].max()) if ok.any() else 0.0,
                 max_abs_b=float(np.abs(hits["b"] - ref["b"])[ok].max()) if ok.any() else 0.0,
                 closer=int((~same & g_hit & ((hits["t"] < ref["t"]) | ~r_hit)).sum()))
+
+
+def oracle_render(scene, params=None, camera=None, mask=None):
+    """CPU restatement of Scene::raytraceImage (oracle/miro_oracle_shade.c).  Returns (float image [h,w,3], Scene::trace calls)."""
+    L = oracle()
+    L.oracle_render.argtypes = [C.POINTER(capi.SceneDesc), C.POINTER(capi.Camera), C.POINTER(capi.RenderParams), C.c_void_p, C.c_void_p]
+    L.oracle_render.restype = C.c_uint64
+    p = params or scene.render_params(); c = camera or scene.camera(); d = scene.desc()
+    img = np.zeros((p.height, p.width, 3), np.float32)
+    m = np.ascontiguousarray(mask, np.uint8) if mask is not None else None
+    n = L.oracle_render(C.byref(d), C.byref(c), C.byref(p), img.ctypes.data, m.ctypes.data if m is not None else None)
+    return img, int(n)

@@ -35,9 +35,9 @@ REFHIT = np.dtype([("t", "f4"), ("a", "f4"), ("b", "f4"), ("mesh", "i4"), ("tri"
 SCENES = {
     "c1_cornell": dict(render=True, stock=True, incoherent=0),
     "c2_explosion": dict(render=True, stock=True, incoherent=1 << 20),
-    "c5_mb_instances": dict(render=False, stock=False, incoherent=1 << 19),
-    "c3_dome_pt": dict(render=True, stock=False, incoherent=0, threads=8),
-    "c4_cornell_pt": dict(render=True, stock=False, incoherent=0, threads=8),
+    "c5_mb_instances": dict(render=True, stock=False, incoherent=1 << 19, threads=8),
+    "c3_dome_pt": dict(render=True, stock=False, incoherent=0, threads=8, converged=32),
+    "c4_cornell_pt": dict(render=True, stock=False, incoherent=0, threads=8, converged=64),
 }
 
 
@@ -82,7 +82,25 @@ def trace(script, rays, tmp, threads=1):
     return np.fromfile(hp, REFHIT), ref_events(p.stderr)
 
 
-def pack(out, meshes, names, script_text, events, rays, hits, ray_index, radiance, image8, shape, radiance_dtype):
+def to_rgbe(a):
+    """float RGB -> shared-exponent RGBE bytes (lossless for texels that were decoded from a Radiance .hdr file)."""
+    m = a.max(axis=-1)
+    e = np.where(m > 1e-38, np.floor(np.log2(np.maximum(m, 1e-38))) + 1, -128).astype(np.int32)
+    scale = np.where(m > 1e-38, np.ldexp(1.0, 8 - e), 0.0)
+    rgb = np.clip(np.floor(a * scale[..., None] + 0.5), 0, 255)
+    # a mantissa that rounds to 256 would need the next exponent
+    bump = (rgb.max(axis=-1) > 255)
+    out = np.concatenate([rgb, (e + 128)[..., None]], axis=-1).astype(np.uint8)
+    assert not bump.any()
+    return out
+
+
+def from_rgbe(b):
+    e = b[..., 3].astype(np.int32)
+    return (b[..., :3].astype(np.float32) * np.ldexp(1.0, e - 136).astype(np.float32)[..., None]) * (e > 0)[..., None]
+
+
+def pack(out, meshes, names, script_text, events, rays, hits, ray_index, radiance, image8, shape, radiance_dtype, textures=None, extra=None):
     d = dict(mesh_names=np.array(names), script=np.array(script_text), events=np.array(json.dumps(events)),
              rays=rays, hits=hits, ray_index=ray_index, image_shape=np.array(shape, np.int32))
     for k, name in enumerate(names):
@@ -94,6 +112,14 @@ def pack(out, meshes, names, script_text, events, rays, hits, ray_index, radianc
         d["radiance"] = radiance.astype(radiance_dtype)
     if image8 is not None:
         d["image8"] = image8
+    for name, (tex, kind) in (textures or {}).items():
+        d["texkind_" + name] = np.array(kind, np.int32)
+        if radiance_dtype == np.float16 and kind == 3 and np.array_equal(from_rgbe(to_rgbe(tex)), tex):
+            d["texrgbe_" + name] = to_rgbe(tex)       # committed fixture: HDR texels as the RGBE bytes they were decoded from
+        else:
+            d["tex_" + name] = tex
+    for k, v in (extra or {}).items():
+        d[k] = v.astype(radiance_dtype) if v.dtype == np.float32 else v
     np.savez_compressed(out, **d)
     print("wrote", out, "%.2f MB" % (os.path.getsize(out) / 1e6))
 
@@ -103,7 +129,7 @@ def run(scene, opt):
     text = open(script).read()
     threads = opt.get("threads", 1)
     with tempfile.TemporaryDirectory() as tmp:
-        cmd = [REF, "--scene", script, "--assets", ASSETS, "--threads", str(threads), "--dump-meshes", tmp,
+        cmd = [REF, "--scene", script, "--assets", ASSETS, "--threads", str(threads), "--dump-meshes", tmp, "--dump-textures", tmp,
                "--dump-primary", os.path.join(tmp, "primary.rays")]
         if opt["render"]:
             cmd += ["--render-float", os.path.join(tmp, "radiance.f32")]
@@ -114,6 +140,24 @@ def run(scene, opt):
             if f.endswith(".mesh"):
                 o, m = read_mesh(os.path.join(tmp, f)); meshes[f[:-5]] = m; order[f[:-5]] = o
         names = sorted(meshes, key=lambda k: order[k])
+        textures = {}
+        for f in os.listdir(tmp):
+            if f.endswith(".tex"):
+                b = open(os.path.join(tmp, f), "rb").read()
+                tw, th, tc, kind = np.frombuffer(b[:16], np.int32)
+                textures[f[:-4]] = (np.frombuffer(b[16:], np.float32).reshape(th, tw, tc).copy(), int(kind))
+        extra = {}
+        if opt.get("converged"):      # a second, converged render of the same scene: numpaths multiplied
+            conv = os.path.join(tmp, "converged.miro")
+            import re
+            n0 = int(re.search(r"numpaths (\d+)", text).group(1))
+            open(conv, "w").write(re.sub(r"numpaths \d+", "numpaths %d" % (n0 * opt["converged"]), text))
+            cf = os.path.join(tmp, "converged.f32")
+            p2 = subprocess.run([REF, "--scene", conv, "--assets", ASSETS, "--threads", str(threads), "--render-float", cf],
+                                stderr=subprocess.PIPE, text=True, check=True)
+            ev2 = [e for e in ref_events(p2.stderr) if e["event"] == "render_float"][0]
+            extra["radiance_converged"] = np.fromfile(cf, np.float32).reshape(ev2["height"], ev2["width"], 3)
+            extra["converged_numpaths"] = np.array(n0 * opt["converged"], np.int32)
         rays = np.fromfile(os.path.join(tmp, "primary.rays"), RAY)
         image8 = None
         if opt["stock"]:
@@ -139,7 +183,7 @@ def run(scene, opt):
         events += ev
     os.makedirs(FULL, exist_ok=True); os.makedirs(GOLDEN, exist_ok=True)
     idx = np.arange(len(rays), dtype=np.int64)
-    pack(os.path.join(FULL, scene + ".npz"), meshes, names, text, events, rays, hits, idx, radiance, image8, shape, np.float32)
+    pack(os.path.join(FULL, scene + ".npz"), meshes, names, text, events, rays, hits, idx, radiance, image8, shape, np.float32, textures, extra)
     # committed subset: every ray that hit has the same chance as a miss; keep primary and incoherent halves
     rng = np.random.default_rng(12345)
     if len(rays) > GOLDEN_RAYS:
@@ -152,7 +196,7 @@ def run(scene, opt):
     small_img = image8
     if radiance is not None and radiance.shape[0] * radiance.shape[1] > 512 * 512:
         small_rad = None; small_img = None      # large images stay in the full fixture only
-    pack(os.path.join(GOLDEN, scene + ".npz"), meshes, names, text, events, rays[sel], hits[sel], sel, small_rad, small_img, shape, np.float16)
+    pack(os.path.join(GOLDEN, scene + ".npz"), meshes, names, text, events, rays[sel], hits[sel], sel, small_rad, small_img, shape, np.float16, textures, extra)
     print(scene, "primary", n_primary, "total rays", len(rays), "hit fraction %.3f" % (hits["mesh"] >= 0).mean())
 
 
