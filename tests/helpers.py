@@ -98,7 +98,7 @@ def oracle_trace_any(scene, rays):
     return np.unpackbits(bits.view(np.uint8), bitorder="little")[:len(rays)].astype(bool)
 
 
-def compare_hits(scene, hits, ref, t_rel=1e-5, edge_eps=1e-4):
+def compare_hits(scene, hits, ref, t_rel=1e-5, edge_eps=1e-4, rays=None):
     """Compare product hits with reference-identity hits (mesh, tri, proxy, t).
 
     Returns a dict of statistics.  A primitive-id mismatch is an *edge case* ("tie") when
@@ -121,7 +121,14 @@ def compare_hits(scene, hits, ref, t_rel=1e-5, edge_eps=1e-4):
     tie = ~same & ((both & (dt <= t_rel)) | on_edge(hits, g_hit) | on_edge(ref, r_hit))
     hard = ~same & ~tie
     ok = same & both
-    return dict(n=len(ref), id_match=float(same.mean()), ties=int(tie.sum()), hard=int(hard.sum()),
+    # instanced hits: the ray is moved into object space (ProxyObject.cpp:78-79), so t carries the rounding of
+    # coordinates of magnitude |o|; for t << |o| "relative to t" is not attainable by ANY float32 implementation.
+    # frac_t_within_pos measures |dt| against max(t, |o|) instead.
+    pos = 1.0
+    if rays is not None and ok.any():
+        scale = np.maximum(np.abs(ref["t"]), np.linalg.norm(rays["o"], axis=1))
+        pos = float((np.abs(hits["t"] - ref["t"])[ok] <= t_rel * scale[ok]).mean())
+    return dict(frac_t_within_pos=pos, n=len(ref), id_match=float(same.mean()), ties=int(tie.sum()), hard=int(hard.sum()),
                 hard_idx=np.nonzero(hard)[0], max_rel_t=float(dt[ok].max()) if ok.any() else 0.0,
                 frac_t_within=float((dt[ok] <= t_rel).mean()) if ok.any() else 1.0,
                 max_abs_a=float(np.abs(hits["a"] - ref["a"])[ok].max()) if ok.any() else 0.0,
