@@ -79,13 +79,25 @@ def test_sharded_render_equals_whole():
     """Buckets b % shard_count == shard_index; the union of the shards is the whole image (RNG keyed by pixel)."""
     fx, sc = load("c4_cornell_pt")
     whole = sc.render()
+    import torch
+    p = sc.render_params()
+    ys, xs = np.mgrid[0:p.height, 0:p.width]
+    bucket = (ys // 32) * ((p.width + 31) // 32) + xs // 32
     parts = np.zeros_like(whole)
     for i in range(3):
-        part = sc.render(shard_index=i, shard_count=3)
-        own = (part != 0).any(axis=2)
-        assert not (own & (parts != 0).any(axis=2)).any()
-        parts += part
+        out = torch.full((p.height, p.width, 3), -1.0, dtype=torch.float32, device="cuda")
+        p.shard_index = i; p.shard_count = 3
+        sc.render_device(out.data_ptr(), params=p)
+        torch.cuda.synchronize()
+        part = out.cpu().numpy()
+        own = bucket % 3 == i
+        assert (part[~own] == -1.0).all()              # pixels of other shards are left untouched
+        assert (part[own] >= 0).all()
+        parts[own] = part[own]
     assert np.allclose(parts, whole, rtol=1e-4, atol=1e-5)
+    # host-pointer variant through Scene::raytraceImage
+    hp = sc.render(shard_index=1, shard_count=3)
+    assert np.allclose(hp[bucket % 3 == 1], whole[bucket % 3 == 1], rtol=1e-4, atol=1e-5)
     sc.close()
 
 
