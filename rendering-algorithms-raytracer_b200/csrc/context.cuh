@@ -76,6 +76,8 @@ struct miro_gpu_ctx {
 
     // counters
     miro::TraceCounters* d_counters = nullptr;
+    uint32_t* d_work = nullptr;                 // [0] next unclaimed ray of the running traversal kernel, [1] blocks that have left
+    int sm_count = 148;
     std::vector<miro::EventPair> events;        // pending (not yet summed) timing pairs
     std::vector<miro::EventPair> event_pool;
     double trace_ms = 0.0, total_ms = 0.0;

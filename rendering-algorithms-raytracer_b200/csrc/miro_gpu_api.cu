@@ -59,38 +59,86 @@ void drain_timing(miro_gpu_ctx* ctx) {
 enum { TRACE_CLOSEST = 0, TRACE_ANY_BITS = 1, TRACE_ANY_ACCUM = 2 };
 
 template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(TRACE_BLOCK)
-k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const uint32_t* __restrict__ d_count,
+__global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS)
+k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const uint32_t* __restrict__ d_count, uint32_t chunk,
         miro_gpu_hit* __restrict__ hits, uint32_t* __restrict__ bits, const float4* __restrict__ sample_E, float4* __restrict__ slots,
-        TraceCounters* __restrict__ ctr) {
+        TraceCounters* __restrict__ ctr, uint32_t* __restrict__ work) {
     constexpr bool ANY = MODE != TRACE_CLOSEST;
     __shared__ unsigned long long stack[SMEM_STACK * TRACE_BLOCK];
     const uint32_t n = d_count ? min(*d_count, n_static) : n_static;
-    const uint32_t stride = gridDim.x * TRACE_BLOCK;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t c_nodes = 0, c_tris = 0, c_insts = 0, c_rays = 0;
-    // warp-uniform loop bound: every lane of a warp iterates the same number of times
-    for (uint32_t base = blockIdx.x * TRACE_BLOCK + (threadIdx.x & ~31u); base < n; base += stride) {
-        const uint32_t i = base + (threadIdx.x & 31u);
-        bool occluded = false;
-        if (i < n) {
-            const float4* rp = rays + (size_t)i * 3;
-            const float4 r0 = __ldcs(rp), r1 = __ldcs(rp + 1), r2 = __ldcs(rp + 2);
-            HitRec h; h.t = r1.w;
-            traverse<ANY, COUNT>(s, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r0.w, r2.x, stack + threadIdx.x, h, c_nodes, c_tris, c_insts);
-            ++c_rays;
-            if (MODE == TRACE_ANY_BITS) occluded = h.prim >= 0;
-            else if (MODE == TRACE_ANY_ACCUM) {
-                if (h.prim < 0) atomicAdd(slots + (size_t)__float_as_uint(r2.z) * 4, __ldcs(sample_E + i));
-            } else {
-                float* o = reinterpret_cast<float*>(hits + i);
-                const bool hit = h.prim >= 0;
-                __stcs(o + 0, hit ? h.t : -1.0f); __stcs(o + 1, hit ? h.a : 0.f); __stcs(o + 2, hit ? h.b : 0.f);
-                __stcs(reinterpret_cast<int*>(o) + 3, h.prim); __stcs(reinterpret_cast<int*>(o) + 4, hit ? h.inst : -1);
+    uint32_t chunk_next = 0, chunk_end = 0;      // warp-uniform: the warp's claimed range of ray indices
+    bool exhausted = false;                      // warp-uniform: the global counter has run past n
+    Lane L; L.done = true; L.cur = MIRO_GPU_CHILD_EMPTY; L.ray_idx = 0; L.cur_inst = -1; L.tmin = 0.f; L.time = 0.f;
+    L.hit.t = 0.f; L.hit.a = L.hit.b = 0.f; L.hit.prim = -1; L.hit.inst = -1;
+    L.r.set(0.f, 0.f, 0.f, 0.f, 0.f, 1.f);
+    TraversalStack st; st.smem = stack + threadIdx.x; st.sp = 0;
+
+    while (true) {
+        // ---- refill: idle slots take the next rays of the warp's chunk (a new chunk is claimed when it runs dry)
+        __syncwarp();
+        const uint32_t idle = __ballot_sync(0xffffffffu, L.done);
+        if (idle == 0xffffffffu && exhausted) break;
+        if (!exhausted && __popc(idle) >= TRACE_REFILL) {
+            if (chunk_next == chunk_end) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(work, chunk);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                chunk_next = min(base, n); chunk_end = min(base + chunk, n);
+                if (chunk_next == chunk_end) exhausted = true;
+            }
+            const uint32_t take = min((uint32_t)__popc(idle), chunk_end - chunk_next);
+            const uint32_t rank = __popc(idle & lt_mask);
+            if (L.done && rank < take) {
+                L.ray_idx = chunk_next + rank;
+                const float4* rp = rays + (size_t)L.ray_idx * 3;
+                const float4 r0 = __ldcs(rp), r1 = __ldcs(rp + 1), r2 = __ldcs(rp + 2);
+                L.r.set(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
+                L.tmin = r0.w; L.time = r2.x;
+                L.hit.t = r1.w; L.hit.a = 0.f; L.hit.b = 0.f; L.hit.prim = -1; L.hit.inst = -1;
+                L.cur = s.root; L.cur_inst = -1; st.sp = 0; L.done = false;
+                ++c_rays;
+            }
+            chunk_next += take;
+            if (idle == 0xffffffffu && take == 0) continue;      // nothing claimed this round: try the next chunk (or leave)
+        }
+        // ---- phase 1: every live lane descends inner nodes until it holds a leaf (or runs out of candidates)
+        if (!L.done) descend<COUNT>(s, L, st, c_nodes);
+        __syncwarp();
+        // ---- phase 2: every live lane intersects the leaf it holds
+        bool finished = false;
+        if (!L.done) {
+            if (L.cur == STACK_SENTINEL) {            // leaving an instance: back to the world-space ray
+                const float4 w0 = __ldg(rays + (size_t)L.ray_idx * 3), w1 = __ldg(rays + (size_t)L.ray_idx * 3 + 1);
+                L.r.set(w0.x, w0.y, w0.z, w1.x, w1.y, w1.z);
+                L.cur_inst = -1; L.cur = MIRO_GPU_CHILD_EMPTY;
+            } else if (L.cur < 0) {
+                finished = intersect_leaf<ANY, COUNT>(s, L, st, rays, c_tris, c_insts);
+            }
+            // ---- pop the next candidate (unless the leaf was an instance, whose root is now `cur`)
+            if (!finished && L.cur == MIRO_GPU_CHILD_EMPTY) {
+                finished = true;
+                while (st.sp > 0) {
+                    const StackEntry e = st.pop();
+                    if (e.ref == STACK_SENTINEL || e.t < L.hit.t) { L.cur = e.ref; finished = false; break; }
+                }
             }
         }
-        if (MODE == TRACE_ANY_BITS) {
-            const uint32_t w = __ballot_sync(0xffffffffu, occluded);
-            if ((threadIdx.x & 31u) == 0) bits[base >> 5] = w;
+        // ---- a finished ray writes its result and frees its slot
+        if (finished) {
+            const uint32_t i = L.ray_idx;
+            const bool hit = L.hit.prim >= 0;
+            if (MODE == TRACE_ANY_BITS) { if (hit) atomicOr(bits + (i >> 5), 1u << (i & 31u)); }
+            else if (MODE == TRACE_ANY_ACCUM) {
+                if (!hit) { const float4 r2 = __ldcs(rays + (size_t)i * 3 + 2); atomicAdd(slots + (size_t)__float_as_uint(r2.z) * 4, __ldcs(sample_E + i)); }
+            } else {
+                float* o = reinterpret_cast<float*>(hits + i);
+                __stcs(o + 0, hit ? L.hit.t : -1.0f); __stcs(o + 1, hit ? L.hit.a : 0.f); __stcs(o + 2, hit ? L.hit.b : 0.f);
+                __stcs(reinterpret_cast<int*>(o) + 3, L.hit.prim); __stcs(reinterpret_cast<int*>(o) + 4, hit ? L.hit.inst : -1);
+            }
+            L.done = true;
         }
     }
     // counters: warp-reduce then one atomic per warp
@@ -103,29 +151,44 @@ k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const
             v_insts += __shfl_down_sync(0xffffffffu, v_insts, o);
         }
     }
-    if ((threadIdx.x & 31u) == 0 && v_rays) {
+    if (lane == 0 && v_rays) {
         atomicAdd(ANY ? &ctr->rays_any : &ctr->rays_closest, v_rays);
         if (COUNT) { atomicAdd(&ctr->nodes, v_nodes); atomicAdd(&ctr->tris, v_tris); atomicAdd(&ctr->insts, v_insts); }
     }
+    // the last block to leave re-arms the work counter for the next launch on this context
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(work + 1, 1u) == gridDim.x - 1) { work[0] = 0; work[1] = 0; __threadfence(); }
+    }
 }
 
-static int trace_grid(miro_gpu_ctx* ctx, size_t n, bool device_count) {
-    size_t blocks = (n + TRACE_BLOCK - 1) / TRACE_BLOCK;
-    if (blocks < 1) blocks = 1;
-    // device-side counts (wavefront queues): persistent-style grid, 148 SMs x 16 resident blocks
-    const size_t persistent = 148 * 16;
-    if (device_count) blocks = std::min(blocks, persistent);
-    return (int)std::min<size_t>(blocks, 0x7fffffff);
+template <int MODE>
+static int trace_grid(miro_gpu_ctx* ctx, size_t n) {
+    // persistent grid: every SM holds as many blocks as fit (asked of the occupancy calculator once per kernel)
+    static int per_sm[2] = {0, 0};
+    int& v = per_sm[ctx->counting ? 1 : 0];
+    if (v == 0) {
+        if (ctx->counting) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace<MODE, true>, TRACE_BLOCK, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace<MODE, false>, TRACE_BLOCK, 0);
+        if (v <= 0) v = 1;
+    }
+    const size_t blocks_needed = (n + TRACE_BLOCK - 1) / TRACE_BLOCK;
+    return (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->sm_count * v, blocks_needed));
 }
 
 template <int MODE>
 static void launch_trace(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, const uint32_t* d_count, miro_gpu_hit* d_hits, uint32_t* d_bits,
                          const float4* d_E, float4* d_slots) {
     if (n == 0) return;
-    const int grid = trace_grid(ctx, n, d_count != nullptr);
+    const int grid = trace_grid<MODE>(ctx, n);
+    // rays are claimed in chunks per warp: small batches use the smallest chunk so that every warp gets work
+    const size_t warps = (size_t)grid * (TRACE_BLOCK / 32);
+    const uint32_t chunk = n >= warps * 256 ? 64u : 32u;
     const float4* r = reinterpret_cast<const float4*>(d_rays);
-    if (ctx->counting) k_trace<MODE, true><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(ctx->scene, r, (uint32_t)n, d_count, d_hits, d_bits, d_E, d_slots, ctx->d_counters);
-    else k_trace<MODE, false><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(ctx->scene, r, (uint32_t)n, d_count, d_hits, d_bits, d_E, d_slots, ctx->d_counters);
+    if (MODE == TRACE_ANY_BITS) cudaMemsetAsync(d_bits, 0, ((n + 31) / 32) * sizeof(uint32_t), ctx->stream);
+    if (ctx->counting) k_trace<MODE, true><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(ctx->scene, r, (uint32_t)n, d_count, chunk, d_hits, d_bits, d_E, d_slots, ctx->d_counters, ctx->d_work);
+    else k_trace<MODE, false><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(ctx->scene, r, (uint32_t)n, d_count, chunk, d_hits, d_bits, d_E, d_slots, ctx->d_counters, ctx->d_work);
     ctx->launches++;
 }
 void launch_trace_closest(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, const uint32_t* d_count, miro_gpu_hit* d_hits) {
@@ -179,6 +242,9 @@ int miro_gpu_create(miro_gpu_ctx** out, int device_id) {
     ctx->stream = ctx->own_stream;
     if ((e = cudaMalloc((void**)&ctx->d_counters, sizeof(TraceCounters))) != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaMalloc(counters)"); }
     cudaMemset(ctx->d_counters, 0, sizeof(TraceCounters));
+    if ((e = cudaMalloc((void**)&ctx->d_work, 2 * sizeof(uint32_t))) != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaMalloc(work counter)"); }
+    cudaMemset(ctx->d_work, 0, 2 * sizeof(uint32_t));
+    ctx->sm_count = prop.multiProcessorCount;
     // the traversal kernels keep their stacks in shared memory and want the rest of the 256 KB as L1
     *out = ctx;
     return MIRO_GPU_OK;
@@ -200,6 +266,7 @@ void miro_gpu_destroy(miro_gpu_ctx* ctx) {
     free_scene(ctx);
     ctx->d_rays.release(); ctx->d_hits.release(); ctx->d_bits.release();
     if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_work) cudaFree(ctx->d_work);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }

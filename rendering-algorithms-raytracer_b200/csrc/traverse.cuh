@@ -8,9 +8,16 @@
 //   MB lanes of intersect4         reference src/BVH.cpp:1316-1335 (two-pose lerp at ray.time)
 //
 // Design (B200-first, not a translation):
-//   * one thread per ray, while-while traversal of 128-byte BVH4 nodes fetched with seven
-//     16-byte vector loads through the read-only path (the whole tree lives in the 126 MB L2;
-//     hot top levels in L1);
+//   * PERSISTENT WARPS with dynamic ray fetch: a warp owns 32 ray slots; lanes whose ray has
+//     finished are refilled from a global work counter (claimed in per-warp chunks) as soon as
+//     enough of them are idle, so a warp never runs at the length of its longest ray with the
+//     other lanes empty (v1's one-thread-per-ray kernel executed 2-9 of 32 lanes per instruction);
+//   * the lanes of a warp are kept in the same PHASE: every round is "all lanes descend inner
+//     nodes until each holds a leaf" -> __syncwarp -> "all lanes intersect their leaf" -> pop,
+//     with explicit reconvergence points (independent thread scheduling does not reconverge by
+//     itself);
+//   * 128-byte BVH4 nodes fetched with seven 16-byte vector loads through the read-only path (the
+//     whole tree lives in the 126 MB L2; hot top levels in L1);
 //   * children are visited nearest-first (4-element sorting network) and the deferred ones go
 //     to a per-thread stack in SHARED memory laid out [entry][lane] (conflict-free, "warp
 //     coherent"); entries carry their entry distance so popped sub-trees behind the current
@@ -36,6 +43,11 @@
 namespace miro {
 
 constexpr int TRACE_BLOCK = 128;        // threads per block of the traversal kernels
+constexpr int TRACE_MIN_BLOCKS = 6;     // resident blocks per SM the kernels are compiled for (register budget)
+#ifndef MIRO_TRACE_REFILL
+#define MIRO_TRACE_REFILL 8
+#endif
+constexpr int TRACE_REFILL = MIRO_TRACE_REFILL;   // idle lanes in a warp that trigger a refill from the work counter
 constexpr int SMEM_STACK = 24;          // per-thread stack entries kept in shared memory
 constexpr int LMEM_STACK = 72;          // overflow entries (local memory, touched only by very deep trees)
 constexpr int32_t STACK_SENTINEL = 0x7ffffffe;   // "leave instance" marker
@@ -144,135 +156,139 @@ __device__ __forceinline__ bool intersect_tri(const RaySpace& r, float tmin, flo
 
 struct StackEntry { int32_t ref; float t; };
 
-// Per-thread traversal stack: first SMEM_STACK entries in shared memory ([entry][lane] layout),
-// the rest in local memory.
+// Per-lane traversal stack: first SMEM_STACK entries in shared memory ([entry][lane] layout, conflict
+// free), the rest in local memory (touched only by very deep trees; depth is validated at upload).
 struct TraversalStack {
-    unsigned long long* smem;   // base + threadIdx.x, stride = blockDim.x
+    unsigned long long* smem;   // base + threadIdx.x, stride = TRACE_BLOCK
     unsigned long long lmem[LMEM_STACK];
     int sp;
     __device__ __forceinline__ void push(int32_t ref, float t) {
         unsigned long long v = ((unsigned long long)__float_as_uint(t) << 32) | (uint32_t)ref;
         if (sp < SMEM_STACK) smem[sp * TRACE_BLOCK] = v;
         else if (sp - SMEM_STACK < LMEM_STACK) lmem[sp - SMEM_STACK] = v;
-        ++sp;    // entries beyond both stacks are dropped by the guard above (trees that deep are rejected at upload)
+        ++sp;
     }
     __device__ __forceinline__ StackEntry pop() {
         --sp;
         StackEntry e;
         if (sp >= SMEM_STACK + LMEM_STACK) { e.ref = MIRO_GPU_CHILD_EMPTY; e.t = 0.f; return e; }
-        unsigned long long v = (sp < SMEM_STACK) ? smem[sp * TRACE_BLOCK] : lmem[sp - SMEM_STACK]; e.ref = (int32_t)(uint32_t)v; e.t = __uint_as_float((uint32_t)(v >> 32));
+        unsigned long long v = (sp < SMEM_STACK) ? smem[sp * TRACE_BLOCK] : lmem[sp - SMEM_STACK];
+        e.ref = (int32_t)(uint32_t)v; e.t = __uint_as_float((uint32_t)(v >> 32));
         return e;
     }
 };
 
 #define MIRO_CSWAP(ta, ca, tb, cb) { if (tb < ta) { float tt = ta; ta = tb; tb = tt; int32_t cc = ca; ca = cb; cb = cc; } }
 
-// Closest-hit (ANY=false) or any-hit (ANY=true) traversal of one ray.  `hit.t` must hold tmax on
-// entry; on return hit.prim >= 0 iff something was hit in [tmin, tmax).
-template <bool ANY, bool COUNT>
-__device__ __forceinline__ void traverse(const DeviceScene& s, float ox, float oy, float oz, float dx, float dy, float dz,
-                                         float tmin, float time, unsigned long long* smem_stack, HitRec& hit,
-                                         uint32_t& n_nodes, uint32_t& n_tris, uint32_t& n_insts) {
-    RaySpace r;
-    r.set(ox, oy, oz, dx, dy, dz);
-    TraversalStack st;
-    st.smem = smem_stack; st.sp = 0;
-    int32_t cur = s.root;
-    int32_t cur_inst = -1;
-    hit.prim = -1; hit.inst = -1; hit.a = 0.f; hit.b = 0.f;
+__device__ __forceinline__ bool ref_is_inner(int32_t ref) { return ref >= 0 && ref != MIRO_GPU_CHILD_EMPTY && ref != STACK_SENTINEL; }
 
-    while (true) {
-        // ---- inner nodes: descend nearest-first until a leaf (or nothing) is reached
-        while (cur >= 0 && cur != MIRO_GPU_CHILD_EMPTY && cur != STACK_SENTINEL) {
-            const float4* n = s.nodes + (size_t)cur * 8;
-            const float4 lox = __ldg(n + 0), loy = __ldg(n + 1), loz = __ldg(n + 2);
-            const float4 hix = __ldg(n + 3), hiy = __ldg(n + 4), hiz = __ldg(n + 5);
-            const int4 ch = __ldg(reinterpret_cast<const int4*>(n + 6));
-            if (COUNT) ++n_nodes;
-            float tn0, tn1, tn2, tn3;
+// One ray slot of a persistent warp.
+struct Lane {
+    RaySpace r;          // current-space ray (world, or object space inside an instance)
+    float tmin, time;
+    HitRec hit;          // hit.t = current tmax
+    int32_t cur;         // node / leaf reference being processed, or MIRO_GPU_CHILD_EMPTY
+    int32_t cur_inst;
+    uint32_t ray_idx;
+    bool done;           // slot is empty
+};
+
+// Inner-node phase: descend nearest-first until `cur` is a leaf reference or nothing is left.
+template <bool COUNT>
+__device__ __forceinline__ void descend(const DeviceScene& s, Lane& L, TraversalStack& st, uint32_t& n_nodes) {
+    const float inf = __int_as_float(0x7f800000);
+    while (ref_is_inner(L.cur)) {
+        const float4* n = s.nodes + (size_t)L.cur * 8;
+        const float4 lox = __ldg(n + 0), loy = __ldg(n + 1), loz = __ldg(n + 2);
+        const float4 hix = __ldg(n + 3), hiy = __ldg(n + 4), hiz = __ldg(n + 5);
+        const int4 ch = __ldg(reinterpret_cast<const int4*>(n + 6));
+        if (COUNT) ++n_nodes;
+        float tn0, tn1, tn2, tn3;
 #define MIRO_SLAB(LX, LY, LZ, HX, HY, HZ, CH, TN) { \
-            float ax = (LX - r.ox) * r.ix, bx = (HX - r.ox) * r.ix; \
-            float ay = (LY - r.oy) * r.iy, by = (HY - r.oy) * r.iy; \
-            float az = (LZ - r.oz) * r.iz, bz = (HZ - r.oz) * r.iz; \
-            float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin)); \
-            float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), hit.t)); \
-            TN = (tn <= tf && CH != MIRO_GPU_CHILD_EMPTY) ? tn : __int_as_float(0x7f800000); }
-            int32_t c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
-            MIRO_SLAB(lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, c0, tn0)
-            MIRO_SLAB(lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, c1, tn1)
-            MIRO_SLAB(lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, c2, tn2)
-            MIRO_SLAB(lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, c3, tn3)
+        float ax = (LX - L.r.ox) * L.r.ix, bx = (HX - L.r.ox) * L.r.ix; \
+        float ay = (LY - L.r.oy) * L.r.iy, by = (HY - L.r.oy) * L.r.iy; \
+        float az = (LZ - L.r.oz) * L.r.iz, bz = (HZ - L.r.oz) * L.r.iz; \
+        float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), L.tmin)); \
+        float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), L.hit.t)); \
+        TN = (tn <= tf && CH != MIRO_GPU_CHILD_EMPTY) ? tn : inf; }
+        int32_t c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
+        MIRO_SLAB(lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, c0, tn0)
+        MIRO_SLAB(lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, c1, tn1)
+        MIRO_SLAB(lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, c2, tn2)
+        MIRO_SLAB(lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, c3, tn3)
 #undef MIRO_SLAB
-            MIRO_CSWAP(tn0, c0, tn1, c1) MIRO_CSWAP(tn2, c2, tn3, c3)
-            MIRO_CSWAP(tn0, c0, tn2, c2) MIRO_CSWAP(tn1, c1, tn3, c3)
-            MIRO_CSWAP(tn1, c1, tn2, c2)
-            const float inf = __int_as_float(0x7f800000);
-            if (tn3 < inf) st.push(c3, tn3);
-            if (tn2 < inf) st.push(c2, tn2);
-            if (tn1 < inf) st.push(c1, tn1);
-            if (tn0 < inf) cur = c0;
-            else cur = MIRO_GPU_CHILD_EMPTY;
-        }
-        // ---- leaf
-        if (cur < 0) {
-            const uint32_t u = (uint32_t)cur;
-            const uint32_t kind = (u >> 29) & 3u;
-            const uint32_t count = ((u >> MIRO_GPU_LEAF_INDEX_BITS) & 7u) + 1u;
-            const uint32_t first = u & ((1u << MIRO_GPU_LEAF_INDEX_BITS) - 1u);
-            if (kind == MIRO_GPU_KIND_TRI) {
-                for (uint32_t i = 0; i < count; ++i) {
-                    const float4* t = s.tris + (size_t)(first + i) * 3;
-                    const float4 p0 = __ldg(t), p1 = __ldg(t + 1), p2 = __ldg(t + 2);
-                    if (COUNT) ++n_tris;
-                    if (intersect_tri(r, tmin, hit.t, p0, p1, p2, hit.t, hit.a, hit.b)) {
-                        hit.prim = (int32_t)(first + i); hit.inst = cur_inst;
-                        if (ANY) return;
-                    }
-                }
-            } else if (kind == MIRO_GPU_KIND_MBTRI) {
-                const float w1 = time, w0 = 1.0f - time;    // src/BVH.cpp:1323-1334
-                for (uint32_t i = 0; i < count; ++i) {
-                    const float4* t = s.mbtris + (size_t)(first + i) * 6;
-                    const float4 a0 = __ldg(t), a1 = __ldg(t + 1), a2 = __ldg(t + 2);
-                    const float4 b0 = __ldg(t + 3), b1 = __ldg(t + 4), b2 = __ldg(t + 5);
-                    if (COUNT) ++n_tris;
-                    float4 p0, p1, p2;
-                    p0.x = w1 * b0.x + w0 * a0.x; p0.y = w1 * b0.y + w0 * a0.y; p0.z = w1 * b0.z + w0 * a0.z;
-                    p1.x = w1 * b1.x + w0 * a1.x; p1.y = w1 * b1.y + w0 * a1.y; p1.z = w1 * b1.z + w0 * a1.z;
-                    p2.x = w1 * b2.x + w0 * a2.x; p2.y = w1 * b2.y + w0 * a2.y; p2.z = w1 * b2.z + w0 * a2.z;
-                    if (intersect_tri(r, tmin, hit.t, p0, p1, p2, hit.t, hit.a, hit.b)) {
-                        hit.prim = (int32_t)(s.n_tris + first + i); hit.inst = cur_inst;
-                        if (ANY) return;
-                    }
-                }
-            } else {   // MIRO_GPU_KIND_INST: enter the first instance, defer the others
-                if (count > 1u) st.push(MIRO_GPU_LEAF(MIRO_GPU_KIND_INST, first + 1u, count - 1u), -__int_as_float(0x7f800000));
-                st.push(STACK_SENTINEL, -__int_as_float(0x7f800000));
-                const float4* m = s.insts + (size_t)first * 4;
-                const float4 r0 = __ldg(m), r1 = __ldg(m + 1), r2 = __ldg(m + 2);
-                const int4 meta = __ldg(reinterpret_cast<const int4*>(m + 3));
-                if (COUNT) ++n_insts;
-                // o' = M^-1 [o 1], d' = M^-1 [d 0]  (src/ProxyObject.cpp:78-79; affine, so w = 1)
-                const float nox = r0.x * ox + r0.y * oy + r0.z * oz + r0.w;
-                const float noy = r1.x * ox + r1.y * oy + r1.z * oz + r1.w;
-                const float noz = r2.x * ox + r2.y * oy + r2.z * oz + r2.w;
-                const float ndx = r0.x * dx + r0.y * dy + r0.z * dz;
-                const float ndy = r1.x * dx + r1.y * dy + r1.z * dz;
-                const float ndz = r2.x * dx + r2.y * dy + r2.z * dz;
-                r.set(nox, noy, noz, ndx, ndy, ndz);
-                cur_inst = (int32_t)first;
-                cur = meta.x;
-                continue;
+        MIRO_CSWAP(tn0, c0, tn1, c1) MIRO_CSWAP(tn2, c2, tn3, c3)
+        MIRO_CSWAP(tn0, c0, tn2, c2) MIRO_CSWAP(tn1, c1, tn3, c3)
+        MIRO_CSWAP(tn1, c1, tn2, c2)
+        if (tn3 < inf) st.push(c3, tn3);
+        if (tn2 < inf) st.push(c2, tn2);
+        if (tn1 < inf) st.push(c1, tn1);
+        if (tn0 < inf) L.cur = c0;
+        else {
+            // nothing hit below this node: pop the next candidate that can still beat the current hit
+            L.cur = MIRO_GPU_CHILD_EMPTY;
+            while (st.sp > 0) {
+                const StackEntry e = st.pop();
+                if (e.ref == STACK_SENTINEL || e.t < L.hit.t) { L.cur = e.ref; break; }
             }
         }
-        // ---- pop
-        while (true) {
-            if (st.sp == 0) return;
-            StackEntry e = st.pop();
-            if (e.ref == STACK_SENTINEL) { r.set(ox, oy, oz, dx, dy, dz); cur_inst = -1; continue; }
-            if (e.t < hit.t) { cur = e.ref; break; }
-        }
     }
+}
+
+// Leaf phase.  Returns true when an ANY query has found its occluder.
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ bool intersect_leaf(const DeviceScene& s, Lane& L, TraversalStack& st, const float4* __restrict__ rays,
+                                               uint32_t& n_tris, uint32_t& n_insts) {
+    const uint32_t u = (uint32_t)L.cur;
+    const uint32_t kind = (u >> 29) & 3u;
+    const uint32_t count = ((u >> MIRO_GPU_LEAF_INDEX_BITS) & 7u) + 1u;
+    const uint32_t first = u & ((1u << MIRO_GPU_LEAF_INDEX_BITS) - 1u);
+    if (kind == MIRO_GPU_KIND_TRI) {
+        for (uint32_t i = 0; i < count; ++i) {
+            const float4* t = s.tris + (size_t)(first + i) * 3;
+            const float4 p0 = __ldg(t), p1 = __ldg(t + 1), p2 = __ldg(t + 2);
+            if (COUNT) ++n_tris;
+            if (intersect_tri(L.r, L.tmin, L.hit.t, p0, p1, p2, L.hit.t, L.hit.a, L.hit.b)) {
+                L.hit.prim = (int32_t)(first + i); L.hit.inst = L.cur_inst;
+                if (ANY) return true;
+            }
+        }
+    } else if (kind == MIRO_GPU_KIND_MBTRI) {
+        const float w1 = L.time, w0 = 1.0f - L.time;    // src/BVH.cpp:1323-1334
+        for (uint32_t i = 0; i < count; ++i) {
+            const float4* t = s.mbtris + (size_t)(first + i) * 6;
+            const float4 a0 = __ldg(t), a1 = __ldg(t + 1), a2 = __ldg(t + 2);
+            const float4 b0 = __ldg(t + 3), b1 = __ldg(t + 4), b2 = __ldg(t + 5);
+            if (COUNT) ++n_tris;
+            float4 p0, p1, p2;
+            p0.x = w1 * b0.x + w0 * a0.x; p0.y = w1 * b0.y + w0 * a0.y; p0.z = w1 * b0.z + w0 * a0.z;
+            p1.x = w1 * b1.x + w0 * a1.x; p1.y = w1 * b1.y + w0 * a1.y; p1.z = w1 * b1.z + w0 * a1.z;
+            p2.x = w1 * b2.x + w0 * a2.x; p2.y = w1 * b2.y + w0 * a2.y; p2.z = w1 * b2.z + w0 * a2.z;
+            if (intersect_tri(L.r, L.tmin, L.hit.t, p0, p1, p2, L.hit.t, L.hit.a, L.hit.b)) {
+                L.hit.prim = (int32_t)(s.n_tris + first + i); L.hit.inst = L.cur_inst;
+                if (ANY) return true;
+            }
+        }
+    } else {   // MIRO_GPU_KIND_INST: enter the first instance, defer the others
+        const float ninf = -__int_as_float(0x7f800000);
+        if (count > 1u) st.push(MIRO_GPU_LEAF(MIRO_GPU_KIND_INST, first + 1u, count - 1u), ninf);
+        st.push(STACK_SENTINEL, ninf);
+        const float4* m = s.insts + (size_t)first * 4;
+        const float4 r0 = __ldg(m), r1 = __ldg(m + 1), r2 = __ldg(m + 2);
+        const int4 meta = __ldg(reinterpret_cast<const int4*>(m + 3));
+        if (COUNT) ++n_insts;
+        // the world-space ray is not kept in registers: instance entry / exit re-read it (L2-resident, rare)
+        const float4 w0 = __ldg(rays + (size_t)L.ray_idx * 3), w1 = __ldg(rays + (size_t)L.ray_idx * 3 + 1);
+        const float wox = w0.x, woy = w0.y, woz = w0.z, wdx = w1.x, wdy = w1.y, wdz = w1.z;
+        // o' = M^-1 [o 1], d' = M^-1 [d 0]  (src/ProxyObject.cpp:78-79; affine, so w = 1)
+        L.r.set(r0.x * wox + r0.y * woy + r0.z * woz + r0.w, r1.x * wox + r1.y * woy + r1.z * woz + r1.w, r2.x * wox + r2.y * woy + r2.z * woz + r2.w,
+                r0.x * wdx + r0.y * wdy + r0.z * wdz, r1.x * wdx + r1.y * wdy + r1.z * wdz, r2.x * wdx + r2.y * wdy + r2.z * wdz);
+        L.cur_inst = (int32_t)first;
+        L.cur = meta.x;
+        return false;
+    }
+    L.cur = MIRO_GPU_CHILD_EMPTY;
+    return false;
 }
 
 }  // namespace miro
