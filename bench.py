@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="miro_gpu", choices=["miro_gpu", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (kernel tuning runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "miro_gpu" else args.warmup
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -329,7 +330,7 @@ def main():
                              "launch_ms": launch_ms[dom], "share_of_step": launch_ms[dom] / sum(launch_ms),
                              "all_launches": [{"ms": launch_ms[i], "Mrays_per_s": N_BATCH / launch_ms[i] * 1e-3,
                                                "GBps": per_launch[i]["bytes"] / launch_ms[i] * 1e-6} for i in range(3)]}}
-        if world == 1:
+        if world == 1 and not args.no_cpu:
             threads = min(os.cpu_count() or 1, 16)
             sample = [prim.reshape(HEIGHT, WIDTH)[::2, ::4].reshape(-1).copy(), inco[::8].copy(), shad[::8].copy()]
             sec, n, kind, used = reference_trace(fx, sample, threads, 3)

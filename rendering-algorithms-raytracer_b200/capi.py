@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmiro_gpu.so")
+LIB_PATH = os.environ.get("MIRO_GPU_LIB") or os.path.join(_HERE, "libmiro_gpu.so")   # MIRO_GPU_LIB: kernel-tuning builds (tools/tune.sh)
 
 OK, EINVAL, ENODEVICE, ECUDA, ENOSCENE, EUNSUPPORTED, ENOMEM = 0, -1, -2, -3, -4, -5, -6
 TMAX = 1e12

@@ -104,27 +104,22 @@ k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const
             chunk_next += take;
             if (idle == 0xffffffffu && take == 0) continue;      // nothing claimed this round: try the next chunk (or leave)
         }
-        // ---- phase 1: every live lane descends inner nodes until it holds a leaf (or runs out of candidates)
-        if (!L.done) descend<COUNT>(s, L, st, c_nodes);
-        __syncwarp();
-        // ---- phase 2: every live lane intersects the leaf it holds
+        // ---- vote: a live lane waits either at an inner node or at a leaf (leaf reference / instance-exit marker)
+        const bool at_node = !L.done && ref_is_inner(L.cur);
+        const bool at_leaf = !L.done && !at_node;
+        const int n_node = __popc(__ballot_sync(0xffffffffu, at_node)), n_leaf = __popc(__ballot_sync(0xffffffffu, at_leaf));
         bool finished = false;
-        if (!L.done) {
+        if (n_node * TRACE_NODE_BIAS_DEN >= n_leaf * TRACE_NODE_BIAS_NUM) {
+            // ---- node round
+            if (at_node) { node_step<COUNT>(s, L, st, c_nodes); finished = L.cur == MIRO_GPU_CHILD_EMPTY; }
+        } else if (at_leaf) {
+            // ---- leaf round
             if (L.cur == STACK_SENTINEL) {            // leaving an instance: back to the world-space ray
                 const float4 w0 = __ldg(rays + (size_t)L.ray_idx * 3), w1 = __ldg(rays + (size_t)L.ray_idx * 3 + 1);
                 L.r.set(w0.x, w0.y, w0.z, w1.x, w1.y, w1.z);
                 L.cur_inst = -1; L.cur = MIRO_GPU_CHILD_EMPTY;
-            } else if (L.cur < 0) {
-                finished = intersect_leaf<ANY, COUNT>(s, L, st, rays, c_tris, c_insts);
-            }
-            // ---- pop the next candidate (unless the leaf was an instance, whose root is now `cur`)
-            if (!finished && L.cur == MIRO_GPU_CHILD_EMPTY) {
-                finished = true;
-                while (st.sp > 0) {
-                    const StackEntry e = st.pop();
-                    if (e.ref == STACK_SENTINEL || e.t < L.hit.t) { L.cur = e.ref; finished = false; break; }
-                }
-            }
+            } else finished = intersect_leaf<ANY, COUNT>(s, L, st, rays, c_tris, c_insts);
+            if (!finished && L.cur == MIRO_GPU_CHILD_EMPTY) { pop_next(L, st); finished = L.cur == MIRO_GPU_CHILD_EMPTY; }
         }
         // ---- a finished ray writes its result and frees its slot
         if (finished) {

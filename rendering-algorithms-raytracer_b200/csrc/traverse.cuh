@@ -12,10 +12,11 @@
 //     finished are refilled from a global work counter (claimed in per-warp chunks) as soon as
 //     enough of them are idle, so a warp never runs at the length of its longest ray with the
 //     other lanes empty (v1's one-thread-per-ray kernel executed 2-9 of 32 lanes per instruction);
-//   * the lanes of a warp are kept in the same PHASE: every round is "all lanes descend inner
-//     nodes until each holds a leaf" -> __syncwarp -> "all lanes intersect their leaf" -> pop,
-//     with explicit reconvergence points (independent thread scheduling does not reconverge by
-//     itself);
+//   * MAJORITY-PHASE scheduling: every lane is either at an inner node or at a leaf; each round
+//     the warp votes (__ballot_sync) and executes ONE step of the kind most lanes wait for —
+//     a node step (4 slab tests, sort, push) or a leaf step (<= 4 triangles / instance entry) —
+//     so both code paths run with most lanes active instead of a while-while loop whose inner
+//     loop runs at the length of the slowest lane (measured: 5.5 of 32 lanes in the node test);
 //   * 128-byte BVH4 nodes fetched with seven 16-byte vector loads through the read-only path (the
 //     whole tree lives in the 126 MB L2; hot top levels in L1);
 //   * children are visited nearest-first (4-element sorting network) and the deferred ones go
@@ -47,7 +48,15 @@ constexpr int TRACE_MIN_BLOCKS = 6;     // resident blocks per SM the kernels ar
 #ifndef MIRO_TRACE_REFILL
 #define MIRO_TRACE_REFILL 8
 #endif
-constexpr int TRACE_REFILL = MIRO_TRACE_REFILL;   // idle lanes in a warp that trigger a refill from the work counter
+constexpr int TRACE_REFILL = MIRO_TRACE_REFILL;
+// a node round is run when  n_node * DEN >= n_leaf * NUM  (NUM/DEN < 1 favours node rounds: leaf rounds cost more and fill up while waiting)
+#ifndef MIRO_NODE_BIAS_NUM
+#define MIRO_NODE_BIAS_NUM 1
+#endif
+#ifndef MIRO_NODE_BIAS_DEN
+#define MIRO_NODE_BIAS_DEN 1
+#endif
+constexpr int TRACE_NODE_BIAS_NUM = MIRO_NODE_BIAS_NUM, TRACE_NODE_BIAS_DEN = MIRO_NODE_BIAS_DEN;   // idle lanes in a warp that trigger a refill from the work counter
 constexpr int SMEM_STACK = 24;          // per-thread stack entries kept in shared memory
 constexpr int LMEM_STACK = 72;          // overflow entries (local memory, touched only by very deep trees)
 constexpr int32_t STACK_SENTINEL = 0x7ffffffe;   // "leave instance" marker
@@ -193,46 +202,46 @@ struct Lane {
     bool done;           // slot is empty
 };
 
-// Inner-node phase: descend nearest-first until `cur` is a leaf reference or nothing is left.
-template <bool COUNT>
-__device__ __forceinline__ void descend(const DeviceScene& s, Lane& L, TraversalStack& st, uint32_t& n_nodes) {
-    const float inf = __int_as_float(0x7f800000);
-    while (ref_is_inner(L.cur)) {
-        const float4* n = s.nodes + (size_t)L.cur * 8;
-        const float4 lox = __ldg(n + 0), loy = __ldg(n + 1), loz = __ldg(n + 2);
-        const float4 hix = __ldg(n + 3), hiy = __ldg(n + 4), hiz = __ldg(n + 5);
-        const int4 ch = __ldg(reinterpret_cast<const int4*>(n + 6));
-        if (COUNT) ++n_nodes;
-        float tn0, tn1, tn2, tn3;
-#define MIRO_SLAB(LX, LY, LZ, HX, HY, HZ, CH, TN) { \
-        float ax = (LX - L.r.ox) * L.r.ix, bx = (HX - L.r.ox) * L.r.ix; \
-        float ay = (LY - L.r.oy) * L.r.iy, by = (HY - L.r.oy) * L.r.iy; \
-        float az = (LZ - L.r.oz) * L.r.iz, bz = (HZ - L.r.oz) * L.r.iz; \
-        float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), L.tmin)); \
-        float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), L.hit.t)); \
-        TN = (tn <= tf && CH != MIRO_GPU_CHILD_EMPTY) ? tn : inf; }
-        int32_t c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
-        MIRO_SLAB(lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, c0, tn0)
-        MIRO_SLAB(lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, c1, tn1)
-        MIRO_SLAB(lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, c2, tn2)
-        MIRO_SLAB(lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, c3, tn3)
-#undef MIRO_SLAB
-        MIRO_CSWAP(tn0, c0, tn1, c1) MIRO_CSWAP(tn2, c2, tn3, c3)
-        MIRO_CSWAP(tn0, c0, tn2, c2) MIRO_CSWAP(tn1, c1, tn3, c3)
-        MIRO_CSWAP(tn1, c1, tn2, c2)
-        if (tn3 < inf) st.push(c3, tn3);
-        if (tn2 < inf) st.push(c2, tn2);
-        if (tn1 < inf) st.push(c1, tn1);
-        if (tn0 < inf) L.cur = c0;
-        else {
-            // nothing hit below this node: pop the next candidate that can still beat the current hit
-            L.cur = MIRO_GPU_CHILD_EMPTY;
-            while (st.sp > 0) {
-                const StackEntry e = st.pop();
-                if (e.ref == STACK_SENTINEL || e.t < L.hit.t) { L.cur = e.ref; break; }
-            }
-        }
+// Pops the next candidate that can still beat the current hit; `cur` = MIRO_GPU_CHILD_EMPTY when the stack runs dry.
+__device__ __forceinline__ void pop_next(Lane& L, TraversalStack& st) {
+    L.cur = MIRO_GPU_CHILD_EMPTY;
+    while (st.sp > 0) {
+        const StackEntry e = st.pop();
+        if (e.ref == STACK_SENTINEL || e.t < L.hit.t) { L.cur = e.ref; break; }
     }
+}
+
+// Node step: test the four children of inner node `cur`, continue with the nearest, defer the others (far to near).
+template <bool COUNT>
+__device__ __forceinline__ void node_step(const DeviceScene& s, Lane& L, TraversalStack& st, uint32_t& n_nodes) {
+    const float inf = __int_as_float(0x7f800000);
+    const float4* n = s.nodes + (size_t)L.cur * 8;
+    const float4 lox = __ldg(n + 0), loy = __ldg(n + 1), loz = __ldg(n + 2);
+    const float4 hix = __ldg(n + 3), hiy = __ldg(n + 4), hiz = __ldg(n + 5);
+    const int4 ch = __ldg(reinterpret_cast<const int4*>(n + 6));
+    if (COUNT) ++n_nodes;
+    float tn0, tn1, tn2, tn3;
+#define MIRO_SLAB(LX, LY, LZ, HX, HY, HZ, CH, TN) { \
+    float ax = (LX - L.r.ox) * L.r.ix, bx = (HX - L.r.ox) * L.r.ix; \
+    float ay = (LY - L.r.oy) * L.r.iy, by = (HY - L.r.oy) * L.r.iy; \
+    float az = (LZ - L.r.oz) * L.r.iz, bz = (HZ - L.r.oz) * L.r.iz; \
+    float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), L.tmin)); \
+    float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), L.hit.t)); \
+    TN = (tn <= tf && CH != MIRO_GPU_CHILD_EMPTY) ? tn : inf; }
+    int32_t c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
+    MIRO_SLAB(lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, c0, tn0)
+    MIRO_SLAB(lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, c1, tn1)
+    MIRO_SLAB(lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, c2, tn2)
+    MIRO_SLAB(lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, c3, tn3)
+#undef MIRO_SLAB
+    MIRO_CSWAP(tn0, c0, tn1, c1) MIRO_CSWAP(tn2, c2, tn3, c3)
+    MIRO_CSWAP(tn0, c0, tn2, c2) MIRO_CSWAP(tn1, c1, tn3, c3)
+    MIRO_CSWAP(tn1, c1, tn2, c2)
+    if (tn3 < inf) st.push(c3, tn3);
+    if (tn2 < inf) st.push(c2, tn2);
+    if (tn1 < inf) st.push(c1, tn1);
+    if (tn0 < inf) L.cur = c0;
+    else pop_next(L, st);
 }
 
 // Leaf phase.  Returns true when an ANY query has found its occluder.
