@@ -73,36 +73,53 @@ k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const
     bool exhausted = false;                      // warp-uniform: the global counter has run past n
     Lane L; L.done = true; L.cur = MIRO_GPU_CHILD_EMPTY; L.ray_idx = 0; L.cur_inst = -1; L.tmin = 0.f; L.time = 0.f;
     L.hit.t = 0.f; L.hit.a = L.hit.b = 0.f; L.hit.prim = -1; L.hit.inst = -1;
-    L.r.set(0.f, 0.f, 0.f, 0.f, 0.f, 1.f);
-    TraversalStack st; st.smem = stack + threadIdx.x; st.sp = 0;
+    L.set_ray(0.f, 0.f, 0.f, 0.f, 0.f, 1.f);
+    unsigned long long overflow[LMEM_STACK];
+    TraversalStack st; st.init(stack + threadIdx.x, overflow);
+
+    auto write_result = [&]() {
+        const uint32_t i = L.ray_idx;
+        const bool hit = L.hit.prim >= 0;
+        if (MODE == TRACE_ANY_BITS) { if (hit) atomicOr(bits + (i >> 5), 1u << (i & 31u)); }
+        else if (MODE == TRACE_ANY_ACCUM) {
+            if (!hit) { const float4 r2 = __ldcs(rays + (size_t)i * 3 + 2); atomicAdd(slots + (size_t)__float_as_uint(r2.z) * 4, __ldcs(sample_E + i)); }
+        } else {
+            float* o = reinterpret_cast<float*>(hits + i);
+            __stcs(o + 0, hit ? L.hit.t : -1.0f); __stcs(o + 1, hit ? L.hit.a : 0.f); __stcs(o + 2, hit ? L.hit.b : 0.f);
+            __stcs(reinterpret_cast<int*>(o) + 3, L.hit.prim); __stcs(reinterpret_cast<int*>(o) + 4, hit ? L.hit.inst : -1);
+        }
+    };
+    bool pending = false;      // the slot's ray has finished; its result is written (with the other idle lanes) at the next refill
 
     while (true) {
-        // ---- refill: idle slots take the next rays of the warp's chunk (a new chunk is claimed when it runs dry)
-        __syncwarp();
+        // ---- refill: idle slots write their results, then take the next rays of the warp's chunk
         const uint32_t idle = __ballot_sync(0xffffffffu, L.done);
-        if (idle == 0xffffffffu && exhausted) break;
-        if (!exhausted && __popc(idle) >= TRACE_REFILL) {
-            if (chunk_next == chunk_end) {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(work, chunk);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                chunk_next = min(base, n); chunk_end = min(base + chunk, n);
-                if (chunk_next == chunk_end) exhausted = true;
+        if (__popc(idle) >= TRACE_REFILL || (exhausted && idle == 0xffffffffu)) {
+            if (pending) { write_result(); pending = false; }
+            if (exhausted) { if (idle == 0xffffffffu) break; }
+            else {
+                if (chunk_next == chunk_end) {
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(work, chunk);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    chunk_next = min(base, n); chunk_end = min(base + chunk, n);
+                    if (chunk_next == chunk_end) exhausted = true;
+                }
+                const uint32_t take = min((uint32_t)__popc(idle), chunk_end - chunk_next);
+                const uint32_t rank = __popc(idle & lt_mask);
+                if (L.done && rank < take) {
+                    L.ray_idx = chunk_next + rank;
+                    const float4* rp = rays + (size_t)L.ray_idx * 3;
+                    const float4 r0 = __ldcs(rp), r1 = __ldcs(rp + 1), r2 = __ldcs(rp + 2);
+                    L.set_ray(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
+                    L.tmin = r0.w; L.time = r2.x;
+                    L.hit.t = r1.w; L.hit.a = 0.f; L.hit.b = 0.f; L.hit.prim = -1; L.hit.inst = -1;
+                    L.cur = s.root; L.cur_inst = -1; st.sp = 0; L.done = false;
+                    ++c_rays;
+                }
+                chunk_next += take;
+                if (idle == 0xffffffffu && take == 0) continue;      // nothing claimed this round: try the next chunk (or leave)
             }
-            const uint32_t take = min((uint32_t)__popc(idle), chunk_end - chunk_next);
-            const uint32_t rank = __popc(idle & lt_mask);
-            if (L.done && rank < take) {
-                L.ray_idx = chunk_next + rank;
-                const float4* rp = rays + (size_t)L.ray_idx * 3;
-                const float4 r0 = __ldcs(rp), r1 = __ldcs(rp + 1), r2 = __ldcs(rp + 2);
-                L.r.set(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
-                L.tmin = r0.w; L.time = r2.x;
-                L.hit.t = r1.w; L.hit.a = 0.f; L.hit.b = 0.f; L.hit.prim = -1; L.hit.inst = -1;
-                L.cur = s.root; L.cur_inst = -1; st.sp = 0; L.done = false;
-                ++c_rays;
-            }
-            chunk_next += take;
-            if (idle == 0xffffffffu && take == 0) continue;      // nothing claimed this round: try the next chunk (or leave)
         }
         // ---- vote: a live lane waits either at an inner node or at a leaf (leaf reference / instance-exit marker)
         const bool at_node = !L.done && ref_is_inner(L.cur);
@@ -116,25 +133,12 @@ k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const
             // ---- leaf round
             if (L.cur == STACK_SENTINEL) {            // leaving an instance: back to the world-space ray
                 const float4 w0 = __ldg(rays + (size_t)L.ray_idx * 3), w1 = __ldg(rays + (size_t)L.ray_idx * 3 + 1);
-                L.r.set(w0.x, w0.y, w0.z, w1.x, w1.y, w1.z);
+                L.set_ray(w0.x, w0.y, w0.z, w1.x, w1.y, w1.z);
                 L.cur_inst = -1; L.cur = MIRO_GPU_CHILD_EMPTY;
-            } else finished = intersect_leaf<ANY, COUNT>(s, L, st, rays, c_tris, c_insts);
+            } else finished = intersect_leaf<ANY, COUNT>(s, L, st, rays, c_tris, c_insts);     // true: any-hit found its occluder
             if (!finished && L.cur == MIRO_GPU_CHILD_EMPTY) { pop_next(L, st); finished = L.cur == MIRO_GPU_CHILD_EMPTY; }
         }
-        // ---- a finished ray writes its result and frees its slot
-        if (finished) {
-            const uint32_t i = L.ray_idx;
-            const bool hit = L.hit.prim >= 0;
-            if (MODE == TRACE_ANY_BITS) { if (hit) atomicOr(bits + (i >> 5), 1u << (i & 31u)); }
-            else if (MODE == TRACE_ANY_ACCUM) {
-                if (!hit) { const float4 r2 = __ldcs(rays + (size_t)i * 3 + 2); atomicAdd(slots + (size_t)__float_as_uint(r2.z) * 4, __ldcs(sample_E + i)); }
-            } else {
-                float* o = reinterpret_cast<float*>(hits + i);
-                __stcs(o + 0, hit ? L.hit.t : -1.0f); __stcs(o + 1, hit ? L.hit.a : 0.f); __stcs(o + 2, hit ? L.hit.b : 0.f);
-                __stcs(reinterpret_cast<int*>(o) + 3, L.hit.prim); __stcs(reinterpret_cast<int*>(o) + 4, hit ? L.hit.inst : -1);
-            }
-            L.done = true;
-        }
+        if (finished) { L.done = true; pending = true; }
     }
     // counters: warp-reduce then one atomic per warp
     unsigned long long v_rays = c_rays, v_nodes = c_nodes, v_tris = c_tris, v_insts = c_insts;

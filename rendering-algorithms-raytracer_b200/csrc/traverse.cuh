@@ -43,8 +43,17 @@
 
 namespace miro {
 
-constexpr int TRACE_BLOCK = 128;        // threads per block of the traversal kernels
-constexpr int TRACE_MIN_BLOCKS = 6;     // resident blocks per SM the kernels are compiled for (register budget)
+#ifndef MIRO_TRACE_BLOCK
+#define MIRO_TRACE_BLOCK 128
+#endif
+#ifndef MIRO_TRACE_MIN_BLOCKS
+#define MIRO_TRACE_MIN_BLOCKS 8
+#endif
+#ifndef MIRO_SMEM_STACK
+#define MIRO_SMEM_STACK 16
+#endif
+constexpr int TRACE_BLOCK = MIRO_TRACE_BLOCK;            // threads per block of the traversal kernels
+constexpr int TRACE_MIN_BLOCKS = MIRO_TRACE_MIN_BLOCKS;  // resident blocks per SM the kernels are compiled for (register budget)
 #ifndef MIRO_TRACE_REFILL
 #define MIRO_TRACE_REFILL 8
 #endif
@@ -57,8 +66,8 @@ constexpr int TRACE_REFILL = MIRO_TRACE_REFILL;
 #define MIRO_NODE_BIAS_DEN 1
 #endif
 constexpr int TRACE_NODE_BIAS_NUM = MIRO_NODE_BIAS_NUM, TRACE_NODE_BIAS_DEN = MIRO_NODE_BIAS_DEN;   // idle lanes in a warp that trigger a refill from the work counter
-constexpr int SMEM_STACK = 24;          // per-thread stack entries kept in shared memory
-constexpr int LMEM_STACK = 72;          // overflow entries (local memory, touched only by very deep trees)
+constexpr int SMEM_STACK = MIRO_SMEM_STACK;   // per-thread stack entries kept in shared memory
+constexpr int LMEM_STACK = 96 - MIRO_SMEM_STACK;          // overflow entries (local memory, touched only by very deep trees)
 constexpr int32_t STACK_SENTINEL = 0x7ffffffe;   // "leave instance" marker
 
 struct DeviceScene {
@@ -69,6 +78,13 @@ struct DeviceScene {
     int32_t root;
     uint32_t n_tris;
 };
+
+// 32-byte read-only global load (sm_100: LDG.E.256): one L1 wavefront where two 16-byte loads take two.  The traversal
+// kernels are bound by L1 wavefronts (every lane reads its own node), so a 128-byte node is fetched as 4 x 32 bytes.
+__device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
 
 struct TraceCounters {
     unsigned long long rays_closest, rays_any, nodes, tris, insts;
@@ -163,84 +179,128 @@ __device__ __forceinline__ bool intersect_tri(const RaySpace& r, float tmin, flo
     return true;
 }
 
-struct StackEntry { int32_t ref; float t; };
+// order-preserving map float -> int (signed integer compare == float compare, any sign)
+__device__ __forceinline__ int float_key(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
 
-// Per-lane traversal stack: first SMEM_STACK entries in shared memory ([entry][lane] layout, conflict
-// free), the rest in local memory (touched only by very deep trees; depth is validated at upload).
+struct StackEntry { int32_t ref; int key; };     // key: float_key(entry distance), low bits cleared (never later than the truth)
+
+// Per-lane traversal stack.  Entries are {reference, entry distance}; the first SMEM_STACK of them live in SHARED
+// memory laid out [entry][lane] (conflict free), addressed with explicit 32-bit shared addresses (ld/st.shared — a
+// generic pointer here made the compiler emit generic LD/ST plus a stack pointer in local memory).  Deeper entries
+// (very deep trees only; depth is validated at upload) overflow into a local-memory array behind one rarely taken branch.
 struct TraversalStack {
-    unsigned long long* smem;   // base + threadIdx.x, stride = TRACE_BLOCK
-    unsigned long long lmem[LMEM_STACK];
+    uint32_t base;                       // shared address of entry 0 of this lane
+    unsigned long long* overflow;        // LMEM_STACK entries of local memory
     int sp;
-    __device__ __forceinline__ void push(int32_t ref, float t) {
-        unsigned long long v = ((unsigned long long)__float_as_uint(t) << 32) | (uint32_t)ref;
-        if (sp < SMEM_STACK) smem[sp * TRACE_BLOCK] = v;
-        else if (sp - SMEM_STACK < LMEM_STACK) lmem[sp - SMEM_STACK] = v;
-        ++sp;
+    __device__ __forceinline__ void init(unsigned long long* smem_lane, unsigned long long* lmem) {
+        base = (uint32_t)__cvta_generic_to_shared(smem_lane); overflow = lmem; sp = 0;
     }
+    __device__ __forceinline__ void store(int slot, int32_t ref, int key) {
+        if (slot < SMEM_STACK)
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" :: "r"(base + (uint32_t)slot * (TRACE_BLOCK * 8u)), "r"(ref), "r"(key) : "memory");
+        else if (slot - SMEM_STACK < LMEM_STACK)
+            overflow[slot - SMEM_STACK] = ((unsigned long long)(uint32_t)key << 32) | (uint32_t)ref;
+    }
+    __device__ __forceinline__ void push(int32_t ref, int key) { store(sp, ref, key); ++sp; }
     __device__ __forceinline__ StackEntry pop() {
         --sp;
         StackEntry e;
-        if (sp >= SMEM_STACK + LMEM_STACK) { e.ref = MIRO_GPU_CHILD_EMPTY; e.t = 0.f; return e; }
-        unsigned long long v = (sp < SMEM_STACK) ? smem[sp * TRACE_BLOCK] : lmem[sp - SMEM_STACK];
-        e.ref = (int32_t)(uint32_t)v; e.t = __uint_as_float((uint32_t)(v >> 32));
+        if (sp < SMEM_STACK)
+            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(e.ref), "=r"(e.key) : "r"(base + (uint32_t)sp * (TRACE_BLOCK * 8u)) : "memory");
+        else if (sp - SMEM_STACK < LMEM_STACK) { const unsigned long long v = overflow[sp - SMEM_STACK]; e.ref = (int32_t)(uint32_t)v; e.key = (int)(uint32_t)(v >> 32); }
+        else { e.ref = MIRO_GPU_CHILD_EMPTY; e.key = 0x7fffffff; }
         return e;
     }
 };
 
-#define MIRO_CSWAP(ta, ca, tb, cb) { if (tb < ta) { float tt = ta; ta = tb; tb = tt; int32_t cc = ca; ca = cb; cb = cc; } }
+// four-way select by a 2-bit slot index, forced to predicated selects (the compiler turns the ternary chain into branches)
+__device__ __forceinline__ int sel4(int sl, int a, int b, int c, int d) {
+    int r;
+    asm("{ .reg .pred p0, p1; .reg .b32 lo, hi;\n\t"
+        "and.b32 lo, %1, 1; setp.ne.b32 p0, lo, 0; and.b32 hi, %1, 2; setp.ne.b32 p1, hi, 0;\n\t"
+        "selp.b32 lo, %3, %2, p0; selp.b32 hi, %5, %4, p0; selp.b32 %0, hi, lo, p1; }"
+        : "=r"(r) : "r"(sl), "r"(a), "r"(b), "r"(c), "r"(d));
+    return r;
+}
+// predicated 8-byte shared store
+__device__ __forceinline__ void sts_if(int cond, uint32_t addr, int ref, int key) {
+    asm volatile("{ .reg .pred q; setp.ne.b32 q, %3, 0; @q st.shared.v2.b32 [%0], {%1, %2}; }" :: "r"(addr), "r"(ref), "r"(key), "r"(cond) : "memory");
+}
 
 __device__ __forceinline__ bool ref_is_inner(int32_t ref) { return ref >= 0 && ref != MIRO_GPU_CHILD_EMPTY && ref != STACK_SENTINEL; }
 
 // One ray slot of a persistent warp.
 struct Lane {
     RaySpace r;          // current-space ray (world, or object space inside an instance)
+    float oix, oiy, oiz; // origin * reciprocal direction (slab test in FMA form)
     float tmin, time;
     HitRec hit;          // hit.t = current tmax
     int32_t cur;         // node / leaf reference being processed, or MIRO_GPU_CHILD_EMPTY
     int32_t cur_inst;
     uint32_t ray_idx;
     bool done;           // slot is empty
+    __device__ __forceinline__ void set_ray(float ox, float oy, float oz, float dx, float dy, float dz) {
+        r.set(ox, oy, oz, dx, dy, dz);
+        oix = ox * r.ix; oiy = oy * r.iy; oiz = oz * r.iz;
+    }
 };
 
 // Pops the next candidate that can still beat the current hit; `cur` = MIRO_GPU_CHILD_EMPTY when the stack runs dry.
 __device__ __forceinline__ void pop_next(Lane& L, TraversalStack& st) {
     L.cur = MIRO_GPU_CHILD_EMPTY;
+    const int limit = float_key(L.hit.t);
     while (st.sp > 0) {
         const StackEntry e = st.pop();
-        if (e.ref == STACK_SENTINEL || e.t < L.hit.t) { L.cur = e.ref; break; }
+        if (e.key < limit) { L.cur = e.ref; break; }       // instance markers carry the smallest key
     }
 }
 
 // Node step: test the four children of inner node `cur`, continue with the nearest, defer the others (far to near).
+// Straight-line code: slab tests in FMA form (plane * 1/d - o/d), a 5-comparator sorting network on integer keys
+// (entry distance with the child slot in its two low mantissa bits — truncation only makes an entry look nearer, which
+// is conservative for culling), predicated pushes.
 template <bool COUNT>
 __device__ __forceinline__ void node_step(const DeviceScene& s, Lane& L, TraversalStack& st, uint32_t& n_nodes) {
-    const float inf = __int_as_float(0x7f800000);
     const float4* n = s.nodes + (size_t)L.cur * 8;
-    const float4 lox = __ldg(n + 0), loy = __ldg(n + 1), loz = __ldg(n + 2);
-    const float4 hix = __ldg(n + 3), hiy = __ldg(n + 4), hiz = __ldg(n + 5);
-    const int4 ch = __ldg(reinterpret_cast<const int4*>(n + 6));
+    float4 lox, loy, loz, hix, hiy, hiz, chf, unused;
+    ldg256(n + 0, lox, loy); ldg256(n + 2, loz, hix); ldg256(n + 4, hiy, hiz); ldg256(n + 6, chf, unused);
     if (COUNT) ++n_nodes;
-    float tn0, tn1, tn2, tn3;
-#define MIRO_SLAB(LX, LY, LZ, HX, HY, HZ, CH, TN) { \
-    float ax = (LX - L.r.ox) * L.r.ix, bx = (HX - L.r.ox) * L.r.ix; \
-    float ay = (LY - L.r.oy) * L.r.iy, by = (HY - L.r.oy) * L.r.iy; \
-    float az = (LZ - L.r.oz) * L.r.iz, bz = (HZ - L.r.oz) * L.r.iz; \
-    float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), L.tmin)); \
-    float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), L.hit.t)); \
-    TN = (tn <= tf && CH != MIRO_GPU_CHILD_EMPTY) ? tn : inf; }
-    int32_t c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
-    MIRO_SLAB(lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, c0, tn0)
-    MIRO_SLAB(lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, c1, tn1)
-    MIRO_SLAB(lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, c2, tn2)
-    MIRO_SLAB(lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, c3, tn3)
+    const int INF_KEY = 0x7fffffff;
+    // the far bound is widened by 2 ulp so that the FMA-form slab test never rejects a box the ray touches
+    const float tmax = L.hit.t;
+    int k0, k1, k2, k3;
+#define MIRO_SLAB(LX, LY, LZ, HX, HY, HZ, CH, SLOT, KEY) { \
+    const float ax = __fmaf_rn(LX, L.r.ix, -L.oix), bx = __fmaf_rn(HX, L.r.ix, -L.oix); \
+    const float ay = __fmaf_rn(LY, L.r.iy, -L.oiy), by = __fmaf_rn(HY, L.r.iy, -L.oiy); \
+    const float az = __fmaf_rn(LZ, L.r.iz, -L.oiz), bz = __fmaf_rn(HZ, L.r.iz, -L.oiz); \
+    const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), L.tmin)); \
+    const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax)) * 1.0000003f; \
+    KEY = (tn <= tf && __float_as_int(CH) != MIRO_GPU_CHILD_EMPTY) ? ((float_key(tn) & ~3) | SLOT) : INF_KEY; }
+    MIRO_SLAB(lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, chf.x, 0, k0)
+    MIRO_SLAB(lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, chf.y, 1, k1)
+    MIRO_SLAB(lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, chf.z, 2, k2)
+    MIRO_SLAB(lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, chf.w, 3, k3)
 #undef MIRO_SLAB
-    MIRO_CSWAP(tn0, c0, tn1, c1) MIRO_CSWAP(tn2, c2, tn3, c3)
-    MIRO_CSWAP(tn0, c0, tn2, c2) MIRO_CSWAP(tn1, c1, tn3, c3)
-    MIRO_CSWAP(tn1, c1, tn2, c2)
-    if (tn3 < inf) st.push(c3, tn3);
-    if (tn2 < inf) st.push(c2, tn2);
-    if (tn1 < inf) st.push(c1, tn1);
-    if (tn0 < inf) L.cur = c0;
+#define MIRO_KSWAP(a, b) { const int lo_ = min(a, b), hi_ = max(a, b); a = lo_; b = hi_; }
+    MIRO_KSWAP(k0, k1) MIRO_KSWAP(k2, k3) MIRO_KSWAP(k0, k2) MIRO_KSWAP(k1, k3) MIRO_KSWAP(k1, k2)
+#undef MIRO_KSWAP
+    const int ch0 = __float_as_int(chf.x), ch1 = __float_as_int(chf.y), ch2 = __float_as_int(chf.z), ch3 = __float_as_int(chf.w);
+    auto child_of = [&](int key) { return sel4(key, ch0, ch1, ch2, ch3); };
+    const int hits = (k0 != INF_KEY) + (k1 != INF_KEY) + (k2 != INF_KEY) + (k3 != INF_KEY);
+    // deferred children go on the stack far to near: k3 (if hit) lowest, k1 on top
+    const int sp = st.sp;
+    if (sp + 3 <= SMEM_STACK) {          // the usual case: three predicated shared stores, no branches
+        const uint32_t a0 = st.base + (uint32_t)sp * (TRACE_BLOCK * 8u);
+        sts_if(hits > 3, a0, child_of(k3), k3 & ~3);
+        sts_if(hits > 2, a0 + (uint32_t)(hits - 3) * (TRACE_BLOCK * 8u), child_of(k2), k2 & ~3);
+        sts_if(hits > 1, a0 + (uint32_t)(hits - 2) * (TRACE_BLOCK * 8u), child_of(k1), k1 & ~3);
+    } else {
+        if (hits > 3) st.store(sp, child_of(k3), k3 & ~3);
+        if (hits > 2) st.store(sp + hits - 3, child_of(k2), k2 & ~3);
+        if (hits > 1) st.store(sp + hits - 2, child_of(k1), k1 & ~3);
+    }
+    st.sp = sp + max(hits - 1, 0);
+    if (hits > 0) L.cur = child_of(k0);
     else pop_next(L, st);
 }
 
@@ -279,7 +339,7 @@ __device__ __forceinline__ bool intersect_leaf(const DeviceScene& s, Lane& L, Tr
             }
         }
     } else {   // MIRO_GPU_KIND_INST: enter the first instance, defer the others
-        const float ninf = -__int_as_float(0x7f800000);
+        const int ninf = (int)0x80000000;
         if (count > 1u) st.push(MIRO_GPU_LEAF(MIRO_GPU_KIND_INST, first + 1u, count - 1u), ninf);
         st.push(STACK_SENTINEL, ninf);
         const float4* m = s.insts + (size_t)first * 4;
@@ -290,7 +350,7 @@ __device__ __forceinline__ bool intersect_leaf(const DeviceScene& s, Lane& L, Tr
         const float4 w0 = __ldg(rays + (size_t)L.ray_idx * 3), w1 = __ldg(rays + (size_t)L.ray_idx * 3 + 1);
         const float wox = w0.x, woy = w0.y, woz = w0.z, wdx = w1.x, wdy = w1.y, wdz = w1.z;
         // o' = M^-1 [o 1], d' = M^-1 [d 0]  (src/ProxyObject.cpp:78-79; affine, so w = 1)
-        L.r.set(r0.x * wox + r0.y * woy + r0.z * woz + r0.w, r1.x * wox + r1.y * woy + r1.z * woz + r1.w, r2.x * wox + r2.y * woy + r2.z * woz + r2.w,
+        L.set_ray(r0.x * wox + r0.y * woy + r0.z * woz + r0.w, r1.x * wox + r1.y * woy + r1.z * woz + r1.w, r2.x * wox + r2.y * woy + r2.z * woz + r2.w,
                 r0.x * wdx + r0.y * wdy + r0.z * wdz, r1.x * wdx + r1.y * wdy + r1.z * wdz, r2.x * wdx + r2.y * wdy + r2.z * wdz);
         L.cur_inst = (int32_t)first;
         L.cur = meta.x;

@@ -1,5 +1,6 @@
 #!/usr/bin/env bash
 # run on the GPU box: bench every build/variants/*.so (and the default lib) and print the three launch times
+shopt -s nullglob
 for lib in default build/variants/*.so; do
   if [ "$lib" = default ]; then unset MIRO_GPU_LIB; else export MIRO_GPU_LIB=$PWD/$lib; fi
   python bench.py --steps 10 --warmup 3 --no-cpu 2>/dev/null | python -c "
