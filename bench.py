@@ -328,8 +328,10 @@ def main():
                              "traffic": traffic, "algorithmic_bytes_per_launch": per_launch[dom]["bytes"],
                              "nodes_per_ray": per_launch[dom]["nodes"] / N_BATCH, "tris_per_ray": per_launch[dom]["tris"] / N_BATCH,
                              "launch_ms": launch_ms[dom], "share_of_step": launch_ms[dom] / sum(launch_ms),
-                             "all_launches": [{"ms": launch_ms[i], "Mrays_per_s": N_BATCH / launch_ms[i] * 1e-3,
-                                               "GBps": per_launch[i]["bytes"] / launch_ms[i] * 1e-6} for i in range(3)]}}
+                             "all_launches": [{"kernel": kernel_names[i], "ms": launch_ms[i], "Mrays_per_s": N_BATCH / launch_ms[i] * 1e-3,
+                                               "GBps": per_launch[i]["bytes"] / launch_ms[i] * 1e-6, "bytes_per_ray": per_launch[i]["bytes"] / N_BATCH,
+                                               "nodes_per_ray": per_launch[i]["nodes"] / N_BATCH, "tris_per_ray": per_launch[i]["tris"] / N_BATCH}
+                                              for i in range(3)]}}
         if world == 1 and not args.no_cpu:
             threads = min(os.cpu_count() or 1, 16)
             sample = [prim.reshape(HEIGHT, WIDTH)[::2, ::4].reshape(-1).copy(), inco[::8].copy(), shad[::8].copy()]

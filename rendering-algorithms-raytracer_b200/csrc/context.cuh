@@ -87,6 +87,8 @@ struct miro_gpu_ctx {
     miro::DeviceBuffer<miro_gpu_ray> d_rays;
     miro::DeviceBuffer<miro_gpu_hit> d_hits;
     miro::DeviceBuffer<uint32_t> d_bits;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;      // H2D / D2H streams of the pipelined host-pointer calls
+    std::vector<cudaEvent_t> pipe_events;
 
     // renderer state (render.cu)
     void* render_state = nullptr;

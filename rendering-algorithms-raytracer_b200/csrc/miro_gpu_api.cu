@@ -266,6 +266,9 @@ void miro_gpu_destroy(miro_gpu_ctx* ctx) {
     ctx->d_rays.release(); ctx->d_hits.release(); ctx->d_bits.release();
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_work) cudaFree(ctx->d_work);
+    for (cudaEvent_t e : ctx->pipe_events) cudaEventDestroy(e);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -431,41 +434,59 @@ int miro_gpu_trace_any_device(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, siz
     return MIRO_GPU_OK;
 }
 
-int miro_gpu_trace_closest(miro_gpu_ctx* ctx, const miro_gpu_ray* rays, size_t n, miro_gpu_hit* hits) {
+// Host-pointer entry points: the batch is cut into chunks and pipelined over three streams — chunk k+1 is on its way
+// up (H2D) and chunk k-1 on its way down (D2H) while chunk k is traversed — so the call costs max(copy, compute), not
+// their sum.  PCIe is full duplex, so the two copy directions overlap as well.
+static int trace_host(miro_gpu_ctx* ctx, const miro_gpu_ray* rays, size_t n, miro_gpu_hit* hits, uint32_t* bits) {
     if (!ctx) return MIRO_GPU_EINVAL;
     if (!ctx->has_scene) return set_error(ctx, MIRO_GPU_ENOSCENE, "trace before upload_scene");
+    if (n > 0xffffffffull) return set_error(ctx, MIRO_GPU_EINVAL, "more than 2^32-1 rays in one call");
     if (n == 0) return MIRO_GPU_OK;
-    if (!rays || !hits) return set_error(ctx, MIRO_GPU_EINVAL, "NULL ray/hit buffer");
+    if (!rays || (!hits && !bits)) return set_error(ctx, MIRO_GPU_EINVAL, "NULL ray/result buffer");
     MIRO_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t chunk = (size_t)1 << 18;                      // rays per chunk (a multiple of 32: whole result words)
+    const size_t n_chunks = (n + chunk - 1) / chunk;
     MIRO_CUDA(ctx, ctx->d_rays.reserve(n));
-    MIRO_CUDA(ctx, ctx->d_hits.reserve(n));
+    if (hits) MIRO_CUDA(ctx, ctx->d_hits.reserve(n)); else MIRO_CUDA(ctx, ctx->d_bits.reserve((n + 31) / 32));
+    if (!ctx->copy_in) {
+        MIRO_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+        MIRO_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    }
+    while (ctx->pipe_events.size() < 2 * n_chunks) {
+        cudaEvent_t e; MIRO_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->pipe_events.push_back(e);
+    }
     EventPair tot = begin_timing(ctx, false);
-    MIRO_CUDA(ctx, cudaMemcpyAsync(ctx->d_rays.ptr, rays, n * sizeof(miro_gpu_ray), cudaMemcpyHostToDevice, ctx->stream));
-    int rc = miro_gpu_trace_closest_device(ctx, ctx->d_rays.ptr, n, ctx->d_hits.ptr);
-    if (rc) return rc;
-    MIRO_CUDA(ctx, cudaMemcpyAsync(hits, ctx->d_hits.ptr, n * sizeof(miro_gpu_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    for (size_t k = 0; k < n_chunks; ++k) {
+        const size_t off = k * chunk, m = std::min(chunk, n - off);
+        cudaEvent_t up = ctx->pipe_events[2 * k], done = ctx->pipe_events[2 * k + 1];
+        MIRO_CUDA(ctx, cudaMemcpyAsync(ctx->d_rays.ptr + off, rays + off, m * sizeof(miro_gpu_ray), cudaMemcpyHostToDevice, ctx->copy_in));
+        MIRO_CUDA(ctx, cudaEventRecord(up, ctx->copy_in));
+        MIRO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, up, 0));
+        EventPair p = begin_timing(ctx, true);
+        if (hits) launch_trace_closest(ctx, ctx->d_rays.ptr + off, m, nullptr, ctx->d_hits.ptr + off);
+        else launch_trace_any(ctx, ctx->d_rays.ptr + off, m, nullptr, ctx->d_bits.ptr + off / 32);
+        end_timing(ctx, p);
+        MIRO_CUDA(ctx, cudaEventRecord(done, ctx->stream));
+        MIRO_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, done, 0));
+        if (hits) MIRO_CUDA(ctx, cudaMemcpyAsync(hits + off, ctx->d_hits.ptr + off, m * sizeof(miro_gpu_hit), cudaMemcpyDeviceToHost, ctx->copy_out));
+        else MIRO_CUDA(ctx, cudaMemcpyAsync(bits + off / 32, ctx->d_bits.ptr + off / 32, ((m + 31) / 32) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_out));
+    }
+    MIRO_CUDA(ctx, cudaGetLastError());
+    MIRO_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
     end_timing(ctx, tot);
     MIRO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MIRO_GPU_OK;
 }
 
+int miro_gpu_trace_closest(miro_gpu_ctx* ctx, const miro_gpu_ray* rays, size_t n, miro_gpu_hit* hits) {
+    if (ctx && n && !hits) return set_error(ctx, MIRO_GPU_EINVAL, "NULL ray/hit buffer");
+    return trace_host(ctx, rays, n, hits, nullptr);
+}
+
 int miro_gpu_trace_any(miro_gpu_ctx* ctx, const miro_gpu_ray* rays, size_t n, uint32_t* occluded_bits) {
-    if (!ctx) return MIRO_GPU_EINVAL;
-    if (!ctx->has_scene) return set_error(ctx, MIRO_GPU_ENOSCENE, "trace before upload_scene");
-    if (n == 0) return MIRO_GPU_OK;
-    if (!rays || !occluded_bits) return set_error(ctx, MIRO_GPU_EINVAL, "NULL ray/bit buffer");
-    MIRO_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t words = (n + 31) / 32;
-    MIRO_CUDA(ctx, ctx->d_rays.reserve(n));
-    MIRO_CUDA(ctx, ctx->d_bits.reserve(words));
-    EventPair tot = begin_timing(ctx, false);
-    MIRO_CUDA(ctx, cudaMemcpyAsync(ctx->d_rays.ptr, rays, n * sizeof(miro_gpu_ray), cudaMemcpyHostToDevice, ctx->stream));
-    int rc = miro_gpu_trace_any_device(ctx, ctx->d_rays.ptr, n, ctx->d_bits.ptr);
-    if (rc) return rc;
-    MIRO_CUDA(ctx, cudaMemcpyAsync(occluded_bits, ctx->d_bits.ptr, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    end_timing(ctx, tot);
-    MIRO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return MIRO_GPU_OK;
+    if (ctx && n && !occluded_bits) return set_error(ctx, MIRO_GPU_EINVAL, "NULL ray/bit buffer");
+    return trace_host(ctx, rays, n, nullptr, occluded_bits);
 }
 
 int miro_gpu_enable_counting(miro_gpu_ctx* ctx, int enable) {

@@ -1,6 +1,7 @@
 // miro_bvh.cpp — binned-SAH binary build + collapse to the 4-wide GPU node layout.  See miro_bvh.h.
 #include "miro_bvh.h"
 #include <math.h>
+#include <stdlib.h>
 #include <float.h>
 #include <algorithm>
 #include <numeric>
@@ -9,7 +10,7 @@ namespace miro {
 namespace {
 
 constexpr int kBins = 16;
-constexpr float kTraversalCost = 1.0f;   // one 4-wide node visit, in units of one triangle test
+static float kTraversalCost = 1.0f;      // one binary split level, in units of one triangle test (tunable: MIRO_BVH_TRAVERSAL_COST)
 constexpr float kPrimCost = 1.0f;
 
 struct Box {
@@ -195,6 +196,7 @@ struct Collapser {
 int32_t build_wide_bvh(const std::vector<BuildPrim>& prims, std::vector<miro_gpu_node>& nodes,
                        std::vector<uint32_t> order[3], BvhStats* stats) {
     if (prims.empty()) return MIRO_GPU_CHILD_EMPTY;
+    if (const char* e = getenv("MIRO_BVH_TRAVERSAL_COST")) { const float v = (float)atof(e); if (v > 0.f) kTraversalCost = v; }
     Builder b(prims);
     const int32_t root = b.build(0, (uint32_t)prims.size(), 0);
     Collapser c{b, nodes, order, BvhStats()};

@@ -131,3 +131,33 @@ def test_render_errors():
     with pytest.raises(mb.MiroError):
         sc.render_device(out.data_ptr(), params=p)
     sc.close()
+
+
+def test_two_gpu_render_nccl(tmp_path):
+    """Two ranks, one GPU each: bucket-sharded miro_gpu_render + one NCCL all_reduce == the single-GPU frame."""
+    import os, subprocess, sys, torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    worker = r'''
+import os, sys
+sys.path.insert(0, os.environ["MIRO_ROOT"]); sys.path.insert(0, os.path.join(os.environ["MIRO_ROOT"], "tests"))
+import numpy as np, torch, torch.distributed as dist
+import helpers
+from miro_b200 import distributed as md
+rank = int(os.environ["RANK"]); torch.cuda.set_device(rank)
+dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%s" % os.environ["MIRO_PORT"], rank=rank, world_size=2, device_id=torch.device("cuda", rank))
+fx = helpers.Fixture(helpers.fixture_path("c4_cornell_pt")); sc = fx.scene().attach(rank)
+full = md.render_scene_distributed(sc, rank, 2)
+if rank == 0:
+    np.save(os.environ["MIRO_OUT"], full.cpu().numpy())
+dist.destroy_process_group(); sc.close()
+'''
+    out = tmp_path / "full.npy"
+    env = dict(os.environ, MIRO_ROOT=helpers.ROOT, MIRO_PORT=str(29600 + os.getpid() % 2000), MIRO_OUT=str(out))
+    procs = [subprocess.Popen([sys.executable, "-c", worker], env=dict(env, RANK=str(r))) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    fx, sc = load("c4_cornell_pt")
+    whole = sc.render()
+    assert np.allclose(np.load(out), whole, rtol=1e-4, atol=1e-5)
+    sc.close()
