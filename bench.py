@@ -32,6 +32,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 WIDTH, HEIGHT = 1920, 1080
 N_BATCH = WIDTH * HEIGHT
+NODE_BYTES = 64      # device node (csrc/traverse.cuh DeviceNode)
 LIGHT_POS = np.array([-2.0, 4.0, 3.0], np.float32)
 SCENE = "c2_explosion"
 WORKLOAD = ("C2 stand-in: explosion01.obj 86914 tris, 1920x1080: 2073600 primary + 2073600 incoherent closest-hit "
@@ -248,7 +249,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # algorithmic bytes: device counters of the shipped layout (128 B nodes, 48 B triangles, 48 B ray in, 20 B hit / 1 bit out)
+    # algorithmic bytes: device counters of the SHIPPED layout (64 B quantized device nodes — the 128 B ABI node is
+    # re-encoded at upload —, 48 B triangles, 64 B instances, 48 B ray in, 20 B hit / 1 bit out)
     sc.enable_counting(True)
     per_launch = []
     for i, f in enumerate((sc.trace_closest_device, sc.trace_closest_device, sc.trace_any_device)):
@@ -257,7 +259,7 @@ def main():
         c = sc.counters()
         out_bytes = 20 * N_BATCH if i < 2 else 4 * ((N_BATCH + 31) // 32)
         per_launch.append({"nodes": c["nodes_fetched"], "tris": c["tris_tested"],
-                           "bytes": c["nodes_fetched"] * 128 + c["tris_tested"] * 48 + c["insts_entered"] * 64 + 48 * N_BATCH + out_bytes})
+                           "bytes": c["nodes_fetched"] * NODE_BYTES + c["tris_tested"] * 48 + c["insts_entered"] * 64 + 48 * N_BATCH + out_bytes})
     sc.enable_counting(False)
 
     sampler = ClockSampler(local); sampler.start()

@@ -351,8 +351,10 @@ int miro_gpu_upload_scene(miro_gpu_ctx* ctx, const miro_gpu_scene_desc* d) {
     MIRO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     free_scene(ctx);
     int rc;
-    const miro_gpu_node* dn; const miro_gpu_tri* dt; const miro_gpu_mbtri* dm; const miro_gpu_instance* di;
-    if ((rc = upload_array(ctx, d->nodes, d->n_nodes, &dn))) return rc;
+    const DeviceNode* dn; const miro_gpu_tri* dt; const miro_gpu_mbtri* dm; const miro_gpu_instance* di;
+    std::vector<DeviceNode> cnodes(d->n_nodes);          // 128-byte ABI nodes -> 64-byte device nodes (traverse.cuh)
+    for (uint32_t i = 0; i < d->n_nodes; ++i) cnodes[i] = compress_node(d->nodes[i]);
+    if ((rc = upload_array(ctx, cnodes.data(), cnodes.size(), &dn))) return rc;
     if ((rc = upload_array(ctx, d->tris, d->n_tris, &dt))) return rc;
     if ((rc = upload_array(ctx, d->mbtris, d->n_mbtris, &dm))) return rc;
     if ((rc = upload_array(ctx, d->instances, d->n_instances, &di))) return rc;

@@ -39,6 +39,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
+#include <math.h>
 #include "../../include/miro_gpu.h"
 
 namespace miro {
@@ -71,7 +73,7 @@ constexpr int LMEM_STACK = 96 - MIRO_SMEM_STACK;          // overflow entries (l
 constexpr int32_t STACK_SENTINEL = 0x7ffffffe;   // "leave instance" marker
 
 struct DeviceScene {
-    const float4* nodes;     // 8 x float4 per node
+    const float4* nodes;     // DeviceNode: 4 x float4 per node (the 64-byte compressed form, see compress_node)
     const float4* tris;      // 3 x float4 per triangle
     const float4* mbtris;    // 6 x float4 per motion-blur triangle
     const float4* insts;     // 4 x float4 per instance
@@ -255,32 +257,81 @@ __device__ __forceinline__ void pop_next(Lane& L, TraversalStack& st) {
     }
 }
 
+// Device node: the 128-byte ABI node (include/miro_gpu.h) is re-encoded at upload into 64 bytes — the traversal kernels
+// are bound by L1 data-pipe wavefronts, which for divergent loads scale with the BYTES each lane fetches:
+//   word 0..2   p = min corner of the union of the children's boxes (float)
+//   word 3      biased power-of-two exponents of the per-axis grid step: ex | ey << 8 | ez << 16 (step = 2^(e-127))
+//   word 4..7   child references (as in miro_gpu_node)
+//   word 8..10  lower bounds of the 4 children on x, y, z: one byte per child, grid units, rounded DOWN
+//   word 11..13 upper bounds, rounded UP            word 14..15 unused
+// A child's box only ever grows (by less than one grid step = extent/255 per side), so no hit is lost; the
+// uncompressed node would only have culled a few more candidates.
+struct DeviceNode { uint32_t w[16]; };
+static_assert(sizeof(DeviceNode) == 64, "DeviceNode layout");
+
+__host__ inline DeviceNode compress_node(const miro_gpu_node& n) {
+    DeviceNode o;
+    for (int i = 0; i < 16; ++i) o.w[i] = 0;
+    const float* lo[3] = {n.lo_x, n.lo_y, n.lo_z};
+    const float* hi[3] = {n.hi_x, n.hi_y, n.hi_z};
+    for (int k = 0; k < 3; ++k) {
+        float pmin = 3.0e38f, pmax = -3.0e38f;
+        for (int c = 0; c < 4; ++c) if (n.child[c] != MIRO_GPU_CHILD_EMPTY) { pmin = fminf(pmin, lo[k][c]); pmax = fmaxf(pmax, hi[k][c]); }
+        if (!(pmin <= pmax)) { pmin = 0.f; pmax = 0.f; }
+        // smallest power of two step with p + 255 * step >= pmax (evaluated in double: exact for these operands)
+        int e = 1;
+        const double ext = (double)pmax - (double)pmin;
+        while (e < 254 && 255.0 * ldexp(1.0, e - 127) < ext) ++e;
+        const double step = ldexp(1.0, e - 127);
+        uint32_t qlo = 0, qhi = 0;
+        for (int c = 0; c < 4; ++c) {
+            uint32_t a = 255u, b = 0u;                     // empty slot: never consulted (its reference is EMPTY)
+            if (n.child[c] != MIRO_GPU_CHILD_EMPTY) {
+                double fa = floor(((double)lo[k][c] - (double)pmin) / step), fb = ceil(((double)hi[k][c] - (double)pmin) / step);
+                fa = fa < 0.0 ? 0.0 : (fa > 255.0 ? 255.0 : fa); fb = fb < 0.0 ? 0.0 : (fb > 255.0 ? 255.0 : fb);
+                a = (uint32_t)fa; b = (uint32_t)fb;
+            }
+            qlo |= a << (8 * c); qhi |= b << (8 * c);
+        }
+        memcpy(&o.w[k], &pmin, 4);
+        o.w[3] |= (uint32_t)e << (8 * k);
+        o.w[8 + k] = qlo; o.w[11 + k] = qhi;
+    }
+    for (int c = 0; c < 4; ++c) o.w[4 + c] = (uint32_t)n.child[c];
+    return o;
+}
+
 // Node step: test the four children of inner node `cur`, continue with the nearest, defer the others (far to near).
-// Straight-line code: slab tests in FMA form (plane * 1/d - o/d), a 5-comparator sorting network on integer keys
-// (entry distance with the child slot in its two low mantissa bits — truncation only makes an entry look nearer, which
-// is conservative for culling), predicated pushes.
+// Straight-line code: two 32-byte loads, byte -> float conversions, slab tests in FMA form (grid unit * step/d +
+// (p - o)/d), a 5-comparator sorting network on integer keys (entry distance with the child slot in its two low
+// mantissa bits — truncation only makes an entry look nearer, which is conservative for culling), predicated pushes.
 template <bool COUNT>
 __device__ __forceinline__ void node_step(const DeviceScene& s, Lane& L, TraversalStack& st, uint32_t& n_nodes) {
-    const float4* n = s.nodes + (size_t)L.cur * 8;
-    float4 lox, loy, loz, hix, hiy, hiz, chf, unused;
-    ldg256(n + 0, lox, loy); ldg256(n + 2, loz, hix); ldg256(n + 4, hiy, hiz); ldg256(n + 6, chf, unused);
+    const float4* n = s.nodes + (size_t)L.cur * 4;
+    float4 h0, chf, q0, q1;
+    ldg256(n + 0, h0, chf); ldg256(n + 2, q0, q1);
     if (COUNT) ++n_nodes;
+    const uint32_t ex = __float_as_uint(h0.w);
+    // per axis: t(q) = q * (step / d) + (p - o) / d
+    const float ax = __uint_as_float((ex & 0xffu) << 23) * L.r.ix, bx = __fmaf_rn(h0.x, L.r.ix, -L.oix);
+    const float ay = __uint_as_float((ex & 0xff00u) << 15) * L.r.iy, by = __fmaf_rn(h0.y, L.r.iy, -L.oiy);
+    const float az = __uint_as_float((ex & 0xff0000u) << 7) * L.r.iz, bz = __fmaf_rn(h0.z, L.r.iz, -L.oiz);
+    const uint32_t lx = __float_as_uint(q0.x), ly = __float_as_uint(q0.y), lz = __float_as_uint(q0.z);
+    const uint32_t hx = __float_as_uint(q0.w), hy = __float_as_uint(q1.x), hz = __float_as_uint(q1.y);
     const int INF_KEY = 0x7fffffff;
-    // the far bound is widened by 2 ulp so that the FMA-form slab test never rejects a box the ray touches
     const float tmax = L.hit.t;
     int k0, k1, k2, k3;
-#define MIRO_SLAB(LX, LY, LZ, HX, HY, HZ, CH, SLOT, KEY) { \
-    const float ax = __fmaf_rn(LX, L.r.ix, -L.oix), bx = __fmaf_rn(HX, L.r.ix, -L.oix); \
-    const float ay = __fmaf_rn(LY, L.r.iy, -L.oiy), by = __fmaf_rn(HY, L.r.iy, -L.oiy); \
-    const float az = __fmaf_rn(LZ, L.r.iz, -L.oiz), bz = __fmaf_rn(HZ, L.r.iz, -L.oiz); \
-    const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), L.tmin)); \
-    const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax)) * 1.0000003f; \
-    KEY = (tn <= tf && __float_as_int(CH) != MIRO_GPU_CHILD_EMPTY) ? ((float_key(tn) & ~3) | SLOT) : INF_KEY; }
-    MIRO_SLAB(lox.x, loy.x, loz.x, hix.x, hiy.x, hiz.x, chf.x, 0, k0)
-    MIRO_SLAB(lox.y, loy.y, loz.y, hix.y, hiy.y, hiz.y, chf.y, 1, k1)
-    MIRO_SLAB(lox.z, loy.z, loz.z, hix.z, hiy.z, hiz.z, chf.z, 2, k2)
-    MIRO_SLAB(lox.w, loy.w, loz.w, hix.w, hiy.w, hiz.w, chf.w, 3, k3)
+#define MIRO_BYTE(W, C) ((float)(((W) >> (8 * (C))) & 0xffu))
+#define MIRO_SLAB(C, CH, KEY) { \
+    const float t0x = __fmaf_rn(MIRO_BYTE(lx, C), ax, bx), t1x = __fmaf_rn(MIRO_BYTE(hx, C), ax, bx); \
+    const float t0y = __fmaf_rn(MIRO_BYTE(ly, C), ay, by), t1y = __fmaf_rn(MIRO_BYTE(hy, C), ay, by); \
+    const float t0z = __fmaf_rn(MIRO_BYTE(lz, C), az, bz), t1z = __fmaf_rn(MIRO_BYTE(hz, C), az, bz); \
+    const float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), L.tmin)); \
+    const float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax)) * 1.0000003f; \
+    KEY = (tn <= tf && __float_as_int(CH) != MIRO_GPU_CHILD_EMPTY) ? ((float_key(tn) & ~3) | C) : INF_KEY; }
+    MIRO_SLAB(0, chf.x, k0) MIRO_SLAB(1, chf.y, k1) MIRO_SLAB(2, chf.z, k2) MIRO_SLAB(3, chf.w, k3)
 #undef MIRO_SLAB
+#undef MIRO_BYTE
 #define MIRO_KSWAP(a, b) { const int lo_ = min(a, b), hi_ = max(a, b); a = lo_; b = hi_; }
     MIRO_KSWAP(k0, k1) MIRO_KSWAP(k2, k3) MIRO_KSWAP(k0, k2) MIRO_KSWAP(k1, k3) MIRO_KSWAP(k1, k2)
 #undef MIRO_KSWAP
