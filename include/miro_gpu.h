@@ -124,12 +124,15 @@ typedef struct miro_gpu_material {  /* 128 bytes */
     float emit_intensity;           /* Blinn::m_lightEmitted */
     float le[3];                    /* Blinn::m_Le           */
     int32_t color_map;              /* texture index or -1   */
-    int32_t alpha_map;              /* -1 (alpha cut-outs are outside the round-1 scope: EUNSUPPORTED) */
-    float reflect_amt, refract_amt; /* must be 0 (specular transport is outside the scope: EUNSUPPORTED) */
-    float spec_gloss;               /* must be 1 */
-    float translucency;             /* must be <= 0.01 */
+    int32_t alpha_map;              /* -1 (alpha cut-outs are outside the scope: EUNSUPPORTED) */
+    float reflect_amt, refract_amt; /* Blinn::m_reflectAmt / m_refractAmt: mirror reflection / refraction, chosen by Fresnel-weighted
+                                       Russian roulette (src/Blinn.cpp:188-204,238-331) */
+    float spec_gloss;               /* Blinn::m_specGloss: < 1 blends the reflection vector with a cosine sample (src/Blinn.cpp:160-165) */
+    float translucency;             /* must be <= 0.01 (EUNSUPPORTED otherwise) */
     uint32_t sample_env;            /* Material::m_sampleEnv */
-    uint32_t reserved[9];
+    float ior[3];                   /* Blinn::m_ior[0..2]; a non-dispersive material refracts with ior[1] (src/Blinn.cpp:183) */
+    uint32_t disperse;              /* Material::m_disperse: must be 0 (EUNSUPPORTED otherwise) */
+    uint32_t reserved[5];
 } miro_gpu_material;
 
 /* ---- lights (reference: src/PointLight.cpp:8-82, src/RectangleLight.cpp:14-137, src/DomeLight.cpp:8-161) */

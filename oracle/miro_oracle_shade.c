@@ -63,7 +63,7 @@ static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
     }
 }
 static float unit(uint32_t u) { return ((float)(u >> 8) + 0.5f) * (1.0f / 16777216.0f); }
-enum { RP_CAMERA = 0, RP_LENS = 1, RP_COSINE = 2, RP_LIGHT = 3 };
+enum { RP_CAMERA = 0, RP_LENS = 1, RP_COSINE = 2, RP_LIGHT = 3, RP_ROULETTE = 4, RP_GLOSS = 5 };
 typedef struct { uint32_t pixel, sample, path_depth; uint64_t seed; } raddr;
 static void rand4(const raddr* a, uint32_t purpose, uint32_t light, uint32_t pass, uint32_t sample, uint32_t attempt, float out[4]) {
     uint32_t c[4] = {a->pixel, a->sample, a->path_depth, (purpose << 28) | (light << 24) | (pass << 23) | ((sample & 0x7ffu) << 12) | (attempt & 0xfffu)};
@@ -158,7 +158,14 @@ typedef struct {
     uint64_t rays;                     /* Scene::trace calls */
 } octx;
 
-typedef struct { v3 o, d; float time; } oray2;
+/* Ray::IORList (src/Ray.h:43-51): the history of refraction indices a ray has traversed; shade() mutates it in place */
+typedef struct { float v[12]; unsigned idx; } iorlist;
+static void ior_init(iorlist* l) { l->v[0] = 1.0f; l->idx = 0; }
+static float ior_top(const iorlist* l) { return l->v[l->idx]; }
+static void ior_pop(iorlist* l) { if (l->idx > 0) l->idx--; }
+static void ior_push(iorlist* l, float x) { if (l->idx < 11) l->idx++; l->v[l->idx] = x; }
+
+typedef struct { v3 o, d; float time; iorlist ior; int bounces; } oray2;
 typedef struct { v3 P, N, geoN; float u, v; uint32_t material; } surf;
 
 static int trace(octx* c, v3 o, v3 d, float time, float tmin, float tmax, miro_gpu_hit* h) {
@@ -292,13 +299,23 @@ static v3 cosine_sample(v3 N, float e1, float e2) {                           /*
     return normalize(add(add(scl(u, cosf(ang) * s2), scl(v, sinf(ang) * s2)), scl(N, s1)));
 }
 
-static v3 shade(octx* c, const oray2* ray, const miro_gpu_hit* hit, uint32_t pixel, uint32_t sample, uint32_t path, int depth);
+static float fresnel(float n1, float n2, float cosThetaI) {                    /* Material::fresnel, src/Material.h:47-55 */
+    const float n1CosTh = n1 * cosThetaI;
+    const float n1_n2SinTh = n1 * sinf(acosf(cosThetaI)) / n2;
+    const float r = sqrtf(1.0f - n1_n2SinTh * n1_n2SinTh);
+    const float n2CosTh = n2 * ((0.0f < r) ? r : 0.0f);                      /* max(0.0f, NaN) = 0 */
+    const float Rs = (n1CosTh - n2CosTh) / (n1CosTh + n2CosTh);
+    return Rs * Rs;
+}
 
-static v3 shade(octx* c, const oray2* ray, const miro_gpu_hit* hit, uint32_t pixel, uint32_t sample, uint32_t path, int depth) {
+/* depth = giBounces; ray->bounces = reflect / refract bounces; isSecondary as in the reference's signature */
+static v3 shade(octx* c, oray2* ray, const miro_gpu_hit* hit, uint32_t pixel, uint32_t sample, uint32_t path, int depth, int isSecondary);
+
+static v3 shade(octx* c, oray2* ray, const miro_gpu_hit* hit, uint32_t pixel, uint32_t sample, uint32_t path, int depth, int isSecondary) {
     const miro_gpu_scene_desc* s = c->s;
     const surf sf = surface_at(c, ray, hit);
     const miro_gpu_material* m = &s->materials[sf.material];
-    raddr addr; addr.pixel = pixel; addr.sample = sample; addr.path_depth = path | ((uint32_t)depth << 16); addr.seed = c->p->seed;
+    raddr addr; addr.pixel = pixel; addr.sample = sample; addr.path_depth = path | ((uint32_t)(depth + ray->bounces) << 16); addr.seed = c->p->seed;
     v3 kd = V(m->kd[0], m->kd[1], m->kd[2]);
     if (m->color_map >= 0) { float t[4]; tex_lookup(&s->textures[m->color_map], sf.u, sf.v, t); kd = V(t[0], t[1], t[2]); }
     const v3 ka = V(m->ka[0], m->ka[1], m->ka[2]);
@@ -310,41 +327,82 @@ static v3 shade(octx* c, const oray2* ray, const miro_gpu_hit* hit, uint32_t pix
         }
         return add(L, ka);
     }
-    /* Blinn.cpp:91-236,335 */
+    /* Blinn.cpp:91-335 (without the texture-map, translucency and dispersion branches) */
     const v3 viewDir = scl(ray->d, -1.f);
     float vDotN = dot(viewDir, sf.N);
     const float vDotGeoN = dot(viewDir, sf.geoN);
     const int nEqGeoN = (vDotN * vDotGeoN >= 0.0f);
     v3 theNormal = nEqGeoN ? sf.N : sf.geoN;
     vDotN = nEqGeoN ? vDotN : vDotGeoN;
-    if (vDotN < 0.0f) { vDotN = -vDotN; theNormal = scl(theNormal, -1.f); }
-    const v3 rVec = add(ray->d, scl(theNormal, 2.f * vDotN));
+    int flip = 0;
+    if (vDotN < 0.0f) { flip = 1; vDotN = -vDotN; theNormal = scl(theNormal, -1.f); }
+    v3 rVec = add(ray->d, scl(theNormal, 2.f * vDotN));
+    if (m->spec_gloss < 1.0f) {                                               /* Blinn.cpp:160-165 */
+        float r[4]; rand4(&addr, RP_GLOSS, 0, 0, 0, 0, r);
+        const v3 randD = cosine_sample(theNormal, r[0], r[1]);
+        rVec = normalize(add(scl(rVec, m->spec_gloss), scl(randD, 1.f - m->spec_gloss)));
+    }
+    const float inIOR = ior_top(&ray->ior);                                   /* Blinn.cpp:167-186 */
+    float outIOR;
+    if (flip) { ior_pop(&ray->ior); outIOR = ior_top(&ray->ior); } else outIOR = m->ior[1];
+    float Rs = 0.f, Ts = 0.f;
+    if (m->reflect_amt > 0.0f || m->refract_amt > 0.0f) { Rs = fresnel(inIOR, outIOR, vDotN); Ts = 1.0f - Rs; }
+    float rr[4]; rand4(&addr, RP_ROULETTE, 0, 0, 0, 0, rr);
+    const float rrWeight = 1.0f - Rs * m->reflect_amt - Ts * m->refract_amt;
+    const float rrWeightRecip = (rrWeight > 0.f) ? 1.f / rrWeight : 1.f;
+    const float rrWeightRecipSpec = (1.f - rrWeight > 0.f) ? 1.f / (1.f - rrWeight) : 1.f;
     const v3 Le = V(m->le[0], m->le[1], m->le[2]), ks = V(m->ks[0], m->ks[1], m->ks[2]);
-    const int isSecondary = depth > 0;
-    v3 Ld = V(0, 0, 0), Ls = V(0, 0, 0);
-    if (c->p->path_trace) {                                                   /* Blinn::calculatePathTracing, Blinn.cpp:39-89 */
-        if (m->emit_intensity > 0.0f || (Le.x + Le.y + Le.z) > 0.0f) Ld = add(Ld, scl(Le, m->emit_intensity));
-        else if (depth < c->p->max_bounces - 1) {
-            float r[4]; rand4(&addr, RP_COSINE, 0, 0, 0, 0, r);
-            oray2 nr; nr.o = sf.P; nr.d = cosine_sample(theNormal, r[0], r[1]); nr.time = ray->time;
-            miro_gpu_hit nh;
-            if (trace(c, nr.o, nr.d, nr.time, O_EPS, MIRO_GPU_TMAX, &nh)) Ld = add(Ld, mul(kd, shade(c, &nr, &nh, pixel, sample, path, depth + 1)));
-            else if (m->sample_env && c->p->sample_env) Ld = add(Ld, mul(kd, environment(c, nr.d)));
-        } else {
-            for (uint32_t li = 0; li < s->n_lights; ++li) {
-                float lightSpec;
-                Ld = add(Ld, mul(sample_light(c, li, sf.P, theNormal, ray->time, V(0, 0, 0), &lightSpec, 1, 1, &addr), kd));
+    v3 Ld = V(0, 0, 0), Ls = V(0, 0, 0), Lr = V(0, 0, 0), Lt = V(0, 0, 0);
+    if (rr[0] <= rrWeight) {
+        if (c->p->path_trace) {                                               /* Blinn::calculatePathTracing, Blinn.cpp:39-89 */
+            if (m->emit_intensity > 0.0f || (Le.x + Le.y + Le.z) > 0.0f) Ld = add(Ld, scl(Le, m->emit_intensity));
+            else if (depth < c->p->max_bounces - 1) {
+                float r[4]; rand4(&addr, RP_COSINE, 0, 0, 0, 0, r);
+                oray2 nr; nr.o = sf.P; nr.d = cosine_sample(theNormal, r[0], r[1]); nr.time = ray->time; nr.bounces = ray->bounces;
+                ior_init(&nr.ior); ior_push(&nr.ior, 1.001f);                  /* Ray randRay(threadID) */
+                ior_pop(&nr.ior); ior_push(&nr.ior, ior_top(&ray->ior));       /* randRay.set(..., ray.r_IOR(), ...) */
+                miro_gpu_hit nh;
+                if (trace(c, nr.o, nr.d, nr.time, O_EPS, MIRO_GPU_TMAX, &nh)) Ld = add(Ld, mul(kd, shade(c, &nr, &nh, pixel, sample, path, depth + 1, 1)));
+                else if (m->sample_env && c->p->sample_env) Ld = add(Ld, mul(kd, environment(c, nr.d)));
+            } else {
+                for (uint32_t li = 0; li < s->n_lights; ++li) {
+                    float lightSpec;
+                    Ld = add(Ld, mul(sample_light(c, li, sf.P, theNormal, ray->time, V(0, 0, 0), &lightSpec, 1, 1, &addr), kd));
+                }
             }
         }
-    }
-    for (uint32_t li = 0; li < s->n_lights; ++li) {
-        float lightSpec = 0.f;
-        const v3 lightPower = sample_light(c, li, sf.P, theNormal, ray->time, rVec, &lightSpec, isSecondary, 0, &addr);
-        if (m->spec_amt != 0.f) Ls = add(Ls, scl(mul(lightPower, ks), m->spec_amt * powf(lightSpec, m->spec_exp)));
-        Ld = add(Ld, mul(lightPower, kd));
+        for (uint32_t li = 0; li < s->n_lights; ++li) {
+            float lightSpec = 0.f;
+            const v3 lightPower = sample_light(c, li, sf.P, theNormal, ray->time, rVec, &lightSpec, isSecondary, 0, &addr);
+            if (m->spec_amt != 0.f) Ls = add(Ls, scl(mul(lightPower, ks), m->spec_amt * powf(lightSpec, m->spec_exp)));
+            Ld = add(Ld, mul(lightPower, kd));
+        }
+    } else {
+        int doEnv = 1;
+        if (rr[1] < m->reflect_amt * Rs) {                                    /* Blinn.cpp:247-268 */
+            if (m->reflect_amt * Rs > 0.0f && ray->bounces < 5) {
+                oray2 nr; nr.o = sf.P; nr.d = rVec; nr.time = ray->time; nr.ior = ray->ior; nr.bounces = ray->bounces + 1;
+                miro_gpu_hit nh;
+                if (trace(c, nr.o, nr.d, nr.time, O_EPS, MIRO_GPU_TMAX, &nh)) { Lr = add(Lr, mul(ks, shade(c, &nr, &nh, pixel, sample, path, depth, 0))); doEnv = 0; }
+            }
+            if (m->reflect_amt * Rs > 0.0f && doEnv) Lr = add(Lr, mul(ks, environment(c, rVec)));
+        } else if (m->refract_amt * Ts > 0.0f) {                              /* Blinn.cpp:270-329, no dispersion */
+            const float snellsQ = inIOR / outIOR;
+            const float sq = sqrtf(1.0f - (snellsQ * snellsQ) * (1.0f - vDotN * vDotN));
+            const float sqrtPart = (0.0f < sq) ? sq : 0.0f;
+            const v3 tVec = normalize(add(scl(ray->d, snellsQ), scl(theNormal, snellsQ * vDotN - sqrtPart)));
+            if (ray->bounces < 5) {
+                ior_push(&ray->ior, outIOR);
+                oray2 nr; nr.o = sf.P; nr.d = tVec; nr.time = ray->time; nr.ior = ray->ior; nr.bounces = ray->bounces + 1;
+                miro_gpu_hit nh;
+                if (trace(c, nr.o, nr.d, nr.time, O_EPS, MIRO_GPU_TMAX, &nh)) { Lt = add(Lt, mul(ks, shade(c, &nr, &nh, pixel, sample, path, depth, 0))); doEnv = 0; }
+                ior_pop(&ray->ior);
+            }
+            if (doEnv) Lt = add(Lt, mul(ks, environment(c, tVec)));
+        }
     }
     Ld = add(Ld, ka);
-    return add(add(Ld, Ls), Le);
+    return add(add(scl(add(Ld, Ls), rrWeightRecip), scl(add(Lr, Lt), rrWeightRecipSpec)), Le);
 }
 
 typedef struct { v3 eye, u, v, w; float top, right, focus, aperture, shutter; } ocam;
@@ -355,7 +413,8 @@ static oray2 eye_ray(const ocam* cm, int x, int y, float minX, float maxX, float
     const float left = -cm->right, bottom = -cm->top;
     const float U = left + (cm->right - left) * (((float)x + xOffset) / (float)W);
     const float Vp = bottom + (cm->top - bottom) * (((float)y + yOffset) / (float)H);
-    oray2 o; o.time = 1.f - r[2] * r[2] * r[2] * cm->shutter;
+    oray2 o; o.time = 1.f - r[2] * r[2] * r[2] * cm->shutter; o.bounces = 0;
+    ior_init(&o.ior); ior_push(&o.ior, 1.001f);                              /* Ray(threadID, o, d, t): IOR = 1.001 pushed, src/Ray.h:70-101 */
     const v3 dir = normalize(sub(add(scl(cm->u, U), scl(cm->v, Vp)), cm->w));
     if (cm->aperture < O_EPS) { o.o = cm->eye; o.d = dir; return o; }
     const v3 focal = add(scl(dir, cm->focus), cm->eye);
@@ -370,11 +429,11 @@ static oray2 eye_ray(const ocam* cm, int x, int y, float minX, float maxX, float
     return o;
 }
 
-static v3 sample_scene(octx* c, const oray2* ray, uint32_t pixel, uint32_t sample) {      /* Scene.cpp:219-243 */
+static v3 sample_scene(octx* c, oray2* ray, uint32_t pixel, uint32_t sample) {      /* Scene.cpp:219-243 */
     miro_gpu_hit h;
     if (trace(c, ray->o, ray->d, ray->time, O_EPS, MIRO_GPU_TMAX, &h)) {
         v3 result = V(0, 0, 0);
-        for (int i = 0; i < c->p->num_paths; i++) result = add(result, scl(shade(c, ray, &h, pixel, sample, (uint32_t)i, 0), 1.0f / (float)c->p->num_paths));
+        for (int i = 0; i < c->p->num_paths; i++) result = add(result, scl(shade(c, ray, &h, pixel, sample, (uint32_t)i, 0, 0), 1.0f / (float)c->p->num_paths));
         return result;
     }
     return environment(c, ray->d);

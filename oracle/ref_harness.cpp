@@ -176,6 +176,8 @@ void loadScene(const std::string& file) {
                     else if (k == "specexp") { float f; ss >> f; m->setSpecExp(f); }
                     else if (k == "specamt") { float f; ss >> f; m->setSpecAmt(f); }
                     else if (k == "ior") { float f; ss >> f; m->setIor(f, 0); m->setIor(f, 1); m->setIor(f, 2); }
+                    else if (k == "ior_i") { int i; float f; ss >> i >> f; m->setIor(f, i); }
+                    else if (k == "disperse") { int v; ss >> v; m->m_disperse = v != 0; }
                     else if (k == "reflect") { float f; ss >> f; m->setReflectAmt(f); }
                     else if (k == "refract") { float f; ss >> f; m->setRefractAmt(f); }
                     else if (k == "gloss") { float f; ss >> f; m->setReflectGloss(f); }

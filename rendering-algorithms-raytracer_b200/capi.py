@@ -56,7 +56,7 @@ class Material(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("kd", C.c_float * 3), ("ka", C.c_float * 3), ("ks", C.c_float * 3),
                 ("spec_exp", C.c_float), ("spec_amt", C.c_float), ("emit_intensity", C.c_float), ("le", C.c_float * 3),
                 ("color_map", C.c_int32), ("alpha_map", C.c_int32), ("reflect_amt", C.c_float), ("refract_amt", C.c_float),
-                ("spec_gloss", C.c_float), ("translucency", C.c_float), ("sample_env", C.c_uint32), ("reserved", C.c_uint32 * 9)]
+                ("spec_gloss", C.c_float), ("translucency", C.c_float), ("sample_env", C.c_uint32), ("ior", C.c_float * 3), ("disperse", C.c_uint32), ("reserved", C.c_uint32 * 5)]
 
 
 class Light(C.Structure):

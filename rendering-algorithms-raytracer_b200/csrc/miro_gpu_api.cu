@@ -340,8 +340,8 @@ int miro_gpu_upload_scene(miro_gpu_ctx* ctx, const miro_gpu_scene_desc* d) {
     for (uint32_t i = 0; i < d->n_materials; ++i) {
         const miro_gpu_material& m = d->materials[i];
         if (m.kind > MIRO_GPU_MAT_BLINN) return set_error(ctx, MIRO_GPU_EINVAL, "unknown material kind");
-        if (m.reflect_amt != 0.f || m.refract_amt != 0.f || m.translucency > 0.01f || (m.kind == MIRO_GPU_MAT_BLINN && m.spec_gloss < 1.f) || m.alpha_map >= 0)
-            return set_error(ctx, MIRO_GPU_EUNSUPPORTED, "material " + std::to_string(i) + " uses reflection/refraction/gloss/translucency/alpha cut-outs (outside the hot-path scope, SURVEY 8f)");
+        if (m.translucency > 0.01f || m.alpha_map >= 0 || m.disperse)
+            return set_error(ctx, MIRO_GPU_EUNSUPPORTED, "material " + std::to_string(i) + " uses translucency / alpha cut-outs / dispersion (outside the hot-path scope, SURVEY 8f)");
         if (m.color_map >= (int32_t)d->n_textures) return set_error(ctx, MIRO_GPU_EINVAL, "material color_map out of range");
     }
     for (uint32_t i = 0; i < d->n_tris + d->n_mbtris && d->prims; ++i)

@@ -36,7 +36,9 @@
 namespace miro {
 
 constexpr int SHADE_BLOCK = 128;
-constexpr uint32_t FLAG_SAMPLE_ENV = 0x80000000u;      // ray.flags bit 31: the spawning material samples the environment on a miss
+// ray.flags of a queued continuation ray: path 0-15 | giBounces 16-23 | bounces 24-26 | FLAG_SECONDARY | FLAG_SAMPLE_ENV
+constexpr uint32_t FLAG_SAMPLE_ENV = 0x80000000u;      // the environment / background is added when the ray leaves the scene
+constexpr uint32_t FLAG_SECONDARY = 0x08000000u;       // shade(..., isSecondary = true): reached through calculatePathTracing
 constexpr size_t WAVE_PATHS_MAX = (size_t)1 << 22;     // paths in flight per wave
 constexpr size_t WAVE_BYTES_BUDGET = (size_t)6 << 30;  // queue memory per context
 
@@ -53,6 +55,7 @@ struct RenderParamsDev {
     uint32_t path_trace, sample_env;
     uint64_t seed;
     float inv_paths;
+    uint32_t has_specular;      // some material has reflect_amt / refract_amt > 0: rays carry an IOR history
 };
 
 struct Queues {
@@ -60,6 +63,7 @@ struct Queues {
     miro_gpu_ray* cs_rays; miro_gpu_hit* cs_hits;
     // bounce queues (ping-pong): rays, throughput, hits
     miro_gpu_ray* q_rays[2]; float4* q_thr[2]; miro_gpu_hit* q_hits;
+    float4* q_ior[2];      // 2 x float4 per ray: the IOR history (only allocated when a material reflects / refracts)
     // shadow queue and light-loop slots
     miro_gpu_ray* sh_rays; float4* sh_E; Slot* slots;
     // device counters: [0] next bounce count, [1] shadow count, [2] slot count, [3] next active-pixel count, [4..7] spare
@@ -70,7 +74,7 @@ struct Queues {
 struct RenderState {
     Queues q{};
     std::vector<void*> allocs;
-    size_t key_paths = 0, key_shadow_per_path = 0, key_slots_per_path = 0;
+    size_t key_paths = 0, key_shadow_per_path = 0, key_slots_per_path = 0; bool key_ior = false;
     // frame buffers
     float4* level_sum = nullptr; float4* result = nullptr; uint32_t* active[2] = {nullptr, nullptr};
     float* rgb_dev = nullptr; size_t frame_pixels = 0;
@@ -141,10 +145,12 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
         const uint32_t idx = base + (threadIdx.x & 31u);
         // ------------------------------------------------------------------ phase 1: evaluate, count
         bool active = idx < n;
-        uint32_t pixel = 0, sample = 0, path = 0, depth = 0;
-        float3x thr = f3(0, 0, 0), o = f3(0, 0, 0), d = f3(0, 0, 1), bounce_dir = f3(0, 0, 0), bounce_thr = f3(0, 0, 0);
+        uint32_t pixel = 0, sample = 0, path = 0, gi = 0, bounces = 0, vertex = 0;
+        float3x thr = f3(0, 0, 0), thr_d = f3(0, 0, 0), o = f3(0, 0, 0), d = f3(0, 0, 1), bounce_dir = f3(0, 0, 0), bounce_thr = f3(0, 0, 0);
         float time = 0.f;
-        bool emit_bounce = false, pt_last = false, blinn = false, bounce_env = false;
+        bool emit_bounce = false, pt_last = false, blinn = false, diffuse = true;
+        uint32_t bounce_flags = 0;
+        IorStack ior; ior.init_camera();
         ShadeCtx c{};
         int n_shadow = 0, n_slots = 0;
         RandAddr addr{};
@@ -158,26 +164,35 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
             o = f3(r0.x, r0.y, r0.z); d = f3(r1.x, r1.y, r1.z); time = r2.x;
             pixel = __float_as_uint(r2.z); sample = __float_as_uint(r2.w);
             const uint32_t flags = __float_as_uint(r2.y);
-            if (PRIMARY) { path = idx - ri * (uint32_t)P.num_paths; depth = 0; thr = f3(P.inv_paths, P.inv_paths, P.inv_paths); }
+            bool secondary = false;
+            if (PRIMARY) { path = idx - ri * (uint32_t)P.num_paths; thr = f3(P.inv_paths, P.inv_paths, P.inv_paths); }
             else {
-                path = flags & 0xffffu; depth = (flags >> 16) & 0x7fffu;
+                path = flags & 0xffffu; gi = (flags >> 16) & 0xffu; bounces = (flags >> 24) & 7u; secondary = (flags & FLAG_SECONDARY) != 0;
                 const float4 t4 = __ldg(q.q_thr[in_q] + idx); thr = f3(t4.x, t4.y, t4.z);
+                if (P.has_specular) {
+                    const float4 i0 = __ldg(q.q_ior[in_q] + 2 * (size_t)idx), i1 = __ldg(q.q_ior[in_q] + 2 * (size_t)idx + 1);
+                    ior.v[0] = i0.x; ior.v[1] = i0.y; ior.v[2] = i0.z; ior.v[3] = i0.w; ior.v[4] = i1.x; ior.v[5] = i1.y; ior.v[6] = i1.z;
+                    ior.idx = (int)__float_as_uint(i1.w);
+                }
             }
-            addr.pixel = pixel; addr.sample = sample; addr.path_depth = path | (depth << 16); addr.seed = P.seed;
+            vertex = gi + bounces;      // ordinal of this vertex along its path: every continuation adds one to gi or to bounces
+            addr.pixel = pixel; addr.sample = sample; addr.path_depth = path | (vertex << 16); addr.seed = P.seed;
             if (hprim < 0) {
-                // Scene::sampleScene miss (Scene.cpp:234-240): env / BG once per camera sample; bounce miss (Blinn.cpp:70-73)
+                // Scene::sampleScene miss (Scene.cpp:234-240): env / BG once per camera sample; continuation-ray miss
+                // (Blinn.cpp:70-73 with the material's and the scene's sampleEnv; Blinn.cpp:262,326 unconditionally)
                 if (PRIMARY) { if (path == 0) add_rgb(level_sum, pixel, environment(sh, d)); }
-                else if ((flags & FLAG_SAMPLE_ENV) && P.sample_env) add_rgb(level_sum, pixel, thr * environment(sh, d));
+                else if (flags & FLAG_SAMPLE_ENV) add_rgb(level_sum, pixel, thr * environment(sh, d));
                 active = false;
             } else {
                 const Surface s = surface_at(sc, sh, o, d, ht, ha, hb, hprim, hinst);
                 const miro_gpu_material* m = sh.materials + s.material;
                 float3x kd = f3(m->kd[0], m->kd[1], m->kd[2]);
                 if (m->color_map >= 0) { const float4 t = tex_lookup(sh.textures[m->color_map], s.u, s.v); kd = f3(t.x, t.y, t.z); }
-                float3x constant = f3(m->ka[0], m->ka[1], m->ka[2]);
-                c.P = s.P; c.kd = kd; c.time = time; c.is_secondary = depth > 0; c.spec_exp = m->spec_exp;
+                const float3x ka = f3(m->ka[0], m->ka[1], m->ka[2]);
+                c.P = s.P; c.kd = kd; c.time = time; c.is_secondary = secondary; c.spec_exp = m->spec_exp;
                 blinn = m->kind == MIRO_GPU_MAT_BLINN;
-                if (!blinn) { c.N = s.N; c.rVec = f3(0, 0, 0); c.tks = f3(0, 0, 0); }
+                thr_d = thr;
+                if (!blinn) { c.N = s.N; c.rVec = f3(0, 0, 0); c.tks = f3(0, 0, 0); add_rgb(level_sum, pixel, thr * ka); }
                 else {
                     // normal selection / flip towards the viewer (Blinn.cpp:144-155)
                     const float3x viewDir = -d;
@@ -186,26 +201,76 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
                     const bool nEqGeoN = (vDotN * vDotGeoN >= 0.0f);
                     float3x theNormal = nEqGeoN ? s.N : s.geoN;
                     vDotN = nEqGeoN ? vDotN : vDotGeoN;
-                    if (vDotN < 0.0f) { vDotN = -vDotN; theNormal = -theNormal; }
+                    bool flip = false;
+                    if (vDotN < 0.0f) { flip = true; vDotN = -vDotN; theNormal = -theNormal; }
                     c.N = theNormal;
-                    c.rVec = d + (2.f * vDotN) * theNormal;                                      // Blinn.cpp:158
-                    c.tks = thr * f3(m->ks[0], m->ks[1], m->ks[2]) * m->spec_amt;
-                    const float3x Le = f3(m->le[0], m->le[1], m->le[2]);
-                    constant = constant + Le;                                                    // "+ m_Le", Blinn.cpp:335
-                    if (P.path_trace) {                                                          // Blinn::calculatePathTracing
-                        if (m->emit_intensity > 0.0f || (Le.x + Le.y + Le.z) > 0.0f) constant = constant + m->emit_intensity * Le;
-                        else if ((int)depth < P.max_bounces - 1) {
-                            const Rand4 r = rand4(addr, RP_COSINE, 0, 0, 0, 0);
-                            bounce_dir = cosine_sample(theNormal, r.x, r.y);
-                            bounce_thr = thr * kd; bounce_env = m->sample_env != 0;
-                            emit_bounce = true;
-                        } else pt_last = true;
+                    float3x rVec = d + (2.f * vDotN) * theNormal;                                 // Blinn.cpp:158
+                    if (m->spec_gloss < 1.0f) {                                                  // Blinn.cpp:160-165
+                        const Rand4 r = rand4(addr, RP_GLOSS, 0, 0, 0, 0);
+                        const float3x randD = cosine_sample(theNormal, r.x, r.y);
+                        rVec = normalize3(m->spec_gloss * rVec + (1.f - m->spec_gloss) * randD);
                     }
+                    c.rVec = rVec;
+                    // IOR bookkeeping (Blinn.cpp:167-186).  The reference pops the history of the ray OBJECT it was handed;
+                    // sampleScene shades the same camera ray numPaths times, so path i of a back-facing primary hit sees the
+                    // history already popped by paths 0..i-1.
+                    if (PRIMARY && flip) for (uint32_t k = 0; k < path && k < 2u; ++k) ior.pop();
+                    const float inIOR = ior.top();
+                    float outIOR;
+                    if (flip) { ior.pop(); outIOR = ior.top(); } else outIOR = m->ior[1];
+                    float Rs = 0.f, Ts = 0.f;
+                    if (m->reflect_amt > 0.0f || m->refract_amt > 0.0f) { Rs = fresnel(inIOR, outIOR, vDotN); Ts = 1.0f - Rs; }
+                    const Rand4 rr = rand4(addr, RP_ROULETTE, 0, 0, 0, 0);
+                    const float rrWeight = 1.0f - Rs * m->reflect_amt - Ts * m->refract_amt;       // Blinn.cpp:195-198
+                    const float rrWeightRecip = (rrWeight > 0.f) ? 1.f / rrWeight : 1.f;
+                    const float rrWeightRecipSpec = (1.f - rrWeight > 0.f) ? 1.f / (1.f - rrWeight) : 1.f;
+                    const float3x ks = f3(m->ks[0], m->ks[1], m->ks[2]);
+                    const float3x Le = f3(m->le[0], m->le[1], m->le[2]);
+                    diffuse = rr.x <= rrWeight;
+                    thr_d = thr * rrWeightRecip;                       // (Ld + Ls) / rrWeight, Blinn.cpp:335
+                    c.tks = thr_d * ks * m->spec_amt;
+                    float3x constant = thr_d * ka + thr * Le;          // "Ld += m_ka" is on both branches; "+ m_Le" is unscaled
+                    const uint32_t base_flags = path | (gi << 16) | (bounces << 24);
+                    if (diffuse) {
+                        if (P.path_trace) {                                                      // Blinn::calculatePathTracing
+                            if (m->emit_intensity > 0.0f || (Le.x + Le.y + Le.z) > 0.0f) constant = constant + thr_d * (m->emit_intensity * Le);
+                            else if ((int)gi < P.max_bounces - 1) {
+                                const Rand4 r = rand4(addr, RP_COSINE, 0, 0, 0, 0);
+                                bounce_dir = cosine_sample(theNormal, r.x, r.y);
+                                bounce_thr = thr_d * kd;
+                                bounce_flags = (path | ((gi + 1u) << 16) | (bounces << 24)) | FLAG_SECONDARY | ((m->sample_env && P.sample_env) ? FLAG_SAMPLE_ENV : 0u);
+                                // randRay.set(..., ray.r_IOR(), ...) on a fresh Ray: history = {1.0, top}  (Blinn.cpp:61, Ray.h:143-176)
+                                const float top = ior.top(); ior.init_camera(); ior.v[1] = top;
+                                emit_bounce = true;
+                            } else pt_last = true;
+                        }
+                    } else {
+                        // mirror reflection or refraction, Blinn.cpp:238-331; one continuation ray, weight ks / (1 - rrWeight)
+                        float3x dir;
+                        bool spawn = false;
+                        if (rr.y < m->reflect_amt * Rs) {
+                            if (m->reflect_amt * Rs > 0.0f) { dir = rVec; spawn = true; }
+                        } else if (m->refract_amt * Ts > 0.0f) {
+                            const float snellsQ = inIOR / outIOR;
+                            const float sqrtPart = fmaxf(0.0f, sqrtf(1.0f - (snellsQ * snellsQ) * (1.0f - vDotN * vDotN)));
+                            dir = normalize3(snellsQ * d + theNormal * (snellsQ * vDotN - sqrtPart));
+                            ior.push(outIOR);
+                            spawn = true;
+                        }
+                        if (spawn) {
+                            bounce_thr = thr * ks * rrWeightRecipSpec;
+                            if (bounces < 5u) {
+                                bounce_dir = dir; emit_bounce = true;
+                                bounce_flags = (path | (gi << 16) | ((bounces + 1u) << 24)) | FLAG_SAMPLE_ENV;   // shade(...) with isSecondary = false
+                            } else constant = constant + bounce_thr * environment(sh, dir);       // "doEnv": no further bounce
+                        }
+                    }
+                    (void)base_flags;
+                    add_rgb(level_sum, pixel, constant);
                 }
-                add_rgb(level_sum, pixel, thr * constant);
-                for_each_light_loop(sh, pt_last, blinn, c.is_secondary, [&](uint32_t li, uint32_t pass, bool secondary, bool with_spec) {
+                if (diffuse) for_each_light_loop(sh, pt_last, blinn, c.is_secondary, [&](uint32_t li, uint32_t pass, bool secondary_, bool with_spec) {
                     int lit = 0;
-                    light_loop(sh, li, c.P, c.N, with_spec ? c.rVec : f3(0, 0, 0), secondary, pass, addr, [&](const LightSample&) { ++lit; });
+                    light_loop(sh, li, c.P, c.N, with_spec ? c.rVec : f3(0, 0, 0), secondary_, pass, addr, [&](const LightSample&) { ++lit; });
                     if (lit) { n_shadow += lit; ++n_slots; }
                 });
             }
@@ -232,8 +297,12 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
             float4* o4 = reinterpret_cast<float4*>(q.q_rays[in_q ^ 1] + b_next);
             o4[0] = make_float4(c.P.x, c.P.y, c.P.z, kEps);
             o4[1] = make_float4(bounce_dir.x, bounce_dir.y, bounce_dir.z, MIRO_GPU_TMAX);
-            o4[2] = make_float4(time, __uint_as_float(path | ((depth + 1u) << 16) | (bounce_env ? FLAG_SAMPLE_ENV : 0u)), __uint_as_float(pixel), __uint_as_float(sample));
+            o4[2] = make_float4(time, __uint_as_float(bounce_flags), __uint_as_float(pixel), __uint_as_float(sample));
             q.q_thr[in_q ^ 1][b_next] = make_float4(bounce_thr.x, bounce_thr.y, bounce_thr.z, 0.f);
+            if (P.has_specular) {
+                q.q_ior[in_q ^ 1][2 * (size_t)b_next] = make_float4(ior.v[0], ior.v[1], ior.v[2], ior.v[3]);
+                q.q_ior[in_q ^ 1][2 * (size_t)b_next + 1] = make_float4(ior.v[4], ior.v[5], ior.v[6], __uint_as_float((uint32_t)ior.idx));
+            }
         }
         if (n_slots == 0) continue;
         if (b_shadow + (uint32_t)n_shadow > shadow_cap || b_slots + (uint32_t)n_slots > slot_cap) continue;   // cannot happen: capacities are worst case
@@ -253,7 +322,7 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
             });
             if (lit) {
                 Slot* sp = q.slots + slot;
-                const float3x tkd = thr * c.kd;
+                const float3x tkd = thr_d * c.kd;
                 sp->acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 sp->tkd = make_float4(tkd.x, tkd.y, tkd.z, __uint_as_float(pixel));
                 sp->tks = with_spec ? make_float4(c.tks.x, c.tks.y, c.tks.z, c.spec_exp) : make_float4(0.f, 0.f, 0.f, 1.f);
@@ -360,20 +429,23 @@ static cudaError_t qalloc(RenderState* st, T** p, size_t n) {
     return e;
 }
 
-static int ensure_queues(miro_gpu_ctx* ctx, RenderState* st, size_t paths, size_t cs, size_t shadow_per_path, size_t slots_per_path) {
-    if (st->key_paths == paths && st->q.cap_cs >= cs && st->key_shadow_per_path == shadow_per_path && st->key_slots_per_path == slots_per_path) return MIRO_GPU_OK;
+static int ensure_queues(miro_gpu_ctx* ctx, RenderState* st, size_t paths, size_t cs, size_t shadow_per_path, size_t slots_per_path, bool with_ior) {
+    if (st->key_paths == paths && st->q.cap_cs >= cs && st->key_shadow_per_path == shadow_per_path && st->key_slots_per_path == slots_per_path && st->key_ior == with_ior) return MIRO_GPU_OK;
     free_queues(st);
     Queues& q = st->q;
     q.cap_cs = cs; q.cap_paths = paths; q.cap_shadow = paths * shadow_per_path; q.cap_slots = paths * slots_per_path;
     MIRO_CUDA(ctx, qalloc(st, &q.cs_rays, q.cap_cs));
     MIRO_CUDA(ctx, qalloc(st, &q.cs_hits, q.cap_cs));
-    for (int i = 0; i < 2; ++i) { MIRO_CUDA(ctx, qalloc(st, &q.q_rays[i], paths)); MIRO_CUDA(ctx, qalloc(st, &q.q_thr[i], paths)); }
+    for (int i = 0; i < 2; ++i) {
+        MIRO_CUDA(ctx, qalloc(st, &q.q_rays[i], paths)); MIRO_CUDA(ctx, qalloc(st, &q.q_thr[i], paths));
+        if (with_ior) MIRO_CUDA(ctx, qalloc(st, &q.q_ior[i], 2 * paths));
+    }
     MIRO_CUDA(ctx, qalloc(st, &q.q_hits, paths));
     MIRO_CUDA(ctx, qalloc(st, &q.sh_rays, q.cap_shadow));
     MIRO_CUDA(ctx, qalloc(st, &q.sh_E, q.cap_shadow));
     MIRO_CUDA(ctx, qalloc(st, &q.slots, q.cap_slots));
     MIRO_CUDA(ctx, qalloc(st, &q.counts, (size_t)8));
-    st->key_paths = paths; st->key_shadow_per_path = shadow_per_path; st->key_slots_per_path = slots_per_path;
+    st->key_paths = paths; st->key_shadow_per_path = shadow_per_path; st->key_slots_per_path = slots_per_path; st->key_ior = with_ior;
     return MIRO_GPU_OK;
 }
 
@@ -412,7 +484,7 @@ extern "C" int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, co
     if (!ctx->has_scene) return set_error(ctx, MIRO_GPU_ENOSCENE, "render before upload_scene");
     if (rp->width <= 0 || rp->height <= 0 || (size_t)rp->width * rp->height > 0x7fffffffu) return set_error(ctx, MIRO_GPU_EINVAL, "bad image size");
     if (rp->num_paths < 1 || rp->num_paths > 0xffff) return set_error(ctx, MIRO_GPU_EINVAL, "num_paths must be in 1..65535");
-    if (rp->max_bounces > 0x7fff) return set_error(ctx, MIRO_GPU_EINVAL, "max_bounces too large");
+    if (rp->max_bounces > 255) return set_error(ctx, MIRO_GPU_EINVAL, "max_bounces > 255 (the reference keeps the count in 8 bits, src/Ray.h:23)");
     const int max_sub = std::max(1, std::max(rp->max_subdivs, rp->min_subdivs));
     if (max_sub > 32) return set_error(ctx, MIRO_GPU_EINVAL, "more than 32 subdivision levels");
     if (ctx->shading.n_prims == 0 && (ctx->n_tris || ctx->n_mbtris)) return set_error(ctx, MIRO_GPU_EINVAL, "scene has no shading records (prims)");
@@ -439,18 +511,20 @@ extern "C" int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, co
     RenderParamsDev P;
     P.width = W; P.height = H; P.num_paths = rp->num_paths; P.max_bounces = rp->max_bounces;
     P.path_trace = rp->path_trace; P.sample_env = rp->sample_env; P.seed = rp->seed; P.inv_paths = 1.0f / (float)rp->num_paths;
+    P.has_specular = 0;
+    for (const miro_gpu_material& m : ctx->host_materials) if (m.kind == MIRO_GPU_MAT_BLINN && (m.reflect_amt > 0.f || m.refract_amt > 0.f)) P.has_specular = 1;
 
     // ---- queue capacities: worst case per path
     size_t light_samples = 0;
     for (const miro_gpu_light& l : ctx->host_lights) light_samples += (size_t)std::max(1, l.num_samples);
     const size_t loops = rp->path_trace ? 2 : 1;
     const size_t shadow_per_path = std::max<size_t>(1, loops * light_samples), slots_per_path = std::max<size_t>(1, loops * ctx->host_lights.size());
-    const size_t bytes_per_path = 2 * (48 + 16) + 20 + shadow_per_path * 64 + slots_per_path * 64 + (48 + 20);
+    const size_t bytes_per_path = 2 * (48 + 16 + (P.has_specular ? 32 : 0)) + 20 + shadow_per_path * 64 + slots_per_path * 64 + (48 + 20);
     size_t paths = std::min<size_t>(WAVE_PATHS_MAX, std::max<size_t>(WAVE_BYTES_BUDGET / bytes_per_path, (size_t)rp->num_paths));
     paths = std::min(paths, pixels * (size_t)max_sub * max_sub * rp->num_paths);
     paths = std::max<size_t>((paths / rp->num_paths) * rp->num_paths, (size_t)rp->num_paths);
     const size_t wave_cs = paths / rp->num_paths;
-    if ((rc = ensure_queues(ctx, st, paths, wave_cs, shadow_per_path, slots_per_path))) return rc;
+    if ((rc = ensure_queues(ctx, st, paths, wave_cs, shadow_per_path, slots_per_path, P.has_specular != 0))) return rc;
     Queues& q = st->q;
     cudaStream_t s = ctx->stream;
 
@@ -472,7 +546,8 @@ extern "C" int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, co
     MIRO_CUDA(ctx, cudaMemcpyAsync(st->active[0], own.data(), own.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     MIRO_CUDA(ctx, cudaMemsetAsync(st->level_sum, 0, pixels * sizeof(float4), s));
     int cur = 0;
-    const int last_depth = rp->path_trace ? std::max(0, rp->max_bounces - 1) : 0;
+    // vertices along a path: up to maxBounces-1 diffuse (GI) continuations and up to 5 reflect / refract continuations (Blinn.cpp:57,247)
+    const int last_depth = (rp->path_trace ? std::max(0, rp->max_bounces - 1) : 0) + (P.has_specular ? 5 : 0);
     for (int level = 1; level <= max_sub && n_active > 0; ++level) {
         const uint32_t k2 = (uint32_t)(level * level);
         const int km1 = level - 1;

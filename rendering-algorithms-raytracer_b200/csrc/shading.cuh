@@ -37,7 +37,7 @@ __host__ __device__ inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32
 }
 __host__ __device__ inline float u32_to_unit(uint32_t u) { return ((float)(u >> 8) + 0.5f) * (1.0f / 16777216.0f); }   // (0,1)
 
-enum RandPurpose : uint32_t { RP_CAMERA = 0, RP_LENS = 1, RP_COSINE = 2, RP_LIGHT = 3 };
+enum RandPurpose : uint32_t { RP_CAMERA = 0, RP_LENS = 1, RP_COSINE = 2, RP_LIGHT = 3, RP_ROULETTE = 4, RP_GLOSS = 5 };
 
 struct RandAddr {
     uint32_t pixel, sample, path_depth;      // path_depth = path | depth << 16
@@ -200,6 +200,25 @@ __device__ inline float3x cosine_sample(float3x N, float e1, float e2) {
     float sn, cs; sincosf(ang, &sn, &cs);
     return normalize3((cs * s2) * u + (sn * s2) * v + s1 * N);
 }
+
+// Fresnel reflectance, full (non-Schlick) form of Material::fresnel (src/Material.h:47-55)
+__device__ inline float fresnel(float n1, float n2, float cosThetaI) {
+    const float n1CosTh = n1 * cosThetaI;
+    const float n1_n2SinTh = n1 * sinf(acosf(cosThetaI)) / n2;
+    const float n2CosTh = n2 * fmaxf(0.0f, sqrtf(1.0f - n1_n2SinTh * n1_n2SinTh));     // fmaxf(0, NaN) = 0: total internal reflection
+    const float Rs = (n1CosTh - n2CosTh) / (n1CosTh + n2CosTh);
+    return Rs * Rs;
+}
+
+// The IOR history a ray carries (Ray::IORList, src/Ray.h:43-51): 7 entries are enough for 2 initial + 5 refractions.
+struct IorStack {
+    float v[7];
+    int idx;
+    __device__ inline void init_camera() { v[0] = 1.0f; v[1] = 1.001f; idx = 1; for (int i = 2; i < 7; ++i) v[i] = 0.f; }   // IORList() + push(1.001)
+    __device__ inline float top() const { return v[idx]; }
+    __device__ inline void pop() { if (idx > 0) idx--; }
+    __device__ inline void push(float x) { if (idx < 6) ++idx; v[idx] = x; }
+};
 
 // ---------------------------------------------------------------------------------------------
 // Light sampling (Light::sampleLight of the three light classes).  One call of the reference's

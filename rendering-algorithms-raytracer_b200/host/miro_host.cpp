@@ -280,6 +280,7 @@ void Blinn::fill(miro_gpu_material& m) const {
     m.spec_exp = m_specExp; m.spec_amt = m_specAmt; m.emit_intensity = m_lightEmitted; copy3(m.le, m_Le);
     m.color_map = m_colorMap ? m_colorMap->ordinal : -1; m.alpha_map = m_alphaMap ? m_alphaMap->ordinal : -1;
     m.reflect_amt = m_reflectAmt; m.refract_amt = m_refractAmt; m.spec_gloss = m_specGloss;
+    m.ior[0] = m_ior[0]; m.ior[1] = m_ior[1]; m.ior[2] = m_ior[2]; m.disperse = m_disperse ? 1u : 0u;
     m.translucency = m_translucency; m.sample_env = m_sampleEnv ? 1u : 0u;
 }
 

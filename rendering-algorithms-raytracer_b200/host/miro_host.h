@@ -94,6 +94,7 @@ public:
     void setSampleEnv(bool b) { m_sampleEnv = b; }
     void setTranslucency(float t) { m_translucency = t; }
     void setRefractAmt(float r) { m_refractAmt = r; }
+    bool m_disperse = false;
     Texture* m_colorMap = nullptr;
     Texture* m_alphaMap = nullptr;
     bool m_sampleEnv = true;

@@ -9,7 +9,7 @@
 //          [noise f] [sampleenv 0|1] [envmap TEX exposure] [seed n]
 //   texture NAME file.{hdr,tga,ppm}
 //   material NAME lambert [kd r g b] [ka r g b] [colormap TEX]
-//   material NAME blinn   [kd ..] [ka ..] [ks ..] [specexp f] [specamt f] [ior f] [reflect f] [refract f]
+//   material NAME blinn   [kd ..] [ka ..] [ks ..] [specexp f] [specamt f] [ior f | ior_i i f] [reflect f] [refract f]
 //                         [gloss f] [translucency f] [emit intensity r g b] [colormap TEX] [alphamap TEX] [sampleenv 0|1]
 //   light point [pos x y z] [power p] [shadows 0|1]
 //   light rect  [v1 x y z] [v2 x y z] [v3 x y z] [power p] [samples n] [noise t] [shadows 0|1]
@@ -113,6 +113,8 @@ bool loadSceneScript(const char* file, const char* assetRoot, LoadedScene& out, 
                     else if (k == "specexp") { float f; ss >> f; m->setSpecExp(f); }
                     else if (k == "specamt") { float f; ss >> f; m->setSpecAmt(f); }
                     else if (k == "ior") { float f; ss >> f; m->setIor(f, 0); m->setIor(f, 1); m->setIor(f, 2); }
+                    else if (k == "ior_i") { int i; float f; ss >> i >> f; if (i < 0 || i > 2) return fail("ior_i: index must be 0..2"); m->setIor(f, i); }   // Blinn::setIor(ior, i)
+                    else if (k == "disperse") { int v; ss >> v; m->m_disperse = v != 0; }
                     else if (k == "reflect") { float f; ss >> f; m->setReflectAmt(f); }
                     else if (k == "refract") { float f; ss >> f; m->setRefractAmt(f); }
                     else if (k == "gloss") { float f; ss >> f; m->setReflectGloss(f); }

@@ -128,12 +128,14 @@ def test_motion_blur_and_instances_flatten():
     sc.close()
 
 
-def test_unsupported_features_fail_loudly():
-    # specular transport is outside the hot-path scope: the upload refuses it rather than rendering it wrong
-    sc = _script_scene("material m blinn kd .5 .5 .5 reflect 0.5\nmesh a a.obj\nobject a m\n", {"a": QUAD})
+def test_specular_material_fields_travel_in_the_desc():
+    # Blinn::setIor(ior, i) sets ONE entry (src/Blinn.h:38); the script's `ior` sets all three, `ior_i` one
+    sc = _script_scene("material m blinn kd .5 .5 .5 reflect 0.5 refract 0.25 gloss 0.9 ior_i 0 2.2 translucency 0.5\nmesh a a.obj\nobject a m\n", {"a": QUAD})
     d = sc.desc()
-    mats = np.ctypeslib.as_array(C.cast(d.materials, C.POINTER(C.c_float)), shape=(1, 32))
-    assert abs(mats[0, 18] - 0.5) < 1e-7       # reflect_amt travels in the desc; miro_gpu_upload_scene rejects it (GPU test)
+    m = d.materials[0]
+    assert abs(m.reflect_amt - 0.5) < 1e-7 and abs(m.refract_amt - 0.25) < 1e-7 and abs(m.spec_gloss - 0.9) < 1e-7
+    assert abs(m.ior[0] - 2.2) < 1e-6 and abs(m.ior[1] - 1.5) < 1e-6 and abs(m.ior[2] - 1.5) < 1e-6 and m.disperse == 0
+    assert abs(m.translucency - 0.5) < 1e-7    # travels in the desc; miro_gpu_upload_scene refuses it (GPU test)
     sc.close()
 
 

@@ -46,7 +46,7 @@ def test_c1_image_matches_reference_and_oracle():
     sc.close()
 
 
-@pytest.mark.parametrize("name", ["c4_cornell_pt", "c5_mb_instances"])
+@pytest.mark.parametrize("name", ["c4_cornell_pt", "c5_mb_instances", "c6_cornell_glass"])
 def test_image_matches_oracle_sample_by_sample(name):
     fx, sc = load(name)
     img = sc.render()
@@ -61,7 +61,7 @@ def test_image_matches_oracle_sample_by_sample(name):
     sc.close()
 
 
-@pytest.mark.parametrize("name,mean_tol", [("c4_cornell_pt", 0.08), ("c3_dome_pt", 0.02)])
+@pytest.mark.parametrize("name,mean_tol", [("c4_cornell_pt", 0.08), ("c3_dome_pt", 0.02), ("c6_cornell_glass", 0.02)])
 def test_path_traced_estimator_matches_reference(name, mean_tol):
     """RMSE(gpu_N, ref_converged) <= 1.1 * RMSE(ref_N, ref_converged) at equal spp."""
     fx, sc = load(name)
@@ -117,6 +117,19 @@ def test_adaptive_levels_and_lens():
     assert ok.mean() > 0.97
     assert abs(img.mean() - oimg.mean()) < 0.005 * oimg.mean()
     sc.close()
+
+
+def test_unsupported_materials_are_refused_at_upload():
+    """Translucency / alpha cut-outs / dispersion are outside the scope: the upload fails loudly instead of rendering them wrong."""
+    import miro_b200 as mb
+    fx = helpers.Fixture(helpers.fixture_path("c1_cornell"))
+    for extra in ("translucency 0.9", "disperse 1"):
+        script = fx.script.replace("material white lambert kd 0.8 0.8 0.8", "material white blinn kd 0.8 0.8 0.8 " + extra)
+        sc = fx.scene(script_override=script)
+        with pytest.raises(mb.MiroError) as e:
+            sc.attach(0)
+        assert "outside the hot-path scope" in str(e.value)
+        sc.close()
 
 
 def test_render_errors():

@@ -35,9 +35,10 @@ REFHIT = np.dtype([("t", "f4"), ("a", "f4"), ("b", "f4"), ("mesh", "i4"), ("tri"
 SCENES = {
     "c1_cornell": dict(render=True, stock=True, incoherent=0),
     "c2_explosion": dict(render=True, stock=True, incoherent=1 << 20),
-    "c5_mb_instances": dict(render=True, stock=False, incoherent=1 << 19, threads=8),
-    "c3_dome_pt": dict(render=True, stock=False, incoherent=0, threads=8, converged=32),
-    "c4_cornell_pt": dict(render=True, stock=False, incoherent=0, threads=8, converged=64),
+    "c5_mb_instances": dict(render=True, stock=False, incoherent=1 << 19, threads=1),
+    "c3_dome_pt": dict(render=True, stock=False, incoherent=0, threads=1, converged=32),
+    "c4_cornell_pt": dict(render=True, stock=False, incoherent=0, threads=1, converged=64),
+    "c6_cornell_glass": dict(render=True, stock=False, incoherent=0, threads=1, converged=16),
 }
 
 
