@@ -161,6 +161,30 @@ def reference_trace(fx, batches, threads, repeat):
     return t1 - t0, len(rays), "port", 1
 
 
+def render_leg(device):
+    """Scene::raytraceImage through miro_gpu_render (wavefront path tracer) on the C4 stand-in at 1024x1024, 16 paths,
+    4 indirect segments: rays = Scene::trace queries counted on the device.  Extra evidence beside the trace metric."""
+    import re
+    import torch
+    import helpers
+    path = helpers.fixture_path("c4_cornell_pt")
+    if path is None:
+        return None
+    fx = helpers.Fixture(path)
+    sc = fx.scene(script_override=re.sub(r"image \d+ \d+", "image 1024 1024", fx.script)).attach(device)
+    p = sc.render_params()
+    out = torch.zeros((p.height, p.width, 3), dtype=torch.float32, device="cuda")
+    sc.render_device(out.data_ptr()); torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(3):
+        sc.reset_counters()
+        t0 = time.time(); sc.render_device(out.data_ptr()); torch.cuda.synchronize(); best = min(best, time.time() - t0)
+    c = sc.counters(); rays = c["rays_closest"] + c["rays_any"]
+    sc.close()
+    return {"workload": "C4 stand-in (Cornell box, Blinn, rectangle light x4 samples, emitter) 1024x1024, 16 paths, maxBounces 5",
+            "rays": int(rays), "ms": best * 1e3, "Mrays_per_s": rays / best * 1e-6, "kernel_launches": int(c["kernel_launches"])}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -334,6 +358,10 @@ def main():
                                                "GBps": per_launch[i]["bytes"] / launch_ms[i] * 1e-6, "bytes_per_ray": per_launch[i]["bytes"] / N_BATCH,
                                                "nodes_per_ray": per_launch[i]["nodes"] / N_BATCH, "tris_per_ray": per_launch[i]["tris"] / N_BATCH}
                                               for i in range(3)]}}
+        line["roofline"]["frac_abi_node_layout"] = (per_launch[dom]["bytes"] + per_launch[dom]["nodes"] * (128 - NODE_BYTES)) / (launch_ms[dom] * 1e-3) * 1e-9 / hbm_peak
+        line["roofline"]["note"] = ("algorithmic bytes count the SHIPPED 64-byte device node; frac_abi_node_layout counts the 128-byte ABI node as kernel "
+                                    "versions <= v4 fetched it (comparable with profiles/bench_r1_v1..v4.json). The BVH is L2-resident: see traffic.")
+        line["render"] = render_leg(local)
         if world == 1 and not args.no_cpu:
             threads = min(os.cpu_count() or 1, 16)
             sample = [prim.reshape(HEIGHT, WIDTH)[::2, ::4].reshape(-1).copy(), inco[::8].copy(), shad[::8].copy()]
