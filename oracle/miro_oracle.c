@@ -70,6 +70,33 @@ static int mt_lane(const oray* r, const float* A, const float* B, const float* C
 static int traverse(const miro_gpu_scene_desc* s, int32_t root, const oray* r, float tMin, ohit* hit, int32_t cur_inst,
                     uint64_t* n_nodes, uint64_t* n_tris);
 
+/* Texture::getLookupAlpha at the hit's interpolated uv (src/Texture.cpp:12-41, src/BVH.cpp:1403-1421); 1 without an alpha map */
+static float hit_alpha(const miro_gpu_scene_desc* s, uint32_t prim, float a, float b) {
+    if (!s->prims) return 1.0f;
+    const miro_gpu_prim* pr = &s->prims[prim];
+    const int32_t am = s->materials[pr->material].alpha_map;
+    if (am < 0) return 1.0f;
+    const miro_gpu_texture* t = &s->textures[am];
+    if (t->channels != 4) return 1.0f;                    /* Texture::getPixel: alpha 1 for RGB / GRAYSCALE images */
+    float u = a, v = b;
+    if (pr->uv[0] != 0xffffffffu) {
+        const float c = 1.0f - a - b;
+        const float *t0 = s->uvs + (size_t)pr->uv[0] * 2, *t1 = s->uvs + (size_t)pr->uv[1] * 2, *t2 = s->uvs + (size_t)pr->uv[2] * 2;
+        u = t0[0] * c + t1[0] * a + t2[0] * b; v = t0[1] * c + t1[1] * a + t2[1] * b;
+    }
+    u = u - (float)(int)u; v = v - (float)(int)v;
+    if (u < 0.0f) u = u + 1.0f;
+    if (v < 0.0f) v = v + 1.0f;
+    v = 1.0f - v;
+    const float px = u * t->width, py = v * t->height;
+    const float x1 = floorf(px), y1 = floorf(py), dx = px - x1, dy = py - y1;
+    #define TEXA(X, Y) t->texels[((size_t)((Y) % t->height) * t->width + ((X) % t->width)) * 4 + 3]
+    const float q1 = TEXA((int)x1, (int)y1) * (1.0f - dx) + TEXA((int)x1 + 1, (int)y1) * dx;
+    const float q2 = TEXA((int)x1, (int)y1 + 1) * (1.0f - dx) + TEXA((int)x1 + 1, (int)y1 + 1) * dx;
+    #undef TEXA
+    return q1 * (1.0f - dy) + q2 * dy;
+}
+
 /* a leaf = one TriCache4 packet */
 static int intersect_leaf(const miro_gpu_scene_desc* s, int32_t ref, const oray* r, float tMin, ohit* hit, int32_t cur_inst,
                           uint64_t* n_nodes, uint64_t* n_tris) {
@@ -92,7 +119,7 @@ static int intersect_leaf(const miro_gpu_scene_desc* s, int32_t ref, const oray*
         return any;
     }
     const float tMax = hit->t;   /* all lanes of the packet see the tMax at entry */
-    float bt = MIRO_GPU_TMAX, ba = 0.f, bb = 0.f; int bl = -1;
+    float ct[4], ca[4], cb[4]; int cvalid[4] = {0, 0, 0, 0};     /* per-lane candidates of the packet */
     for (uint32_t i = 0; i < count; ++i) {
         float A[3], B[3], C[3], t, a, b;
         if (kind == MIRO_GPU_KIND_TRI) {
@@ -108,7 +135,20 @@ static int intersect_leaf(const miro_gpu_scene_desc* s, int32_t ref, const oray*
             }
         }
         (*n_tris)++;
-        if (mt_lane(r, A, B, C, tMin, tMax, &t, &a, &b) && t < bt) { bt = t; ba = a; bb = b; bl = (int)i; }
+        if (mt_lane(r, A, B, C, tMin, tMax, &t, &a, &b)) { ct[i] = t; ca[i] = a; cb[i] = b; cvalid[i] = 1; }
+    }
+    /* nearest valid lane (lowest index on ties); a lane whose alpha map says "cut out" (< 0.5) is dropped and the next
+     * nearest is tried (src/BVH.cpp:1387-1435) */
+    float bt = MIRO_GPU_TMAX, ba = 0.f, bb = 0.f; int bl = -1;
+    for (int tries = 0; tries < 4; ++tries) {
+        int li = -1; float lowest = MIRO_GPU_TMAX;
+        for (uint32_t i = 0; i < count; ++i) if (cvalid[i] && ct[i] < lowest) { lowest = ct[i]; li = (int)i; }
+        if (li < 0) break;
+        cvalid[li] = 0;
+        const uint32_t prim = (kind == MIRO_GPU_KIND_TRI ? 0u : s->n_tris) + first + (uint32_t)li;
+        if (hit_alpha(s, prim, ca[li], cb[li]) < 0.5f) continue;
+        bt = lowest; ba = ca[li]; bb = cb[li]; bl = li;
+        break;
     }
     if (bl >= 0 && bt < hit->t) {
         hit->t = bt; hit->a = ba; hit->b = bb; hit->inst = cur_inst;

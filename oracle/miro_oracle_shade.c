@@ -66,7 +66,7 @@ static float unit(uint32_t u) { return ((float)(u >> 8) + 0.5f) * (1.0f / 167772
 enum { RP_CAMERA = 0, RP_LENS = 1, RP_COSINE = 2, RP_LIGHT = 3, RP_ROULETTE = 4, RP_GLOSS = 5 };
 typedef struct { uint32_t pixel, sample, path_depth; uint64_t seed; } raddr;
 static void rand4(const raddr* a, uint32_t purpose, uint32_t light, uint32_t pass, uint32_t sample, uint32_t attempt, float out[4]) {
-    uint32_t c[4] = {a->pixel, a->sample, a->path_depth, (purpose << 28) | (light << 24) | (pass << 23) | ((sample & 0x7ffu) << 12) | (attempt & 0xfffu)};
+    uint32_t c[4] = {a->pixel, a->sample, a->path_depth, (purpose << 28) | ((pass >> 1) << 27) | (light << 24) | ((pass & 1u) << 23) | ((sample & 0x7ffu) << 12) | (attempt & 0xfffu)};
     philox4x32_10(c, (uint32_t)a->seed, (uint32_t)(a->seed >> 32));
     for (int k = 0; k < 4; ++k) out[k] = unit(c[k]);
 }
@@ -376,6 +376,14 @@ static v3 shade(octx* c, oray2* ray, const miro_gpu_hit* hit, uint32_t pixel, ui
             const v3 lightPower = sample_light(c, li, sf.P, theNormal, ray->time, rVec, &lightSpec, isSecondary, 0, &addr);
             if (m->spec_amt != 0.f) Ls = add(Ls, scl(mul(lightPower, ks), m->spec_amt * powf(lightSpec, m->spec_exp)));
             Ld = add(Ld, mul(lightPower, kd));
+        }
+        if (m->translucency > 0.01f) {                                        /* Blinn.cpp:223-236: lights seen from the back side */
+            v3 lightTotal = V(0, 0, 0);
+            for (uint32_t li = 0; li < s->n_lights; ++li) {
+                float lightSpec = 0.f;
+                lightTotal = add(lightTotal, sample_light(c, li, sf.P, scl(theNormal, -1.f), .001f, rVec, &lightSpec, isSecondary, 2, &addr));
+            }
+            Ld = add(Ld, mul(scl(lightTotal, m->translucency), kd));          /* "translucency" shares Ld's 1/rrWeight */
         }
     } else {
         int doEnv = 1;

@@ -65,6 +65,7 @@ struct miro_gpu_ctx {
     std::string error;
     bool has_scene = false;
     bool counting = false;
+    bool has_alpha = false;       // some material has an alpha map with an alpha channel: traversal kernels evaluate cut-outs
 
     // scene storage (device)
     std::vector<void*> scene_allocs;

@@ -58,7 +58,7 @@ void drain_timing(miro_gpu_ctx* ctx) {
 // (sample_E[i] = E.rgb, specular input) is added to the accumulator of its light loop (slot index in ray.user0).
 enum { TRACE_CLOSEST = 0, TRACE_ANY_BITS = 1, TRACE_ANY_ACCUM = 2 };
 
-template <int MODE, bool COUNT>
+template <int MODE, bool COUNT, bool ALPHA>
 __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS)
 k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const uint32_t* __restrict__ d_count, uint32_t chunk,
         miro_gpu_hit* __restrict__ hits, uint32_t* __restrict__ bits, const float4* __restrict__ sample_E, float4* __restrict__ slots,
@@ -135,7 +135,7 @@ k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const
                 const float4 w0 = __ldg(rays + (size_t)L.ray_idx * 3), w1 = __ldg(rays + (size_t)L.ray_idx * 3 + 1);
                 L.set_ray(w0.x, w0.y, w0.z, w1.x, w1.y, w1.z);
                 L.cur_inst = -1; L.cur = MIRO_GPU_CHILD_EMPTY;
-            } else finished = intersect_leaf<ANY, COUNT>(s, L, st, rays, c_tris, c_insts);     // true: any-hit found its occluder
+            } else finished = intersect_leaf<ANY, COUNT, ALPHA>(s, L, st, rays, c_tris, c_insts);     // true: any-hit found its occluder
             if (!finished && L.cur == MIRO_GPU_CHILD_EMPTY) { pop_next(L, st); finished = L.cur == MIRO_GPU_CHILD_EMPTY; }
         }
         if (finished) { L.done = true; pending = true; }
@@ -165,11 +165,16 @@ k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const
 template <int MODE>
 static int trace_grid(miro_gpu_ctx* ctx, size_t n) {
     // persistent grid: every SM holds as many blocks as fit (asked of the occupancy calculator once per kernel)
-    static int per_sm[2] = {0, 0};
-    int& v = per_sm[ctx->counting ? 1 : 0];
+    static int per_sm[4] = {0, 0, 0, 0};
+    int& v = per_sm[(ctx->counting ? 1 : 0) + (ctx->has_alpha ? 2 : 0)];
     if (v == 0) {
-        if (ctx->counting) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace<MODE, true>, TRACE_BLOCK, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace<MODE, false>, TRACE_BLOCK, 0);
+        if (ctx->has_alpha) {
+            if (ctx->counting) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace<MODE, true, true>, TRACE_BLOCK, 0);
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace<MODE, false, true>, TRACE_BLOCK, 0);
+        } else {
+            if (ctx->counting) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace<MODE, true, false>, TRACE_BLOCK, 0);
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace<MODE, false, false>, TRACE_BLOCK, 0);
+        }
         if (v <= 0) v = 1;
     }
     const size_t blocks_needed = (n + TRACE_BLOCK - 1) / TRACE_BLOCK;
@@ -186,8 +191,10 @@ static void launch_trace(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n
     const uint32_t chunk = n >= warps * 256 ? 64u : 32u;
     const float4* r = reinterpret_cast<const float4*>(d_rays);
     if (MODE == TRACE_ANY_BITS) cudaMemsetAsync(d_bits, 0, ((n + 31) / 32) * sizeof(uint32_t), ctx->stream);
-    if (ctx->counting) k_trace<MODE, true><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(ctx->scene, r, (uint32_t)n, d_count, chunk, d_hits, d_bits, d_E, d_slots, ctx->d_counters, ctx->d_work);
-    else k_trace<MODE, false><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(ctx->scene, r, (uint32_t)n, d_count, chunk, d_hits, d_bits, d_E, d_slots, ctx->d_counters, ctx->d_work);
+#define MIRO_LAUNCH(COUNT, ALPHA) k_trace<MODE, COUNT, ALPHA><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(ctx->scene, r, (uint32_t)n, d_count, chunk, d_hits, d_bits, d_E, d_slots, ctx->d_counters, ctx->d_work)
+    if (ctx->has_alpha) { if (ctx->counting) MIRO_LAUNCH(true, true); else MIRO_LAUNCH(false, true); }
+    else { if (ctx->counting) MIRO_LAUNCH(true, false); else MIRO_LAUNCH(false, false); }
+#undef MIRO_LAUNCH
     ctx->launches++;
 }
 void launch_trace_closest(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, const uint32_t* d_count, miro_gpu_hit* d_hits) {
@@ -340,8 +347,9 @@ int miro_gpu_upload_scene(miro_gpu_ctx* ctx, const miro_gpu_scene_desc* d) {
     for (uint32_t i = 0; i < d->n_materials; ++i) {
         const miro_gpu_material& m = d->materials[i];
         if (m.kind > MIRO_GPU_MAT_BLINN) return set_error(ctx, MIRO_GPU_EINVAL, "unknown material kind");
-        if (m.translucency > 0.01f || m.alpha_map >= 0 || m.disperse)
-            return set_error(ctx, MIRO_GPU_EUNSUPPORTED, "material " + std::to_string(i) + " uses translucency / alpha cut-outs / dispersion (outside the hot-path scope, SURVEY 8f)");
+        if (m.disperse)
+            return set_error(ctx, MIRO_GPU_EUNSUPPORTED, "material " + std::to_string(i) + " uses dispersion (outside the hot-path scope, SURVEY 8f)");
+        if (m.alpha_map >= (int32_t)d->n_textures) return set_error(ctx, MIRO_GPU_EINVAL, "material alpha_map out of range");
         if (m.color_map >= (int32_t)d->n_textures) return set_error(ctx, MIRO_GPU_EINVAL, "material color_map out of range");
     }
     for (uint32_t i = 0; i < d->n_tris + d->n_mbtris && d->prims; ++i)
@@ -392,6 +400,12 @@ int miro_gpu_upload_scene(miro_gpu_ctx* ctx, const miro_gpu_scene_desc* d) {
         tex[i].texels = p; tex[i].width = t.width; tex[i].height = t.height; tex[i].channels = t.channels; tex[i].pad = 0;
     }
     if ((rc = upload_array(ctx, tex.data(), tex.size(), &sh.textures))) return rc;
+    // alpha cut-outs are part of Scene::trace (intersect4, src/BVH.cpp:1401-1435): the traversal kernels get what they need
+    ctx->has_alpha = false;
+    for (uint32_t i = 0; i < d->n_materials; ++i) if (d->materials[i].alpha_map >= 0 && d->textures[d->materials[i].alpha_map].channels == 4) ctx->has_alpha = true;
+    static_assert(sizeof(AlphaTexture) == sizeof(DeviceTexture), "AlphaTexture mirrors DeviceTexture");
+    ctx->scene.alpha = AlphaData{sh.prims, sh.uvs, sh.materials, reinterpret_cast<const AlphaTexture*>(sh.textures)};
+    if (ctx->has_alpha && !d->prims) return set_error(ctx, MIRO_GPU_EINVAL, "alpha-mapped materials need the prims table");
     // dome lights: importance tables (DomeLight::setTexture, src/DomeLight.cpp:8-78)
     std::vector<DeviceDome> domes(std::max<uint32_t>(d->n_lights, 1));
     memset(domes.data(), 0, domes.size() * sizeof(DeviceDome));

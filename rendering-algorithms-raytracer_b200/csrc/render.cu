@@ -128,11 +128,13 @@ struct ShadeCtx {
 
 // Runs every light loop of one shading event; F(light, pass, normal, rVec, is_secondary, with_spec) is called once per loop.
 template <class F>
-__device__ __forceinline__ void for_each_light_loop(const DeviceShading& sh, bool pt_last_bounce, bool blinn, bool secondary, F&& f) {
+__device__ __forceinline__ void for_each_light_loop(const DeviceShading& sh, bool pt_last_bounce, bool blinn, bool secondary, bool translucent, F&& f) {
     if (pt_last_bounce)                                  // Blinn::calculatePathTracing, last bounce (Blinn.cpp:76-87): rVec = 0, isSecondary = true
         for (uint32_t li = 0; li < sh.n_lights; ++li) f(li, 1u, true, false);
     for (uint32_t li = 0; li < sh.n_lights; ++li)        // Lambert.cpp:41-46 (isSecondary defaults to false) / Blinn.cpp:212-221
         f(li, 0u, blinn ? secondary : false, blinn);
+    if (translucent)                                     // Blinn.cpp:223-236: the lights seen from the back side (normal -N, time .001)
+        for (uint32_t li = 0; li < sh.n_lights; ++li) f(li, 2u, secondary, false);
 }
 
 template <bool PRIMARY>
@@ -148,7 +150,8 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
         uint32_t pixel = 0, sample = 0, path = 0, gi = 0, bounces = 0, vertex = 0;
         float3x thr = f3(0, 0, 0), thr_d = f3(0, 0, 0), o = f3(0, 0, 0), d = f3(0, 0, 1), bounce_dir = f3(0, 0, 0), bounce_thr = f3(0, 0, 0);
         float time = 0.f;
-        bool emit_bounce = false, pt_last = false, blinn = false, diffuse = true;
+        bool emit_bounce = false, pt_last = false, blinn = false, diffuse = true, translucent = false;
+        float transl = 0.f;
         uint32_t bounce_flags = 0;
         IorStack ior; ior.init_camera();
         ShadeCtx c{};
@@ -227,6 +230,7 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
                     const float3x ks = f3(m->ks[0], m->ks[1], m->ks[2]);
                     const float3x Le = f3(m->le[0], m->le[1], m->le[2]);
                     diffuse = rr.x <= rrWeight;
+                    transl = m->translucency; translucent = diffuse && transl > 0.01f;
                     thr_d = thr * rrWeightRecip;                       // (Ld + Ls) / rrWeight, Blinn.cpp:335
                     c.tks = thr_d * ks * m->spec_amt;
                     float3x constant = thr_d * ka + thr * Le;          // "Ld += m_ka" is on both branches; "+ m_Le" is unscaled
@@ -268,9 +272,9 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
                     (void)base_flags;
                     add_rgb(level_sum, pixel, constant);
                 }
-                if (diffuse) for_each_light_loop(sh, pt_last, blinn, c.is_secondary, [&](uint32_t li, uint32_t pass, bool secondary_, bool with_spec) {
+                if (diffuse) for_each_light_loop(sh, pt_last, blinn, c.is_secondary, translucent, [&](uint32_t li, uint32_t pass, bool secondary_, bool with_spec) {
                     int lit = 0;
-                    light_loop(sh, li, c.P, c.N, with_spec ? c.rVec : f3(0, 0, 0), secondary_, pass, addr, [&](const LightSample&) { ++lit; });
+                    light_loop(sh, li, c.P, pass == 2u ? -c.N : c.N, with_spec ? c.rVec : f3(0, 0, 0), secondary_, pass, addr, [&](const LightSample&) { ++lit; });
                     if (lit) { n_shadow += lit; ++n_slots; }
                 });
             }
@@ -307,22 +311,23 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
         if (n_slots == 0) continue;
         if (b_shadow + (uint32_t)n_shadow > shadow_cap || b_slots + (uint32_t)n_slots > slot_cap) continue;   // cannot happen: capacities are worst case
         uint32_t w_shadow = b_shadow, w_slot = b_slots;
-        for_each_light_loop(sh, pt_last, blinn, c.is_secondary, [&](uint32_t li, uint32_t pass, bool secondary, bool with_spec) {
+        for_each_light_loop(sh, pt_last, blinn, c.is_secondary, translucent, [&](uint32_t li, uint32_t pass, bool secondary, bool with_spec) {
             const uint32_t slot = w_slot;
             int lit = 0;
             const bool shadows = sh.lights[li].cast_shadows != 0;
-            const int done = light_loop(sh, li, c.P, c.N, with_spec ? c.rVec : f3(0, 0, 0), secondary, pass, addr, [&](const LightSample& ls) {
+            const float ray_time = pass == 2u ? .001f : c.time;           // the translucency loop passes .001f as the time (Blinn.cpp:232)
+            const int done = light_loop(sh, li, c.P, pass == 2u ? -c.N : c.N, with_spec ? c.rVec : f3(0, 0, 0), secondary, pass, addr, [&](const LightSample& ls) {
                 float4* o4 = reinterpret_cast<float4*>(q.sh_rays + w_shadow);
                 // a light that casts no shadows gets an empty interval: never occluded
                 __stcs(o4 + 0, make_float4(c.P.x, c.P.y, c.P.z, shadows ? ls.tmin : 1.f));
                 __stcs(o4 + 1, make_float4(ls.dir.x, ls.dir.y, ls.dir.z, shadows ? ls.tmax : 0.f));
-                __stcs(o4 + 2, make_float4(c.time, 0.f, __uint_as_float(slot), 0.f));
+                __stcs(o4 + 2, make_float4(ray_time, 0.f, __uint_as_float(slot), 0.f));
                 __stcs(q.sh_E + w_shadow, make_float4(ls.E.x, ls.E.y, ls.E.z, ls.spec));
                 ++w_shadow; ++lit;
             });
             if (lit) {
                 Slot* sp = q.slots + slot;
-                const float3x tkd = thr_d * c.kd;
+                const float3x tkd = pass == 2u ? thr_d * c.kd * transl : thr_d * c.kd;
                 sp->acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 sp->tkd = make_float4(tkd.x, tkd.y, tkd.z, __uint_as_float(pixel));
                 sp->tks = with_spec ? make_float4(c.tks.x, c.tks.y, c.tks.z, c.spec_exp) : make_float4(0.f, 0.f, 0.f, 1.f);
@@ -517,7 +522,9 @@ extern "C" int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, co
     // ---- queue capacities: worst case per path
     size_t light_samples = 0;
     for (const miro_gpu_light& l : ctx->host_lights) light_samples += (size_t)std::max(1, l.num_samples);
-    const size_t loops = rp->path_trace ? 2 : 1;
+    bool any_translucent = false;
+    for (const miro_gpu_material& m : ctx->host_materials) if (m.kind == MIRO_GPU_MAT_BLINN && m.translucency > 0.01f) any_translucent = true;
+    const size_t loops = (rp->path_trace ? 2 : 1) + (any_translucent ? 1 : 0);
     const size_t shadow_per_path = std::max<size_t>(1, loops * light_samples), slots_per_path = std::max<size_t>(1, loops * ctx->host_lights.size());
     const size_t bytes_per_path = 2 * (48 + 16 + (P.has_specular ? 32 : 0)) + 20 + shadow_per_path * 64 + slots_per_path * 64 + (48 + 20);
     size_t paths = std::min<size_t>(WAVE_PATHS_MAX, std::max<size_t>(WAVE_BYTES_BUDGET / bytes_per_path, (size_t)rp->num_paths));

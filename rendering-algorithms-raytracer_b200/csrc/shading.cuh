@@ -44,7 +44,7 @@ struct RandAddr {
     uint64_t seed;
 };
 __host__ __device__ inline Rand4 rand4(const RandAddr& a, uint32_t purpose, uint32_t light, uint32_t pass, uint32_t sample, uint32_t attempt) {
-    uint32_t c[4] = {a.pixel, a.sample, a.path_depth, (purpose << 28) | (light << 24) | (pass << 23) | ((sample & 0x7ffu) << 12) | (attempt & 0xfffu)};
+    uint32_t c[4] = {a.pixel, a.sample, a.path_depth, (purpose << 28) | ((pass >> 1) << 27) | (light << 24) | ((pass & 1u) << 23) | ((sample & 0x7ffu) << 12) | (attempt & 0xfffu)};
     philox4x32_10(c, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
     Rand4 r; r.x = u32_to_unit(c[0]); r.y = u32_to_unit(c[1]); r.z = u32_to_unit(c[2]); r.w = u32_to_unit(c[3]);
     return r;

@@ -72,7 +72,18 @@ constexpr int SMEM_STACK = MIRO_SMEM_STACK;   // per-thread stack entries kept i
 constexpr int LMEM_STACK = 96 - MIRO_SMEM_STACK;          // overflow entries (local memory, touched only by very deep trees)
 constexpr int32_t STACK_SENTINEL = 0x7ffffffe;   // "leave instance" marker
 
+// What the traversal needs to evaluate alpha cut-outs (intersect4's alpha-map test, src/BVH.cpp:1401-1435); all NULL
+// when no material has an alpha map (the kernels are then instantiated without the test).
+struct AlphaTexture { const float* texels; int32_t width, height, channels, pad; };
+struct AlphaData {
+    const miro_gpu_prim* prims;
+    const float* uvs;
+    const miro_gpu_material* materials;
+    const AlphaTexture* textures;
+};
+
 struct DeviceScene {
+    AlphaData alpha;
     const float4* nodes;     // DeviceNode: 4 x float4 per node (the 64-byte compressed form, see compress_node)
     const float4* tris;      // 3 x float4 per triangle
     const float4* mbtris;    // 6 x float4 per motion-blur triangle
@@ -355,8 +366,36 @@ __device__ __forceinline__ void node_step(const DeviceScene& s, Lane& L, Travers
     else pop_next(L, st);
 }
 
+// Texture::getLookupAlpha (src/Texture.cpp:12-41) for the hit (prim, a, b): the bilinearly filtered alpha channel at the
+// interpolated uv; 1 when the primitive's material has no alpha map (or the map has no alpha channel, Texture.cpp:109-111).
+__device__ __forceinline__ float hit_alpha(const AlphaData& A, uint32_t prim, float a, float b) {
+    const miro_gpu_prim* pr = A.prims + prim;
+    const int32_t am = A.materials[__ldg(&pr->material)].alpha_map;
+    if (am < 0) return 1.0f;
+    const AlphaTexture t = A.textures[am];
+    if (t.channels != 4) return 1.0f;
+    float u = a, v = b;
+    const uint32_t i0 = __ldg(&pr->uv[0]);
+    if (i0 != 0xffffffffu) {
+        const float c = 1.0f - a - b;
+        const float* t0 = A.uvs + (size_t)i0 * 2; const float* t1 = A.uvs + (size_t)__ldg(&pr->uv[1]) * 2; const float* t2 = A.uvs + (size_t)__ldg(&pr->uv[2]) * 2;
+        u = __ldg(t0) * c + __ldg(t1) * a + __ldg(t2) * b;
+        v = __ldg(t0 + 1) * c + __ldg(t1 + 1) * a + __ldg(t2 + 1) * b;
+    }
+    u = u - float(int(u)); v = v - float(int(v));
+    if (u < 0.0f) u = u + 1.0f;
+    if (v < 0.0f) v = v + 1.0f;
+    v = 1.0f - v;
+    const float px = u * t.width, py = v * t.height;
+    const float x1 = floorf(px), y1 = floorf(py), dx = px - x1, dy = py - y1;
+    auto texel = [&](int x, int y) { x = x % t.width; y = y % t.height; return __ldg(t.texels + ((size_t)y * t.width + x) * 4 + 3); };
+    const float q1 = texel((int)x1, (int)y1) * (1.0f - dx) + texel((int)x1 + 1, (int)y1) * dx;
+    const float q2 = texel((int)x1, (int)y1 + 1) * (1.0f - dx) + texel((int)x1 + 1, (int)y1 + 1) * dx;
+    return q1 * (1.0f - dy) + q2 * dy;
+}
+
 // Leaf phase.  Returns true when an ANY query has found its occluder.
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, bool ALPHA>
 __device__ __forceinline__ bool intersect_leaf(const DeviceScene& s, Lane& L, TraversalStack& st, const float4* __restrict__ rays,
                                                uint32_t& n_tris, uint32_t& n_insts) {
     const uint32_t u = (uint32_t)L.cur;
@@ -368,7 +407,9 @@ __device__ __forceinline__ bool intersect_leaf(const DeviceScene& s, Lane& L, Tr
             const float4* t = s.tris + (size_t)(first + i) * 3;
             const float4 p0 = __ldg(t), p1 = __ldg(t + 1), p2 = __ldg(t + 2);
             if (COUNT) ++n_tris;
-            if (intersect_tri(L.r, L.tmin, L.hit.t, p0, p1, p2, L.hit.t, L.hit.a, L.hit.b)) {
+            float ht, ha, hb;
+            if (intersect_tri(L.r, L.tmin, L.hit.t, p0, p1, p2, ht, ha, hb) && (!ALPHA || hit_alpha(s.alpha, first + i, ha, hb) >= 0.5f)) {
+                L.hit.t = ht; L.hit.a = ha; L.hit.b = hb;
                 L.hit.prim = (int32_t)(first + i); L.hit.inst = L.cur_inst;
                 if (ANY) return true;
             }
@@ -384,7 +425,9 @@ __device__ __forceinline__ bool intersect_leaf(const DeviceScene& s, Lane& L, Tr
             p0.x = w1 * b0.x + w0 * a0.x; p0.y = w1 * b0.y + w0 * a0.y; p0.z = w1 * b0.z + w0 * a0.z;
             p1.x = w1 * b1.x + w0 * a1.x; p1.y = w1 * b1.y + w0 * a1.y; p1.z = w1 * b1.z + w0 * a1.z;
             p2.x = w1 * b2.x + w0 * a2.x; p2.y = w1 * b2.y + w0 * a2.y; p2.z = w1 * b2.z + w0 * a2.z;
-            if (intersect_tri(L.r, L.tmin, L.hit.t, p0, p1, p2, L.hit.t, L.hit.a, L.hit.b)) {
+            float ht, ha, hb;
+            if (intersect_tri(L.r, L.tmin, L.hit.t, p0, p1, p2, ht, ha, hb) && (!ALPHA || hit_alpha(s.alpha, s.n_tris + first + i, ha, hb) >= 0.5f)) {
+                L.hit.t = ht; L.hit.a = ha; L.hit.b = hb;
                 L.hit.prim = (int32_t)(s.n_tris + first + i); L.hit.inst = L.cur_inst;
                 if (ANY) return true;
             }

@@ -71,3 +71,16 @@ def test_motion_blur_instances_image_matches_reference():
     blk = lambda a: a.reshape(32, 8, 32, 8, 3).mean(axis=(1, 3))
     assert np.abs(blk(img) - blk(ref)).mean() < 0.01
     sc.close()
+
+
+def test_alpha_mapped_translucent_foliage_matches_reference():
+    """alpha cut-outs (primary and shadow rays) + translucency, deterministic except for the pixel jitter."""
+    fx, sc = load("c7_foliage")
+    img, rays = helpers.oracle_render(sc)
+    ref = fx.radiance
+    assert abs(rays - ref_rays(fx)) <= 2e-3 * ref_rays(fx)
+    assert abs(img.mean() - ref.mean()) <= 0.005 * ref.mean()
+    blk = lambda a: a.reshape(32, 8, 32, 8, 3).mean(axis=(1, 3))
+    assert np.abs(blk(img) - blk(ref)).mean() < 0.004
+    assert (np.abs(img - ref).max(axis=2) < 0.02).mean() > 0.85
+    sc.close()

@@ -5,7 +5,7 @@ import pytest
 
 import helpers
 
-SCENES = ["c1_cornell", "c2_explosion", "c5_mb_instances"]
+SCENES = ["c1_cornell", "c2_explosion", "c5_mb_instances", "c7_foliage"]      # c7: alpha cut-outs inside Scene::trace
 
 
 @pytest.fixture(scope="module", params=SCENES)

@@ -46,7 +46,7 @@ def test_c1_image_matches_reference_and_oracle():
     sc.close()
 
 
-@pytest.mark.parametrize("name", ["c4_cornell_pt", "c5_mb_instances", "c6_cornell_glass"])
+@pytest.mark.parametrize("name", ["c4_cornell_pt", "c5_mb_instances", "c6_cornell_glass", "c7_foliage"])
 def test_image_matches_oracle_sample_by_sample(name):
     fx, sc = load(name)
     img = sc.render()
@@ -120,10 +120,10 @@ def test_adaptive_levels_and_lens():
 
 
 def test_unsupported_materials_are_refused_at_upload():
-    """Translucency / alpha cut-outs / dispersion are outside the scope: the upload fails loudly instead of rendering them wrong."""
+    """Dispersion is outside the scope: the upload fails loudly instead of rendering it wrong."""
     import miro_b200 as mb
     fx = helpers.Fixture(helpers.fixture_path("c1_cornell"))
-    for extra in ("translucency 0.9", "disperse 1"):
+    for extra in ("disperse 1",):
         script = fx.script.replace("material white lambert kd 0.8 0.8 0.8", "material white blinn kd 0.8 0.8 0.8 " + extra)
         sc = fx.scene(script_override=script)
         with pytest.raises(mb.MiroError) as e:

@@ -38,6 +38,7 @@ SCENES = {
     "c5_mb_instances": dict(render=True, stock=False, incoherent=1 << 19, threads=1),
     "c3_dome_pt": dict(render=True, stock=False, incoherent=0, threads=1, converged=32),
     "c4_cornell_pt": dict(render=True, stock=False, incoherent=0, threads=1, converged=64),
+    "c7_foliage": dict(render=True, stock=False, incoherent=1 << 18, threads=1),
     "c6_cornell_glass": dict(render=True, stock=False, incoherent=0, threads=1, converged=16),
 }
 
