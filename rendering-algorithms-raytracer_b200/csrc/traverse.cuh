@@ -327,18 +327,21 @@ __device__ __forceinline__ void node_step(const DeviceScene& s, Lane& L, Travers
     const float ax = __uint_as_float((ex & 0xffu) << 23) * L.r.ix, bx = __fmaf_rn(h0.x, L.r.ix, -L.oix);
     const float ay = __uint_as_float((ex & 0xff00u) << 15) * L.r.iy, by = __fmaf_rn(h0.y, L.r.iy, -L.oiy);
     const float az = __uint_as_float((ex & 0xff0000u) << 7) * L.r.iz, bz = __fmaf_rn(h0.z, L.r.iz, -L.oiz);
+    // near / far planes by the sign of the ray direction (the same for all four children): whole-word selects, so the
+    // per-child test needs no min/max of plane pairs
     const uint32_t lx = __float_as_uint(q0.x), ly = __float_as_uint(q0.y), lz = __float_as_uint(q0.z);
     const uint32_t hx = __float_as_uint(q0.w), hy = __float_as_uint(q1.x), hz = __float_as_uint(q1.y);
+    const bool ngx = L.r.ix < 0.f, ngy = L.r.iy < 0.f, ngz = L.r.iz < 0.f;
+    const uint32_t nx = ngx ? hx : lx, fx = ngx ? lx : hx;
+    const uint32_t ny = ngy ? hy : ly, fy = ngy ? ly : hy;
+    const uint32_t nz = ngz ? hz : lz, fz = ngz ? lz : hz;
     const int INF_KEY = 0x7fffffff;
     const float tmax = L.hit.t;
     int k0, k1, k2, k3;
 #define MIRO_BYTE(W, C) ((float)(((W) >> (8 * (C))) & 0xffu))
 #define MIRO_SLAB(C, CH, KEY) { \
-    const float t0x = __fmaf_rn(MIRO_BYTE(lx, C), ax, bx), t1x = __fmaf_rn(MIRO_BYTE(hx, C), ax, bx); \
-    const float t0y = __fmaf_rn(MIRO_BYTE(ly, C), ay, by), t1y = __fmaf_rn(MIRO_BYTE(hy, C), ay, by); \
-    const float t0z = __fmaf_rn(MIRO_BYTE(lz, C), az, bz), t1z = __fmaf_rn(MIRO_BYTE(hz, C), az, bz); \
-    const float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), L.tmin)); \
-    const float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax)) * 1.0000003f; \
+    const float tn = fmaxf(fmaxf(__fmaf_rn(MIRO_BYTE(nx, C), ax, bx), __fmaf_rn(MIRO_BYTE(ny, C), ay, by)), fmaxf(__fmaf_rn(MIRO_BYTE(nz, C), az, bz), L.tmin)); \
+    const float tf = fminf(fminf(__fmaf_rn(MIRO_BYTE(fx, C), ax, bx), __fmaf_rn(MIRO_BYTE(fy, C), ay, by)), fminf(__fmaf_rn(MIRO_BYTE(fz, C), az, bz), tmax)) * 1.0000003f; \
     KEY = (tn <= tf && __float_as_int(CH) != MIRO_GPU_CHILD_EMPTY) ? ((float_key(tn) & ~3) | C) : INF_KEY; }
     MIRO_SLAB(0, chf.x, k0) MIRO_SLAB(1, chf.y, k1) MIRO_SLAB(2, chf.z, k2) MIRO_SLAB(3, chf.w, k3)
 #undef MIRO_SLAB
