@@ -119,30 +119,14 @@ class ClockSampler(threading.Thread):
 
 
 def write_obj_scene(fx, tmp):
-    """Materialise the fixture's geometry as OBJ + script so the reference binary can load it with its own loader."""
-    script = fx.script
-    for k, name in enumerate(fx.names):
-        m = fx.mesh(k)
-        path = os.path.join(tmp, name + ".obj")
-        with open(path, "w") as f:
-            for v in m["vertices"]:
-                f.write("v %.9g %.9g %.9g\n" % tuple(v))
-            for t in m["vidx"]:
-                f.write("f %d %d %d\n" % (t[0] + 1, t[1] + 1, t[2] + 1))
-        lines = []
-        for line in script.splitlines():
-            tok = line.split()
-            if len(tok) >= 3 and tok[0] == "mesh" and tok[1] == name:
-                line = "mesh %s %s" % (name, path)
-            lines.append(line)
-        script = "\n".join(lines) + "\n"
-    sp = os.path.join(tmp, "scene.miro")
-    open(sp, "w").write(script)
-    return sp
+    import helpers
+    return helpers.write_obj_scene(fx, tmp)
 
 
-def reference_trace(fx, batches, threads, repeat):
-    """Time the reference's own Scene::trace (oracle/_ref/miro_ref) on the host cores; falls back to the oracle port."""
+def reference_trace(fx, batches, threads, repeat, warmup=0, mean=False):
+    """Time the reference's own Scene::trace (oracle/_ref/miro_ref) on the host cores — ONE process: scene load and BVH
+    build once, then `warmup` untimed and `repeat` timed passes over the batch (best, or mean when `mean`).
+    Falls back to the oracle port when the reference binary is absent."""
     import helpers
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "miro_ref")
     rays = np.concatenate(batches)
@@ -150,15 +134,19 @@ def reference_trace(fx, batches, threads, repeat):
         with tempfile.TemporaryDirectory() as tmp:
             sp = write_obj_scene(fx, tmp)
             rp = os.path.join(tmp, "rays.bin"); rays.tofile(rp)
-            p = subprocess.run([ref_bin, "--scene", sp, "--assets", tmp, "--threads", str(threads), "--repeat", str(repeat), "--trace", rp],
+            p = subprocess.run([ref_bin, "--scene", sp, "--assets", tmp, "--threads", str(threads), "--repeat", str(repeat), "--warmup", str(warmup), "--trace", rp],
                                stderr=subprocess.PIPE, text=True)
             ev = [json.loads(l) for l in p.stderr.splitlines() if l.startswith("{")]
             tr = [e for e in ev if e.get("event") == "trace"]
             if p.returncode == 0 and tr:
-                return tr[0]["seconds"], len(rays), "reference", tr[0]["threads"]
+                return tr[0]["mean_seconds" if mean else "seconds"], len(rays), "reference", tr[0]["threads"]
     sc = fx.scene()
-    t0 = time.time(); helpers.oracle_trace_closest(sc, rays); t1 = time.time()
-    return t1 - t0, len(rays), "port", 1
+    ts = []
+    for it in range(-warmup, repeat):
+        t0 = time.time(); helpers.oracle_trace_closest(sc, rays); t1 = time.time()
+        if it >= 0:
+            ts.append(t1 - t0)
+    return (float(np.mean(ts)) if mean else min(ts)), len(rays), "port", 1
 
 
 def render_leg(device):
@@ -221,13 +209,8 @@ def main():
         sample = [prim.reshape(HEIGHT, WIDTH)[::2, ::4].reshape(-1).copy(), inco[::stride].copy()]
         ohits, _ = helpers.oracle_trace_closest(sc_cpu, sample[1])
         sample.append(shadow_rays(sample[1], ohits, LIGHT_POS))
-        for _ in range(args.warmup):
-            reference_trace(fx, sample, threads, 1)
-        ts = []
-        for _ in range(args.steps):
-            sec, n, kind, used = reference_trace(fx, sample, threads, 1)
-            ts.append(sec)
-        sec = float(np.mean(ts)); n = sum(len(b) for b in sample)
+        # K timed + W untimed passes inside one run of the reference binary (scene load / BVH build outside the timed region)
+        sec, n, kind, used = reference_trace(fx, sample, threads, max(args.steps, 1), max(args.warmup, 0), mean=True)
         val = n / sec * 1e-6
         line = {"impl": "reference", "metric": "Mrays/s", "value": val, "unit": "Mrays/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -318,11 +318,12 @@ void dumpPrimary(const std::string& out) {
 }
 
 // --trace: Scene::trace (Scene.cpp:295) over a caller-supplied ray buffer.
-double traceRays(const std::string& in, const std::string& out, int threads, int repeat) {
+double g_traceMean = 0.0;       // mean seconds over the timed repeats of the last traceRays call
+double traceRays(const std::string& in, const std::string& out, int threads, int repeat, int warmup) {
     std::vector<RayRec> rays = readVec<RayRec>(in);
     std::vector<RefHit> hits(rays.size());
-    double best = 1e30;
-    for (int it = 0; it < repeat; ++it) {
+    double best = 1e30, sum = 0.0;
+    for (int it = -warmup; it < repeat; ++it) {
         double t0 = omp_get_wtime();
         #pragma omp parallel for schedule(dynamic, 1024) num_threads(threads)
         for (long i = 0; i < (long)rays.size(); i++) {
@@ -333,8 +334,10 @@ double traceRays(const std::string& in, const std::string& out, int threads, int
             bool hit = g_scene->trace(tid, h, r, q.tmin);
             hits[i] = toRefHit(hit, h);
         }
-        double t1 = omp_get_wtime(); if (t1 - t0 < best) best = t1 - t0;
+        double t1 = omp_get_wtime();
+        if (it >= 0) { if (t1 - t0 < best) best = t1 - t0; sum += t1 - t0; }
     }
+    g_traceMean = sum / (repeat > 0 ? repeat : 1);
     if (!out.empty()) writeVec(out, hits);
     return best;
 }
@@ -445,7 +448,7 @@ void dumpQBVH(const std::string& path) {
 
 int main(int argc, char** argv) {
     std::string scene, dumpPrim, traceIn, traceOut, floatOut, ppmOut, meshDir, qbvhOut, texDir;
-    int threads = 1, repeat = 1; bool stock = false, doFloat = false;
+    int threads = 1, repeat = 1, warmup = 0; bool stock = false, doFloat = false;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         #define NEXT() (i + 1 < argc ? std::string(argv[++i]) : (die("missing value for " + a), std::string()))
@@ -453,6 +456,7 @@ int main(int argc, char** argv) {
         else if (a == "--assets") g_assetRoot = NEXT();
         else if (a == "--threads") threads = atoi(NEXT().c_str());
         else if (a == "--repeat") repeat = atoi(NEXT().c_str());
+        else if (a == "--warmup") warmup = atoi(NEXT().c_str());
         else if (a == "--dump-primary") dumpPrim = NEXT();
         else if (a == "--trace") { traceIn = NEXT(); }
         else if (a == "--hits") traceOut = NEXT();
@@ -479,9 +483,10 @@ int main(int argc, char** argv) {
     if (!dumpPrim.empty()) dumpPrimary(dumpPrim);
     if (!traceIn.empty()) {
         resetTraceCalls();
-        double s = traceRays(traceIn, traceOut, threads, repeat);
-        unsigned long long n = traceCalls() / (unsigned long long)repeat;
-        fprintf(stderr, "{\"event\":\"trace\",\"rays\":%llu,\"seconds\":%.6f,\"mrays_per_s\":%.4f,\"threads\":%d}\n", n, s, n / s * 1e-6, threads);
+        double s = traceRays(traceIn, traceOut, threads, repeat, warmup);
+        unsigned long long n = traceCalls() / (unsigned long long)(repeat + warmup);
+        fprintf(stderr, "{\"event\":\"trace\",\"rays\":%llu,\"seconds\":%.6f,\"mean_seconds\":%.6f,\"mrays_per_s\":%.4f,\"threads\":%d,\"repeat\":%d,\"warmup\":%d}\n",
+                n, s, g_traceMean, n / s * 1e-6, threads, repeat, warmup);
     }
     if (doFloat) {
         resetTraceCalls();

@@ -146,3 +146,26 @@ def oracle_render(scene, params=None, camera=None, mask=None):
     m = np.ascontiguousarray(mask, np.uint8) if mask is not None else None
     n = L.oracle_render(C.byref(d), C.byref(c), C.byref(p), img.ctypes.data, m.ctypes.data if m is not None else None)
     return img, int(n)
+
+
+def write_obj_scene(fx, tmp):
+    """Materialise the fixture's geometry as OBJ + script so the reference binary can load it with its own loader."""
+    script = fx.script
+    for k, name in enumerate(fx.names):
+        m = fx.mesh(k)
+        path = os.path.join(tmp, name + ".obj")
+        with open(path, "w") as f:
+            for v in m["vertices"]:
+                f.write("v %.9g %.9g %.9g\n" % tuple(v))
+            for t in m["vidx"]:
+                f.write("f %d %d %d\n" % (t[0] + 1, t[1] + 1, t[2] + 1))
+        lines = []
+        for line in script.splitlines():
+            tok = line.split()
+            if len(tok) >= 3 and tok[0] == "mesh" and tok[1] == name:
+                line = "mesh %s %s" % (name, path)
+            lines.append(line)
+        script = "\n".join(lines) + "\n"
+    sp = os.path.join(tmp, "scene.miro")
+    open(sp, "w").write(script)
+    return sp

@@ -174,3 +174,23 @@ dist.destroy_process_group(); sc.close()
     whole = sc.render()
     assert np.allclose(np.load(out), whole, rtol=1e-4, atol=1e-5)
     sc.close()
+
+
+def test_headless_cli_writes_the_reference_ppm(tmp_path):
+    """miro_render scene.miro out.ppm (SURVEY 8f-4): OBJ loader + script + GPU render + Image::Map + bottom-up PPM, against the
+    8-bit image of the reference's stock render (+-1 LSB except crack / tie pixels)."""
+    import os, subprocess
+    exe = os.path.join(helpers.ROOT, "rendering-algorithms-raytracer_b200", "miro_render")
+    if not os.path.exists(exe):
+        pytest.skip("miro_render not built")
+    fx = helpers.Fixture(helpers.fixture_path("c1_cornell"))
+    sp = helpers.write_obj_scene(fx, str(tmp_path))
+    out = tmp_path / "o.ppm"
+    p = subprocess.run([exe, sp, str(out), "--assets", str(tmp_path), "--stats"], stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr
+    assert '"rays":' in p.stderr
+    raw = open(out, "rb").read().split(b"\n", 3)
+    w, h = map(int, raw[1].split())
+    img = np.frombuffer(raw[3], np.uint8).reshape(h, w, 3)[::-1]       # PPM rows are top-down
+    d8 = np.abs(img.astype(int) - fx.image8.astype(int)).max(axis=2)
+    assert (d8 <= 1).mean() > 0.998
