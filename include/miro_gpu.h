@@ -124,14 +124,14 @@ typedef struct miro_gpu_material {  /* 128 bytes */
     float emit_intensity;           /* Blinn::m_lightEmitted */
     float le[3];                    /* Blinn::m_Le           */
     int32_t color_map;              /* texture index or -1   */
-    int32_t alpha_map;              /* -1 (alpha cut-outs are outside the scope: EUNSUPPORTED) */
+    int32_t alpha_map;              /* texture index or -1: hits where its alpha channel reads < 0.5 are ignored by every trace (src/BVH.cpp:1401-1435) */
     float reflect_amt, refract_amt; /* Blinn::m_reflectAmt / m_refractAmt: mirror reflection / refraction, chosen by Fresnel-weighted
                                        Russian roulette (src/Blinn.cpp:188-204,238-331) */
     float spec_gloss;               /* Blinn::m_specGloss: < 1 blends the reflection vector with a cosine sample (src/Blinn.cpp:160-165) */
-    float translucency;             /* must be <= 0.01 (EUNSUPPORTED otherwise) */
+    float translucency;             /* Material::m_translucency: > 0.01 adds the lights seen from the back side (src/Blinn.cpp:223-236) */
     uint32_t sample_env;            /* Material::m_sampleEnv */
     float ior[3];                   /* Blinn::m_ior[0..2]; a non-dispersive material refracts with ior[1] (src/Blinn.cpp:183) */
-    uint32_t disperse;              /* Material::m_disperse: must be 0 (EUNSUPPORTED otherwise) */
+    uint32_t disperse;              /* Material::m_disperse: a refraction splits into one ray per colour channel with ior[0..2] (src/Blinn.cpp:275-302) */
     uint32_t reserved[5];
 } miro_gpu_material;
 

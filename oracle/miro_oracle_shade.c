@@ -165,7 +165,7 @@ static float ior_top(const iorlist* l) { return l->v[l->idx]; }
 static void ior_pop(iorlist* l) { if (l->idx > 0) l->idx--; }
 static void ior_push(iorlist* l, float x) { if (l->idx < 11) l->idx++; l->v[l->idx] = x; }
 
-typedef struct { v3 o, d; float time; iorlist ior; int bounces; } oray2;
+typedef struct { v3 o, d; float time; iorlist ior; int bounces; int is_refract; } oray2;
 typedef struct { v3 P, N, geoN; float u, v; uint32_t material; } surf;
 
 static int trace(octx* c, v3 o, v3 d, float time, float tmin, float tmax, miro_gpu_hit* h) {
@@ -343,8 +343,10 @@ static v3 shade(octx* c, oray2* ray, const miro_gpu_hit* hit, uint32_t pixel, ui
         rVec = normalize(add(scl(rVec, m->spec_gloss), scl(randD, 1.f - m->spec_gloss)));
     }
     const float inIOR = ior_top(&ray->ior);                                   /* Blinn.cpp:167-186 */
+    const int dispersive = m->disperse && !ray->is_refract;
     float outIOR;
-    if (flip) { ior_pop(&ray->ior); outIOR = ior_top(&ray->ior); } else outIOR = m->ior[1];
+    if (dispersive) outIOR = m->ior[0];
+    else if (flip) { ior_pop(&ray->ior); outIOR = ior_top(&ray->ior); } else outIOR = m->ior[1];
     float Rs = 0.f, Ts = 0.f;
     if (m->reflect_amt > 0.0f || m->refract_amt > 0.0f) { Rs = fresnel(inIOR, outIOR, vDotN); Ts = 1.0f - Rs; }
     float rr[4]; rand4(&addr, RP_ROULETTE, 0, 0, 0, 0, rr);
@@ -358,7 +360,7 @@ static v3 shade(octx* c, oray2* ray, const miro_gpu_hit* hit, uint32_t pixel, ui
             if (m->emit_intensity > 0.0f || (Le.x + Le.y + Le.z) > 0.0f) Ld = add(Ld, scl(Le, m->emit_intensity));
             else if (depth < c->p->max_bounces - 1) {
                 float r[4]; rand4(&addr, RP_COSINE, 0, 0, 0, 0, r);
-                oray2 nr; nr.o = sf.P; nr.d = cosine_sample(theNormal, r[0], r[1]); nr.time = ray->time; nr.bounces = ray->bounces;
+                oray2 nr; nr.o = sf.P; nr.d = cosine_sample(theNormal, r[0], r[1]); nr.time = ray->time; nr.bounces = ray->bounces; nr.is_refract = 0;
                 ior_init(&nr.ior); ior_push(&nr.ior, 1.001f);                  /* Ray randRay(threadID) */
                 ior_pop(&nr.ior); ior_push(&nr.ior, ior_top(&ray->ior));       /* randRay.set(..., ray.r_IOR(), ...) */
                 miro_gpu_hit nh;
@@ -389,19 +391,40 @@ static v3 shade(octx* c, oray2* ray, const miro_gpu_hit* hit, uint32_t pixel, ui
         int doEnv = 1;
         if (rr[1] < m->reflect_amt * Rs) {                                    /* Blinn.cpp:247-268 */
             if (m->reflect_amt * Rs > 0.0f && ray->bounces < 5) {
-                oray2 nr; nr.o = sf.P; nr.d = rVec; nr.time = ray->time; nr.ior = ray->ior; nr.bounces = ray->bounces + 1;
+                oray2 nr; nr.o = sf.P; nr.d = rVec; nr.time = ray->time; nr.ior = ray->ior; nr.bounces = ray->bounces + 1; nr.is_refract = 0;
                 miro_gpu_hit nh;
                 if (trace(c, nr.o, nr.d, nr.time, O_EPS, MIRO_GPU_TMAX, &nh)) { Lr = add(Lr, mul(ks, shade(c, &nr, &nh, pixel, sample, path, depth, 0))); doEnv = 0; }
             }
             if (m->reflect_amt * Rs > 0.0f && doEnv) Lr = add(Lr, mul(ks, environment(c, rVec)));
-        } else if (m->refract_amt * Ts > 0.0f) {                              /* Blinn.cpp:270-329, no dispersion */
+        } else if (m->refract_amt * Ts > 0.0f && dispersive) {                /* Blinn.cpp:275-302: one ray per colour channel */
+            v3 tVec = V(0, 0, 0);
+            for (int i = 0; i < 3; i++) {
+                const float snellsQ = inIOR / m->ior[i];
+                const float sq = sqrtf(1.0f - (snellsQ * snellsQ) * (1.0f - vDotN * vDotN));
+                const float sqrtPart = (0.0f < sq) ? sq : 0.0f;
+                tVec = normalize(add(scl(ray->d, snellsQ), scl(theNormal, snellsQ * vDotN - sqrtPart)));
+                if (ray->bounces < 5) {
+                    ior_push(&ray->ior, m->ior[i]);
+                    oray2 nr; nr.o = sf.P; nr.d = tVec; nr.time = ray->time; nr.ior = ray->ior; nr.bounces = ray->bounces + 1; nr.is_refract = 1;
+                    miro_gpu_hit nh;
+                    if (trace(c, nr.o, nr.d, nr.time, O_EPS, MIRO_GPU_TMAX, &nh)) {
+                        const v3 refraction = shade(c, &nr, &nh, pixel, sample, path, depth, 0);
+                        const v3 mask = V(i == 0 ? 1.f : 0.f, i == 1 ? 1.f : 0.f, i == 2 ? 1.f : 0.f);
+                        Lt = add(Lt, mul(ks, mul(refraction, mask)));
+                        doEnv = 0;
+                    }
+                    ior_pop(&ray->ior);
+                }
+            }
+            if (doEnv) Lt = add(Lt, mul(ks, environment(c, tVec)));
+        } else if (m->refract_amt * Ts > 0.0f) {                              /* Blinn.cpp:303-322, no dispersion */
             const float snellsQ = inIOR / outIOR;
             const float sq = sqrtf(1.0f - (snellsQ * snellsQ) * (1.0f - vDotN * vDotN));
             const float sqrtPart = (0.0f < sq) ? sq : 0.0f;
             const v3 tVec = normalize(add(scl(ray->d, snellsQ), scl(theNormal, snellsQ * vDotN - sqrtPart)));
             if (ray->bounces < 5) {
                 ior_push(&ray->ior, outIOR);
-                oray2 nr; nr.o = sf.P; nr.d = tVec; nr.time = ray->time; nr.ior = ray->ior; nr.bounces = ray->bounces + 1;
+                oray2 nr; nr.o = sf.P; nr.d = tVec; nr.time = ray->time; nr.ior = ray->ior; nr.bounces = ray->bounces + 1; nr.is_refract = 1;
                 miro_gpu_hit nh;
                 if (trace(c, nr.o, nr.d, nr.time, O_EPS, MIRO_GPU_TMAX, &nh)) { Lt = add(Lt, mul(ks, shade(c, &nr, &nh, pixel, sample, path, depth, 0))); doEnv = 0; }
                 ior_pop(&ray->ior);
@@ -421,7 +444,7 @@ static oray2 eye_ray(const ocam* cm, int x, int y, float minX, float maxX, float
     const float left = -cm->right, bottom = -cm->top;
     const float U = left + (cm->right - left) * (((float)x + xOffset) / (float)W);
     const float Vp = bottom + (cm->top - bottom) * (((float)y + yOffset) / (float)H);
-    oray2 o; o.time = 1.f - r[2] * r[2] * r[2] * cm->shutter; o.bounces = 0;
+    oray2 o; o.time = 1.f - r[2] * r[2] * r[2] * cm->shutter; o.bounces = 0; o.is_refract = 0;
     ior_init(&o.ior); ior_push(&o.ior, 1.001f);                              /* Ray(threadID, o, d, t): IOR = 1.001 pushed, src/Ray.h:70-101 */
     const v3 dir = normalize(sub(add(scl(cm->u, U), scl(cm->v, Vp)), cm->w));
     if (cm->aperture < O_EPS) { o.o = cm->eye; o.d = dir; return o; }

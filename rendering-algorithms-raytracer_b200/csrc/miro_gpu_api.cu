@@ -347,8 +347,6 @@ int miro_gpu_upload_scene(miro_gpu_ctx* ctx, const miro_gpu_scene_desc* d) {
     for (uint32_t i = 0; i < d->n_materials; ++i) {
         const miro_gpu_material& m = d->materials[i];
         if (m.kind > MIRO_GPU_MAT_BLINN) return set_error(ctx, MIRO_GPU_EINVAL, "unknown material kind");
-        if (m.disperse)
-            return set_error(ctx, MIRO_GPU_EUNSUPPORTED, "material " + std::to_string(i) + " uses dispersion (outside the hot-path scope, SURVEY 8f)");
         if (m.alpha_map >= (int32_t)d->n_textures) return set_error(ctx, MIRO_GPU_EINVAL, "material alpha_map out of range");
         if (m.color_map >= (int32_t)d->n_textures) return set_error(ctx, MIRO_GPU_EINVAL, "material color_map out of range");
     }

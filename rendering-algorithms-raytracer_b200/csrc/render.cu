@@ -39,6 +39,8 @@ constexpr int SHADE_BLOCK = 128;
 // ray.flags of a queued continuation ray: path 0-15 | giBounces 16-23 | bounces 24-26 | FLAG_SECONDARY | FLAG_SAMPLE_ENV
 constexpr uint32_t FLAG_SAMPLE_ENV = 0x80000000u;      // the environment / background is added when the ray leaves the scene
 constexpr uint32_t FLAG_SECONDARY = 0x08000000u;       // shade(..., isSecondary = true): reached through calculatePathTracing
+constexpr uint32_t FLAG_REFRACT = 0x10000000u;         // IS_REFRACT_RAY (src/Ray.h:15): a dispersive material does not split such a ray again
+// bits 29-30: 1 + colour channel of a dispersion ray (Blinn.cpp:275-302); its throughput is masked to that channel when it is shaded
 constexpr size_t WAVE_PATHS_MAX = (size_t)1 << 22;     // paths in flight per wave
 constexpr size_t WAVE_BYTES_BUDGET = (size_t)6 << 30;  // queue memory per context
 
@@ -56,6 +58,7 @@ struct RenderParamsDev {
     uint64_t seed;
     float inv_paths;
     uint32_t has_specular;      // some material has reflect_amt / refract_amt > 0: rays carry an IOR history
+    uint32_t next_cap;          // capacity of the continuation-ray queues (3x the wave when a material disperses)
 };
 
 struct Queues {
@@ -74,7 +77,7 @@ struct Queues {
 struct RenderState {
     Queues q{};
     std::vector<void*> allocs;
-    size_t key_paths = 0, key_shadow_per_path = 0, key_slots_per_path = 0; bool key_ior = false;
+    size_t key_paths = 0, key_shadow_per_path = 0, key_slots_per_path = 0, key_next_mult = 1; bool key_ior = false;
     // frame buffers
     float4* level_sum = nullptr; float4* result = nullptr; uint32_t* active[2] = {nullptr, nullptr};
     float* rgb_dev = nullptr; size_t frame_pixels = 0;
@@ -141,7 +144,7 @@ template <bool PRIMARY>
 __global__ void __launch_bounds__(SHADE_BLOCK)
 k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q, uint32_t n_static, const uint32_t* __restrict__ d_count,
         float4* __restrict__ level_sum, uint32_t shadow_cap, uint32_t slot_cap) {
-    const uint32_t n = PRIMARY ? n_static : *d_count;
+    const uint32_t n = PRIMARY ? n_static : min(*d_count, P.next_cap);
     const uint32_t stride = gridDim.x * SHADE_BLOCK;
     for (uint32_t base = blockIdx.x * SHADE_BLOCK + (threadIdx.x & ~31u); base < n; base += stride) {
         const uint32_t idx = base + (threadIdx.x & 31u);
@@ -150,7 +153,8 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
         uint32_t pixel = 0, sample = 0, path = 0, gi = 0, bounces = 0, vertex = 0;
         float3x thr = f3(0, 0, 0), thr_d = f3(0, 0, 0), o = f3(0, 0, 0), d = f3(0, 0, 1), bounce_dir = f3(0, 0, 0), bounce_thr = f3(0, 0, 0);
         float time = 0.f;
-        bool emit_bounce = false, pt_last = false, blinn = false, diffuse = true, translucent = false;
+        bool emit_bounce = false, pt_last = false, blinn = false, diffuse = true, translucent = false, disperse_split = false;
+        float disp_in = 1.f, disp_vdn = 0.f; uint32_t disp_mat = 0;
         float transl = 0.f;
         uint32_t bounce_flags = 0;
         IorStack ior; ior.init_camera();
@@ -168,10 +172,12 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
             pixel = __float_as_uint(r2.z); sample = __float_as_uint(r2.w);
             const uint32_t flags = __float_as_uint(r2.y);
             bool secondary = false;
+            uint32_t channel = 0;
             if (PRIMARY) { path = idx - ri * (uint32_t)P.num_paths; thr = f3(P.inv_paths, P.inv_paths, P.inv_paths); }
             else {
                 path = flags & 0xffffu; gi = (flags >> 16) & 0xffu; bounces = (flags >> 24) & 7u; secondary = (flags & FLAG_SECONDARY) != 0;
                 const float4 t4 = __ldg(q.q_thr[in_q] + idx); thr = f3(t4.x, t4.y, t4.z);
+                channel = (flags >> 29) & 3u;
                 if (P.has_specular) {
                     const float4 i0 = __ldg(q.q_ior[in_q] + 2 * (size_t)idx), i1 = __ldg(q.q_ior[in_q] + 2 * (size_t)idx + 1);
                     ior.v[0] = i0.x; ior.v[1] = i0.y; ior.v[2] = i0.z; ior.v[3] = i0.w; ior.v[4] = i1.x; ior.v[5] = i1.y; ior.v[6] = i1.z;
@@ -184,9 +190,14 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
                 // Scene::sampleScene miss (Scene.cpp:234-240): env / BG once per camera sample; continuation-ray miss
                 // (Blinn.cpp:70-73 with the material's and the scene's sampleEnv; Blinn.cpp:262,326 unconditionally)
                 if (PRIMARY) { if (path == 0) add_rgb(level_sum, pixel, environment(sh, d)); }
-                else if (flags & FLAG_SAMPLE_ENV) add_rgb(level_sum, pixel, thr * environment(sh, d));
+                else if (channel) {
+                    // dispersion rays: the environment is added ONCE, unmasked, along the last (blue) ray, and only when all
+                    // three rays of the split left the scene (Blinn.cpp:281-302,324-327); the three are queue neighbours
+                    if (channel == 3u && __ldg(&q.q_hits[idx - 1].prim) < 0 && __ldg(&q.q_hits[idx - 2].prim) < 0) add_rgb(level_sum, pixel, thr * environment(sh, d));
+                } else if (flags & FLAG_SAMPLE_ENV) add_rgb(level_sum, pixel, thr * environment(sh, d));
                 active = false;
             } else {
+                if (channel) thr = thr * f3(channel == 1u ? 1.f : 0.f, channel == 2u ? 1.f : 0.f, channel == 3u ? 1.f : 0.f);      // "refraction * mask"
                 const Surface s = surface_at(sc, sh, o, d, ht, ha, hb, hprim, hinst);
                 const miro_gpu_material* m = sh.materials + s.material;
                 float3x kd = f3(m->kd[0], m->kd[1], m->kd[2]);
@@ -217,10 +228,12 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
                     // IOR bookkeeping (Blinn.cpp:167-186).  The reference pops the history of the ray OBJECT it was handed;
                     // sampleScene shades the same camera ray numPaths times, so path i of a back-facing primary hit sees the
                     // history already popped by paths 0..i-1.
-                    if (PRIMARY && flip) for (uint32_t k = 0; k < path && k < 2u; ++k) ior.pop();
+                    const bool dispersive = m->disperse && !(flags & FLAG_REFRACT);            // Blinn.cpp:169
+                    if (PRIMARY && flip && !dispersive) for (uint32_t k = 0; k < path && k < 2u; ++k) ior.pop();
                     const float inIOR = ior.top();
                     float outIOR;
-                    if (flip) { ior.pop(); outIOR = ior.top(); } else outIOR = m->ior[1];
+                    if (dispersive) outIOR = m->ior[0];                                        // no pop on this branch
+                    else if (flip) { ior.pop(); outIOR = ior.top(); } else outIOR = m->ior[1];
                     float Rs = 0.f, Ts = 0.f;
                     if (m->reflect_amt > 0.0f || m->refract_amt > 0.0f) { Rs = fresnel(inIOR, outIOR, vDotN); Ts = 1.0f - Rs; }
                     const Rand4 rr = rand4(addr, RP_ROULETTE, 0, 0, 0, 0);
@@ -254,18 +267,29 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
                         bool spawn = false;
                         if (rr.y < m->reflect_amt * Rs) {
                             if (m->reflect_amt * Rs > 0.0f) { dir = rVec; spawn = true; }
+                        } else if (m->refract_amt * Ts > 0.0f && dispersive) {
+                            // one refraction ray per colour channel, each with its own IOR (Blinn.cpp:275-302)
+                            bounce_thr = thr * ks * rrWeightRecipSpec;
+                            if (bounces < 5u) {
+                                disperse_split = true; disp_in = inIOR; disp_vdn = vDotN; disp_mat = s.material;
+                                bounce_flags = (path | (gi << 16) | ((bounces + 1u) << 24)) | FLAG_REFRACT;
+                            } else {
+                                const float snellsQ = inIOR / m->ior[2];
+                                const float sqrtPart = fmaxf(0.0f, sqrtf(1.0f - (snellsQ * snellsQ) * (1.0f - vDotN * vDotN)));
+                                constant = constant + bounce_thr * environment(sh, normalize3(snellsQ * d + theNormal * (snellsQ * vDotN - sqrtPart)));
+                            }
                         } else if (m->refract_amt * Ts > 0.0f) {
                             const float snellsQ = inIOR / outIOR;
                             const float sqrtPart = fmaxf(0.0f, sqrtf(1.0f - (snellsQ * snellsQ) * (1.0f - vDotN * vDotN)));
                             dir = normalize3(snellsQ * d + theNormal * (snellsQ * vDotN - sqrtPart));
                             ior.push(outIOR);
-                            spawn = true;
+                            spawn = true; bounce_flags = FLAG_REFRACT;
                         }
                         if (spawn) {
                             bounce_thr = thr * ks * rrWeightRecipSpec;
                             if (bounces < 5u) {
                                 bounce_dir = dir; emit_bounce = true;
-                                bounce_flags = (path | (gi << 16) | ((bounces + 1u) << 24)) | FLAG_SAMPLE_ENV;   // shade(...) with isSecondary = false
+                                bounce_flags = (bounce_flags & FLAG_REFRACT) | (path | (gi << 16) | ((bounces + 1u) << 24)) | FLAG_SAMPLE_ENV;   // shade(...) with isSecondary = false
                             } else constant = constant + bounce_thr * environment(sh, dir);       // "doEnv": no further bounce
                         }
                     }
@@ -281,7 +305,8 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
         }
         // ------------------------------------------------------------------ phase 2: claim queue space (warp aggregated)
         const uint32_t lane = threadIdx.x & 31u;
-        uint32_t s_shadow = (uint32_t)n_shadow, s_slots = (uint32_t)n_slots, s_next = emit_bounce ? 1u : 0u;
+        const uint32_t n_next = disperse_split ? 3u : (emit_bounce ? 1u : 0u);
+        uint32_t s_shadow = (uint32_t)n_shadow, s_slots = (uint32_t)n_slots, s_next = n_next;
         for (int off = 1; off < 32; off <<= 1) {
             const uint32_t a = __shfl_up_sync(0xffffffffu, s_shadow, off), b = __shfl_up_sync(0xffffffffu, s_slots, off), e = __shfl_up_sync(0xffffffffu, s_next, off);
             if ((int)lane >= off) { s_shadow += a; s_slots += b; s_next += e; }
@@ -294,10 +319,28 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
         }
         b_shadow = __shfl_sync(0xffffffffu, b_shadow, 31) + s_shadow - (uint32_t)n_shadow;
         b_slots = __shfl_sync(0xffffffffu, b_slots, 31) + s_slots - (uint32_t)n_slots;
-        b_next = __shfl_sync(0xffffffffu, b_next, 31) + s_next - (emit_bounce ? 1u : 0u);
+        b_next = __shfl_sync(0xffffffffu, b_next, 31) + s_next - n_next;
         if (!active) continue;
         // ------------------------------------------------------------------ phase 3: emit
-        if (emit_bounce) {
+        if (n_next && b_next + n_next > P.next_cap) { atomicAdd(q.counts + 5, n_next); }      // queue full: reported as an error by the host
+        else if (disperse_split) {
+            const miro_gpu_material* m = sh.materials + disp_mat;
+            for (uint32_t ch = 0; ch < 3u; ++ch) {
+                const float oi = m->ior[ch];
+                const float snellsQ = disp_in / oi;
+                const float sqrtPart = fmaxf(0.0f, sqrtf(1.0f - (snellsQ * snellsQ) * (1.0f - disp_vdn * disp_vdn)));
+                const float3x tv = normalize3(snellsQ * d + c.N * (snellsQ * disp_vdn - sqrtPart));
+                IorStack st2 = ior; st2.push(oi);
+                const uint32_t k = b_next + ch;
+                float4* o4 = reinterpret_cast<float4*>(q.q_rays[in_q ^ 1] + k);
+                o4[0] = make_float4(c.P.x, c.P.y, c.P.z, kEps);
+                o4[1] = make_float4(tv.x, tv.y, tv.z, MIRO_GPU_TMAX);
+                o4[2] = make_float4(time, __uint_as_float(bounce_flags | ((ch + 1u) << 29)), __uint_as_float(pixel), __uint_as_float(sample));
+                q.q_thr[in_q ^ 1][k] = make_float4(bounce_thr.x, bounce_thr.y, bounce_thr.z, 0.f);     // unmasked: masked when shaded
+                q.q_ior[in_q ^ 1][2 * (size_t)k] = make_float4(st2.v[0], st2.v[1], st2.v[2], st2.v[3]);
+                q.q_ior[in_q ^ 1][2 * (size_t)k + 1] = make_float4(st2.v[4], st2.v[5], st2.v[6], __uint_as_float((uint32_t)st2.idx));
+            }
+        } else if (emit_bounce) {
             float4* o4 = reinterpret_cast<float4*>(q.q_rays[in_q ^ 1] + b_next);
             o4[0] = make_float4(c.P.x, c.P.y, c.P.z, kEps);
             o4[1] = make_float4(bounce_dir.x, bounce_dir.y, bounce_dir.z, MIRO_GPU_TMAX);
@@ -434,23 +477,24 @@ static cudaError_t qalloc(RenderState* st, T** p, size_t n) {
     return e;
 }
 
-static int ensure_queues(miro_gpu_ctx* ctx, RenderState* st, size_t paths, size_t cs, size_t shadow_per_path, size_t slots_per_path, bool with_ior) {
-    if (st->key_paths == paths && st->q.cap_cs >= cs && st->key_shadow_per_path == shadow_per_path && st->key_slots_per_path == slots_per_path && st->key_ior == with_ior) return MIRO_GPU_OK;
+static int ensure_queues(miro_gpu_ctx* ctx, RenderState* st, size_t paths, size_t cs, size_t shadow_per_path, size_t slots_per_path, bool with_ior, size_t next_mult) {
+    if (st->key_next_mult == next_mult && st->key_paths == paths && st->q.cap_cs >= cs && st->key_shadow_per_path == shadow_per_path && st->key_slots_per_path == slots_per_path && st->key_ior == with_ior) return MIRO_GPU_OK;
     free_queues(st);
     Queues& q = st->q;
-    q.cap_cs = cs; q.cap_paths = paths; q.cap_shadow = paths * shadow_per_path; q.cap_slots = paths * slots_per_path;
+    // a vertex of ANY continuation ray can run every light loop, so the shadow / slot queues scale with the continuation queue
+    q.cap_cs = cs; q.cap_paths = paths * next_mult; q.cap_shadow = q.cap_paths * shadow_per_path; q.cap_slots = q.cap_paths * slots_per_path;
     MIRO_CUDA(ctx, qalloc(st, &q.cs_rays, q.cap_cs));
     MIRO_CUDA(ctx, qalloc(st, &q.cs_hits, q.cap_cs));
     for (int i = 0; i < 2; ++i) {
-        MIRO_CUDA(ctx, qalloc(st, &q.q_rays[i], paths)); MIRO_CUDA(ctx, qalloc(st, &q.q_thr[i], paths));
-        if (with_ior) MIRO_CUDA(ctx, qalloc(st, &q.q_ior[i], 2 * paths));
+        MIRO_CUDA(ctx, qalloc(st, &q.q_rays[i], q.cap_paths)); MIRO_CUDA(ctx, qalloc(st, &q.q_thr[i], q.cap_paths));
+        if (with_ior) MIRO_CUDA(ctx, qalloc(st, &q.q_ior[i], 2 * q.cap_paths));
     }
-    MIRO_CUDA(ctx, qalloc(st, &q.q_hits, paths));
+    MIRO_CUDA(ctx, qalloc(st, &q.q_hits, q.cap_paths));
     MIRO_CUDA(ctx, qalloc(st, &q.sh_rays, q.cap_shadow));
     MIRO_CUDA(ctx, qalloc(st, &q.sh_E, q.cap_shadow));
     MIRO_CUDA(ctx, qalloc(st, &q.slots, q.cap_slots));
     MIRO_CUDA(ctx, qalloc(st, &q.counts, (size_t)8));
-    st->key_paths = paths; st->key_shadow_per_path = shadow_per_path; st->key_slots_per_path = slots_per_path; st->key_ior = with_ior;
+    st->key_next_mult = next_mult; st->key_paths = paths; st->key_shadow_per_path = shadow_per_path; st->key_slots_per_path = slots_per_path; st->key_ior = with_ior;
     return MIRO_GPU_OK;
 }
 
@@ -517,7 +561,9 @@ extern "C" int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, co
     P.width = W; P.height = H; P.num_paths = rp->num_paths; P.max_bounces = rp->max_bounces;
     P.path_trace = rp->path_trace; P.sample_env = rp->sample_env; P.seed = rp->seed; P.inv_paths = 1.0f / (float)rp->num_paths;
     P.has_specular = 0;
-    for (const miro_gpu_material& m : ctx->host_materials) if (m.kind == MIRO_GPU_MAT_BLINN && (m.reflect_amt > 0.f || m.refract_amt > 0.f)) P.has_specular = 1;
+    bool any_disperse = false;
+    for (const miro_gpu_material& m : ctx->host_materials) if (m.kind == MIRO_GPU_MAT_BLINN && (m.reflect_amt > 0.f || m.refract_amt > 0.f)) { P.has_specular = 1; if (m.disperse && m.refract_amt > 0.f) any_disperse = true; }
+    const size_t next_mult = any_disperse ? 3 : 1;      // a dispersive refraction turns one path into three (Blinn.cpp:275-302)
 
     // ---- queue capacities: worst case per path
     size_t light_samples = 0;
@@ -526,12 +572,13 @@ extern "C" int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, co
     for (const miro_gpu_material& m : ctx->host_materials) if (m.kind == MIRO_GPU_MAT_BLINN && m.translucency > 0.01f) any_translucent = true;
     const size_t loops = (rp->path_trace ? 2 : 1) + (any_translucent ? 1 : 0);
     const size_t shadow_per_path = std::max<size_t>(1, loops * light_samples), slots_per_path = std::max<size_t>(1, loops * ctx->host_lights.size());
-    const size_t bytes_per_path = 2 * (48 + 16 + (P.has_specular ? 32 : 0)) + 20 + shadow_per_path * 64 + slots_per_path * 64 + (48 + 20);
+    const size_t bytes_per_path = next_mult * (2 * (48 + 16 + (P.has_specular ? 32 : 0)) + 20 + shadow_per_path * 64 + slots_per_path * 64) + (48 + 20);
     size_t paths = std::min<size_t>(WAVE_PATHS_MAX, std::max<size_t>(WAVE_BYTES_BUDGET / bytes_per_path, (size_t)rp->num_paths));
     paths = std::min(paths, pixels * (size_t)max_sub * max_sub * rp->num_paths);
     paths = std::max<size_t>((paths / rp->num_paths) * rp->num_paths, (size_t)rp->num_paths);
     const size_t wave_cs = paths / rp->num_paths;
-    if ((rc = ensure_queues(ctx, st, paths, wave_cs, shadow_per_path, slots_per_path, P.has_specular != 0))) return rc;
+    if ((rc = ensure_queues(ctx, st, paths, wave_cs, shadow_per_path, slots_per_path, P.has_specular != 0, next_mult))) return rc;
+    P.next_cap = (uint32_t)(paths * next_mult);
     Queues& q = st->q;
     cudaStream_t s = ctx->stream;
 
@@ -552,6 +599,7 @@ extern "C" int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, co
     EventPair tot = begin_timing(ctx, false);
     MIRO_CUDA(ctx, cudaMemcpyAsync(st->active[0], own.data(), own.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     MIRO_CUDA(ctx, cudaMemsetAsync(st->level_sum, 0, pixels * sizeof(float4), s));
+    MIRO_CUDA(ctx, cudaMemsetAsync(q.counts + 5, 0, sizeof(uint32_t), s));
     int cur = 0;
     // vertices along a path: up to maxBounces-1 diffuse (GI) continuations and up to 5 reflect / refract continuations (Blinn.cpp:57,247)
     const int last_depth = (rp->path_trace ? std::max(0, rp->max_bounces - 1) : 0) + (P.has_specular ? 5 : 0);
@@ -619,7 +667,10 @@ extern "C" int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, co
             for (uint32_t p : own) { rgb_out[(size_t)p * 3] = tmp[(size_t)p * 3]; rgb_out[(size_t)p * 3 + 1] = tmp[(size_t)p * 3 + 1]; rgb_out[(size_t)p * 3 + 2] = tmp[(size_t)p * 3 + 2]; }
         }
     }
+    if (any_disperse) MIRO_CUDA(ctx, cudaMemcpyAsync(st->h_count + 1, q.counts + 5, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     end_timing(ctx, tot);
     MIRO_CUDA(ctx, cudaStreamSynchronize(s));
+    if (any_disperse && st->h_count[1])
+        return set_error(ctx, MIRO_GPU_ENOMEM, "continuation-ray queue overflow: " + std::to_string(st->h_count[1]) + " dispersion rays were dropped (paths split more than 3x per wave)");
     return MIRO_GPU_OK;
 }

@@ -39,6 +39,7 @@ SCENES = {
     "c3_dome_pt": dict(render=True, stock=False, incoherent=0, threads=1, converged=32),
     "c4_cornell_pt": dict(render=True, stock=False, incoherent=0, threads=1, converged=64),
     "c7_foliage": dict(render=True, stock=False, incoherent=1 << 18, threads=1),
+    "c8_dispersion": dict(render=True, stock=False, incoherent=0, threads=1, converged=16),
     "c6_cornell_glass": dict(render=True, stock=False, incoherent=0, threads=1, converged=16),
 }
 
