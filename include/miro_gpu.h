@@ -204,7 +204,12 @@ typedef struct miro_gpu_render_params {
        (bucket order of src/Scene.cpp:160-175).  shard_count <= 1 renders everything.  Pixels outside the
        shard are left untouched in rgb_out. */
     int32_t shard_index, shard_count;
-    uint32_t reserved[4];
+    /* sample sharding (multi-GPU, path-traced configs): this call traces the paths p of every camera sample with
+       p % path_shard_count == path_shard_index, each still weighted 1 / num_paths, so the SUM of the shards' images is the
+       whole image (better balance than tiles when parts of the image are empty).  path_shard_count <= 1: all paths.
+       Needs min_subdivs == max_subdivs (the adaptive cut-off looks at the complete pixel value): EINVAL otherwise. */
+    int32_t path_shard_index, path_shard_count;
+    uint32_t reserved[2];
 } miro_gpu_render_params;
 
 typedef struct miro_gpu_counters {

@@ -95,7 +95,8 @@ class RenderParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("min_subdivs", C.c_int32), ("max_subdivs", C.c_int32),
                 ("noise_threshold", C.c_float), ("num_paths", C.c_int32), ("max_bounces", C.c_int32),
                 ("path_trace", C.c_uint32), ("sample_env", C.c_uint32), ("seed", C.c_uint64),
-                ("shard_index", C.c_int32), ("shard_count", C.c_int32), ("reserved", C.c_uint32 * 4)]
+                ("shard_index", C.c_int32), ("shard_count", C.c_int32), ("path_shard_index", C.c_int32), ("path_shard_count", C.c_int32),
+                ("reserved", C.c_uint32 * 2)]
 
 
 class Counters(C.Structure):

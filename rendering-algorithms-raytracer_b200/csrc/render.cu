@@ -6,7 +6,8 @@
 //   Scene::sampleScene            Scene.cpp:219-243   trace the camera ray, mean of numPaths shade() calls, miss -> env / BG
 //   Camera::eyeRayAdaptive        Camera.cpp:116-174
 //   Lambert::shade                Lambert.cpp:19-53
-//   Blinn::shade (diffuse + specular highlight part), Blinn::calculatePathTracing   Blinn.cpp:39-236,335
+//   Blinn::shade (diffuse, highlight, translucency, reflection / refraction / dispersion with Fresnel-weighted Russian
+//   roulette), Blinn::calculatePathTracing   Blinn.cpp:39-335
 //   Point/Rectangle/DomeLight::sampleLight   PointLight.cpp:8-82, RectangleLight.cpp:42-137, DomeLight.cpp:80-161
 //
 // The reference's shade() <-> trace() recursion becomes a loop over path depth; all state lives in queues in HBM:
@@ -59,6 +60,8 @@ struct RenderParamsDev {
     float inv_paths;
     uint32_t has_specular;      // some material has reflect_amt / refract_amt > 0: rays carry an IOR history
     uint32_t next_cap;          // capacity of the continuation-ray queues (3x the wave when a material disperses)
+    int local_paths;            // paths per camera sample traced by THIS call (sample sharding), path = k * path_stride + path_first
+    int path_first, path_stride;
 };
 
 struct Queues {
@@ -119,9 +122,6 @@ k_raygen(DeviceCamera cam, RenderParamsDev P, const uint32_t* __restrict__ activ
 }
 
 // ---------------------------------------------------------------------------------------------
-// What one shading event emits.
-struct LoopPlan { int n_shadow; int n_slots; };
-
 struct ShadeCtx {
     float3x P, N, rVec, kd, tks;      // hit point, shading normal, reflection vector, diffuse colour, throughput*ks*specAmt
     float spec_exp;
@@ -162,7 +162,7 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
         int n_shadow = 0, n_slots = 0;
         RandAddr addr{};
         if (active) {
-            const uint32_t ri = PRIMARY ? idx / (uint32_t)P.num_paths : idx;
+            const uint32_t ri = PRIMARY ? idx / (uint32_t)P.local_paths : idx;
             const float4* rp = reinterpret_cast<const float4*>((PRIMARY ? q.cs_rays : q.q_rays[in_q]) + ri);
             const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
             const miro_gpu_hit* hp = (PRIMARY ? q.cs_hits : q.q_hits) + ri;
@@ -173,7 +173,7 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
             const uint32_t flags = __float_as_uint(r2.y);
             bool secondary = false;
             uint32_t channel = 0;
-            if (PRIMARY) { path = idx - ri * (uint32_t)P.num_paths; thr = f3(P.inv_paths, P.inv_paths, P.inv_paths); }
+            if (PRIMARY) { path = (idx - ri * (uint32_t)P.local_paths) * (uint32_t)P.path_stride + (uint32_t)P.path_first; thr = f3(P.inv_paths, P.inv_paths, P.inv_paths); }
             else {
                 path = flags & 0xffffu; gi = (flags >> 16) & 0xffu; bounces = (flags >> 24) & 7u; secondary = (flags & FLAG_SECONDARY) != 0;
                 const float4 t4 = __ldg(q.q_thr[in_q] + idx); thr = f3(t4.x, t4.y, t4.z);
@@ -247,7 +247,6 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
                     thr_d = thr * rrWeightRecip;                       // (Ld + Ls) / rrWeight, Blinn.cpp:335
                     c.tks = thr_d * ks * m->spec_amt;
                     float3x constant = thr_d * ka + thr * Le;          // "Ld += m_ka" is on both branches; "+ m_Le" is unscaled
-                    const uint32_t base_flags = path | (gi << 16) | (bounces << 24);
                     if (diffuse) {
                         if (P.path_trace) {                                                      // Blinn::calculatePathTracing
                             if (m->emit_intensity > 0.0f || (Le.x + Le.y + Le.z) > 0.0f) constant = constant + thr_d * (m->emit_intensity * Le);
@@ -293,7 +292,6 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
                             } else constant = constant + bounce_thr * environment(sh, dir);       // "doEnv": no further bounce
                         }
                     }
-                    (void)base_flags;
                     add_rgb(level_sum, pixel, constant);
                 }
                 if (diffuse) for_each_light_loop(sh, pt_last, blinn, c.is_secondary, translucent, [&](uint32_t li, uint32_t pass, bool secondary_, bool with_spec) {
@@ -561,6 +559,11 @@ extern "C" int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, co
     P.width = W; P.height = H; P.num_paths = rp->num_paths; P.max_bounces = rp->max_bounces;
     P.path_trace = rp->path_trace; P.sample_env = rp->sample_env; P.seed = rp->seed; P.inv_paths = 1.0f / (float)rp->num_paths;
     P.has_specular = 0;
+    const int pcount = std::max(1, rp->path_shard_count), pindex = rp->path_shard_index;
+    if (pindex < 0 || pindex >= pcount) return set_error(ctx, MIRO_GPU_EINVAL, "path_shard_index out of range");
+    if (pcount > 1 && rp->min_subdivs != rp->max_subdivs) return set_error(ctx, MIRO_GPU_EINVAL, "sample sharding needs min_subdivs == max_subdivs (the adaptive cut-off needs the complete pixel value)");
+    P.path_first = pindex; P.path_stride = pcount;
+    P.local_paths = (rp->num_paths - pindex + pcount - 1) / pcount;       // paths p < num_paths with p % pcount == pindex
     bool any_disperse = false;
     for (const miro_gpu_material& m : ctx->host_materials) if (m.kind == MIRO_GPU_MAT_BLINN && (m.reflect_amt > 0.f || m.refract_amt > 0.f)) { P.has_specular = 1; if (m.disperse && m.refract_amt > 0.f) any_disperse = true; }
     const size_t next_mult = any_disperse ? 3 : 1;      // a dispersive refraction turns one path into three (Blinn.cpp:275-302)
@@ -610,11 +613,12 @@ extern "C" int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, co
         const uint64_t total_cs = (uint64_t)n_active * k2;
         for (uint64_t first = 0; first < total_cs; first += wave_cs) {
             const uint32_t n_cs = (uint32_t)std::min<uint64_t>(wave_cs, total_cs - first);
+            if (P.local_paths == 0) break;          // sample sharding: this shard owns none of the num_paths paths
             k_raygen<<<grid_for(n_cs, SHADE_BLOCK), SHADE_BLOCK, 0, s>>>(dc, P, st->active[cur], (uint32_t)first, n_cs, level, ordinal_base, q.cs_rays);
             ctx->launches++;
             launch_trace_closest(ctx, q.cs_rays, n_cs, nullptr, q.cs_hits);
             MIRO_CUDA(ctx, cudaMemsetAsync(q.counts, 0, 3 * sizeof(uint32_t), s));
-            const size_t n_threads = (size_t)n_cs * rp->num_paths;
+            const size_t n_threads = (size_t)n_cs * P.local_paths;
             k_shade<true><<<std::min(grid_for(n_threads, SHADE_BLOCK), kPersistentGrid * 4), SHADE_BLOCK, 0, s>>>(
                 ctx->scene, ctx->shading, P, q, 0, (uint32_t)n_threads, nullptr, st->level_sum, (uint32_t)q.cap_shadow, (uint32_t)q.cap_slots);
             ctx->launches++;

@@ -233,8 +233,6 @@ struct LightSample {
     bool lit;           // false: contributes nothing (back-facing); no shadow ray
 };
 
-struct LightLoopResult { int samples_done; };
-
 // Calls f(const LightSample&) for every LIT sample, in order; returns samplesDone (the divisor of the mean).
 template <class F>
 __device__ inline int light_loop(const DeviceShading& sh, uint32_t li, float3x from, float3x normal, float3x rVec, bool isSecondary,

@@ -29,15 +29,23 @@ def render_sharded(render_fn, width, height, rank, world, group=None, device="cp
     return frame
 
 
-def render_scene_distributed(scene, rank, world, group=None):
-    """Scene::raytraceImage across the ranks of a process group: each rank's GPU renders its buckets (miro_gpu_render
-    writing straight into the torch CUDA tensor), then one NCCL all_reduce."""
+def render_scene_distributed(scene, rank, world, group=None, mode="tiles"):
+    """Scene::raytraceImage across the ranks of a process group: each rank's GPU renders its share (miro_gpu_render writing
+    straight into the torch CUDA tensor), then one NCCL all_reduce(SUM).
+    mode "tiles":   32x32 buckets round-robin (any configuration);
+    mode "samples": every rank renders the whole frame with the paths p % world == rank of each camera sample, each weighted
+                    1 / numPaths (path-traced configurations with min_subdivs == max_subdivs; better balanced when parts of
+                    the image are empty).  The sum is the whole image in both modes (random numbers are keyed by pixel,
+                    sample and path, not by rank)."""
     import torch
     p = scene.render_params()
     cam = scene.camera()
 
     def fn(frame, si, sc):
-        p.shard_index, p.shard_count = si, sc
+        if mode == "samples":
+            p.path_shard_index, p.path_shard_count = si, sc
+        else:
+            p.shard_index, p.shard_count = si, sc
         scene.render_device(frame.data_ptr(), params=p, camera=cam)
         torch.cuda.synchronize()
     return render_sharded(fn, p.width, p.height, rank, world, group, device=torch.device("cuda", torch.cuda.current_device()))

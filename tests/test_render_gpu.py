@@ -101,6 +101,32 @@ def test_sharded_render_equals_whole():
     sc.close()
 
 
+def test_sample_sharded_render_sums_to_whole():
+    """path_shard_index / path_shard_count: the images of the path shards add up to the whole image."""
+    import torch
+    fx, sc = load("c4_cornell_pt")
+    whole = sc.render()
+    p = sc.render_params()
+    acc = np.zeros_like(whole)
+    for i in range(3):
+        out = torch.zeros((p.height, p.width, 3), dtype=torch.float32, device="cuda")
+        p.path_shard_index = i; p.path_shard_count = 3
+        sc.render_device(out.data_ptr(), params=p)
+        torch.cuda.synchronize()
+        acc += out.cpu().numpy()
+    assert np.allclose(acc, whole, rtol=2e-4, atol=2e-5)
+    # more shards than paths: the surplus shards render nothing
+    p.num_paths = 2; p.path_shard_index = 2; p.path_shard_count = 4
+    out = torch.zeros((p.height, p.width, 3), dtype=torch.float32, device="cuda")
+    sc.render_device(out.data_ptr(), params=p); torch.cuda.synchronize()
+    assert float(out.abs().max()) == 0.0
+    import miro_b200 as mb
+    p = sc.render_params(); p.path_shard_count = 2; p.min_subdivs = 1; p.max_subdivs = 2
+    with pytest.raises(mb.MiroError):
+        sc.render_device(out.data_ptr(), params=p)
+    sc.close()
+
+
 def test_adaptive_levels_and_lens():
     """min/max subdivs > 1 (stratified levels, gamma-space cut-off) and a thin lens, against the oracle."""
     fx, sc = load("c1_cornell")
@@ -167,8 +193,9 @@ rank = int(os.environ["RANK"]); torch.cuda.set_device(rank)
 dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%s" % os.environ["MIRO_PORT"], rank=rank, world_size=2, device_id=torch.device("cuda", rank))
 fx = helpers.Fixture(helpers.fixture_path("c4_cornell_pt")); sc = fx.scene().attach(rank)
 full = md.render_scene_distributed(sc, rank, 2)
+full_s = md.render_scene_distributed(sc, rank, 2, mode="samples")
 if rank == 0:
-    np.save(os.environ["MIRO_OUT"], full.cpu().numpy())
+    np.save(os.environ["MIRO_OUT"], full.cpu().numpy()); np.save(os.environ["MIRO_OUT"] + ".samples.npy", full_s.cpu().numpy())
 dist.destroy_process_group(); sc.close()
 '''
     out = tmp_path / "full.npy"
@@ -179,6 +206,7 @@ dist.destroy_process_group(); sc.close()
     fx, sc = load("c4_cornell_pt")
     whole = sc.render()
     assert np.allclose(np.load(out), whole, rtol=1e-4, atol=1e-5)
+    assert np.allclose(np.load(str(out) + ".samples.npy"), whole, rtol=2e-4, atol=2e-5)
     sc.close()
 
 
