@@ -123,3 +123,32 @@ def test_full_size_batches_against_reference(name):
     again = sc.trace_closest(r)
     assert (again["prim"][h] == hits["prim"][h]).mean() > 0.9999 and np.array_equal(again["t"][h][again["prim"][h] == hits["prim"][h]], hits["t"][h][again["prim"][h] == hits["prim"][h]])
     sc.close()
+
+
+def test_forty_thousand_instances():
+    """BASELINE config C5 at the reference's scale: makeProxyGrid's 201 x 201 = 40 401 ProxyObject instances of testGrass.obj
+    (5 172 triangles each: 209 M instanced triangles) + the motion-blur bullets, against the oracle."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("make_scenes", os.path.join(helpers.ROOT, "tools", "make_scenes.py"))
+    ms = importlib.util.module_from_spec(spec); spec.loader.exec_module(ms)
+    fx = helpers.Fixture(helpers.fixture_path("c5_mb_instances"))
+    sc = fx.scene(script_override=ms.c5(201, name=None)).attach(0)
+    d = sc.desc()
+    assert d.n_instances == 201 * 201 and d.n_mbtris == 720
+    rng = np.random.default_rng(5)
+    n = 100_000
+    o = np.stack([rng.uniform(-25, 17, n), rng.uniform(0.05, 14, n), rng.uniform(-20, 20, n)], 1)
+    dirs = rng.normal(size=(n, 3)); dirs[:, 1] = -np.abs(dirs[:, 1]) * 0.5; dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    rays = __import__("miro_b200").make_rays(o, dirs, time=0.0)
+    rays["time"] = rng.uniform(0, 1, n).astype(np.float32)
+    g = sc.trace_closest(rays)
+    oh, _ = helpers.oracle_trace_closest(sc, rays)
+    same = (g["prim"] == oh["prim"]) & (g["inst"] == oh["inst"])
+    hit = g["prim"] >= 0
+    print("40k instances: hit frac %.3f id match %.6f" % (hit.mean(), same.mean()))
+    assert hit.mean() > 0.2 and same.mean() >= 0.9995
+    both = same & hit
+    scale = np.maximum(np.abs(oh["t"]), np.linalg.norm(rays["o"], axis=1))
+    assert (np.abs(g["t"] - oh["t"])[both] <= 1e-5 * scale[both]).mean() >= 0.9999
+    assert (sc.trace_any(rays) == hit).all()
+    sc.close()
