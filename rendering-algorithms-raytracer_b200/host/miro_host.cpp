@@ -455,6 +455,22 @@ static void refBounds(const FlatScene& f, const std::vector<miro_gpu_tri>& srcTr
     }
 }
 
+// Boxes that together bound a BLAS: the children of its top `depth`+1 levels.  An instance's world-space bounds are the
+// union of these boxes transformed one by one — tighter than the eight transformed corners of the single root box the
+// reference uses (ProxyObject::getAABB, src/ProxyObject.cpp:16-44), which a rotation inflates by up to sqrt(2) per axis;
+// rays over an instanced field enter fewer instances.  Still conservative: every triangle lies inside one of the boxes.
+static void collectBoxes(const FlatScene& f, int32_t ref, int depth, std::vector<float>& out) {
+    if (ref < 0 || ref == MIRO_GPU_CHILD_EMPTY) return;
+    const miro_gpu_node& n = f.nodes[ref];
+    for (int i = 0; i < 4; ++i) {
+        const int32_t c = n.child[i];
+        if (c == MIRO_GPU_CHILD_EMPTY) continue;
+        if (c >= 0 && depth > 0) { collectBoxes(f, c, depth - 1, out); continue; }
+        const float b[6] = {n.lo_x[i], n.lo_y[i], n.lo_z[i], n.hi_x[i], n.hi_y[i], n.hi_z[i]};
+        out.insert(out.end(), b, b + 6);
+    }
+}
+
 bool Scene::preCalc() {
     m_error.clear();
     m_flat = FlatScene();
@@ -463,6 +479,7 @@ bool Scene::preCalc() {
     m_meshNormalBase.clear(); m_meshUvBase.clear();
     std::vector<uint32_t> order[3];
     std::map<ProxyBLAS*, std::pair<int32_t, std::pair<std::vector<float>, std::vector<float>>>> blasInfo;   // root, (lo, hi)
+    std::map<ProxyBLAS*, std::vector<float>> blasBoxes;      // per BLAS: 6 floats per bounding sub-box (collectBoxes)
 
     std::vector<BuildPrim> top;
     top.reserve(m_objects.size());
@@ -484,6 +501,9 @@ bool Scene::preCalc() {
                 std::vector<float> lo(3), hi(3);
                 refBounds(m_flat, m_srcTris, order[MIRO_GPU_KIND_TRI], root, lo.data(), hi.data());
                 blasInfo[o.m_blas] = std::make_pair(root, std::make_pair(lo, hi));
+                std::vector<float>& boxes = blasBoxes[o.m_blas];
+                collectBoxes(m_flat, root, 2, boxes);
+                if (boxes.empty()) { boxes.insert(boxes.end(), lo.begin(), lo.end()); boxes.insert(boxes.end(), hi.begin(), hi.end()); }   // single-leaf BLAS
                 o.m_blas->root_ref = root; o.m_blas->flattened = true;
             }
             const auto& bi = blasInfo[o.m_blas];
@@ -495,14 +515,18 @@ bool Scene::preCalc() {
             in.blas_root = bi.first; in.reserved[0] = proxyOrdinal++;
             const Matrix4x4 it = inv.transposed();
             for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) m_srcInstNxf.push_back(it.at(r, c));
-            // ProxyObject::getAABB: the eight transformed corners (src/ProxyObject.cpp:16-44)
-            const std::vector<float>&lo = bi.second.first, &hi = bi.second.second;
+            // world bounds: the transformed corners of the BLAS's sub-boxes (cf. ProxyObject::getAABB, src/ProxyObject.cpp:16-44,
+            // which transforms the single root box)
+            const std::vector<float>& boxes = blasBoxes[o.m_blas];
             for (int k = 0; k < 3; ++k) { bp.lo[k] = FLT_MAX; bp.hi[k] = -FLT_MAX; }
-            for (int c = 0; c < 8; ++c) {
-                Vector3 p((c & 1) ? hi[0] : lo[0], (c & 2) ? hi[1] : lo[1], (c & 4) ? hi[2] : lo[2]);
-                p = o.m_transform.transformPoint(p);
-                bp.lo[0] = std::min(bp.lo[0], p.x); bp.lo[1] = std::min(bp.lo[1], p.y); bp.lo[2] = std::min(bp.lo[2], p.z);
-                bp.hi[0] = std::max(bp.hi[0], p.x); bp.hi[1] = std::max(bp.hi[1], p.y); bp.hi[2] = std::max(bp.hi[2], p.z);
+            for (size_t b = 0; b + 6 <= boxes.size(); b += 6) {
+                const float* lo = &boxes[b]; const float* hi = lo + 3;
+                for (int c = 0; c < 8; ++c) {
+                    Vector3 p((c & 1) ? hi[0] : lo[0], (c & 2) ? hi[1] : lo[1], (c & 4) ? hi[2] : lo[2]);
+                    p = o.m_transform.transformPoint(p);
+                    bp.lo[0] = std::min(bp.lo[0], p.x); bp.lo[1] = std::min(bp.lo[1], p.y); bp.lo[2] = std::min(bp.lo[2], p.z);
+                    bp.hi[0] = std::max(bp.hi[0], p.x); bp.hi[1] = std::max(bp.hi[1], p.y); bp.hi[2] = std::max(bp.hi[2], p.z);
+                }
             }
             bp.kind = MIRO_GPU_KIND_INST; bp.index = (uint32_t)m_srcInst.size();
             m_srcInst.push_back(in);
