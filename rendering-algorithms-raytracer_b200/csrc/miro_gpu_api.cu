@@ -186,9 +186,13 @@ static void launch_trace(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n
                          const float4* d_E, float4* d_slots) {
     if (n == 0) return;
     const int grid = trace_grid<MODE>(ctx, n);
-    // rays are claimed in chunks per warp: small batches use the smallest chunk so that every warp gets work
-    const size_t warps = (size_t)grid * (TRACE_BLOCK / 32);
-    const uint32_t chunk = n >= warps * 256 ? 64u : 32u;
+    // rays are claimed one warp-load (32) at a time: measured on the coherent 1080p batch, 64-ray chunks left a tail worth 15 %
+    // of the launch (a warp stuck with two heavy chunks while the rest of the GPU had drained); 16 is no better than 32
+#ifdef MIRO_TRACE_CHUNK
+    const uint32_t chunk = MIRO_TRACE_CHUNK;
+#else
+    const uint32_t chunk = 32u;
+#endif
     const float4* r = reinterpret_cast<const float4*>(d_rays);
     if (MODE == TRACE_ANY_BITS) cudaMemsetAsync(d_bits, 0, ((n + 31) / 32) * sizeof(uint32_t), ctx->stream);
 #define MIRO_LAUNCH(COUNT, ALPHA) k_trace<MODE, COUNT, ALPHA><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(ctx->scene, r, (uint32_t)n, d_count, chunk, d_hits, d_bits, d_E, d_slots, ctx->d_counters, ctx->d_work)
