@@ -69,6 +69,11 @@ typedef struct miro_gpu_hit {   /* 20 bytes */
  *            MIRO_GPU_CHILD_EMPTY  unused slot (flagsIsValid[i] == false)
  *            otherwise (bit 31 set) a leaf reference, see MIRO_GPU_LEAF().             */
 #define MIRO_GPU_CHILD_EMPTY ((int32_t)0x7fffffff)
+/* miro_gpu_scene_desc::root value asking miro_gpu_upload_scene to BUILD the acceleration structure on the GPU (LBVH) over
+ * `tris`, given in any order, with nodes == NULL / n_nodes == 0.  Static triangles only (n_mbtris == n_instances == 0,
+ * MIRO_GPU_EUNSUPPORTED otherwise).  Hit records keep referring to the caller's triangle order.  Replaces the host
+ * BVH::build (src/BVH.cpp:457-1106) for scenes that change every frame; the host-built SAH tree traverses faster. */
+#define MIRO_GPU_ROOT_BUILD_ON_DEVICE ((int32_t)0x7ffffffd)
 #define MIRO_GPU_KIND_TRI 0u    /* static triangle      (reference: Object,      objectType OBJECT) */
 #define MIRO_GPU_KIND_MBTRI 1u  /* motion-blur triangle (reference: MBObject,    MB_OBJECT)         */
 #define MIRO_GPU_KIND_INST 2u   /* instance             (reference: ProxyObject, PROXY_OBJECT)      */

@@ -143,6 +143,7 @@ void loadScene(const std::string& file) {
                 else if (k == "noise") { float v; ss >> v; g_scene->setNoise(v); }
                 else if (k == "sampleenv") { int v; ss >> v; g_scene->setSampleEnv(v != 0); }
                 else if (k == "envmap") { std::string t; float e; ss >> t >> e; g_scene->setEnvMap(getTexture(t)); g_scene->setEnvExposure(e); }
+                else if (k == "seed" || k == "devicebuild") { std::string ignored; ss >> ignored; }      // product-side options
                 else die("scene: unknown key " + k);
             }
         }

@@ -14,6 +14,7 @@ OK, EINVAL, ENODEVICE, ECUDA, ENOSCENE, EUNSUPPORTED, ENOMEM = 0, -1, -2, -3, -4
 TMAX = 1e12
 EPSILON = 0.001
 CHILD_EMPTY = 0x7FFFFFFF
+ROOT_BUILD_ON_DEVICE = 0x7FFFFFFD
 KIND_TRI, KIND_MBTRI, KIND_INST = 0, 1, 2
 LEAF_INDEX_BITS = 26
 

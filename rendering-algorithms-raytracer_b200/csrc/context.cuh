@@ -79,6 +79,7 @@ struct miro_gpu_ctx {
     miro::TraceCounters* d_counters = nullptr;
     uint32_t* d_work = nullptr;                 // [0] next unclaimed ray of the running traversal kernel, [1] blocks that have left
     int sm_count = 148;
+    int build_levels = 0;                       // depth of the last device-built wide tree
     std::vector<miro::EventPair> events;        // pending (not yet summed) timing pairs
     std::vector<miro::EventPair> event_pool;
     double trace_ms = 0.0, total_ms = 0.0;
@@ -113,5 +114,10 @@ void launch_trace_any(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, c
 void launch_trace_shadow(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, const uint32_t* d_count, const float4* d_E, float4* d_slots);
 
 void render_state_free(miro_gpu_ctx* ctx);
+
+// build.cu: LBVH over static triangles on the device
+int build_lbvh_on_device(miro_gpu_ctx* ctx, const float4* d_tris_in, uint32_t n, const DeviceNode** out_nodes, uint32_t* out_n_nodes,
+                         int32_t* out_root, const float4** out_tris, const uint32_t** out_perm);
+int reorder_prims_on_device(miro_gpu_ctx* ctx, const miro_gpu_prim* d_in, const uint32_t* d_perm, uint32_t n, const miro_gpu_prim** out);
 
 }  // namespace miro

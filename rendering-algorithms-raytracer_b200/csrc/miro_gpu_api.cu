@@ -162,6 +162,12 @@ k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const
     }
 }
 
+// Device-built trees: hit records leave the library in the CALLER's triangle numbering.
+__global__ void k_translate_hits(miro_gpu_hit* __restrict__ hits, uint32_t n, const uint32_t* __restrict__ prim_map) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && hits[i].prim >= 0) hits[i].prim = (int32_t)prim_map[hits[i].prim];
+}
+
 template <int MODE>
 static int trace_grid(miro_gpu_ctx* ctx, size_t n) {
     // persistent grid: every SM holds as many blocks as fit (asked of the occupancy calculator once per kernel)
@@ -336,9 +342,12 @@ int miro_gpu_upload_scene(miro_gpu_ctx* ctx, const miro_gpu_scene_desc* d) {
     if (d->n_tris >= (1u << MIRO_GPU_LEAF_INDEX_BITS) || d->n_mbtris >= (1u << MIRO_GPU_LEAF_INDEX_BITS) || d->n_instances >= (1u << MIRO_GPU_LEAF_INDEX_BITS))
         return set_error(ctx, MIRO_GPU_EUNSUPPORTED, "scene desc: more than 2^26 primitives of one kind");
     if (d->n_lights > MIRO_GPU_MAX_LIGHTS) return set_error(ctx, MIRO_GPU_EUNSUPPORTED, "more than MIRO_GPU_MAX_LIGHTS lights");
+    const bool device_build = d->root == MIRO_GPU_ROOT_BUILD_ON_DEVICE;
+    if (device_build && (d->n_mbtris || d->n_instances || d->n_nodes))
+        return set_error(ctx, MIRO_GPU_EUNSUPPORTED, "device BVH build handles static triangles only (no motion-blur triangles, instances or host nodes)");
     // validate the trees and bound the traversal stack: <= 3 pushes per level, + 2 for an instance hop
     std::string err;
-    int top = tree_depth(d, d->root, 0, err);
+    int top = device_build ? 0 : tree_depth(d, d->root, 0, err);
     if (top < 0) return set_error(ctx, MIRO_GPU_EINVAL, "scene desc: " + err);
     int blas = 0;
     for (uint32_t i = 0; i < d->n_instances; ++i) {
@@ -362,24 +371,44 @@ int miro_gpu_upload_scene(miro_gpu_ctx* ctx, const miro_gpu_scene_desc* d) {
     free_scene(ctx);
     int rc;
     const DeviceNode* dn; const miro_gpu_tri* dt; const miro_gpu_mbtri* dm; const miro_gpu_instance* di;
-    std::vector<DeviceNode> cnodes(d->n_nodes);          // 128-byte ABI nodes -> 64-byte device nodes (traverse.cuh)
-    for (uint32_t i = 0; i < d->n_nodes; ++i) cnodes[i] = compress_node(d->nodes[i]);
-    if ((rc = upload_array(ctx, cnodes.data(), cnodes.size(), &dn))) return rc;
-    if ((rc = upload_array(ctx, d->tris, d->n_tris, &dt))) return rc;
+    const uint32_t* d_perm = nullptr;
+    int32_t root = d->root;
+    if (device_build) {
+        // triangles in the caller's order go up once; the build sorts them into leaf order on the device
+        const miro_gpu_tri* d_in;
+        if ((rc = upload_array(ctx, d->tris, d->n_tris, &d_in))) return rc;
+        uint32_t n_nodes = 0; const float4* sorted = nullptr;
+        if ((rc = build_lbvh_on_device(ctx, reinterpret_cast<const float4*>(d_in), d->n_tris, &dn, &n_nodes, &root, &sorted, &d_perm))) return rc;
+        dt = reinterpret_cast<const miro_gpu_tri*>(sorted);
+        if (3 * ctx->build_levels + 2 > SMEM_STACK + LMEM_STACK) return set_error(ctx, MIRO_GPU_EUNSUPPORTED, "device-built BVH too deep for the traversal stack");
+        ctx->n_nodes = n_nodes;
+    } else {
+        std::vector<DeviceNode> cnodes(d->n_nodes);          // 128-byte ABI nodes -> 64-byte device nodes (traverse.cuh)
+        for (uint32_t i = 0; i < d->n_nodes; ++i) cnodes[i] = compress_node(d->nodes[i]);
+        if ((rc = upload_array(ctx, cnodes.data(), cnodes.size(), &dn))) return rc;
+        if ((rc = upload_array(ctx, d->tris, d->n_tris, &dt))) return rc;
+    }
     if ((rc = upload_array(ctx, d->mbtris, d->n_mbtris, &dm))) return rc;
     if ((rc = upload_array(ctx, d->instances, d->n_instances, &di))) return rc;
     ctx->scene.nodes = reinterpret_cast<const float4*>(dn);
     ctx->scene.tris = reinterpret_cast<const float4*>(dt);
     ctx->scene.mbtris = reinterpret_cast<const float4*>(dm);
     ctx->scene.insts = reinterpret_cast<const float4*>(di);
-    ctx->scene.root = d->root;
+    ctx->scene.root = root;
     ctx->scene.n_tris = d->n_tris;
-    ctx->n_nodes = d->n_nodes; ctx->n_tris = d->n_tris; ctx->n_mbtris = d->n_mbtris; ctx->n_insts = d->n_instances;
+    ctx->scene.prim_map = d_perm;
+    if (!device_build) ctx->n_nodes = d->n_nodes;
+    ctx->n_tris = d->n_tris; ctx->n_mbtris = d->n_mbtris; ctx->n_insts = d->n_instances;
 
     DeviceShading& sh = ctx->shading;
     memset(&sh, 0, sizeof(sh));
     const uint32_t n_prims = d->prims ? d->n_tris + d->n_mbtris : 0;
     if ((rc = upload_array(ctx, d->prims, n_prims, &sh.prims))) return rc;
+    if (device_build && n_prims) {       // shading records follow the triangles into leaf order
+        const miro_gpu_prim* sorted_prims;
+        if ((rc = reorder_prims_on_device(ctx, sh.prims, d_perm, n_prims, &sorted_prims))) return rc;
+        sh.prims = sorted_prims;
+    }
     if ((rc = upload_array(ctx, d->normals, (size_t)d->n_normals * 3, &sh.normals))) return rc;
     if ((rc = upload_array(ctx, d->uvs, (size_t)d->n_uvs * 2, &sh.uvs))) return rc;
     if ((rc = upload_array(ctx, d->inst_normal_xform, d->inst_normal_xform ? (size_t)d->n_instances * 9 : 0, &sh.inst_nxf))) return rc;
@@ -433,6 +462,7 @@ int miro_gpu_trace_closest_device(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays,
     MIRO_CUDA(ctx, cudaSetDevice(ctx->device));
     EventPair p = begin_timing(ctx, true);
     launch_trace_closest(ctx, d_rays, n, nullptr, d_hits);
+    if (ctx->scene.prim_map) { k_translate_hits<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_hits, (uint32_t)n, ctx->scene.prim_map); ctx->launches++; }
     end_timing(ctx, p);
     MIRO_CUDA(ctx, cudaGetLastError());
     return MIRO_GPU_OK;
@@ -482,7 +512,10 @@ static int trace_host(miro_gpu_ctx* ctx, const miro_gpu_ray* rays, size_t n, mir
         MIRO_CUDA(ctx, cudaEventRecord(up, ctx->copy_in));
         MIRO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, up, 0));
         EventPair p = begin_timing(ctx, true);
-        if (hits) launch_trace_closest(ctx, ctx->d_rays.ptr + off, m, nullptr, ctx->d_hits.ptr + off);
+        if (hits) {
+            launch_trace_closest(ctx, ctx->d_rays.ptr + off, m, nullptr, ctx->d_hits.ptr + off);
+            if (ctx->scene.prim_map) { k_translate_hits<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_hits.ptr + off, (uint32_t)m, ctx->scene.prim_map); ctx->launches++; }
+        }
         else launch_trace_any(ctx, ctx->d_rays.ptr + off, m, nullptr, ctx->d_bits.ptr + off / 32);
         end_timing(ctx, p);
         MIRO_CUDA(ctx, cudaEventRecord(done, ctx->stream));

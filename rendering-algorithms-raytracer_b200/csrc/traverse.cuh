@@ -90,6 +90,7 @@ struct DeviceScene {
     const float4* insts;     // 4 x float4 per instance
     int32_t root;
     uint32_t n_tris;
+    const uint32_t* prim_map;   // device-built trees only: caller's triangle index of device triangle i (NULL otherwise)
 };
 
 // 32-byte read-only global load (sm_100: LDG.E.256): one L1 wavefront where two 16-byte loads take two.  The traversal
@@ -280,7 +281,7 @@ __device__ __forceinline__ void pop_next(Lane& L, TraversalStack& st) {
 struct DeviceNode { uint32_t w[16]; };
 static_assert(sizeof(DeviceNode) == 64, "DeviceNode layout");
 
-__host__ inline DeviceNode compress_node(const miro_gpu_node& n) {
+__host__ __device__ inline DeviceNode compress_node(const miro_gpu_node& n) {
     DeviceNode o;
     for (int i = 0; i < 16; ++i) o.w[i] = 0;
     const float* lo[3] = {n.lo_x, n.lo_y, n.lo_z};
@@ -304,7 +305,7 @@ __host__ inline DeviceNode compress_node(const miro_gpu_node& n) {
             }
             qlo |= a << (8 * c); qhi |= b << (8 * c);
         }
-        memcpy(&o.w[k], &pmin, 4);
+        union { float f; uint32_t u; } cv; cv.f = pmin; o.w[k] = cv.u;
         o.w[3] |= (uint32_t)e << (8 * k);
         o.w[8 + k] = qlo; o.w[11 + k] = qhi;
     }

@@ -536,7 +536,13 @@ bool Scene::preCalc() {
         }
         top.push_back(bp);
     }
-    m_flat.root = build_wide_bvh(top, m_flat.nodes, order, &m_flat.top_stats);
+    bool onDevice = m_buildOnDevice;
+    for (const BuildPrim& bp : top) if (bp.kind != MIRO_GPU_KIND_TRI) onDevice = false;
+    if (onDevice) {
+        // hand the triangles over in object order; miro_gpu_upload_scene builds an LBVH over them on the GPU
+        m_flat.root = MIRO_GPU_ROOT_BUILD_ON_DEVICE;
+        for (const BuildPrim& bp : top) order[MIRO_GPU_KIND_TRI].push_back(bp.index);
+    } else m_flat.root = build_wide_bvh(top, m_flat.nodes, order, &m_flat.top_stats);
 
     // gather primitives into leaf order
     m_flat.tris.resize(order[0].size()); m_flat.mbtris.resize(order[1].size()); m_flat.instances.resize(order[2].size());

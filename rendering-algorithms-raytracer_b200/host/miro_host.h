@@ -251,6 +251,9 @@ public:
     void setNoise(float n) { m_noiseThreshold = n; }
     void setSampleEnv(bool b) { m_sampleLightFromEnv = b; }
     void setSeed(uint64_t s) { m_seed = s; }
+    // Build the acceleration structure on the GPU at attach() instead of on the host in preCalc() (static triangles only;
+    // falls back to the host build when the scene has motion-blur objects or instances).
+    void setBuildOnDevice(bool b) { m_buildOnDevice = b; }
 
     // Scene::preCalc (src/Scene.cpp:63-79): build the BVHs and flatten.  Pure host work; no GPU needed.
     // Returns false (see lastError()) when the scene uses something outside the supported scope.
@@ -286,6 +289,7 @@ protected:
     float m_envExposure = 1.f;
     float m_noiseThreshold = 0.01f;
     bool m_sampleLightFromEnv = false;
+    bool m_buildOnDevice = false;
     uint64_t m_seed = 3163513;             // the reference seeds its MT19937 with this (src/Scene.cpp:24)
     FlatScene m_flat;
     std::vector<const Material*> m_materialList;

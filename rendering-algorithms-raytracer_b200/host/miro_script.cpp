@@ -6,7 +6,7 @@
 //   image W H
 //   camera [eye x y z] [lookat x y z] [viewdir x y z] [up x y z] [fov deg] [focus f] [aperture a] [shutter s]
 //   scene  [bgcolor r g b] [pathtrace 0|1] [numpaths n] [maxbounces n] [minsubdivs n] [maxsubdivs n]
-//          [noise f] [sampleenv 0|1] [envmap TEX exposure] [seed n]
+//          [noise f] [sampleenv 0|1] [envmap TEX exposure] [seed n] [devicebuild 0|1]
 //   texture NAME file.{hdr,tga,ppm}
 //   material NAME lambert [kd r g b] [ka r g b] [colormap TEX]
 //   material NAME blinn   [kd ..] [ka ..] [ks ..] [specexp f] [specamt f] [ior f | ior_i i f] [reflect f] [refract f]
@@ -74,6 +74,7 @@ bool loadSceneScript(const char* file, const char* assetRoot, LoadedScene& out, 
                 else if (k == "noise") { float v; ss >> v; out.scene->setNoise(v); }
                 else if (k == "sampleenv") { int v; ss >> v; out.scene->setSampleEnv(v != 0); }
                 else if (k == "seed") { unsigned long long v; ss >> v; out.scene->setSeed(v); }
+                else if (k == "devicebuild") { int v; ss >> v; out.scene->setBuildOnDevice(v != 0); }
                 else if (k == "envmap") {
                     std::string t; float e; ss >> t >> e;
                     if (!textures.count(t)) return fail("unknown texture " + t);
