@@ -293,6 +293,7 @@ __host__ __device__ inline DeviceNode compress_node(const miro_gpu_node& n) {
         // smallest power of two step with p + 255 * step >= pmax (evaluated in double: exact for these operands)
         int e = 1;
         const double ext = (double)pmax - (double)pmin;
+        if (ext > 0.0) { int ex; frexp(ext / 255.0, &ex); e = ex + 126; e = e < 1 ? 1 : (e > 254 ? 254 : e); }    // 2^(ex-1) <= ext/255 < 2^ex
         while (e < 254 && 255.0 * ldexp(1.0, e - 127) < ext) ++e;
         const double step = ldexp(1.0, e - 127);
         uint32_t qlo = 0, qhi = 0;
