@@ -149,6 +149,26 @@ def reference_trace(fx, batches, threads, repeat, warmup=0, mean=False):
     return (float(np.mean(ts)) if mean else min(ts)), len(rays), "port", 1
 
 
+def bind_to_gpu_numa_node(device):
+    """Pin this rank to the CPUs local to its GPU (sysfs local_cpulist of the GPU's PCI function) BEFORE any pinned host
+    buffer is allocated, so the e2e leg's H2D / D2H copies do not cross the socket interconnect.  Best effort."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        txt = open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def render_leg(device):
     """Scene::raytraceImage through miro_gpu_render (wavefront path tracer) on the C4 stand-in at 1024x1024, 16 paths,
     4 indirect segments: rays = Scene::trace queries counted on the device.  Extra evidence beside the trace metric."""
@@ -226,6 +246,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this framework has no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
+    bind_to_gpu_numa_node(local)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <float.h>
+#include <stdlib.h>
 #include "context.cuh"
 
 namespace miro {
@@ -77,6 +78,8 @@ struct BinTree {
     int* first; int* last;      // range of sorted triangles covered by internal node i
     float* lo;  float* hi;      // 3 floats per internal node
     int* visits;                // bottom-up arrival counters
+    float* cost;                // SAH cost of the subtree as built (per internal node)
+    int* is_leaf;               // the subtree is cheaper as ONE leaf of <= 4 triangles than split (decided bottom-up)
 };
 
 __global__ void k_radix_tree(const unsigned long long* __restrict__ keys, int n, BinTree t) {
@@ -107,7 +110,7 @@ __global__ void k_radix_tree(const unsigned long long* __restrict__ keys, int n,
 }
 
 // Bounds of every internal node, bottom-up: the second thread to arrive at a node owns it (its two children are complete).
-__global__ void k_fit(const float4* __restrict__ tris_sorted, int n, BinTree t) {
+__global__ void k_fit(const float4* __restrict__ tris_sorted, int n, BinTree t, float level_cost) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int node = t.leaf_parent[i];
@@ -116,20 +119,32 @@ __global__ void k_fit(const float4* __restrict__ tris_sorted, int n, BinTree t) 
         if (atomicAdd(&t.visits[node], 1) == 0) return;
         float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
         const int c[2] = {t.left[node], t.right[node]};
+        float child_term = 0.f;           // sum over the two children of area * subtree cost
         for (int k = 0; k < 2; ++k) {
+            float clo[3], chi[3], ccost;
             if (c[k] < 0) {
                 const float4* p = tris_sorted + 3 * (size_t)(~c[k]);
-                for (int v = 0; v < 3; ++v) {
-                    const float4 q = p[v];
-                    lo[0] = fminf(lo[0], q.x); lo[1] = fminf(lo[1], q.y); lo[2] = fminf(lo[2], q.z);
-                    hi[0] = fmaxf(hi[0], q.x); hi[1] = fmaxf(hi[1], q.y); hi[2] = fmaxf(hi[2], q.z);
-                }
+                clo[0] = fminf(p[0].x, fminf(p[1].x, p[2].x)); clo[1] = fminf(p[0].y, fminf(p[1].y, p[2].y)); clo[2] = fminf(p[0].z, fminf(p[1].z, p[2].z));
+                chi[0] = fmaxf(p[0].x, fmaxf(p[1].x, p[2].x)); chi[1] = fmaxf(p[0].y, fmaxf(p[1].y, p[2].y)); chi[2] = fmaxf(p[0].z, fmaxf(p[1].z, p[2].z));
+                ccost = 1.f;
             } else {
                 // written by another thread before its atomicAdd: read through L2
-                for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], __ldcg(&t.lo[3 * c[k] + a])); hi[a] = fmaxf(hi[a], __ldcg(&t.hi[3 * c[k] + a])); }
+                for (int a = 0; a < 3; ++a) { clo[a] = __ldcg(&t.lo[3 * c[k] + a]); chi[a] = __ldcg(&t.hi[3 * c[k] + a]); }
+                ccost = __ldcg(&t.cost[c[k]]);
             }
+            const float dx = chi[0] - clo[0], dy = chi[1] - clo[1], dz = chi[2] - clo[2];
+            child_term += (dx * dy + dy * dz + dz * dx) * ccost;
+            for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], clo[a]); hi[a] = fmaxf(hi[a], chi[a]); }
         }
         for (int a = 0; a < 3; ++a) { t.lo[3 * node + a] = lo[a]; t.hi[3 * node + a] = hi[a]; }
+        // surface-area heuristic, bottom-up: keep the split only when it is cheaper than one leaf holding the whole range
+        const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        const float area = fmaxf(dx * dy + dy * dz + dz * dx, 1e-30f);
+        const int count = t.last[node] - t.first[node] + 1;
+        const float split_cost = level_cost + child_term / area;    // level_cost: one binary level of a 4-wide node, in triangle tests
+        const bool leaf = count <= (int)MIRO_GPU_MAX_LEAF && (float)count <= split_cost;
+        t.cost[node] = leaf ? (float)count : split_cost;
+        t.is_leaf[node] = leaf ? 1 : 0;
         node = t.parent[node];
     }
 }
@@ -150,6 +165,7 @@ __global__ void k_gather_prims(const miro_gpu_prim* __restrict__ in, const uint3
 struct WideItem { int bin; int wide; };
 
 __device__ __forceinline__ int range_size(const BinTree& t, int c) { return c < 0 ? 1 : t.last[c] - t.first[c] + 1; }
+__device__ __forceinline__ bool is_leaf_child(const BinTree& t, int c) { return c < 0 || t.is_leaf[c]; }
 
 __global__ void k_collapse(BinTree t, const float4* __restrict__ tris_sorted, const WideItem* __restrict__ in, int n_in,
                            WideItem* __restrict__ out, int* __restrict__ n_out, int* __restrict__ n_wide, DeviceNode* __restrict__ nodes) {
@@ -160,8 +176,8 @@ __global__ void k_collapse(BinTree t, const float4* __restrict__ tris_sorted, co
     int kids[4]; int nk = 2;
     kids[0] = t.left[it.bin]; kids[1] = t.right[it.bin];
     while (nk < 4) {
-        int best = -1, best_sz = MIRO_GPU_MAX_LEAF;
-        for (int k = 0; k < nk; ++k) { const int sz = range_size(t, kids[k]); if (kids[k] >= 0 && sz > best_sz) { best_sz = sz; best = k; } }
+        int best = -1, best_sz = 0;
+        for (int k = 0; k < nk; ++k) { const int sz = range_size(t, kids[k]); if (!is_leaf_child(t, kids[k]) && sz > best_sz) { best_sz = sz; best = k; } }
         if (best < 0) break;
         const int c = kids[best];
         kids[best] = t.left[c]; kids[nk++] = t.right[c];
@@ -185,7 +201,7 @@ __global__ void k_collapse(BinTree t, const float4* __restrict__ tris_sorted, co
             for (int a = 0; a < 3; ++a) { lo[a] = t.lo[3 * c + a]; hi[a] = t.hi[3 * c + a]; }
         }
         nd.lo_x[k] = lo[0]; nd.lo_y[k] = lo[1]; nd.lo_z[k] = lo[2]; nd.hi_x[k] = hi[0]; nd.hi_y[k] = hi[1]; nd.hi_z[k] = hi[2];
-        if (count <= (int)MIRO_GPU_MAX_LEAF) nd.child[k] = MIRO_GPU_LEAF(MIRO_GPU_KIND_TRI, first, count);
+        if (is_leaf_child(t, c)) nd.child[k] = MIRO_GPU_LEAF(MIRO_GPU_KIND_TRI, first, count);
         else {
             const int w = atomicAdd(n_wide, 1);
             nd.child[k] = w;
@@ -229,7 +245,7 @@ int build_lbvh_on_device(miro_gpu_ctx* ctx, const float4* d_tris_in, uint32_t n,
     Scratch<Bounds6> bounds; Scratch<unsigned long long> keys_in, keys_out; Scratch<uint32_t> vals_in; Scratch<unsigned char> tmp;
     Scratch<int> ints; Scratch<float> boxes; Scratch<WideItem> queue; Scratch<int> counters;
     MIRO_CUDA(ctx, bounds.alloc(1)); MIRO_CUDA(ctx, keys_in.alloc(n)); MIRO_CUDA(ctx, keys_out.alloc(n)); MIRO_CUDA(ctx, vals_in.alloc(n));
-    MIRO_CUDA(ctx, ints.alloc((size_t)n * 7)); MIRO_CUDA(ctx, boxes.alloc((size_t)n * 6)); MIRO_CUDA(ctx, queue.alloc((size_t)n * 2)); MIRO_CUDA(ctx, counters.alloc(4));
+    MIRO_CUDA(ctx, ints.alloc((size_t)n * 8)); MIRO_CUDA(ctx, boxes.alloc((size_t)n * 7)); MIRO_CUDA(ctx, queue.alloc((size_t)n * 2)); MIRO_CUDA(ctx, counters.alloc(4));
     // 1. centroid bounds, Morton keys
     const Bounds6 init = {{INT_MAX, INT_MAX, INT_MAX}, {INT_MIN, INT_MIN, INT_MIN}};
     MIRO_CUDA(ctx, cudaMemcpyAsync(bounds.p, &init, sizeof(init), cudaMemcpyHostToDevice, s));
@@ -245,12 +261,14 @@ int build_lbvh_on_device(miro_gpu_ctx* ctx, const float4* d_tris_in, uint32_t n,
     BinTree t;
     t.left = ints.p; t.right = ints.p + n; t.parent = ints.p + 2 * (size_t)n; t.leaf_parent = ints.p + 3 * (size_t)n;
     t.first = ints.p + 4 * (size_t)n; t.last = ints.p + 5 * (size_t)n; t.visits = ints.p + 6 * (size_t)n;
-    t.lo = boxes.p; t.hi = boxes.p + 3 * (size_t)n;
+    t.lo = boxes.p; t.hi = boxes.p + 3 * (size_t)n; t.cost = boxes.p + 6 * (size_t)n; t.is_leaf = ints.p + 7 * (size_t)n;
     MIRO_CUDA(ctx, cudaMemsetAsync(t.visits, 0, (size_t)n * sizeof(int), s));
     k_radix_tree<<<grid(n - 1), B, 0, s>>>(keys_out.p, (int)n, t);
-    k_fit<<<grid(n), B, 0, s>>>(tris_sorted, (int)n, t);
-    // 4. collapse to the wide tree, one launch per level; at most n/2 wide nodes (each has >= 2 children and > 4 triangles)
-    const size_t max_wide = (size_t)n / 2 + 1;
+    float level_cost = 1.0f;
+    if (const char* e = getenv("MIRO_LBVH_LEVEL_COST")) { const float v = (float)atof(e); if (v > 0.f) level_cost = v; }      // tuning aid
+    k_fit<<<grid(n), B, 0, s>>>(tris_sorted, (int)n, t, level_cost);
+    // 4. collapse to the wide tree, one launch per level; a wide node stands for a binary internal node: at most n - 1 of them
+    const size_t max_wide = (size_t)n;
     MIRO_CUDA(ctx, cudaMalloc((void**)&nodes, max_wide * sizeof(DeviceNode))); keep(nodes);
     WideItem* q[2] = {queue.p, queue.p + n};
     const WideItem root_item = {0, 0};
