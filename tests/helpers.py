@@ -169,3 +169,83 @@ def write_obj_scene(fx, tmp):
     sp = os.path.join(tmp, "scene.miro")
     open(sp, "w").write(script)
     return sp
+
+
+class ReferenceTreeScene:
+    """The reference's OWN QBVH (dumped by oracle/ref_harness.cpp --dump-qbvh: QBVH_Node bounds / children / TriCache4 lanes,
+    src/BVH.h:89-104) flattened 1:1 into the miro_gpu_node / leaf-ordered triangle layout of include/miro_gpu.h — what the
+    flattenQ() glue of INTEGRATION.md produces inside Miro — held as numpy arrays behind a miro_gpu_scene_desc."""
+
+    def __init__(self, fx):
+        z = fx.z
+        bounds, child, leaves = z["qbvh_bounds"], z["qbvh_child"], z["qbvh_leaves"]
+        meshes = [fx.mesh(k) for k in range(len(fx.names))]
+        nbase = np.cumsum([0] + [len(m["normals"]) for m in meshes])
+        tris, prims = [], []
+        leaf_ref = np.zeros(len(leaves), np.int64)
+        for li, lanes in enumerate(leaves):
+            first, count = len(tris), 0
+            for mesh, tri, kind in lanes:
+                if mesh < 0:
+                    continue
+                assert kind == 0, "only plain Objects in these fixtures"
+                m = meshes[mesh]
+                tris.append(m["vertices"][m["vidx"][tri]])
+                prims.append(list(nbase[mesh] + m["nidx"][tri]) + [0xffffffff] * 3 + [0, mesh, tri, 0, 0, 0])
+                count += 1
+            leaf_ref[li] = (0x80000000 | ((count - 1) << 26) | first) - (1 << 32)      # MIRO_GPU_LEAF(KIND_TRI, first, count)
+        self.nodes = np.zeros((len(bounds), 32), np.float32)
+        self.nodes[:, :24] = bounds
+        ch = self.nodes[:, 24:28].view(np.int32)
+        for i in range(len(child)):
+            for k in range(4):
+                c = int(child[i, k])
+                ch[i, k] = capi.CHILD_EMPTY if c == -(1 << 31) else (c if c >= 0 else leaf_ref[~c])
+        t = np.zeros((len(tris), 3, 4), np.float32); t[:, :, :3] = np.array(tris, np.float32)
+        self.tris = t
+        self.prims = np.array(prims, np.uint32)
+        self.normals = np.concatenate([m["normals"] for m in meshes]).astype(np.float32)
+        self.material = capi.Material(); self.material.kind = 0
+        self.material.kd[:] = [0.8, 0.8, 0.8]; self.material.spec_gloss = 1.0; self.material.color_map = -1; self.material.alpha_map = -1
+        d = capi.SceneDesc(); d.abi_version = 1
+        d.nodes = self.nodes.ctypes.data_as(C.POINTER(capi.Node)); d.n_nodes = len(self.nodes); d.root = 0
+        d.tris = self.tris.ctypes.data_as(C.POINTER(capi.Tri)); d.n_tris = len(self.tris)
+        d.prims = self.prims.ctypes.data_as(C.POINTER(capi.Prim))
+        d.normals = self.normals.ctypes.data_as(C.POINTER(C.c_float)); d.n_normals = len(self.normals)
+        d.materials = C.pointer(self.material); d.n_materials = 1
+        d.env_map = -1; d.env_exposure = 1.0
+        self.d = d
+        self.mesh_of = self.prims[:, 7].astype(np.int64); self.tri_of = self.prims[:, 8].astype(np.int64)
+        self.ctx = None
+
+    def desc(self):
+        return self.d
+
+    def resolve_hits(self, hits):
+        prim = hits["prim"]; ok = prim >= 0
+        mesh = np.full(len(hits), -1, np.int64); tri = np.full(len(hits), -1, np.int64)
+        mesh[ok] = self.mesh_of[prim[ok]]; tri[ok] = self.tri_of[prim[ok]]
+        return mesh, tri, np.full(len(hits), -1, np.int64)
+
+    def attach(self, device=0):
+        L = capi.lib()
+        ctx = C.c_void_p()
+        rc = L.miro_gpu_create(C.byref(ctx), device)
+        if rc:
+            raise mb.MiroError("miro_gpu_create: " + L.miro_gpu_last_error(None).decode())
+        self.ctx, self.L = ctx, L
+        rc = L.miro_gpu_upload_scene(ctx, C.byref(self.d))
+        if rc:
+            raise mb.MiroError("miro_gpu_upload_scene: " + L.miro_gpu_last_error(ctx).decode())
+        return self
+
+    def trace_closest(self, rays):
+        rays = np.ascontiguousarray(rays, mb.RAY_DTYPE); hits = np.empty(len(rays), mb.HIT_DTYPE)
+        rc = self.L.miro_gpu_trace_closest(self.ctx, rays.ctypes.data, len(rays), hits.ctypes.data)
+        if rc:
+            raise mb.MiroError(self.L.miro_gpu_last_error(self.ctx).decode())
+        return hits
+
+    def close(self):
+        if self.ctx:
+            self.L.miro_gpu_destroy(self.ctx); self.ctx = None

@@ -152,3 +152,16 @@ def test_forty_thousand_instances():
     assert (np.abs(g["t"] - oh["t"])[both] <= 1e-5 * scale[both]).mean() >= 0.9999
     assert (sc.trace_any(rays) == hit).all()
     sc.close()
+
+
+@pytest.mark.parametrize("name", ["c1_cornell", "c2_explosion"])
+def test_gpu_traces_the_references_own_tree(name):
+    """Drop-in boundary: the reference's own QBVH, flattened 1:1 as INTEGRATION.md's flattenQ() would inside Miro, uploaded
+    through miro_gpu_upload_scene and traced through miro_gpu_trace_closest."""
+    fx = helpers.Fixture(helpers.fixture_path(name))
+    sc = helpers.ReferenceTreeScene(fx).attach(0)
+    hits = sc.trace_closest(fx.rays)
+    st = helpers.compare_hits(sc, hits, fx.hits, t_rel=1e-5, rays=fx.rays)
+    print(name, {k: v for k, v in st.items() if k != "hard_idx"})
+    assert st["hard"] == 0 and st["id_match"] >= 0.999 and st["frac_t_within"] == 1.0, st
+    sc.close()

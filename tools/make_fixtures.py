@@ -33,8 +33,8 @@ REFHIT = np.dtype([("t", "f4"), ("a", "f4"), ("b", "f4"), ("mesh", "i4"), ("tri"
 
 # per scene: render the float image? run the stock 8-bit render? how many incoherent rays to add?
 SCENES = {
-    "c1_cornell": dict(render=True, stock=True, incoherent=0),
-    "c2_explosion": dict(render=True, stock=True, incoherent=1 << 20),
+    "c1_cornell": dict(render=True, stock=True, incoherent=0, qbvh=True),
+    "c2_explosion": dict(render=True, stock=True, incoherent=1 << 20, qbvh=True),
     "c5_mb_instances": dict(render=True, stock=False, incoherent=1 << 19, threads=1),
     "c3_dome_pt": dict(render=True, stock=False, incoherent=0, threads=1, converged=32),
     "c4_cornell_pt": dict(render=True, stock=False, incoherent=0, threads=1, converged=64),
@@ -122,7 +122,7 @@ def pack(out, meshes, names, script_text, events, rays, hits, ray_index, radianc
         else:
             d["tex_" + name] = tex
     for k, v in (extra or {}).items():
-        d[k] = v.astype(radiance_dtype) if v.dtype == np.float32 else v
+        d[k] = v.astype(radiance_dtype) if (v.dtype == np.float32 and not k.startswith("qbvh")) else v
     np.savez_compressed(out, **d)
     print("wrote", out, "%.2f MB" % (os.path.getsize(out) / 1e6))
 
@@ -132,7 +132,7 @@ def run(scene, opt):
     text = open(script).read()
     threads = opt.get("threads", 1)
     with tempfile.TemporaryDirectory() as tmp:
-        cmd = [REF, "--scene", script, "--assets", ASSETS, "--threads", str(threads), "--dump-meshes", tmp, "--dump-textures", tmp,
+        cmd = [REF, "--scene", script, "--assets", ASSETS, "--threads", str(threads), "--dump-meshes", tmp, "--dump-textures", tmp, "--dump-qbvh", os.path.join(tmp, "qbvh.bin"),
                "--dump-primary", os.path.join(tmp, "primary.rays")]
         if opt["render"]:
             cmd += ["--render-float", os.path.join(tmp, "radiance.f32")]
@@ -150,6 +150,13 @@ def run(scene, opt):
                 tw, th, tc, kind = np.frombuffer(b[:16], np.int32)
                 textures[f[:-4]] = (np.frombuffer(b[16:], np.float32).reshape(th, tw, tc).copy(), int(kind))
         extra = {}
+        if opt.get("qbvh"):           # the reference's own QBVH (BVH.cpp:100-389), walked by the harness: bounds, children, leaf lanes
+            b = open(os.path.join(tmp, "qbvh.bin"), "rb").read()
+            nn, nl = np.frombuffer(b[:8], np.int32)
+            off = 8
+            extra["qbvh_bounds"] = np.frombuffer(b[off:off + nn * 96], np.float32).reshape(nn, 24).copy(); off += nn * 96
+            extra["qbvh_child"] = np.frombuffer(b[off:off + nn * 16], np.int32).reshape(nn, 4).copy(); off += nn * 16
+            extra["qbvh_leaves"] = np.frombuffer(b[off:off + nl * 48], np.int32).reshape(nl, 4, 3).copy()
         if opt.get("converged"):      # a second, converged render of the same scene: numpaths multiplied
             conv = os.path.join(tmp, "converged.miro")
             import re
