@@ -10,6 +10,7 @@ namespace miro {
 namespace {
 
 constexpr int kBins = 16;
+static uint32_t kMaxLeaf = MIRO_GPU_MAX_LEAF;   // tuning aid: MIRO_BVH_MAX_LEAF (the ABI's leaf reference holds up to 8)
 static float kTraversalCost = 1.0f;      // one binary split level, in units of one triangle test (tunable: MIRO_BVH_TRAVERSAL_COST)
 constexpr float kPrimCost = 1.0f;
 
@@ -74,7 +75,7 @@ struct Builder {
 
         uint32_t mid = 0;
         bool have_split = false;
-        if (!homog && count <= MIRO_GPU_MAX_LEAF) {
+        if (!homog && count <= kMaxLeaf) {
             // a would-be leaf with mixed primitive kinds: separate the kinds (leaves are homogeneous)
             const uint32_t k0 = prims[idx[first]].kind;
             auto it = std::partition(idx.begin() + first, idx.begin() + first + count, [&](uint32_t p) { return prims[p].kind == k0; });
@@ -108,7 +109,7 @@ struct Builder {
                     if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
                 }
             }
-            if (count <= MIRO_GPU_MAX_LEAF && homog && !(best_cost < kPrimCost * count)) {
+            if (count <= kMaxLeaf && homog && !(best_cost < kPrimCost * count)) {
                 bn[me].first = first; bn[me].count = count; return me;   // a leaf is cheaper
             }
             if (best_axis >= 0 && depth < 40) {   // beyond 40 levels fall through to balanced median splits
@@ -123,7 +124,7 @@ struct Builder {
             }
             if (!have_split) {
                 // all centroids coincide (or a degenerate partition): median split in index order
-                if (count <= MIRO_GPU_MAX_LEAF && homog) { bn[me].first = first; bn[me].count = count; return me; }
+                if (count <= kMaxLeaf && homog) { bn[me].first = first; bn[me].count = count; return me; }
                 int axis = 0; float e = -1.f;
                 for (int k = 0; k < 3; ++k) if (box.hi[k] - box.lo[k] > e) { e = box.hi[k] - box.lo[k]; axis = k; }
                 mid = count / 2;
@@ -196,6 +197,7 @@ struct Collapser {
 int32_t build_wide_bvh(const std::vector<BuildPrim>& prims, std::vector<miro_gpu_node>& nodes,
                        std::vector<uint32_t> order[3], BvhStats* stats) {
     if (prims.empty()) return MIRO_GPU_CHILD_EMPTY;
+    if (const char* e = getenv("MIRO_BVH_MAX_LEAF")) { const int v = atoi(e); if (v >= 1 && v <= 8) kMaxLeaf = (uint32_t)v; }
     if (const char* e = getenv("MIRO_BVH_TRAVERSAL_COST")) { const float v = (float)atof(e); if (v > 0.f) kTraversalCost = v; }
     Builder b(prims);
     const int32_t root = b.build(0, (uint32_t)prims.size(), 0);
