@@ -213,7 +213,8 @@ def main():
     hbm_peak, peak_src = peaks()
     config = {"workload": WORKLOAD, "scene": SCENE, "triangles": int(sum(len(fx.mesh(k)["vidx"]) for k in range(len(fx.names)))),
               "rays_per_step_per_gpu": 3 * N_BATCH, "l2_policy": "inputs_larger_than_L2 (298 MB of rays per step; the 6 MB BVH stays L2-resident by nature of the workload)",
-              "sharding": "rays per rank, scene replicated, no collective"}
+              "sharding": "rays per rank, scene replicated, no collective",
+              "launch_chaining": "the 3 traversal launches of a step are chained with programmatic dependent launch (miro_gpu_set_trace_chaining) in the timed region; per-launch times come from a separate, unchained pass"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -291,20 +292,35 @@ def main():
     sc.enable_counting(False)
 
     sampler = ClockSampler(local); sampler.start()
+    sc.set_trace_chaining(True)
     for _ in range(args.warmup):
         step()
     barrier()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    # timed region: K steps back to back, bracketed by two events on the launching stream (no events between the launches of a
+    # step: consecutive traversal launches are chained by programmatic dependent launch, which an event record would break)
+    sc.set_trace_chaining(True)       # all ray buffers of the step were complete long before: the contract holds
+    e_first, e_last = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
+    e_first.record(stream)
+    for k in range(args.steps):
+        step()
+    e_last.record(stream)
+    stream.synchronize()
+    barrier()
+    clocks = sampler.finish()
+    total_ms = e_first.elapsed_time(e_last)
+    sc.set_trace_chaining(False)
+    # the chained launches must have produced what the unchained ones produce
+    chk = d_hits[1].cpu().numpy().view(mb.HIT_DTYPE).reshape(-1)
+    assert np.array_equal(chk["prim"], inco_hits["prim"]) and np.array_equal(chk["t"], inco_hits["t"])
+    # per-launch durations (roofline of the dominant kernel): a second pass with an event after every launch
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     for k in range(args.steps):
         ev[k][0].record(stream)
         sc.trace_closest_device(d_rays[0].data_ptr(), N_BATCH, d_hits[0].data_ptr()); ev[k][1].record(stream)
         sc.trace_closest_device(d_rays[1].data_ptr(), N_BATCH, d_hits[1].data_ptr()); ev[k][2].record(stream)
         sc.trace_any_device(d_rays[2].data_ptr(), N_BATCH, d_bits.data_ptr()); ev[k][3].record(stream)
     stream.synchronize()
-    barrier()
-    clocks = sampler.finish()
-    total_ms = ev[0][0].elapsed_time(ev[-1][3])
     launch_ms = [float(np.mean([ev[k][i].elapsed_time(ev[k][i + 1]) for k in range(args.steps)])) for i in range(3)]
     if world > 1:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)

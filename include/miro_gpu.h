@@ -223,8 +223,8 @@ typedef struct miro_gpu_counters {
     uint64_t nodes_fetched;     /* 128-byte nodes fetched (only counted when counting is enabled) */
     uint64_t tris_tested;       /* triangles tested */
     uint64_t insts_entered;     /* instance transforms fetched */
-    double trace_ms;            /* device time of the traversal kernels (CUDA events) */
-    double total_ms;            /* device time of everything the last trace/render call launched */
+    double trace_ms;            /* device time of the traversal kernels (CUDA events), accumulated while counting is enabled */
+    double total_ms;            /* device time of whole trace / render calls, accumulated while counting is enabled */
     uint64_t kernel_launches;   /* kernels launched by this context since the last reset */
 } miro_gpu_counters;
 
@@ -245,6 +245,17 @@ size_t miro_gpu_sizeof(int k);
  * NULL restores the context's own stream.  Lets the caller order work against torch streams. */
 int miro_gpu_set_stream(miro_gpu_ctx* ctx, void* cuda_stream);
 
+/* Trace chaining (default off).  When on, consecutive miro_gpu_trace_*_device calls of this context are launched with
+ * programmatic dependent launch: the next traversal kernel starts filling the SMs while the previous one drains its last rays
+ * (each kernel has a start-up ramp and a tail at falling occupancy; on the 3-launch benchmark step this is worth ~20 %).
+ * CONTRACT while it is on: the inputs of a trace call (ray buffer, device-side count) must already be complete when the
+ * PREVIOUS trace call of the context is issued — i.e. they must not be produced by work enqueued on the stream between the two
+ * calls, because the later kernel no longer waits for the complete end of everything before it — and two consecutive calls
+ * must not write overlapping output ranges with different values (their order of writing is not defined).  Outputs are complete, as
+ * always, for any work enqueued after the call that does not use this mechanism (copies, other kernels, events).
+ * miro_gpu_render never chains its own launches.  Timing events (enable_counting) break the chain. */
+int miro_gpu_set_trace_chaining(miro_gpu_ctx* ctx, int on);
+
 /* Copy a flattened scene to the device (replaces any previous scene of this context). */
 int miro_gpu_upload_scene(miro_gpu_ctx* ctx, const miro_gpu_scene_desc* desc);
 
@@ -261,8 +272,9 @@ int miro_gpu_trace_any_device(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, siz
  * linear radiance before Image::Map.  rgb_out may be a host or a device pointer. */
 int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, const miro_gpu_render_params* params, float* rgb_out);
 
-/* Counters.  enable != 0 switches the traversal kernels to their instrumented variant (node / triangle
- * / instance fetch counts, used for the roofline's algorithmic bytes); ray counts and times are always kept. */
+/* Counters.  enable != 0 switches the traversal kernels to their instrumented variant (node / triangle / instance fetch
+ * counts, used for the roofline's algorithmic bytes) and brackets the library's launches with timing events; ray counts
+ * and launch counts are always kept. */
 int miro_gpu_enable_counting(miro_gpu_ctx* ctx, int enable);
 int miro_gpu_get_counters(miro_gpu_ctx* ctx, miro_gpu_counters* out);
 int miro_gpu_reset_counters(miro_gpu_ctx* ctx);

@@ -65,6 +65,8 @@ struct miro_gpu_ctx {
     std::string error;
     bool has_scene = false;
     bool counting = false;
+    bool chain_traces = false;    // miro_gpu_set_trace_chaining: consecutive *_device trace launches may overlap (PDL)
+    bool in_api_trace = false;    // set around the launches of miro_gpu_trace_*_device (the only ones that may chain)
     bool has_alpha = false;       // some material has an alpha map with an alpha channel: traversal kernels evaluate cut-outs
 
     // scene storage (device)
@@ -79,6 +81,7 @@ struct miro_gpu_ctx {
     miro::TraceCounters* d_counters = nullptr;
     uint32_t* d_work = nullptr;                 // [0] next unclaimed ray of the running traversal kernel, [1] blocks that have left
     int sm_count = 148;
+    uint64_t work_slot = 0;                     // next pair of the work-counter ring
     int build_levels = 0;                       // depth of the last device-built wide tree
     std::vector<miro::EventPair> events;        // pending (not yet summed) timing pairs
     std::vector<miro::EventPair> event_pool;

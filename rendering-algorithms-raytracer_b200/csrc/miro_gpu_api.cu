@@ -24,8 +24,11 @@ int cuda_fail(miro_gpu_ctx* ctx, cudaError_t e, const char* what) {
     return set_error(ctx, MIRO_GPU_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 
+// Device timing of the library's launches (miro_gpu_counters::trace_ms / total_ms) is kept only while counting is enabled:
+// an event record between two traversal launches would break their programmatic-dependent-launch chaining.
 EventPair begin_timing(miro_gpu_ctx* ctx, bool trace) {
     EventPair p;
+    if (!ctx->counting) { p.a = p.b = nullptr; p.trace = trace; return p; }
     if (!ctx->event_pool.empty()) { p = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
     else { cudaEventCreate(&p.a); cudaEventCreate(&p.b); }
     p.trace = trace;
@@ -33,6 +36,7 @@ EventPair begin_timing(miro_gpu_ctx* ctx, bool trace) {
     return p;
 }
 void end_timing(miro_gpu_ctx* ctx, EventPair p) {
+    if (!p.a) return;
     cudaEventRecord(p.b, ctx->stream);
     ctx->events.push_back(p);
     if (ctx->events.size() > 4096) drain_timing(ctx);
@@ -57,6 +61,7 @@ void drain_timing(miro_gpu_ctx* ctx) {
 // MODE: 0 closest hit -> hit records; 1 any hit -> one bit per ray; 2 any hit -> the unoccluded ray's light sample
 // (sample_E[i] = E.rgb, specular input) is added to the accumulator of its light loop (slot index in ray.user0).
 enum { TRACE_CLOSEST = 0, TRACE_ANY_BITS = 1, TRACE_ANY_ACCUM = 2 };
+constexpr int WORK_RING = 8;      // pairs of work counters; launch k uses pair k % WORK_RING and re-arms it when its last block leaves
 
 template <int MODE, bool COUNT, bool ALPHA>
 __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS)
@@ -103,7 +108,17 @@ k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const
                     if (lane == 0) base = atomicAdd(work, chunk);
                     base = __shfl_sync(0xffffffffu, base, 0);
                     chunk_next = min(base, n); chunk_end = min(base + chunk, n);
-                    if (chunk_next == chunk_end) exhausted = true;
+                    if (chunk_next == chunk_end) {
+                        exhausted = true;
+                        // programmatic dependent launch: from here on this block only drains its last rays, so the next
+                        // traversal launch on the stream may start filling the SMs as blocks of this one leave
+                        if (lane == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+                    } else if (MODE == TRACE_ANY_BITS) {
+                        // a 32-ray claim is exactly one result word, and only this warp ever touches it: clear it here
+                        // (no memset node between two launches, which would serialise them)
+                        if (lane == 0) bits[chunk_next >> 5] = 0u;
+                        __syncwarp();
+                    }
                 }
                 const uint32_t take = min((uint32_t)__popc(idle), chunk_end - chunk_next);
                 const uint32_t rank = __popc(idle & lt_mask);
@@ -157,8 +172,14 @@ k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const
     // the last block to leave re-arms the work counter for the next launch on this context
     __syncthreads();
     if (threadIdx.x == 0) {
+        // chained launches: no block of this launch retires before the launch chained in front of it has completed and
+        // flushed (a no-op without the launch attribute).  A block waiting here still holds its SM slot and a grid fills
+        // the SMs (launch bounds = resident blocks), so only about two consecutive launches ever coexist — the ring of
+        // WORK_RING work-counter pairs cannot wrap onto a live launch, and "this launch is complete" implies "all
+        // earlier ones are".
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         __threadfence();
-        if (atomicAdd(work + 1, 1u) == gridDim.x - 1) { work[0] = 0; work[1] = 0; __threadfence(); }
+        if (atomicAdd(work + 1, 1u) == gridDim.x - 1) { work[0] = 0; work[1] = 0; __threadfence(); }      // this launch's own pair (ring of pairs)
     }
 }
 
@@ -200,8 +221,17 @@ static void launch_trace(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n
     const uint32_t chunk = 32u;
 #endif
     const float4* r = reinterpret_cast<const float4*>(d_rays);
-    if (MODE == TRACE_ANY_BITS) cudaMemsetAsync(d_bits, 0, ((n + 31) / 32) * sizeof(uint32_t), ctx->stream);
-#define MIRO_LAUNCH(COUNT, ALPHA) k_trace<MODE, COUNT, ALPHA><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(ctx->scene, r, (uint32_t)n, d_count, chunk, d_hits, d_bits, d_E, d_slots, ctx->d_counters, ctx->d_work)
+    // Every launch has its own pair of work counters out of a ring, so consecutive traversal launches can overlap.  When the
+    // caller has switched trace chaining on (miro_gpu_set_trace_chaining: it vouches that the inputs do not depend on work
+    // enqueued since the previous trace call), the launch carries the programmatic-dependent-launch attribute: the tail of
+    // launch k, where warps drain their last rays at falling occupancy, overlaps the start of launch k+1.
+    uint32_t* work = ctx->d_work + 2 * (ctx->work_slot++ % WORK_RING);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TRACE_BLOCK); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = (ctx->chain_traces && ctx->in_api_trace) ? 1 : 0;
+#define MIRO_LAUNCH(COUNT, ALPHA) cudaLaunchKernelEx(&cfg, k_trace<MODE, COUNT, ALPHA>, ctx->scene, r, (uint32_t)n, d_count, chunk, d_hits, d_bits, d_E, d_slots, ctx->d_counters, work)
     if (ctx->has_alpha) { if (ctx->counting) MIRO_LAUNCH(true, true); else MIRO_LAUNCH(false, true); }
     else { if (ctx->counting) MIRO_LAUNCH(true, false); else MIRO_LAUNCH(false, false); }
 #undef MIRO_LAUNCH
@@ -258,8 +288,8 @@ int miro_gpu_create(miro_gpu_ctx** out, int device_id) {
     ctx->stream = ctx->own_stream;
     if ((e = cudaMalloc((void**)&ctx->d_counters, sizeof(TraceCounters))) != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaMalloc(counters)"); }
     cudaMemset(ctx->d_counters, 0, sizeof(TraceCounters));
-    if ((e = cudaMalloc((void**)&ctx->d_work, 2 * sizeof(uint32_t))) != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaMalloc(work counter)"); }
-    cudaMemset(ctx->d_work, 0, 2 * sizeof(uint32_t));
+    if ((e = cudaMalloc((void**)&ctx->d_work, 2 * WORK_RING * sizeof(uint32_t))) != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaMalloc(work counter)"); }
+    cudaMemset(ctx->d_work, 0, 2 * WORK_RING * sizeof(uint32_t));
     ctx->sm_count = prop.multiProcessorCount;
     // the traversal kernels keep their stacks in shared memory and want the rest of the 256 KB as L1
     *out = ctx;
@@ -461,7 +491,9 @@ int miro_gpu_trace_closest_device(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays,
     if (!d_rays || !d_hits) return set_error(ctx, MIRO_GPU_EINVAL, "NULL ray/hit buffer");
     MIRO_CUDA(ctx, cudaSetDevice(ctx->device));
     EventPair p = begin_timing(ctx, true);
+    ctx->in_api_trace = true;
     launch_trace_closest(ctx, d_rays, n, nullptr, d_hits);
+    ctx->in_api_trace = false;
     if (ctx->scene.prim_map) { k_translate_hits<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_hits, (uint32_t)n, ctx->scene.prim_map); ctx->launches++; }
     end_timing(ctx, p);
     MIRO_CUDA(ctx, cudaGetLastError());
@@ -476,7 +508,9 @@ int miro_gpu_trace_any_device(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, siz
     if (!d_rays || !d_bits) return set_error(ctx, MIRO_GPU_EINVAL, "NULL ray/bit buffer");
     MIRO_CUDA(ctx, cudaSetDevice(ctx->device));
     EventPair p = begin_timing(ctx, true);
+    ctx->in_api_trace = true;
     launch_trace_any(ctx, d_rays, n, nullptr, d_bits);
+    ctx->in_api_trace = false;
     end_timing(ctx, p);
     MIRO_CUDA(ctx, cudaGetLastError());
     return MIRO_GPU_OK;
@@ -538,6 +572,12 @@ int miro_gpu_trace_closest(miro_gpu_ctx* ctx, const miro_gpu_ray* rays, size_t n
 int miro_gpu_trace_any(miro_gpu_ctx* ctx, const miro_gpu_ray* rays, size_t n, uint32_t* occluded_bits) {
     if (ctx && n && !occluded_bits) return set_error(ctx, MIRO_GPU_EINVAL, "NULL ray/bit buffer");
     return trace_host(ctx, rays, n, nullptr, occluded_bits);
+}
+
+int miro_gpu_set_trace_chaining(miro_gpu_ctx* ctx, int on) {
+    if (!ctx) return MIRO_GPU_EINVAL;
+    ctx->chain_traces = on != 0;
+    return MIRO_GPU_OK;
 }
 
 int miro_gpu_enable_counting(miro_gpu_ctx* ctx, int enable) {

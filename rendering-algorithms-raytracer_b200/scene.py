@@ -172,6 +172,10 @@ class MiroScene:
         p = params or self.render_params(); c = camera or self.camera()
         self._gpu_check(self.L.miro_gpu_render(self.ctx, C.byref(c), C.byref(p), d_rgb_ptr), "render")
 
+    def set_trace_chaining(self, on=True):
+        """Let consecutive trace_*_device launches overlap (see miro_gpu_set_trace_chaining for the contract)."""
+        self._gpu_check(self.L.miro_gpu_set_trace_chaining(self.ctx, 1 if on else 0), "set_trace_chaining")
+
     def enable_counting(self, on=True):
         self._gpu_check(self.L.miro_gpu_enable_counting(self.ctx, 1 if on else 0), "enable_counting")
 

@@ -165,3 +165,34 @@ def test_gpu_traces_the_references_own_tree(name):
     print(name, {k: v for k, v in st.items() if k != "hard_idx"})
     assert st["hard"] == 0 and st["id_match"] >= 0.999 and st["frac_t_within"] == 1.0, st
     sc.close()
+
+
+def test_chained_launches_give_identical_results():
+    """miro_gpu_set_trace_chaining: consecutive *_device launches overlap (programmatic dependent launch); results must be
+    those of unchained launches, also when many short launches follow each other and result words are cleared in-kernel."""
+    import torch
+    fx = helpers.Fixture(helpers.fixture_path("c2_explosion"))
+    sc = fx.scene().attach(0)
+    rays = fx.rays
+    n = len(rays)
+    want = sc.trace_closest(rays); want_occ = sc.trace_any(rays)
+    d_rays = torch.from_numpy(rays.view(np.uint8).reshape(n, -1)).cuda()
+    stream = torch.cuda.Stream(); sc.set_stream(stream.cuda_stream)
+    hits = [torch.full((n, 20), 0xff, dtype=torch.uint8, device="cuda") for _ in range(4)]
+    bits = [torch.full(((n + 31) // 32,), -1, dtype=torch.int32, device="cuda") for _ in range(4)]     # stale ones: the kernel must clear
+    torch.cuda.synchronize()
+    sc.set_trace_chaining(True)
+    for rep in range(3):
+        for k in range(4):
+            sc.trace_closest_device(d_rays.data_ptr(), n, hits[k].data_ptr())
+            sc.trace_any_device(d_rays.data_ptr(), n, bits[k].data_ptr())
+            m = 1000 + 37 * k                                   # short, ragged launches in between
+            sc.trace_closest_device(d_rays.data_ptr(), m, hits[k].data_ptr())
+    stream.synchronize()
+    sc.set_trace_chaining(False); sc.set_stream(None)
+    for k in range(4):
+        h = hits[k].cpu().numpy().view(mb.HIT_DTYPE).reshape(-1)
+        assert h.tobytes() == want.tobytes()
+        occ = np.unpackbits(bits[k].cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
+        assert (occ == want_occ).all()
+    sc.close()
