@@ -93,6 +93,8 @@ struct miro_gpu_ctx {
     miro::DeviceBuffer<miro_gpu_hit> d_hits;
     miro::DeviceBuffer<uint32_t> d_bits;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;      // H2D / D2H streams of the pipelined host-pointer calls
+    cudaStream_t trace_aux[3] = {nullptr, nullptr, nullptr}; // further kernel streams of those calls (chunk kernels overlap their tails)
+    cudaEvent_t fork_event = nullptr;
     std::vector<cudaEvent_t> pipe_events;
 
     // renderer state (render.cu)

@@ -2,6 +2,7 @@
 // See include/miro_gpu.h for the reference interfaces each entry point replaces.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <math.h>
 #include <algorithm>
@@ -316,6 +317,8 @@ void miro_gpu_destroy(miro_gpu_ctx* ctx) {
     for (cudaEvent_t e : ctx->pipe_events) cudaEventDestroy(e);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+    for (cudaStream_t a : ctx->trace_aux) if (a) cudaStreamDestroy(a);
+    if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -526,25 +529,53 @@ static int trace_host(miro_gpu_ctx* ctx, const miro_gpu_ray* rays, size_t n, mir
     if (n == 0) return MIRO_GPU_OK;
     if (!rays || (!hits && !bits)) return set_error(ctx, MIRO_GPU_EINVAL, "NULL ray/result buffer");
     MIRO_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t chunk = (size_t)1 << 18;                      // rays per chunk (a multiple of 32: whole result words)
-    const size_t n_chunks = (n + chunk - 1) / chunk;
+    // Chunked pipeline: H2D of chunk k+1, traversal of chunk k and D2H of chunk k-1 overlap.  Measured on B200 (tools/e2e_sweep.sh,
+    // tools/e2e_timeline.py): the call is bound by the H2D stream (48 B per ray over PCIe, 43-54 GB/s with the D2H running
+    // against it); 256 K-ray chunks are the optimum (smaller: per-chunk kernel tails and copy latencies; larger: fill / drain).
+    // MIRO_GPU_CHUNK (log2 rays), MIRO_GPU_KSTREAMS and MIRO_GPU_TIMELINE are tuning / diagnostic switches.
+    static const int chunk_log2 = getenv("MIRO_GPU_CHUNK") ? std::min(26, std::max(5, atoi(getenv("MIRO_GPU_CHUNK")))) : 18;
+    const size_t chunk = (size_t)1 << chunk_log2;              // rays per chunk (a multiple of 32: whole result words)
+    std::vector<size_t> bounds;                                // chunk k = [bounds[k], bounds[k+1])
+    for (size_t off = 0; off < n; off += chunk) bounds.push_back(off);
+    bounds.push_back(n);
+    const size_t n_chunks = bounds.size() - 1;
     MIRO_CUDA(ctx, ctx->d_rays.reserve(n));
     if (hits) MIRO_CUDA(ctx, ctx->d_hits.reserve(n)); else MIRO_CUDA(ctx, ctx->d_bits.reserve((n + 31) / 32));
     if (!ctx->copy_in) {
         MIRO_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
         MIRO_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+        for (cudaStream_t& a : ctx->trace_aux) MIRO_CUDA(ctx, cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+        MIRO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
+    }
+    // The chunk kernels rotate over k_streams streams: a traversal launch ends with a tail of ~150 us in which its last warps
+    // walk their longest rays alone (a chain of dependent node fetches); on one stream that tail is paid once per chunk and made
+    // the kernel stage, not the PCIe copy, the slowest stage of the pipeline.  On rotating streams the next chunk's kernel fills
+    // the SMs the tail leaves idle.  Work the caller enqueued on the context's stream before this call is waited for by all of them.
+    static const int k_streams = getenv("MIRO_GPU_KSTREAMS") ? std::min(4, std::max(1, atoi(getenv("MIRO_GPU_KSTREAMS")))) : 2;
+    cudaStream_t const user_stream = ctx->stream;
+    struct Restore { miro_gpu_ctx* c; cudaStream_t s; ~Restore() { c->stream = s; } } restore{ctx, user_stream};      // also on error returns
+    if (k_streams > 1) {
+        MIRO_CUDA(ctx, cudaEventRecord(ctx->fork_event, user_stream));
+        for (int a = 0; a + 1 < k_streams; ++a) MIRO_CUDA(ctx, cudaStreamWaitEvent(ctx->trace_aux[a], ctx->fork_event, 0));
     }
     while (ctx->pipe_events.size() < 2 * n_chunks) {
         cudaEvent_t e; MIRO_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->pipe_events.push_back(e);
     }
     EventPair tot = begin_timing(ctx, false);
+    static const bool timeline = getenv("MIRO_GPU_TIMELINE") != nullptr;      // diagnostic: per-chunk device timeline on stderr
+    std::vector<cudaEvent_t> tl;
+    auto mark = [&](cudaStream_t st) { if (timeline) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tl.push_back(e); } };
+    mark(ctx->copy_in);
     for (size_t k = 0; k < n_chunks; ++k) {
-        const size_t off = k * chunk, m = std::min(chunk, n - off);
+        const size_t off = bounds[k], m = bounds[k + 1] - off;
         cudaEvent_t up = ctx->pipe_events[2 * k], done = ctx->pipe_events[2 * k + 1];
         MIRO_CUDA(ctx, cudaMemcpyAsync(ctx->d_rays.ptr + off, rays + off, m * sizeof(miro_gpu_ray), cudaMemcpyHostToDevice, ctx->copy_in));
         MIRO_CUDA(ctx, cudaEventRecord(up, ctx->copy_in));
+        mark(ctx->copy_in);
+        ctx->stream = (k % k_streams == 0) ? user_stream : ctx->trace_aux[k % k_streams - 1];
         MIRO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, up, 0));
+        mark(ctx->stream);
         EventPair p = begin_timing(ctx, true);
         if (hits) {
             launch_trace_closest(ctx, ctx->d_rays.ptr + off, m, nullptr, ctx->d_hits.ptr + off);
@@ -553,12 +584,22 @@ static int trace_host(miro_gpu_ctx* ctx, const miro_gpu_ray* rays, size_t n, mir
         else launch_trace_any(ctx, ctx->d_rays.ptr + off, m, nullptr, ctx->d_bits.ptr + off / 32);
         end_timing(ctx, p);
         MIRO_CUDA(ctx, cudaEventRecord(done, ctx->stream));
+        mark(ctx->stream);
         MIRO_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, done, 0));
         if (hits) MIRO_CUDA(ctx, cudaMemcpyAsync(hits + off, ctx->d_hits.ptr + off, m * sizeof(miro_gpu_hit), cudaMemcpyDeviceToHost, ctx->copy_out));
         else MIRO_CUDA(ctx, cudaMemcpyAsync(bits + off / 32, ctx->d_bits.ptr + off / 32, ((m + 31) / 32) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_out));
+        mark(ctx->copy_out);
+        ctx->stream = user_stream;
     }
     MIRO_CUDA(ctx, cudaGetLastError());
     MIRO_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
+    if (timeline) {     // order of marks: start, then per chunk {h2d end, kernel begin, kernel end, d2h end}
+        cudaDeviceSynchronize();
+        fprintf(stderr, "timeline n=%zu chunks=%zu (us from start: h2d_end kernel_begin kernel_end d2h_end)\n", n, n_chunks);
+        for (size_t i = 1; i < tl.size(); ++i) { float ms = 0; cudaEventElapsedTime(&ms, tl[0], tl[i]); fprintf(stderr, "%8.1f%s", ms * 1e3, (i % 4 == 0) ? "\n" : " "); }
+        fprintf(stderr, "\n");
+        for (cudaEvent_t e : tl) cudaEventDestroy(e);
+    }
     end_timing(ctx, tot);
     MIRO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MIRO_GPU_OK;
