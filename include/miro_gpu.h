@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MIRO_GPU_ABI_VERSION 1
+#define MIRO_GPU_ABI_VERSION 2
 
 enum {
     MIRO_GPU_OK = 0,
@@ -137,7 +137,11 @@ typedef struct miro_gpu_material {  /* 128 bytes */
     uint32_t sample_env;            /* Material::m_sampleEnv */
     float ior[3];                   /* Blinn::m_ior[0..2]; a non-dispersive material refracts with ior[1] (src/Blinn.cpp:183) */
     uint32_t disperse;              /* Material::m_disperse: a refraction splits into one ray per colour channel with ior[0..2] (src/Blinn.cpp:275-302) */
-    uint32_t reserved[5];
+    /* Blinn only (src/Blinn.cpp:120-142), texture index or -1.  normal_map: N = texel.x*T + texel.y*BT + texel.z*N with the
+     * texel as stored (no [0,1] -> [-1,1] remap, no renormalisation — the reference's behaviour); the other three scale
+     * spec_amt / reflect_amt / refract_amt by the mean of the texel's RGB. */
+    int32_t normal_map, specular_map, reflect_map, refract_map;
+    uint32_t reserved;
 } miro_gpu_material;
 
 /* ---- lights (reference: src/PointLight.cpp:8-82, src/RectangleLight.cpp:14-137, src/DomeLight.cpp:8-161) */
@@ -179,6 +183,8 @@ typedef struct miro_gpu_scene_desc {
     const float* normals;             uint32_t n_normals;   /* xyz triples */
     const float* uvs;                 uint32_t n_uvs;       /* uv pairs (may be NULL/0) */
     const float* inst_normal_xform;   /* n_instances x 9: rows 0..2 of (M^-1)^T, src/Ray.cpp:27-31 */
+    const float* tangents;            /* n_normals xyz triples, indexed by a primitive's NORMAL indices (src/Ray.cpp:22,35-36; */
+    const float* bitangents;          /*  TriangleMesh::preCalc, src/TriangleMesh.cpp:107-150); both may be NULL: T = BT = 0   */
     const miro_gpu_material* materials; uint32_t n_materials;
     const miro_gpu_light* lights;       uint32_t n_lights;
     const miro_gpu_texture* textures;   uint32_t n_textures;

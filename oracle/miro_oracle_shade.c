@@ -166,7 +166,7 @@ static void ior_pop(iorlist* l) { if (l->idx > 0) l->idx--; }
 static void ior_push(iorlist* l, float x) { if (l->idx < 11) l->idx++; l->v[l->idx] = x; }
 
 typedef struct { v3 o, d; float time; iorlist ior; int bounces; int is_refract; } oray2;
-typedef struct { v3 P, N, geoN; float u, v; uint32_t material; } surf;
+typedef struct { v3 P, N, geoN, T, BT; float u, v; uint32_t material; } surf;
 
 static int trace(octx* c, v3 o, v3 d, float time, float tmin, float tmax, miro_gpu_hit* h) {
     const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
@@ -183,6 +183,7 @@ static surf surface_at(const octx* c, const oray2* r, const miro_gpu_hit* h) {  
     const miro_gpu_scene_desc* s = c->s;
     surf o;
     o.P = add(r->o, scl(r->d, h->t));
+    o.T = V(0, 0, 0); o.BT = V(0, 0, 0);
     const miro_gpu_prim* pr = &s->prims[h->prim];
     o.material = pr->material;
     const miro_gpu_tri* t = (uint32_t)h->prim < s->n_tris ? &s->tris[h->prim] : &s->mbtris[(uint32_t)h->prim - s->n_tris].pose[0];
@@ -200,6 +201,12 @@ static surf surface_at(const octx* c, const oray2* r, const miro_gpu_hit* h) {  
     if (pr->uv[0] != 0xffffffffu) {
         const float *t0 = s->uvs + (size_t)pr->uv[0] * 2, *t1 = s->uvs + (size_t)pr->uv[1] * 2, *t2 = s->uvs + (size_t)pr->uv[2] * 2;
         o.u = t0[0] * cc + t1[0] * a + t2[0] * b; o.v = t0[1] * cc + t1[1] * a + t2[1] * b;
+        if (s->tangents && s->bitangents) {        /* Ray.cpp:35-36: indexed by the NORMAL indices, not transformed by the proxy */
+            const float *g0 = s->tangents + (size_t)pr->n[0] * 3, *g1 = s->tangents + (size_t)pr->n[1] * 3, *g2 = s->tangents + (size_t)pr->n[2] * 3;
+            o.T = normalize(V(g0[0] * cc + g1[0] * a + g2[0] * b, g0[1] * cc + g1[1] * a + g2[1] * b, g0[2] * cc + g1[2] * a + g2[2] * b));
+            const float *h0 = s->bitangents + (size_t)pr->n[0] * 3, *h1 = s->bitangents + (size_t)pr->n[1] * 3, *h2 = s->bitangents + (size_t)pr->n[2] * 3;
+            o.BT = normalize(V(h0[0] * cc + h1[0] * a + h2[0] * b, h0[1] * cc + h1[1] * a + h2[1] * b, h0[2] * cc + h1[2] * a + h2[2] * b));
+        }
     } else { o.u = a; o.v = b; }
     return o;
 }
@@ -327,12 +334,18 @@ static v3 shade(octx* c, oray2* ray, const miro_gpu_hit* hit, uint32_t pixel, ui
         }
         return add(L, ka);
     }
-    /* Blinn.cpp:91-335 (without the texture-map, translucency and dispersion branches) */
+    /* Blinn.cpp:91-335.  Texture maps, Blinn.cpp:120-142: the normal map is applied with the texel as stored. */
+    v3 sN = sf.N;
+    float spec_amt = m->spec_amt, reflect_amt = m->reflect_amt, refract_amt = m->refract_amt;
+    if (m->normal_map >= 0) { float t[4]; tex_lookup(&s->textures[m->normal_map], sf.u, sf.v, t); sN = add(add(scl(sf.T, t[0]), scl(sf.BT, t[1])), scl(sf.N, t[2])); }
+    if (m->specular_map >= 0) { float t[4]; tex_lookup(&s->textures[m->specular_map], sf.u, sf.v, t); spec_amt = (t[0] + t[1] + t[2]) * 0.3333333f * spec_amt; }
+    if (m->reflect_map >= 0) { float t[4]; tex_lookup(&s->textures[m->reflect_map], sf.u, sf.v, t); reflect_amt = (t[0] + t[1] + t[2]) * 0.3333333f * reflect_amt; }
+    if (m->refract_map >= 0) { float t[4]; tex_lookup(&s->textures[m->refract_map], sf.u, sf.v, t); refract_amt = (t[0] + t[1] + t[2]) * 0.3333333f * refract_amt; }
     const v3 viewDir = scl(ray->d, -1.f);
-    float vDotN = dot(viewDir, sf.N);
+    float vDotN = dot(viewDir, sN);
     const float vDotGeoN = dot(viewDir, sf.geoN);
     const int nEqGeoN = (vDotN * vDotGeoN >= 0.0f);
-    v3 theNormal = nEqGeoN ? sf.N : sf.geoN;
+    v3 theNormal = nEqGeoN ? sN : sf.geoN;
     vDotN = nEqGeoN ? vDotN : vDotGeoN;
     int flip = 0;
     if (vDotN < 0.0f) { flip = 1; vDotN = -vDotN; theNormal = scl(theNormal, -1.f); }
@@ -350,7 +363,7 @@ static v3 shade(octx* c, oray2* ray, const miro_gpu_hit* hit, uint32_t pixel, ui
     float Rs = 0.f, Ts = 0.f;
     if (m->reflect_amt > 0.0f || m->refract_amt > 0.0f) { Rs = fresnel(inIOR, outIOR, vDotN); Ts = 1.0f - Rs; }
     float rr[4]; rand4(&addr, RP_ROULETTE, 0, 0, 0, 0, rr);
-    const float rrWeight = 1.0f - Rs * m->reflect_amt - Ts * m->refract_amt;
+    const float rrWeight = 1.0f - Rs * reflect_amt - Ts * refract_amt;
     const float rrWeightRecip = (rrWeight > 0.f) ? 1.f / rrWeight : 1.f;
     const float rrWeightRecipSpec = (1.f - rrWeight > 0.f) ? 1.f / (1.f - rrWeight) : 1.f;
     const v3 Le = V(m->le[0], m->le[1], m->le[2]), ks = V(m->ks[0], m->ks[1], m->ks[2]);
@@ -376,7 +389,7 @@ static v3 shade(octx* c, oray2* ray, const miro_gpu_hit* hit, uint32_t pixel, ui
         for (uint32_t li = 0; li < s->n_lights; ++li) {
             float lightSpec = 0.f;
             const v3 lightPower = sample_light(c, li, sf.P, theNormal, ray->time, rVec, &lightSpec, isSecondary, 0, &addr);
-            if (m->spec_amt != 0.f) Ls = add(Ls, scl(mul(lightPower, ks), m->spec_amt * powf(lightSpec, m->spec_exp)));
+            if (spec_amt != 0.f) Ls = add(Ls, scl(mul(lightPower, ks), spec_amt * powf(lightSpec, m->spec_exp)));
             Ld = add(Ld, mul(lightPower, kd));
         }
         if (m->translucency > 0.01f) {                                        /* Blinn.cpp:223-236: lights seen from the back side */
@@ -389,14 +402,14 @@ static v3 shade(octx* c, oray2* ray, const miro_gpu_hit* hit, uint32_t pixel, ui
         }
     } else {
         int doEnv = 1;
-        if (rr[1] < m->reflect_amt * Rs) {                                    /* Blinn.cpp:247-268 */
-            if (m->reflect_amt * Rs > 0.0f && ray->bounces < 5) {
+        if (rr[1] < reflect_amt * Rs) {                                    /* Blinn.cpp:247-268 */
+            if (reflect_amt * Rs > 0.0f && ray->bounces < 5) {
                 oray2 nr; nr.o = sf.P; nr.d = rVec; nr.time = ray->time; nr.ior = ray->ior; nr.bounces = ray->bounces + 1; nr.is_refract = 0;
                 miro_gpu_hit nh;
                 if (trace(c, nr.o, nr.d, nr.time, O_EPS, MIRO_GPU_TMAX, &nh)) { Lr = add(Lr, mul(ks, shade(c, &nr, &nh, pixel, sample, path, depth, 0))); doEnv = 0; }
             }
-            if (m->reflect_amt * Rs > 0.0f && doEnv) Lr = add(Lr, mul(ks, environment(c, rVec)));
-        } else if (m->refract_amt * Ts > 0.0f && dispersive) {                /* Blinn.cpp:275-302: one ray per colour channel */
+            if (reflect_amt * Rs > 0.0f && doEnv) Lr = add(Lr, mul(ks, environment(c, rVec)));
+        } else if (refract_amt * Ts > 0.0f && dispersive) {                /* Blinn.cpp:275-302: one ray per colour channel */
             v3 tVec = V(0, 0, 0);
             for (int i = 0; i < 3; i++) {
                 const float snellsQ = inIOR / m->ior[i];
@@ -417,7 +430,7 @@ static v3 shade(octx* c, oray2* ray, const miro_gpu_hit* hit, uint32_t pixel, ui
                 }
             }
             if (doEnv) Lt = add(Lt, mul(ks, environment(c, tVec)));
-        } else if (m->refract_amt * Ts > 0.0f) {                              /* Blinn.cpp:303-322, no dispersion */
+        } else if (refract_amt * Ts > 0.0f) {                              /* Blinn.cpp:303-322, no dispersion */
             const float snellsQ = inIOR / outIOR;
             const float sq = sqrtf(1.0f - (snellsQ * snellsQ) * (1.0f - vDotN * vDotN));
             const float sqrtPart = (0.0f < sq) ? sq : 0.0f;

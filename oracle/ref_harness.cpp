@@ -186,6 +186,10 @@ void loadScene(const std::string& file) {
                     else if (k == "emit") { float i; ss >> i; Vector3 c = read3(ss); m->setLightEmittedIntensity(i); m->setLightEmittedColor(c); }
                     else if (k == "colormap") { std::string t; ss >> t; m->setColorMap(getTexture(t)); }
                     else if (k == "alphamap") { std::string t; ss >> t; m->setAlphaMap(getTexture(t)); }
+                    else if (k == "normalmap") { std::string t; ss >> t; m->setNormalMap(getTexture(t)); }
+                    else if (k == "specularmap") { std::string t; ss >> t; m->setSpecularMap(getTexture(t)); }
+                    else if (k == "reflectmap") { std::string t; ss >> t; m->setReflectMap(getTexture(t)); }
+                    else if (k == "refractmap") { std::string t; ss >> t; m->setRefractMap(getTexture(t)); }
                     else if (k == "sampleenv") { int v; ss >> v; m->setSampleEnv(v != 0); }
                     else die("blinn: unknown key " + k);
                 }

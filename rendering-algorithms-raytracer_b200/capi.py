@@ -57,7 +57,8 @@ class Material(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("kd", C.c_float * 3), ("ka", C.c_float * 3), ("ks", C.c_float * 3),
                 ("spec_exp", C.c_float), ("spec_amt", C.c_float), ("emit_intensity", C.c_float), ("le", C.c_float * 3),
                 ("color_map", C.c_int32), ("alpha_map", C.c_int32), ("reflect_amt", C.c_float), ("refract_amt", C.c_float),
-                ("spec_gloss", C.c_float), ("translucency", C.c_float), ("sample_env", C.c_uint32), ("ior", C.c_float * 3), ("disperse", C.c_uint32), ("reserved", C.c_uint32 * 5)]
+                ("spec_gloss", C.c_float), ("translucency", C.c_float), ("sample_env", C.c_uint32), ("ior", C.c_float * 3), ("disperse", C.c_uint32),
+                ("normal_map", C.c_int32), ("specular_map", C.c_int32), ("reflect_map", C.c_int32), ("refract_map", C.c_int32), ("reserved", C.c_uint32)]
 
 
 class Light(C.Structure):
@@ -81,6 +82,7 @@ class SceneDesc(C.Structure):
                 ("normals", C.POINTER(C.c_float)), ("n_normals", C.c_uint32),
                 ("uvs", C.POINTER(C.c_float)), ("n_uvs", C.c_uint32),
                 ("inst_normal_xform", C.POINTER(C.c_float)),
+                ("tangents", C.POINTER(C.c_float)), ("bitangents", C.POINTER(C.c_float)),
                 ("materials", C.POINTER(Material)), ("n_materials", C.c_uint32),
                 ("lights", C.POINTER(Light)), ("n_lights", C.c_uint32),
                 ("textures", C.POINTER(Texture)), ("n_textures", C.c_uint32),

@@ -26,6 +26,8 @@ struct DeviceDome {            // per DomeLight: alias table over the nu x nv ce
 struct DeviceShading {
     const miro_gpu_prim* prims;
     const float* normals;
+    const float* tangents;     // n_normals x 3, indexed like normals; NULL: T = BT = 0
+    const float* bitangents;
     const float* uvs;
     const float* inst_nxf;     // n_instances x 9
     const miro_gpu_material* materials;

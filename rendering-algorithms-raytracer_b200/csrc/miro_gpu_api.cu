@@ -395,6 +395,8 @@ int miro_gpu_upload_scene(miro_gpu_ctx* ctx, const miro_gpu_scene_desc* d) {
         if (m.kind > MIRO_GPU_MAT_BLINN) return set_error(ctx, MIRO_GPU_EINVAL, "unknown material kind");
         if (m.alpha_map >= (int32_t)d->n_textures) return set_error(ctx, MIRO_GPU_EINVAL, "material alpha_map out of range");
         if (m.color_map >= (int32_t)d->n_textures) return set_error(ctx, MIRO_GPU_EINVAL, "material color_map out of range");
+        if (m.normal_map >= (int32_t)d->n_textures || m.specular_map >= (int32_t)d->n_textures || m.reflect_map >= (int32_t)d->n_textures ||
+            m.refract_map >= (int32_t)d->n_textures) return set_error(ctx, MIRO_GPU_EINVAL, "material normal/specular/reflect/refract map out of range");
     }
     for (uint32_t i = 0; i < d->n_tris + d->n_mbtris && d->prims; ++i)
         if (d->prims[i].material >= d->n_materials) return set_error(ctx, MIRO_GPU_EINVAL, "prim material out of range");
@@ -443,6 +445,8 @@ int miro_gpu_upload_scene(miro_gpu_ctx* ctx, const miro_gpu_scene_desc* d) {
         sh.prims = sorted_prims;
     }
     if ((rc = upload_array(ctx, d->normals, (size_t)d->n_normals * 3, &sh.normals))) return rc;
+    if ((rc = upload_array(ctx, d->tangents, d->tangents ? (size_t)d->n_normals * 3 : 0, &sh.tangents))) return rc;
+    if ((rc = upload_array(ctx, d->bitangents, d->bitangents ? (size_t)d->n_normals * 3 : 0, &sh.bitangents))) return rc;
     if ((rc = upload_array(ctx, d->uvs, (size_t)d->n_uvs * 2, &sh.uvs))) return rc;
     if ((rc = upload_array(ctx, d->inst_normal_xform, d->inst_normal_xform ? (size_t)d->n_instances * 9 : 0, &sh.inst_nxf))) return rc;
     if ((rc = upload_array(ctx, d->materials, d->n_materials, &sh.materials))) return rc;

@@ -208,12 +208,20 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
                 thr_d = thr;
                 if (!blinn) { c.N = s.N; c.rVec = f3(0, 0, 0); c.tks = f3(0, 0, 0); add_rgb(level_sum, pixel, thr * ka); }
                 else {
+                    // texture maps of Blinn::shade (Blinn.cpp:120-142): the normal map perturbs N in the tangent frame with the
+                    // texel as stored (no remap to [-1,1], no renormalisation); the others scale an amount by the texel's mean RGB
+                    float3x sN = s.N;
+                    float spec_amt = m->spec_amt, reflect_amt = m->reflect_amt, refract_amt = m->refract_amt;
+                    if (m->normal_map >= 0) { const float4 t = tex_lookup(sh.textures[m->normal_map], s.u, s.v); sN = t.x * s.T + t.y * s.BT + t.z * s.N; }
+                    if (m->specular_map >= 0) { const float4 t = tex_lookup(sh.textures[m->specular_map], s.u, s.v); spec_amt = (t.x + t.y + t.z) * 0.3333333f * spec_amt; }
+                    if (m->reflect_map >= 0) { const float4 t = tex_lookup(sh.textures[m->reflect_map], s.u, s.v); reflect_amt = (t.x + t.y + t.z) * 0.3333333f * reflect_amt; }
+                    if (m->refract_map >= 0) { const float4 t = tex_lookup(sh.textures[m->refract_map], s.u, s.v); refract_amt = (t.x + t.y + t.z) * 0.3333333f * refract_amt; }
                     // normal selection / flip towards the viewer (Blinn.cpp:144-155)
                     const float3x viewDir = -d;
-                    float vDotN = dot3(viewDir, s.N);
+                    float vDotN = dot3(viewDir, sN);
                     const float vDotGeoN = dot3(viewDir, s.geoN);
                     const bool nEqGeoN = (vDotN * vDotGeoN >= 0.0f);
-                    float3x theNormal = nEqGeoN ? s.N : s.geoN;
+                    float3x theNormal = nEqGeoN ? sN : s.geoN;
                     vDotN = nEqGeoN ? vDotN : vDotGeoN;
                     bool flip = false;
                     if (vDotN < 0.0f) { flip = true; vDotN = -vDotN; theNormal = -theNormal; }
@@ -235,9 +243,9 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
                     if (dispersive) outIOR = m->ior[0];                                        // no pop on this branch
                     else if (flip) { ior.pop(); outIOR = ior.top(); } else outIOR = m->ior[1];
                     float Rs = 0.f, Ts = 0.f;
-                    if (m->reflect_amt > 0.0f || m->refract_amt > 0.0f) { Rs = fresnel(inIOR, outIOR, vDotN); Ts = 1.0f - Rs; }
+                    if (m->reflect_amt > 0.0f || m->refract_amt > 0.0f) { Rs = fresnel(inIOR, outIOR, vDotN); Ts = 1.0f - Rs; }      // the members, not the mapped amounts (Blinn.cpp:189)
                     const Rand4 rr = rand4(addr, RP_ROULETTE, 0, 0, 0, 0);
-                    const float rrWeight = 1.0f - Rs * m->reflect_amt - Ts * m->refract_amt;       // Blinn.cpp:195-198
+                    const float rrWeight = 1.0f - Rs * reflect_amt - Ts * refract_amt;       // Blinn.cpp:195-198
                     const float rrWeightRecip = (rrWeight > 0.f) ? 1.f / rrWeight : 1.f;
                     const float rrWeightRecipSpec = (1.f - rrWeight > 0.f) ? 1.f / (1.f - rrWeight) : 1.f;
                     const float3x ks = f3(m->ks[0], m->ks[1], m->ks[2]);
@@ -245,7 +253,7 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
                     diffuse = rr.x <= rrWeight;
                     transl = m->translucency; translucent = diffuse && transl > 0.01f;
                     thr_d = thr * rrWeightRecip;                       // (Ld + Ls) / rrWeight, Blinn.cpp:335
-                    c.tks = thr_d * ks * m->spec_amt;
+                    c.tks = thr_d * ks * spec_amt;
                     float3x constant = thr_d * ka + thr * Le;          // "Ld += m_ka" is on both branches; "+ m_Le" is unscaled
                     if (diffuse) {
                         if (P.path_trace) {                                                      // Blinn::calculatePathTracing
@@ -264,9 +272,9 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
                         // mirror reflection or refraction, Blinn.cpp:238-331; one continuation ray, weight ks / (1 - rrWeight)
                         float3x dir;
                         bool spawn = false;
-                        if (rr.y < m->reflect_amt * Rs) {
-                            if (m->reflect_amt * Rs > 0.0f) { dir = rVec; spawn = true; }
-                        } else if (m->refract_amt * Ts > 0.0f && dispersive) {
+                        if (rr.y < reflect_amt * Rs) {
+                            if (reflect_amt * Rs > 0.0f) { dir = rVec; spawn = true; }
+                        } else if (refract_amt * Ts > 0.0f && dispersive) {
                             // one refraction ray per colour channel, each with its own IOR (Blinn.cpp:275-302)
                             bounce_thr = thr * ks * rrWeightRecipSpec;
                             if (bounces < 5u) {
@@ -277,7 +285,7 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
                                 const float sqrtPart = fmaxf(0.0f, sqrtf(1.0f - (snellsQ * snellsQ) * (1.0f - vDotN * vDotN)));
                                 constant = constant + bounce_thr * environment(sh, normalize3(snellsQ * d + theNormal * (snellsQ * vDotN - sqrtPart)));
                             }
-                        } else if (m->refract_amt * Ts > 0.0f) {
+                        } else if (refract_amt * Ts > 0.0f) {
                             const float snellsQ = inIOR / outIOR;
                             const float sqrtPart = fmaxf(0.0f, sqrtf(1.0f - (snellsQ * snellsQ) * (1.0f - vDotN * vDotN)));
                             dir = normalize3(snellsQ * d + theNormal * (snellsQ * vDotN - sqrtPart));

@@ -153,6 +153,7 @@ __device__ inline float3x environment(const DeviceShading& sh, float3x d) {
 // Hit attributes (HitInfo::getAllInfos, src/Ray.cpp:5-50)
 struct Surface {
     float3x P, N, geoN;
+    float3x T, BT;         // interpolated tangent / bitangent; evaluated only for normal-mapped materials (zero otherwise)
     float u, v;
     uint32_t material;
 };
@@ -181,10 +182,20 @@ __device__ inline Surface surface_at(const DeviceScene& sc, const DeviceShading&
         s.geoN = normalize3(f3(dot3(r0, s.geoN), dot3(r1, s.geoN), dot3(r2, s.geoN)));
         s.N = normalize3(f3(dot3(r0, s.N), dot3(r1, s.N), dot3(r2, s.N)));
     }
+    s.T = f3(0, 0, 0); s.BT = f3(0, 0, 0);
     if (q0.w != 0xffffffffu) {
         const float* t0 = sh.uvs + (size_t)q0.w * 2; const float* t1 = sh.uvs + (size_t)q1.x * 2; const float* t2 = sh.uvs + (size_t)q1.y * 2;
         s.u = __ldg(t0) * c + __ldg(t1) * a + __ldg(t2) * b;
         s.v = __ldg(t0 + 1) * c + __ldg(t1 + 1) * a + __ldg(t2 + 1) * b;
+        // tangent frame, indexed by the NORMAL index triple and not transformed by an instance (src/Ray.cpp:22,35-36)
+        if (sh.tangents && sh.bitangents && sh.materials[s.material].normal_map >= 0) {
+            const float* g0 = sh.tangents + (size_t)q0.x * 3; const float* g1 = sh.tangents + (size_t)q0.y * 3; const float* g2 = sh.tangents + (size_t)q0.z * 3;
+            s.T = normalize3(f3(__ldg(g0) * c + __ldg(g1) * a + __ldg(g2) * b, __ldg(g0 + 1) * c + __ldg(g1 + 1) * a + __ldg(g2 + 1) * b,
+                                __ldg(g0 + 2) * c + __ldg(g1 + 2) * a + __ldg(g2 + 2) * b));
+            const float* h0 = sh.bitangents + (size_t)q0.x * 3; const float* h1 = sh.bitangents + (size_t)q0.y * 3; const float* h2 = sh.bitangents + (size_t)q0.z * 3;
+            s.BT = normalize3(f3(__ldg(h0) * c + __ldg(h1) * a + __ldg(h2) * b, __ldg(h0 + 1) * c + __ldg(h1 + 1) * a + __ldg(h2 + 1) * b,
+                                 __ldg(h0 + 2) * c + __ldg(h1 + 2) * a + __ldg(h2 + 2) * b));
+        }
     } else { s.u = a; s.v = b; }
     return s;
 }

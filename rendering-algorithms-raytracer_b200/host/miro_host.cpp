@@ -10,6 +10,28 @@
 namespace miro {
 
 // =====================================================================================  meshes
+void TriangleMesh::computeTangents(std::vector<Vector3>& tangents, std::vector<Vector3>& bitangents) const {
+    tangents.clear(); bitangents.clear();
+    if (m_texCoordIndices.empty()) return;
+    tangents.assign(m_normals.size(), Vector3(0.f)); bitangents.assign(m_normals.size(), Vector3(0.f));
+    for (uint32_t i = 0; i < m_numTris; ++i) {
+        const TupleI3 vi = m_vertexIndices[i], ti = m_texCoordIndices[i], ni = m_normalIndices[i];
+        const Vector3 A = m_vertices[vi.x], AB = m_vertices[vi.y] - A, AC = m_vertices[vi.z] - A;
+        const float e1x = m_texCoords[ti.y].x - m_texCoords[ti.x].x, e1y = m_texCoords[ti.y].y - m_texCoords[ti.x].y;
+        const float e2x = m_texCoords[ti.z].x - m_texCoords[ti.x].x, e2y = m_texCoords[ti.z].y - m_texCoords[ti.x].y;
+        const float cp = e1y * e2x - e1x * e2y;
+        if (cp == 0.0f) continue;
+        const float mul = 1.f / cp;
+        const Vector3 tangent = ((AB * -e2x + AC * e1y) * mul).normalized();
+        const uint32_t idx[3] = {ni.x, ni.y, ni.z};
+        for (uint32_t k : idx) {
+            const Vector3 normal = m_normals[k];
+            tangents[k] = (tangent - normal * dot(normal, tangent)).normalized();
+            bitangents[k] = cross(tangents[k], normal);
+        }
+    }
+}
+
 void TriangleMesh::makeFlatNormals() {
     // faces without normals: one flat normal per face (src/TriangleMeshLoad.cpp:194-206)
     m_normals.clear(); m_normalIndices.resize(m_numTris);
@@ -265,6 +287,7 @@ void Lambert::fill(miro_gpu_material& m) const {
     m.kind = MIRO_GPU_MAT_LAMBERT; copy3(m.kd, m_kd); copy3(m.ka, m_ka);
     m.spec_exp = 1.f; m.spec_gloss = 1.f;
     m.color_map = m_colorMap ? m_colorMap->ordinal : -1; m.alpha_map = m_alphaMap ? m_alphaMap->ordinal : -1;
+    m.normal_map = m.specular_map = m.reflect_map = m.refract_map = -1;      // Lambert::shade reads the colour map only (src/Lambert.cpp:19-53)
     m.translucency = m_translucency; m.refract_amt = m_refractAmt; m.sample_env = m_sampleEnv ? 1u : 0u;
 }
 
@@ -279,6 +302,8 @@ void Blinn::fill(miro_gpu_material& m) const {
     m.kind = MIRO_GPU_MAT_BLINN; copy3(m.kd, m_kd); copy3(m.ka, m_ka); copy3(m.ks, m_ks);
     m.spec_exp = m_specExp; m.spec_amt = m_specAmt; m.emit_intensity = m_lightEmitted; copy3(m.le, m_Le);
     m.color_map = m_colorMap ? m_colorMap->ordinal : -1; m.alpha_map = m_alphaMap ? m_alphaMap->ordinal : -1;
+    m.normal_map = m_normalMap ? m_normalMap->ordinal : -1; m.specular_map = m_specularMap ? m_specularMap->ordinal : -1;
+    m.reflect_map = m_reflectMap ? m_reflectMap->ordinal : -1; m.refract_map = m_refractMap ? m_refractMap->ordinal : -1;
     m.reflect_amt = m_reflectAmt; m.refract_amt = m_refractAmt; m.spec_gloss = m_specGloss;
     m.ior[0] = m_ior[0]; m.ior[1] = m_ior[1]; m.ior[2] = m_ior[2]; m.disperse = m_disperse ? 1u : 0u;
     m.translucency = m_translucency; m.sample_env = m_sampleEnv ? 1u : 0u;
@@ -357,6 +382,8 @@ miro_gpu_scene_desc FlatScene::desc() const {
     d.normals = normals.data(); d.n_normals = (uint32_t)(normals.size() / 3);
     d.uvs = uvs.empty() ? nullptr : uvs.data(); d.n_uvs = (uint32_t)(uvs.size() / 2);
     d.inst_normal_xform = inst_nxf.empty() ? nullptr : inst_nxf.data();
+    d.tangents = tangents.size() == normals.size() ? tangents.data() : nullptr;
+    d.bitangents = bitangents.size() == normals.size() ? bitangents.data() : nullptr;
     d.materials = materials.data(); d.n_materials = (uint32_t)materials.size();
     d.lights = lights.data(); d.n_lights = (uint32_t)lights.size();
     d.textures = textures.data(); d.n_textures = (uint32_t)textures.size();
@@ -380,6 +407,11 @@ int Scene::meshOrdinal(TriangleMesh* m) {
         if (m_meshNormalBase.size() <= (size_t)m->ordinal) { m_meshNormalBase.resize(m->ordinal + 1, 0); m_meshUvBase.resize(m->ordinal + 1, 0); }
         m_meshNormalBase[m->ordinal] = (uint32_t)(m_flat.normals.size() / 3);
         for (const Vector3& n : m->m_normals) { m_flat.normals.push_back(n.x); m_flat.normals.push_back(n.y); m_flat.normals.push_back(n.z); }
+        std::vector<Vector3> tg, bt;
+        m->computeTangents(tg, bt);
+        tg.resize(m->m_normals.size(), Vector3(0.f)); bt.resize(m->m_normals.size(), Vector3(0.f));      // no uvs: T = BT = 0 (src/Ray.cpp:44-45)
+        for (const Vector3& t : tg) { m_flat.tangents.push_back(t.x); m_flat.tangents.push_back(t.y); m_flat.tangents.push_back(t.z); }
+        for (const Vector3& t : bt) { m_flat.bitangents.push_back(t.x); m_flat.bitangents.push_back(t.y); m_flat.bitangents.push_back(t.z); }
         m_meshUvBase[m->ordinal] = (uint32_t)(m_flat.uvs.size() / 2);
         for (const TriangleMesh::VectorR2& t : m->m_texCoords) { m_flat.uvs.push_back(t.x); m_flat.uvs.push_back(t.y); }
     }
@@ -395,6 +427,7 @@ int Scene::materialOrdinal(const Material* m) {
     auto it = std::find(m_materialList.begin(), m_materialList.end(), m);
     if (it != m_materialList.end()) return (int)(it - m_materialList.begin());
     textureOrdinal(m->m_colorMap); textureOrdinal(m->m_alphaMap);
+    textureOrdinal(m->m_normalMap); textureOrdinal(m->m_specularMap); textureOrdinal(m->m_reflectMap); textureOrdinal(m->m_refractMap);
     const_cast<Material*>(m)->ordinal = (int)m_materialList.size();
     m_materialList.push_back(m);
     return m->ordinal;

@@ -42,6 +42,11 @@ public:
     std::vector<TupleI3> m_vertexIndices, m_normalIndices, m_texCoordIndices;   // m_texCoordIndices empty: no uvs
     uint32_t m_numTris = 0;
     int ordinal = -1;          // set by Scene when first referenced (reported back in hits)
+    // Per-normal-index tangents / bitangents for normal mapping (TriangleMesh::preCalc, src/TriangleMesh.cpp:107-150): every
+    // triangle with a non-degenerate uv mapping writes the Gram-Schmidt tangent of its three corners, later triangles
+    // overwrite earlier ones.  Entries no triangle writes are ZERO here (the reference leaves them uninitialised).  Empty
+    // when the mesh has no texture coordinates.
+    void computeTangents(std::vector<Vector3>& tangents, std::vector<Vector3>& bitangents) const;
 private:
     void makeFlatNormals();
 };
@@ -91,12 +96,20 @@ public:
     virtual uint32_t kind() const = 0;
     void setColorMap(Texture* t) { m_colorMap = t; }
     void setAlphaMap(Texture* t) { m_alphaMap = t; }
+    void setNormalMap(Texture* t) { m_normalMap = t; }        // src/Material.h:22-25; used by Blinn::shade only (src/Blinn.cpp:120-142)
+    void setSpecularMap(Texture* t) { m_specularMap = t; }
+    void setReflectMap(Texture* t) { m_reflectMap = t; }
+    void setRefractMap(Texture* t) { m_refractMap = t; }
     void setSampleEnv(bool b) { m_sampleEnv = b; }
     void setTranslucency(float t) { m_translucency = t; }
     void setRefractAmt(float r) { m_refractAmt = r; }
     bool m_disperse = false;
     Texture* m_colorMap = nullptr;
     Texture* m_alphaMap = nullptr;
+    Texture* m_normalMap = nullptr;
+    Texture* m_specularMap = nullptr;
+    Texture* m_reflectMap = nullptr;
+    Texture* m_refractMap = nullptr;
     bool m_sampleEnv = true;
     float m_translucency = 0.f;
     float m_refractAmt = 0.f;
@@ -221,7 +234,7 @@ struct FlatScene {
     std::vector<miro_gpu_mbtri> mbtris;
     std::vector<miro_gpu_instance> instances;
     std::vector<miro_gpu_prim> prims;
-    std::vector<float> normals, uvs, inst_nxf;
+    std::vector<float> normals, tangents, bitangents, uvs, inst_nxf;      // tangents / bitangents: same indexing as normals
     std::vector<miro_gpu_material> materials;
     std::vector<miro_gpu_light> lights;
     std::vector<miro_gpu_texture> textures;

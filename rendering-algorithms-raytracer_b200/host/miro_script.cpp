@@ -11,6 +11,7 @@
 //   material NAME lambert [kd r g b] [ka r g b] [colormap TEX]
 //   material NAME blinn   [kd ..] [ka ..] [ks ..] [specexp f] [specamt f] [ior f | ior_i i f] [reflect f] [refract f]
 //                         [gloss f] [translucency f] [emit intensity r g b] [colormap TEX] [alphamap TEX] [sampleenv 0|1]
+//                         [normalmap TEX] [specularmap TEX] [reflectmap TEX] [refractmap TEX]
 //   light point [pos x y z] [power p] [shadows 0|1]
 //   light rect  [v1 x y z] [v2 x y z] [v3 x y z] [power p] [samples n] [noise t] [shadows 0|1]
 //   light dome  [tex TEX] [power gain] [samples n] [noise t]
@@ -123,6 +124,11 @@ bool loadSceneScript(const char* file, const char* assetRoot, LoadedScene& out, 
                     else if (k == "emit") { float i; ss >> i; Vector3 c = read3(ss); m->setLightEmittedIntensity(i); m->setLightEmittedColor(c); }
                     else if (k == "colormap") { std::string t; ss >> t; if (!textures.count(t)) return fail("unknown texture " + t); m->setColorMap(textures[t]); }
                     else if (k == "alphamap") { std::string t; ss >> t; if (!textures.count(t)) return fail("unknown texture " + t); m->setAlphaMap(textures[t]); }
+                    else if (k == "normalmap" || k == "specularmap" || k == "reflectmap" || k == "refractmap") {
+                        std::string t; ss >> t; if (!textures.count(t)) return fail("unknown texture " + t);
+                        if (k == "normalmap") m->setNormalMap(textures[t]); else if (k == "specularmap") m->setSpecularMap(textures[t]);
+                        else if (k == "reflectmap") m->setReflectMap(textures[t]); else m->setRefractMap(textures[t]);
+                    }
                     else if (k == "sampleenv") { int v; ss >> v; m->setSampleEnv(v != 0); }
                     else return fail("blinn: unknown key " + k);
                 }

@@ -207,7 +207,8 @@ class ReferenceTreeScene:
         self.normals = np.concatenate([m["normals"] for m in meshes]).astype(np.float32)
         self.material = capi.Material(); self.material.kind = 0
         self.material.kd[:] = [0.8, 0.8, 0.8]; self.material.spec_gloss = 1.0; self.material.color_map = -1; self.material.alpha_map = -1
-        d = capi.SceneDesc(); d.abi_version = 1
+        self.material.normal_map = self.material.specular_map = self.material.reflect_map = self.material.refract_map = -1
+        d = capi.SceneDesc(); d.abi_version = capi.lib().miro_gpu_abi_version()
         d.nodes = self.nodes.ctypes.data_as(C.POINTER(capi.Node)); d.n_nodes = len(self.nodes); d.root = 0
         d.tris = self.tris.ctypes.data_as(C.POINTER(capi.Tri)); d.n_tris = len(self.tris)
         d.prims = self.prims.ctypes.data_as(C.POINTER(capi.Prim))

@@ -36,7 +36,7 @@ def test_struct_sizes_match_the_header():
     assert C.sizeof(capi.Instance) == 64 and C.sizeof(capi.Prim) == 48
     assert C.sizeof(capi.Material) == 128 and C.sizeof(capi.Light) == 64
     L = capi.lib()
-    assert L.miro_gpu_abi_version() == 1
+    assert L.miro_gpu_abi_version() == 2
     if hasattr(L, "miro_gpu_sizeof"):
         L.miro_gpu_sizeof.argtypes = [C.c_int]; L.miro_gpu_sizeof.restype = C.c_size_t
         for k, t in enumerate([capi.Ray, capi.Hit, capi.Node, capi.Tri, capi.MBTri, capi.Instance, capi.Prim, capi.Material,

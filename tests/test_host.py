@@ -139,6 +139,45 @@ def test_specular_material_fields_travel_in_the_desc():
     sc.close()
 
 
+def test_tangent_frame_and_texture_maps_travel_in_the_desc(tmp_path):
+    """TriangleMesh::preCalc (src/TriangleMesh.cpp:107-150): per NORMAL index, the reference's tangent made orthogonal to the
+    normal, bitangent = cross(tangent, normal); a triangle with a degenerate uv mapping writes nothing; meshes without uvs
+    get zeros (src/Ray.cpp:44-45).  Material map indices (src/Blinn.cpp:120-142) travel; Lambert ignores them."""
+    obj = tmp_path / "t.obj"
+    # quad in the xy plane, u along +x, v along +y, two normals; third triangle has a degenerate uv mapping and its own normal
+    obj.write_text("v 0 0 0\nv 2 0 0\nv 2 2 0\nv 0 2 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nvn 0 0 1\nvn 0 0 1\nvn 0 1 0\n"
+                   "f 1/1/1 2/2/1 3/3/2\nf 1/1/1 3/3/2 4/4/2\nf 1/1/3 2/1/3 3/1/3\n")
+    import struct
+    tga = tmp_path / "x.tga"
+    tga.write_bytes(struct.pack("<BBBHHBHHHHBB", 0, 0, 2, 0, 0, 0, 0, 0, 2, 2, 24, 0) + bytes([128] * 12))
+    script = tmp_path / "s.miro"
+    script.write_text("image 8 4\ntexture x x.tga\nmaterial m blinn kd .5 .5 .5 normalmap x specularmap x reflectmap x refractmap x\n"
+                      "material l lambert colormap x\nmesh t t.obj\nobject t m\n")
+    sc = mb.MiroScene(); sc.load_script(script, tmp_path)
+    d = sc.desc()
+    assert d.n_normals == 3 and bool(d.tangents) and bool(d.bitangents)
+    T = np.ctypeslib.as_array(d.tangents, shape=(3, 3)); B = np.ctypeslib.as_array(d.bitangents, shape=(3, 3))
+    # the reference's tangent is (AB * -du2 + AC * dv1) / (dv1 du2 - du1 dv2) — not the textbook d(position)/du; reproduced, not
+    # corrected: triangle 1 gives (1,0,0), triangle 2 gives (0,-1,0) and, coming later, overwrites both normal indices
+    assert np.allclose(T[:2], [[0, -1, 0], [0, -1, 0]], atol=1e-6)
+    assert np.allclose(B[:2], [[-1, 0, 0], [-1, 0, 0]], atol=1e-6)          # cross(T, N)
+    assert np.allclose(T[2], 0) and np.allclose(B[2], 0)                      # degenerate uv mapping: never written
+    m = d.materials[0]
+    assert m.kind == 1 and m.normal_map == m.specular_map == m.reflect_map == m.refract_map == 0 and m.color_map == -1
+    sc.close()
+    script.write_text("image 8 4\ntexture x x.tga\nmaterial l lambert colormap x\nmesh t t.obj\nobject t l\n")
+    sc = mb.MiroScene(); sc.load_script(script, tmp_path)
+    m = sc.desc().materials[0]
+    assert m.kind == 0 and m.color_map == 0 and m.normal_map == m.specular_map == m.reflect_map == m.refract_map == -1
+    sc.close()
+    # no texture coordinates: zero tangents
+    obj.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n")
+    sc = mb.MiroScene(); sc.load_script(script, tmp_path)
+    d = sc.desc()
+    assert not d.tangents or np.allclose(np.ctypeslib.as_array(d.tangents, shape=(d.n_normals, 3)), 0)
+    sc.close()
+
+
 def test_obj_loader_and_ppm_writer(tmp_path):
     obj = tmp_path / "t.obj"
     obj.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nv 1 1 0\nvt 0 0\nvt 1 0\nvt 0 1\nvn 0 0 1\nf 1/1/1 2/2/1 3/3/1\nf 2/2/1 4/3/1 3/3/1\n")

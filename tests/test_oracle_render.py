@@ -84,3 +84,26 @@ def test_alpha_mapped_translucent_foliage_matches_reference():
     assert np.abs(blk(img) - blk(ref)).mean() < 0.004
     assert (np.abs(img - ref).max(axis=2) < 0.02).mean() > 0.85
     sc.close()
+
+
+def test_texture_maps_match_reference():
+    """SURVEY 8(f)-2, rest: normal map (tangent frame per normal index, also through an instance), specular / reflect /
+    refract maps (src/Blinn.cpp:120-142).  The normal- and specular-mapped objects are deterministic up to the pixel jitter;
+    the reflect-mapped floor and the refract-mapped sphere go through the Russian roulette and are compared as estimators."""
+    fx, sc = load("c9_texmaps")
+    img, rays = helpers.oracle_render(sc)
+    ref, conv = fx.radiance.astype(np.float32), fx.radiance_converged.astype(np.float32)
+    assert np.isfinite(img).all()
+    assert abs(rays - ref_rays(fx)) <= 5e-3 * ref_rays(fx)
+    assert rmse(img, conv) <= 1.1 * rmse(ref, conv)
+    assert abs(np.minimum(img, 4).mean() - np.minimum(conv, 4).mean()) <= 0.015 * np.minimum(conv, 4).mean()
+    h, idx = fx.hits, fx.z["ray_index"]
+    H, W = ref.shape[:2]
+    for name, frac in (("ball", 0.9), ("bulb", 0.85), ("bulb0", 0.7)):      # bumpy: normal + specular map; bulb: main.cpp:420-424, direct and instanced
+        sel = idx[h["mesh"] == list(fx.names).index(name)]; sel = sel[sel < H * W]
+        assert len(sel) > 500
+        y, x = sel // W, sel % W
+        d = np.abs(img[y, x] - conv[y, x]).max(axis=1)
+        print(name, len(sel), d.mean(), (d < 0.02).mean(), img[y, x].mean(), conv[y, x].mean())
+        assert (d < 0.02).mean() > frac and abs(img[y, x].mean() - conv[y, x].mean()) <= 0.015 * conv[y, x].mean()
+    sc.close()

@@ -46,7 +46,7 @@ def test_c1_image_matches_reference_and_oracle():
     sc.close()
 
 
-@pytest.mark.parametrize("name", ["c4_cornell_pt", "c5_mb_instances", "c6_cornell_glass", "c7_foliage"])
+@pytest.mark.parametrize("name", ["c4_cornell_pt", "c5_mb_instances", "c6_cornell_glass", "c7_foliage", "c9_texmaps"])
 def test_image_matches_oracle_sample_by_sample(name):
     fx, sc = load(name)
     img = sc.render()

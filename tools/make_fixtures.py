@@ -41,6 +41,7 @@ SCENES = {
     "c7_foliage": dict(render=True, stock=False, incoherent=1 << 18, threads=1),
     "c8_dispersion": dict(render=True, stock=False, incoherent=0, threads=1, converged=16),
     "c6_cornell_glass": dict(render=True, stock=False, incoherent=0, threads=1, converged=16),
+    "c9_texmaps": dict(render=True, stock=False, incoherent=0, threads=1, converged=16),
 }
 
 
