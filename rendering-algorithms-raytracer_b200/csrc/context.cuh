@@ -83,7 +83,10 @@ struct miro_gpu_ctx {
     miro::TraceCounters* d_counters = nullptr;
     uint32_t* d_work = nullptr;                 // [0] next unclaimed ray of the running traversal kernel, [1] blocks that have left
     int sm_count = 148;
-    uint64_t work_slot = 0;                     // next pair of the work-counter ring
+    uint64_t work_slot[4] = {0, 0, 0, 0};       // next pair of each lane's work-counter ring
+    int work_lane = 0;                          // which ring the next traversal launch uses: callers that spread launches over
+                                                // several streams give every stream its own lane (launches of one lane are
+                                                // stream-ordered or PDL-chained, so a ring never wraps onto a live launch)
     int build_levels = 0;                       // depth of the last device-built wide tree
     std::vector<miro::EventPair> events;        // pending (not yet summed) timing pairs
     std::vector<miro::EventPair> event_pool;

@@ -62,7 +62,8 @@ void drain_timing(miro_gpu_ctx* ctx) {
 // MODE: 0 closest hit -> hit records; 1 any hit -> one bit per ray; 2 any hit -> the unoccluded ray's light sample
 // (sample_E[i] = E.rgb, specular input) is added to the accumulator of its light loop (slot index in ray.user0).
 enum { TRACE_CLOSEST = 0, TRACE_ANY_BITS = 1, TRACE_ANY_ACCUM = 2 };
-constexpr int WORK_RING = 8;      // pairs of work counters; launch k uses pair k % WORK_RING and re-arms it when its last block leaves
+constexpr int WORK_RING = 8;      // pairs of work counters per lane; launch k of a lane uses pair k % WORK_RING and re-arms it when its last block leaves
+constexpr int WORK_LANES = 4;     // lanes = streams a caller may spread traversal launches over (miro_gpu_ctx::work_lane)
 
 template <int MODE, bool COUNT, bool ALPHA>
 __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS)
@@ -226,7 +227,7 @@ static void launch_trace(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n
     // caller has switched trace chaining on (miro_gpu_set_trace_chaining: it vouches that the inputs do not depend on work
     // enqueued since the previous trace call), the launch carries the programmatic-dependent-launch attribute: the tail of
     // launch k, where warps drain their last rays at falling occupancy, overlaps the start of launch k+1.
-    uint32_t* work = ctx->d_work + 2 * (ctx->work_slot++ % WORK_RING);
+    uint32_t* work = ctx->d_work + 2 * ((size_t)ctx->work_lane * WORK_RING + ctx->work_slot[ctx->work_lane]++ % WORK_RING);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TRACE_BLOCK); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
@@ -289,8 +290,8 @@ int miro_gpu_create(miro_gpu_ctx** out, int device_id) {
     ctx->stream = ctx->own_stream;
     if ((e = cudaMalloc((void**)&ctx->d_counters, sizeof(TraceCounters))) != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaMalloc(counters)"); }
     cudaMemset(ctx->d_counters, 0, sizeof(TraceCounters));
-    if ((e = cudaMalloc((void**)&ctx->d_work, 2 * WORK_RING * sizeof(uint32_t))) != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaMalloc(work counter)"); }
-    cudaMemset(ctx->d_work, 0, 2 * WORK_RING * sizeof(uint32_t));
+    if ((e = cudaMalloc((void**)&ctx->d_work, 2 * WORK_RING * WORK_LANES * sizeof(uint32_t))) != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaMalloc(work counter)"); }
+    cudaMemset(ctx->d_work, 0, 2 * WORK_RING * WORK_LANES * sizeof(uint32_t));
     ctx->sm_count = prop.multiProcessorCount;
     // the traversal kernels keep their stacks in shared memory and want the rest of the 256 KB as L1
     *out = ctx;
@@ -557,7 +558,7 @@ static int trace_host(miro_gpu_ctx* ctx, const miro_gpu_ray* rays, size_t n, mir
     // the SMs the tail leaves idle.  Work the caller enqueued on the context's stream before this call is waited for by all of them.
     static const int k_streams = getenv("MIRO_GPU_KSTREAMS") ? std::min(4, std::max(1, atoi(getenv("MIRO_GPU_KSTREAMS")))) : 2;
     cudaStream_t const user_stream = ctx->stream;
-    struct Restore { miro_gpu_ctx* c; cudaStream_t s; ~Restore() { c->stream = s; } } restore{ctx, user_stream};      // also on error returns
+    struct Restore { miro_gpu_ctx* c; cudaStream_t s; ~Restore() { c->stream = s; c->work_lane = 0; } } restore{ctx, user_stream};      // also on error returns
     if (k_streams > 1) {
         MIRO_CUDA(ctx, cudaEventRecord(ctx->fork_event, user_stream));
         for (int a = 0; a + 1 < k_streams; ++a) MIRO_CUDA(ctx, cudaStreamWaitEvent(ctx->trace_aux[a], ctx->fork_event, 0));
@@ -578,6 +579,7 @@ static int trace_host(miro_gpu_ctx* ctx, const miro_gpu_ray* rays, size_t n, mir
         MIRO_CUDA(ctx, cudaEventRecord(up, ctx->copy_in));
         mark(ctx->copy_in);
         ctx->stream = (k % k_streams == 0) ? user_stream : ctx->trace_aux[k % k_streams - 1];
+        ctx->work_lane = (int)(k % k_streams);
         MIRO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, up, 0));
         mark(ctx->stream);
         EventPair p = begin_timing(ctx, true);
@@ -593,7 +595,7 @@ static int trace_host(miro_gpu_ctx* ctx, const miro_gpu_ray* rays, size_t n, mir
         if (hits) MIRO_CUDA(ctx, cudaMemcpyAsync(hits + off, ctx->d_hits.ptr + off, m * sizeof(miro_gpu_hit), cudaMemcpyDeviceToHost, ctx->copy_out));
         else MIRO_CUDA(ctx, cudaMemcpyAsync(bits + off / 32, ctx->d_bits.ptr + off / 32, ((m + 31) / 32) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_out));
         mark(ctx->copy_out);
-        ctx->stream = user_stream;
+        ctx->stream = user_stream; ctx->work_lane = 0;
     }
     MIRO_CUDA(ctx, cudaGetLastError());
     MIRO_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));

@@ -28,6 +28,7 @@
 // what it will emit (the light loops are pure functions of the counter-based RNG), the warp scans the counts, then
 // every thread EMITS at its offset.  Pixel sums are float atomics (red.global.add.f32).
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <math.h>
 #include <string.h>
 #include <algorithm>
@@ -43,7 +44,8 @@ constexpr uint32_t FLAG_SECONDARY = 0x08000000u;       // shade(..., isSecondary
 constexpr uint32_t FLAG_REFRACT = 0x10000000u;         // IS_REFRACT_RAY (src/Ray.h:15): a dispersive material does not split such a ray again
 // bits 29-30: 1 + colour channel of a dispersion ray (Blinn.cpp:275-302); its throughput is masked to that channel when it is shaded
 constexpr size_t WAVE_PATHS_MAX = (size_t)1 << 22;     // paths in flight per wave
-constexpr size_t WAVE_BYTES_BUDGET = (size_t)6 << 30;  // queue memory per context
+constexpr size_t WAVE_BYTES_BUDGET = (size_t)12 << 30; // queue memory per context (two queue sets)
+constexpr size_t WAVE_SPLIT_MIN = (size_t)1 << 17;     // a frame is cut into two overlapping waves only if each keeps this many paths
 
 struct Slot {            // one light loop (one Light::sampleLight call of the reference): 64 bytes
     float4 acc;          // sum over unoccluded samples: E.rgb, specular input
@@ -78,7 +80,11 @@ struct Queues {
 };
 
 struct RenderState {
-    Queues q{};
+    // Two queue sets: consecutive waves run on two streams, so the tail of one wave's traversal launches (its last warps
+    // walking their longest rays alone, ~100 us per launch, ~90 launches per wave) is filled by the other wave's kernels.
+    Queues q[2]{};
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::vector<void*> allocs;
     size_t key_paths = 0, key_shadow_per_path = 0, key_slots_per_path = 0, key_next_mult = 1; bool key_ior = false;
     // frame buffers
@@ -461,7 +467,7 @@ static RenderState* state_of(miro_gpu_ctx* ctx) {
 static void free_queues(RenderState* st) {
     for (void* p : st->allocs) cudaFree(p);
     st->allocs.clear();
-    st->q = Queues{};
+    st->q[0] = Queues{}; st->q[1] = Queues{};
     st->key_paths = 0;
 }
 
@@ -471,6 +477,9 @@ void render_state_free(miro_gpu_ctx* ctx) {
     free_queues(st);
     cudaFree(st->level_sum); cudaFree(st->result); cudaFree(st->active[0]); cudaFree(st->active[1]); cudaFree(st->rgb_dev); cudaFree(st->gamma_lut);
     if (st->h_count) cudaFreeHost(st->h_count);
+    if (st->aux) cudaStreamDestroy(st->aux);
+    if (st->ev_fork) cudaEventDestroy(st->ev_fork);
+    if (st->ev_join) cudaEventDestroy(st->ev_join);
     delete st;
     ctx->render_state = nullptr;
 }
@@ -484,9 +493,10 @@ static cudaError_t qalloc(RenderState* st, T** p, size_t n) {
 }
 
 static int ensure_queues(miro_gpu_ctx* ctx, RenderState* st, size_t paths, size_t cs, size_t shadow_per_path, size_t slots_per_path, bool with_ior, size_t next_mult) {
-    if (st->key_next_mult == next_mult && st->key_paths == paths && st->q.cap_cs >= cs && st->key_shadow_per_path == shadow_per_path && st->key_slots_per_path == slots_per_path && st->key_ior == with_ior) return MIRO_GPU_OK;
+    if (st->key_next_mult == next_mult && st->key_paths == paths && st->q[0].cap_cs >= cs && st->key_shadow_per_path == shadow_per_path && st->key_slots_per_path == slots_per_path && st->key_ior == with_ior) return MIRO_GPU_OK;
     free_queues(st);
-    Queues& q = st->q;
+    for (int set = 0; set < 2; ++set) {
+    Queues& q = st->q[set];
     // a vertex of ANY continuation ray can run every light loop, so the shadow / slot queues scale with the continuation queue
     q.cap_cs = cs; q.cap_paths = paths * next_mult; q.cap_shadow = q.cap_paths * shadow_per_path; q.cap_slots = q.cap_paths * slots_per_path;
     MIRO_CUDA(ctx, qalloc(st, &q.cs_rays, q.cap_cs));
@@ -500,6 +510,7 @@ static int ensure_queues(miro_gpu_ctx* ctx, RenderState* st, size_t paths, size_
     MIRO_CUDA(ctx, qalloc(st, &q.sh_E, q.cap_shadow));
     MIRO_CUDA(ctx, qalloc(st, &q.slots, q.cap_slots));
     MIRO_CUDA(ctx, qalloc(st, &q.counts, (size_t)8));
+    }
     st->key_next_mult = next_mult; st->key_paths = paths; st->key_shadow_per_path = shadow_per_path; st->key_slots_per_path = slots_per_path; st->key_ior = with_ior;
     return MIRO_GPU_OK;
 }
@@ -513,6 +524,9 @@ static int ensure_frame(miro_gpu_ctx* ctx, RenderState* st, size_t pixels) {
         MIRO_CUDA(ctx, cudaMalloc((void**)&st->gamma_lut, lut.size() * sizeof(float)));
         MIRO_CUDA(ctx, cudaMemcpy(st->gamma_lut, lut.data(), lut.size() * sizeof(float), cudaMemcpyHostToDevice));
         MIRO_CUDA(ctx, cudaMallocHost((void**)&st->h_count, 8 * sizeof(uint32_t)));
+        MIRO_CUDA(ctx, cudaStreamCreateWithFlags(&st->aux, cudaStreamNonBlocking));
+        MIRO_CUDA(ctx, cudaEventCreateWithFlags(&st->ev_fork, cudaEventDisableTiming));
+        MIRO_CUDA(ctx, cudaEventCreateWithFlags(&st->ev_join, cudaEventDisableTiming));
     }
     if (st->frame_pixels >= pixels) return MIRO_GPU_OK;
     cudaFree(st->level_sum); cudaFree(st->result); cudaFree(st->active[0]); cudaFree(st->active[1]); cudaFree(st->rgb_dev);
@@ -584,14 +598,15 @@ extern "C" int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, co
     const size_t loops = (rp->path_trace ? 2 : 1) + (any_translucent ? 1 : 0);
     const size_t shadow_per_path = std::max<size_t>(1, loops * light_samples), slots_per_path = std::max<size_t>(1, loops * ctx->host_lights.size());
     const size_t bytes_per_path = next_mult * (2 * (48 + 16 + (P.has_specular ? 32 : 0)) + 20 + shadow_per_path * 64 + slots_per_path * 64) + (48 + 20);
-    size_t paths = std::min<size_t>(WAVE_PATHS_MAX, std::max<size_t>(WAVE_BYTES_BUDGET / bytes_per_path, (size_t)rp->num_paths));
-    paths = std::min(paths, pixels * (size_t)max_sub * max_sub * rp->num_paths);
+    size_t paths = std::min<size_t>(WAVE_PATHS_MAX, std::max<size_t>(WAVE_BYTES_BUDGET / 2 / bytes_per_path, (size_t)rp->num_paths));
+    const size_t frame_paths = pixels * (size_t)max_sub * max_sub * rp->num_paths;
+    paths = std::min(paths, frame_paths);
     paths = std::max<size_t>((paths / rp->num_paths) * rp->num_paths, (size_t)rp->num_paths);
     const size_t wave_cs = paths / rp->num_paths;
     if ((rc = ensure_queues(ctx, st, paths, wave_cs, shadow_per_path, slots_per_path, P.has_specular != 0, next_mult))) return rc;
     P.next_cap = (uint32_t)(paths * next_mult);
-    Queues& q = st->q;
     cudaStream_t s = ctx->stream;
+    struct Restore { miro_gpu_ctx* c; cudaStream_t s; ~Restore() { c->stream = s; c->work_lane = 0; } } restore{ctx, s};      // also on error returns
 
     // ---- pixels of this shard: 32x32 buckets in the order of Scene.cpp:160-175, bucket b owned when b % shard_count == shard_index
     std::vector<uint32_t> own;
@@ -610,7 +625,8 @@ extern "C" int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, co
     EventPair tot = begin_timing(ctx, false);
     MIRO_CUDA(ctx, cudaMemcpyAsync(st->active[0], own.data(), own.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     MIRO_CUDA(ctx, cudaMemsetAsync(st->level_sum, 0, pixels * sizeof(float4), s));
-    MIRO_CUDA(ctx, cudaMemsetAsync(q.counts + 5, 0, sizeof(uint32_t), s));
+    MIRO_CUDA(ctx, cudaMemsetAsync(st->q[0].counts + 5, 0, sizeof(uint32_t), s));
+    MIRO_CUDA(ctx, cudaMemsetAsync(st->q[1].counts + 5, 0, sizeof(uint32_t), s));
     int cur = 0;
     // vertices along a path: up to maxBounces-1 diffuse (GI) continuations and up to 5 reflect / refract continuations (Blinn.cpp:57,247)
     const int last_depth = (rp->path_trace ? std::max(0, rp->max_bounces - 1) : 0) + (P.has_specular ? 5 : 0);
@@ -619,34 +635,50 @@ extern "C" int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, co
         const int km1 = level - 1;
         const uint32_t ordinal_base = (uint32_t)(km1 * (km1 + 1) * (2 * km1 + 1) / 6);
         const uint64_t total_cs = (uint64_t)n_active * k2;
-        for (uint64_t first = 0; first < total_cs; first += wave_cs) {
-            const uint32_t n_cs = (uint32_t)std::min<uint64_t>(wave_cs, total_cs - first);
-            if (P.local_paths == 0) break;          // sample sharding: this shard owns none of the num_paths paths
-            k_raygen<<<grid_for(n_cs, SHADE_BLOCK), SHADE_BLOCK, 0, s>>>(dc, P, st->active[cur], (uint32_t)first, n_cs, level, ordinal_base, q.cs_rays);
+        // waves alternate between the context's stream (queue set 0) and the auxiliary stream (set 1); both start after
+        // everything enqueued so far (active list, previous level) and the level resolve waits for both
+        // a level that fits one wave is still cut in two when both halves stay large, so that there is something to overlap
+        static const bool overlap = getenv("MIRO_GPU_RENDER_SERIAL") == nullptr;      // A/B switch: one stream, one queue set
+        uint64_t level_wave_cs = wave_cs;
+        if (overlap && total_cs * (uint64_t)std::max(1, P.local_paths) >= 2 * WAVE_SPLIT_MIN) level_wave_cs = std::min<uint64_t>(level_wave_cs, (total_cs + 1) / 2);
+        const bool none = P.local_paths == 0;      // sample sharding: this shard owns none of the num_paths paths (its frame is zero)
+        const bool two = total_cs > level_wave_cs && !none && overlap;
+        if (two) { MIRO_CUDA(ctx, cudaEventRecord(st->ev_fork, s)); MIRO_CUDA(ctx, cudaStreamWaitEvent(st->aux, st->ev_fork, 0)); }
+        int wave = 0;
+        for (uint64_t first = 0; first < total_cs && !none; first += level_wave_cs, ++wave) {
+            const int set = two ? (wave & 1) : 0;
+            Queues& q = st->q[set];
+            cudaStream_t ws = set ? st->aux : s;
+            ctx->stream = ws; ctx->work_lane = set;
+            const uint32_t n_cs = (uint32_t)std::min<uint64_t>(level_wave_cs, total_cs - first);
+            k_raygen<<<grid_for(n_cs, SHADE_BLOCK), SHADE_BLOCK, 0, ws>>>(dc, P, st->active[cur], (uint32_t)first, n_cs, level, ordinal_base, q.cs_rays);
             ctx->launches++;
             launch_trace_closest(ctx, q.cs_rays, n_cs, nullptr, q.cs_hits);
-            MIRO_CUDA(ctx, cudaMemsetAsync(q.counts, 0, 3 * sizeof(uint32_t), s));
+            MIRO_CUDA(ctx, cudaMemsetAsync(q.counts, 0, 3 * sizeof(uint32_t), ws));
             const size_t n_threads = (size_t)n_cs * P.local_paths;
-            k_shade<true><<<std::min(grid_for(n_threads, SHADE_BLOCK), kPersistentGrid * 4), SHADE_BLOCK, 0, s>>>(
+            k_shade<true><<<std::min(grid_for(n_threads, SHADE_BLOCK), kPersistentGrid * 4), SHADE_BLOCK, 0, ws>>>(
                 ctx->scene, ctx->shading, P, q, 0, (uint32_t)n_threads, nullptr, st->level_sum, (uint32_t)q.cap_shadow, (uint32_t)q.cap_slots);
             ctx->launches++;
             int in_q = 1;      // k_shade<PRIMARY> wrote its bounce rays to q_rays[0 ^ 1]
             for (int depth = 0; depth <= last_depth; ++depth) {
                 // shadow rays of the vertices at `depth`, then the per-loop resolve
                 launch_trace_shadow(ctx, q.sh_rays, q.cap_shadow, q.counts + 1, q.sh_E, reinterpret_cast<float4*>(q.slots));
-                k_resolve_slots<<<kPersistentGrid, SHADE_BLOCK, 0, s>>>(q.slots, q.counts + 2, st->level_sum);
+                k_resolve_slots<<<kPersistentGrid, SHADE_BLOCK, 0, ws>>>(q.slots, q.counts + 2, st->level_sum);
                 ctx->launches++;
                 if (depth == last_depth) break;
                 // bounce rays spawned at `depth` -> vertices at depth + 1
-                MIRO_CUDA(ctx, cudaMemcpyAsync(q.counts + 4, q.counts + 0, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
-                MIRO_CUDA(ctx, cudaMemsetAsync(q.counts, 0, 3 * sizeof(uint32_t), s));
+                MIRO_CUDA(ctx, cudaMemcpyAsync(q.counts + 4, q.counts + 0, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ws));
+                MIRO_CUDA(ctx, cudaMemsetAsync(q.counts, 0, 3 * sizeof(uint32_t), ws));
                 launch_trace_closest(ctx, q.q_rays[in_q], q.cap_paths, q.counts + 4, q.q_hits);
-                k_shade<false><<<kPersistentGrid * 4, SHADE_BLOCK, 0, s>>>(ctx->scene, ctx->shading, P, q, in_q, 0, q.counts + 4, st->level_sum,
+                k_shade<false><<<kPersistentGrid * 4, SHADE_BLOCK, 0, ws>>>(ctx->scene, ctx->shading, P, q, in_q, 0, q.counts + 4, st->level_sum,
                                                                            (uint32_t)q.cap_shadow, (uint32_t)q.cap_slots);
                 ctx->launches++;
                 in_q ^= 1;
             }
+            ctx->stream = s; ctx->work_lane = 0;
         }
+        if (two) { MIRO_CUDA(ctx, cudaEventRecord(st->ev_join, st->aux)); MIRO_CUDA(ctx, cudaStreamWaitEvent(s, st->ev_join, 0)); }
+        Queues& q = st->q[0];
         MIRO_CUDA(ctx, cudaMemsetAsync(q.counts + 3, 0, sizeof(uint32_t), s));
         k_level_resolve<<<grid_for(n_active, SHADE_BLOCK), SHADE_BLOCK, 0, s>>>(st->active[cur], n_active, level, rp->min_subdivs, rp->max_subdivs, rp->noise_threshold,
                                                                                st->gamma_lut, st->level_sum, st->result, st->active[cur ^ 1], q.counts + 3);
@@ -679,10 +711,13 @@ extern "C" int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, co
             for (uint32_t p : own) { rgb_out[(size_t)p * 3] = tmp[(size_t)p * 3]; rgb_out[(size_t)p * 3 + 1] = tmp[(size_t)p * 3 + 1]; rgb_out[(size_t)p * 3 + 2] = tmp[(size_t)p * 3 + 2]; }
         }
     }
-    if (any_disperse) MIRO_CUDA(ctx, cudaMemcpyAsync(st->h_count + 1, q.counts + 5, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    if (any_disperse) {
+        MIRO_CUDA(ctx, cudaMemcpyAsync(st->h_count + 1, st->q[0].counts + 5, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        MIRO_CUDA(ctx, cudaMemcpyAsync(st->h_count + 2, st->q[1].counts + 5, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    }
     end_timing(ctx, tot);
     MIRO_CUDA(ctx, cudaStreamSynchronize(s));
-    if (any_disperse && st->h_count[1])
-        return set_error(ctx, MIRO_GPU_ENOMEM, "continuation-ray queue overflow: " + std::to_string(st->h_count[1]) + " dispersion rays were dropped (paths split more than 3x per wave)");
+    if (any_disperse && (st->h_count[1] || st->h_count[2]))
+        return set_error(ctx, MIRO_GPU_ENOMEM, "continuation-ray queue overflow: " + std::to_string(st->h_count[1] + st->h_count[2]) + " dispersion rays were dropped (paths split more than 3x per wave)");
     return MIRO_GPU_OK;
 }
