@@ -196,3 +196,35 @@ def test_chained_launches_give_identical_results():
         occ = np.unpackbits(bits[k].cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
         assert (occ == want_occ).all()
     sc.close()
+
+
+def test_host_pointer_pipeline_settings_do_not_change_results(tmp_path):
+    """The host-pointer calls cut a batch into chunks and rotate the chunk kernels over several streams (csrc/miro_gpu_api.cu
+    trace_host); chunk size and stream count are read from the environment once per process, so the variants run in child
+    processes: tiny ragged chunks on 1, 3 and 4 kernel streams must return exactly what the default returns."""
+    import subprocess, sys, textwrap
+    fx = helpers.Fixture(helpers.fixture_path("c2_explosion"))
+    sc = fx.scene().attach(0)
+    rays = fx.rays[:20011]                                   # ragged: not a multiple of 32
+    want = sc.trace_closest(rays); want_occ = sc.trace_any(rays)
+    sc.close()
+    np.save(tmp_path / "hits.npy", want.view(np.uint8)); np.save(tmp_path / "occ.npy", want_occ)
+    child = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import helpers, miro_b200 as mb
+        fx = helpers.Fixture(helpers.fixture_path("c2_explosion"))
+        sc = fx.scene().attach(0)
+        rays = fx.rays[:20011]
+        for rep in range(2):
+            h = sc.trace_closest(rays); o = sc.trace_any(rays)
+            assert h.view(np.uint8).tobytes() == np.load(%r).tobytes(), "closest-hit records differ"
+            assert (o == np.load(%r)).all(), "occlusion bits differ"
+        sc.close()
+        print("ok")
+    """) % (helpers.ROOT, str(helpers.ROOT) + "/tests", str(tmp_path / "hits.npy"), str(tmp_path / "occ.npy"))
+    import os
+    for chunk, ks in ((10, 1), (10, 3), (11, 4), (12, 2)):
+        env = dict(os.environ, MIRO_GPU_CHUNK=str(chunk), MIRO_GPU_KSTREAMS=str(ks))
+        p = subprocess.run([sys.executable, "-c", child], env=env, capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0 and "ok" in p.stdout, (chunk, ks, p.stdout[-500:], p.stderr[-1500:])
