@@ -355,6 +355,30 @@ def main():
     e2e_val = 3 * N_BATCH * e2e_steps * world / e2e_s * 1e-6
     assert np.array_equal(out_hits[1].numpy().view(mb.HIT_DTYPE).reshape(-1)["prim"], inco_hits["prim"])
 
+    # the same step with 32-byte packed rays (miro_gpu_trace_*_packed: the scene is static, so time / flags / user words carry
+    # nothing): a third less over PCIe, which is what bounds the host-pointer calls
+    pinned32 = [torch.from_numpy(mb.pack_rays(b).view(np.uint8).reshape(len(b), -1).copy()).pin_memory() for b in batches]
+
+    def e2e_packed_step():
+        L.miro_gpu_trace_closest_packed(sc.ctx, pinned32[0].data_ptr(), N_BATCH, out_hits[0].data_ptr())
+        L.miro_gpu_trace_closest_packed(sc.ctx, pinned32[1].data_ptr(), N_BATCH, out_hits[1].data_ptr())
+        L.miro_gpu_trace_any_packed(sc.ctx, pinned32[2].data_ptr(), N_BATCH, out_bits.data_ptr())
+    for _ in range(2):
+        e2e_packed_step()
+    barrier()
+    t0 = time.time()
+    for _ in range(e2e_steps):
+        e2e_packed_step()
+    torch.cuda.synchronize()
+    e2e32_s = time.time() - t0
+    if world > 1:
+        t = torch.tensor([e2e32_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e32_s = float(t.item())
+    e2e32_val = 3 * N_BATCH * e2e_steps * world / e2e32_s * 1e-6
+    chk32 = out_hits[1].numpy().view(mb.HIT_DTYPE).reshape(-1)
+    assert np.array_equal(chk32["prim"], inco_hits["prim"]) and np.array_equal(chk32["t"], inco_hits["t"])
+
     if rank == 0:
         dom = int(np.argmax(launch_ms))
         kernel_names = ["k_trace<closest> primary", "k_trace<closest> incoherent", "k_trace<any> shadow"]
@@ -368,7 +392,11 @@ def main():
                 "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
                 "gpu_launches": 3 * args.steps,
                 "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": 3 * N_BATCH * 48,
-                        "d2h_bytes_per_step": 2 * N_BATCH * 20 + 4 * ((N_BATCH + 31) // 32), "steps": e2e_steps},
+                        "d2h_bytes_per_step": 2 * N_BATCH * 20 + 4 * ((N_BATCH + 31) // 32), "steps": e2e_steps,
+                        "ray_format": "miro_gpu_ray, 48 B (the general ABI record)"},
+                "e2e_packed": {"value": e2e32_val, "unit": "Mrays/s", "h2d_bytes_per_step": 3 * N_BATCH * 32,
+                               "d2h_bytes_per_step": 2 * N_BATCH * 20 + 4 * ((N_BATCH + 31) // 32), "steps": e2e_steps,
+                               "ray_format": "miro_gpu_ray32, 32 B (static scenes: no time / flags words); identical hits asserted"},
                 "roofline": {"bound": "hbm", "kernel": kernel_names[dom],
                              "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": peak_src,
                              "traffic": traffic, "algorithmic_bytes_per_launch": per_launch[dom]["bytes"],

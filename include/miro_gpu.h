@@ -55,6 +55,13 @@ typedef struct miro_gpu_ray {   /* 48 bytes, 16-byte aligned: three 16-byte vect
     uint32_t user0, user1;      /* opaque to the tracer */
 } miro_gpu_ray;
 
+/* Packed ray for static scenes: the first two 16-byte words of miro_gpu_ray (time = 0, no flags / user words).  A third less
+ * to move over PCIe, which is what bounds the host-pointer calls. */
+typedef struct miro_gpu_ray32 {  /* 32 bytes, 16-byte aligned */
+    float o[3]; float tmin;
+    float d[3]; float tmax;
+} miro_gpu_ray32;
+
 typedef struct miro_gpu_hit {   /* 20 bytes */
     float t, a, b;              /* distance; barycentric weights of vertex 1 and vertex 2 (HitInfo::a,b) */
     int32_t prim;               /* index into miro_gpu_scene_desc::prims, -1 = miss */
@@ -273,6 +280,11 @@ int miro_gpu_trace_any(miro_gpu_ctx* ctx, const miro_gpu_ray* rays, size_t n, ui
  * context's stream — the caller synchronises. */
 int miro_gpu_trace_closest_device(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, miro_gpu_hit* d_hits);
 int miro_gpu_trace_any_device(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, uint32_t* d_occluded_bits);
+
+/* The same two queries for packed rays (host pointers; pipelined like miro_gpu_trace_closest / _any).  Results are those of the
+ * 48-byte call with time = 0. */
+int miro_gpu_trace_closest_packed(miro_gpu_ctx* ctx, const miro_gpu_ray32* rays, size_t n, miro_gpu_hit* hits);
+int miro_gpu_trace_any_packed(miro_gpu_ctx* ctx, const miro_gpu_ray32* rays, size_t n, uint32_t* occluded_bits);
 
 /* Scene::raytraceImage.  rgb_out: width*height*3 floats, row 0 = bottom row (src/Image.cpp:150-151),
  * linear radiance before Image::Map.  rgb_out may be a host or a device pointer. */

@@ -4,4 +4,4 @@ The product is the native library libmiro_gpu.so (CUDA kernels for sm_100a + C++
 this package is the ctypes plumbing the tests and the benchmark use to reach its C ABI.
 """
 from . import capi  # noqa: F401
-from .scene import MiroScene, MiroError, RAY_DTYPE, HIT_DTYPE, make_rays  # noqa: F401
+from .scene import MiroScene, MiroError, RAY_DTYPE, RAY32_DTYPE, HIT_DTYPE, make_rays, pack_rays  # noqa: F401

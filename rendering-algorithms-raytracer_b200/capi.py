@@ -110,7 +110,7 @@ class Counters(C.Structure):
 
 # every symbol include/miro_gpu.h and include/miro_host.h declare (checked by tests/test_abi.py)
 GPU_SYMBOLS = ["miro_gpu_create", "miro_gpu_destroy", "miro_gpu_last_error", "miro_gpu_abi_version", "miro_gpu_sizeof", "miro_gpu_set_stream", "miro_gpu_set_trace_chaining",
-               "miro_gpu_upload_scene", "miro_gpu_trace_closest", "miro_gpu_trace_any", "miro_gpu_trace_closest_device",
+               "miro_gpu_upload_scene", "miro_gpu_trace_closest", "miro_gpu_trace_any", "miro_gpu_trace_closest_packed", "miro_gpu_trace_any_packed", "miro_gpu_trace_closest_device",
                "miro_gpu_trace_any_device", "miro_gpu_render", "miro_gpu_enable_counting", "miro_gpu_get_counters",
                "miro_gpu_reset_counters"]
 HOST_SYMBOLS = ["miro_host_new", "miro_host_free", "miro_host_error", "miro_host_preload_mesh", "miro_host_preload_image",
@@ -136,7 +136,8 @@ def lib():
     L.miro_gpu_abi_version.argtypes = []; L.miro_gpu_abi_version.restype = i32
     L.miro_gpu_set_stream.argtypes = [vp, vp]; L.miro_gpu_set_stream.restype = i32
     L.miro_gpu_upload_scene.argtypes = [vp, C.POINTER(SceneDesc)]; L.miro_gpu_upload_scene.restype = i32
-    for name in ("miro_gpu_trace_closest", "miro_gpu_trace_any", "miro_gpu_trace_closest_device", "miro_gpu_trace_any_device"):
+    for name in ("miro_gpu_trace_closest", "miro_gpu_trace_any", "miro_gpu_trace_closest_device", "miro_gpu_trace_any_device",
+                 "miro_gpu_trace_closest_packed", "miro_gpu_trace_any_packed"):
         f = getattr(L, name); f.argtypes = [vp, vp, sz, vp]; f.restype = i32
     L.miro_gpu_render.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), vp]; L.miro_gpu_render.restype = i32
     L.miro_gpu_enable_counting.argtypes = [vp, i32]; L.miro_gpu_enable_counting.restype = i32

@@ -120,6 +120,8 @@ void drain_timing(miro_gpu_ctx* ctx);
 // launches the traversal kernel over device buffers (count either n, or *d_count when non-null)
 void launch_trace_closest(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, const uint32_t* d_count, miro_gpu_hit* d_hits);
 void launch_trace_any(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, const uint32_t* d_count, uint32_t* d_bits);
+void launch_trace_closest_packed(miro_gpu_ctx* ctx, const miro_gpu_ray32* d_rays, size_t n, miro_gpu_hit* d_hits);
+void launch_trace_any_packed(miro_gpu_ctx* ctx, const miro_gpu_ray32* d_rays, size_t n, uint32_t* d_bits);
 // any-hit traversal of shadow rays; an unoccluded ray adds d_E[i] to d_slots[4 * ray.user0] (see render.cu)
 void launch_trace_shadow(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, const uint32_t* d_count, const float4* d_E, float4* d_slots);
 

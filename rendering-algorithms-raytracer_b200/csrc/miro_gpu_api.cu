@@ -65,12 +65,14 @@ enum { TRACE_CLOSEST = 0, TRACE_ANY_BITS = 1, TRACE_ANY_ACCUM = 2 };
 constexpr int WORK_RING = 8;      // pairs of work counters per lane; launch k of a lane uses pair k % WORK_RING and re-arms it when its last block leaves
 constexpr int WORK_LANES = 4;     // lanes = streams a caller may spread traversal launches over (miro_gpu_ctx::work_lane)
 
-template <int MODE, bool COUNT, bool ALPHA>
+// PACKED: rays are miro_gpu_ray32 records (two 16-byte words: o, tmin | d, tmax; time = 0) instead of miro_gpu_ray (three).
+template <int MODE, bool COUNT, bool ALPHA, bool PACKED>
 __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS)
 k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const uint32_t* __restrict__ d_count, uint32_t chunk,
         miro_gpu_hit* __restrict__ hits, uint32_t* __restrict__ bits, const float4* __restrict__ sample_E, float4* __restrict__ slots,
         TraceCounters* __restrict__ ctr, uint32_t* __restrict__ work) {
     constexpr bool ANY = MODE != TRACE_CLOSEST;
+    constexpr uint32_t RAY_F4 = PACKED ? 2u : 3u;       // 16-byte words per ray record
     __shared__ unsigned long long stack[SMEM_STACK * TRACE_BLOCK];
     const uint32_t n = d_count ? min(*d_count, n_static) : n_static;
     const uint32_t lane = threadIdx.x & 31u;
@@ -126,10 +128,10 @@ k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const
                 const uint32_t rank = __popc(idle & lt_mask);
                 if (L.done && rank < take) {
                     L.ray_idx = chunk_next + rank;
-                    const float4* rp = rays + (size_t)L.ray_idx * 3;
-                    const float4 r0 = __ldcs(rp), r1 = __ldcs(rp + 1), r2 = __ldcs(rp + 2);
+                    const float4* rp = rays + (size_t)L.ray_idx * RAY_F4;
+                    const float4 r0 = __ldcs(rp), r1 = __ldcs(rp + 1);
                     L.set_ray(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
-                    L.tmin = r0.w; L.time = r2.x;
+                    L.tmin = r0.w; L.time = PACKED ? 0.f : __ldcs(reinterpret_cast<const float*>(rp + 2));
                     L.hit.t = r1.w; L.hit.a = 0.f; L.hit.b = 0.f; L.hit.prim = -1; L.hit.inst = -1;
                     L.cur = s.root; L.cur_inst = -1; st.sp = 0; L.done = false;
                     ++c_rays;
@@ -149,10 +151,10 @@ k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const
         } else if (at_leaf) {
             // ---- leaf round
             if (L.cur == STACK_SENTINEL) {            // leaving an instance: back to the world-space ray
-                const float4 w0 = __ldg(rays + (size_t)L.ray_idx * 3), w1 = __ldg(rays + (size_t)L.ray_idx * 3 + 1);
+                const float4 w0 = __ldg(rays + (size_t)L.ray_idx * RAY_F4), w1 = __ldg(rays + (size_t)L.ray_idx * RAY_F4 + 1);
                 L.set_ray(w0.x, w0.y, w0.z, w1.x, w1.y, w1.z);
                 L.cur_inst = -1; L.cur = MIRO_GPU_CHILD_EMPTY;
-            } else finished = intersect_leaf<ANY, COUNT, ALPHA>(s, L, st, rays, c_tris, c_insts);     // true: any-hit found its occluder
+            } else finished = intersect_leaf<ANY, COUNT, ALPHA>(s, L, st, rays, RAY_F4, c_tris, c_insts);     // true: any-hit found its occluder
             if (!finished && L.cur == MIRO_GPU_CHILD_EMPTY) { pop_next(L, st); finished = L.cur == MIRO_GPU_CHILD_EMPTY; }
         }
         if (finished) { L.done = true; pending = true; }
@@ -198,11 +200,11 @@ static int trace_grid(miro_gpu_ctx* ctx, size_t n) {
     int& v = per_sm[(ctx->counting ? 1 : 0) + (ctx->has_alpha ? 2 : 0)];
     if (v == 0) {
         if (ctx->has_alpha) {
-            if (ctx->counting) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace<MODE, true, true>, TRACE_BLOCK, 0);
-            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace<MODE, false, true>, TRACE_BLOCK, 0);
+            if (ctx->counting) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace<MODE, true, true, false>, TRACE_BLOCK, 0);
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace<MODE, false, true, false>, TRACE_BLOCK, 0);
         } else {
-            if (ctx->counting) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace<MODE, true, false>, TRACE_BLOCK, 0);
-            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace<MODE, false, false>, TRACE_BLOCK, 0);
+            if (ctx->counting) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace<MODE, true, false, false>, TRACE_BLOCK, 0);
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace<MODE, false, false, false>, TRACE_BLOCK, 0);
         }
         if (v <= 0) v = 1;
     }
@@ -210,8 +212,8 @@ static int trace_grid(miro_gpu_ctx* ctx, size_t n) {
     return (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->sm_count * v, blocks_needed));
 }
 
-template <int MODE>
-static void launch_trace(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, const uint32_t* d_count, miro_gpu_hit* d_hits, uint32_t* d_bits,
+template <int MODE, bool PACKED = false>
+static void launch_trace(miro_gpu_ctx* ctx, const void* d_rays, size_t n, const uint32_t* d_count, miro_gpu_hit* d_hits, uint32_t* d_bits,
                          const float4* d_E, float4* d_slots) {
     if (n == 0) return;
     const int grid = trace_grid<MODE>(ctx, n);
@@ -233,7 +235,7 @@ static void launch_trace(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = (ctx->chain_traces && ctx->in_api_trace) ? 1 : 0;
-#define MIRO_LAUNCH(COUNT, ALPHA) cudaLaunchKernelEx(&cfg, k_trace<MODE, COUNT, ALPHA>, ctx->scene, r, (uint32_t)n, d_count, chunk, d_hits, d_bits, d_E, d_slots, ctx->d_counters, work)
+#define MIRO_LAUNCH(COUNT, ALPHA) cudaLaunchKernelEx(&cfg, k_trace<MODE, COUNT, ALPHA, PACKED>, ctx->scene, r, (uint32_t)n, d_count, chunk, d_hits, d_bits, d_E, d_slots, ctx->d_counters, work)
     if (ctx->has_alpha) { if (ctx->counting) MIRO_LAUNCH(true, true); else MIRO_LAUNCH(false, true); }
     else { if (ctx->counting) MIRO_LAUNCH(true, false); else MIRO_LAUNCH(false, false); }
 #undef MIRO_LAUNCH
@@ -244,6 +246,12 @@ void launch_trace_closest(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t 
 }
 void launch_trace_any(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, const uint32_t* d_count, uint32_t* d_bits) {
     launch_trace<TRACE_ANY_BITS>(ctx, d_rays, n, d_count, nullptr, d_bits, nullptr, nullptr);
+}
+void launch_trace_closest_packed(miro_gpu_ctx* ctx, const miro_gpu_ray32* d_rays, size_t n, miro_gpu_hit* d_hits) {
+    launch_trace<TRACE_CLOSEST, true>(ctx, d_rays, n, nullptr, d_hits, nullptr, nullptr, nullptr);
+}
+void launch_trace_any_packed(miro_gpu_ctx* ctx, const miro_gpu_ray32* d_rays, size_t n, uint32_t* d_bits) {
+    launch_trace<TRACE_ANY_BITS, true>(ctx, d_rays, n, nullptr, nullptr, d_bits, nullptr, nullptr);
 }
 void launch_trace_shadow(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, const uint32_t* d_count, const float4* d_E, float4* d_slots) {
     launch_trace<TRACE_ANY_ACCUM>(ctx, d_rays, n, d_count, nullptr, nullptr, d_E, d_slots);
@@ -256,6 +264,7 @@ extern "C" {
 
 int miro_gpu_abi_version(void) { return MIRO_GPU_ABI_VERSION; }
 
+static_assert(sizeof(miro_gpu_ray32) == 32, "include/miro_gpu.h layout changed");
 static_assert(sizeof(miro_gpu_ray) == 48 && sizeof(miro_gpu_hit) == 20 && sizeof(miro_gpu_node) == 128 && sizeof(miro_gpu_tri) == 48 &&
               sizeof(miro_gpu_mbtri) == 96 && sizeof(miro_gpu_instance) == 64 && sizeof(miro_gpu_prim) == 48 &&
               sizeof(miro_gpu_material) == 128 && sizeof(miro_gpu_light) == 64, "include/miro_gpu.h layout changed");
@@ -527,7 +536,9 @@ int miro_gpu_trace_any_device(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, siz
 // Host-pointer entry points: the batch is cut into chunks and pipelined over three streams — chunk k+1 is on its way
 // up (H2D) and chunk k-1 on its way down (D2H) while chunk k is traversed — so the call costs max(copy, compute), not
 // their sum.  PCIe is full duplex, so the two copy directions overlap as well.
-static int trace_host(miro_gpu_ctx* ctx, const miro_gpu_ray* rays, size_t n, miro_gpu_hit* hits, uint32_t* bits) {
+static int trace_host(miro_gpu_ctx* ctx, const void* rays_v, size_t n, miro_gpu_hit* hits, uint32_t* bits, bool packed = false) {
+    const char* rays = static_cast<const char*>(rays_v);
+    const size_t ray_bytes = packed ? sizeof(miro_gpu_ray32) : sizeof(miro_gpu_ray);
     if (!ctx) return MIRO_GPU_EINVAL;
     if (!ctx->has_scene) return set_error(ctx, MIRO_GPU_ENOSCENE, "trace before upload_scene");
     if (n > 0xffffffffull) return set_error(ctx, MIRO_GPU_EINVAL, "more than 2^32-1 rays in one call");
@@ -575,7 +586,8 @@ static int trace_host(miro_gpu_ctx* ctx, const miro_gpu_ray* rays, size_t n, mir
     for (size_t k = 0; k < n_chunks; ++k) {
         const size_t off = bounds[k], m = bounds[k + 1] - off;
         cudaEvent_t up = ctx->pipe_events[2 * k], done = ctx->pipe_events[2 * k + 1];
-        MIRO_CUDA(ctx, cudaMemcpyAsync(ctx->d_rays.ptr + off, rays + off, m * sizeof(miro_gpu_ray), cudaMemcpyHostToDevice, ctx->copy_in));
+        char* const d_chunk = reinterpret_cast<char*>(ctx->d_rays.ptr) + off * ray_bytes;      // the staging buffer holds either record size
+        MIRO_CUDA(ctx, cudaMemcpyAsync(d_chunk, rays + off * ray_bytes, m * ray_bytes, cudaMemcpyHostToDevice, ctx->copy_in));
         MIRO_CUDA(ctx, cudaEventRecord(up, ctx->copy_in));
         mark(ctx->copy_in);
         ctx->stream = (k % k_streams == 0) ? user_stream : ctx->trace_aux[k % k_streams - 1];
@@ -584,10 +596,12 @@ static int trace_host(miro_gpu_ctx* ctx, const miro_gpu_ray* rays, size_t n, mir
         mark(ctx->stream);
         EventPair p = begin_timing(ctx, true);
         if (hits) {
-            launch_trace_closest(ctx, ctx->d_rays.ptr + off, m, nullptr, ctx->d_hits.ptr + off);
+            if (packed) launch_trace_closest_packed(ctx, reinterpret_cast<const miro_gpu_ray32*>(d_chunk), m, ctx->d_hits.ptr + off);
+            else launch_trace_closest(ctx, reinterpret_cast<const miro_gpu_ray*>(d_chunk), m, nullptr, ctx->d_hits.ptr + off);
             if (ctx->scene.prim_map) { k_translate_hits<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_hits.ptr + off, (uint32_t)m, ctx->scene.prim_map); ctx->launches++; }
         }
-        else launch_trace_any(ctx, ctx->d_rays.ptr + off, m, nullptr, ctx->d_bits.ptr + off / 32);
+        else if (packed) launch_trace_any_packed(ctx, reinterpret_cast<const miro_gpu_ray32*>(d_chunk), m, ctx->d_bits.ptr + off / 32);
+        else launch_trace_any(ctx, reinterpret_cast<const miro_gpu_ray*>(d_chunk), m, nullptr, ctx->d_bits.ptr + off / 32);
         end_timing(ctx, p);
         MIRO_CUDA(ctx, cudaEventRecord(done, ctx->stream));
         mark(ctx->stream);
@@ -619,6 +633,16 @@ int miro_gpu_trace_closest(miro_gpu_ctx* ctx, const miro_gpu_ray* rays, size_t n
 int miro_gpu_trace_any(miro_gpu_ctx* ctx, const miro_gpu_ray* rays, size_t n, uint32_t* occluded_bits) {
     if (ctx && n && !occluded_bits) return set_error(ctx, MIRO_GPU_EINVAL, "NULL ray/bit buffer");
     return trace_host(ctx, rays, n, nullptr, occluded_bits);
+}
+
+int miro_gpu_trace_closest_packed(miro_gpu_ctx* ctx, const miro_gpu_ray32* rays, size_t n, miro_gpu_hit* hits) {
+    if (ctx && n && !hits) return set_error(ctx, MIRO_GPU_EINVAL, "NULL ray/hit buffer");
+    return trace_host(ctx, rays, n, hits, nullptr, true);
+}
+
+int miro_gpu_trace_any_packed(miro_gpu_ctx* ctx, const miro_gpu_ray32* rays, size_t n, uint32_t* occluded_bits) {
+    if (ctx && n && !occluded_bits) return set_error(ctx, MIRO_GPU_EINVAL, "NULL ray/bit buffer");
+    return trace_host(ctx, rays, n, nullptr, occluded_bits, true);
 }
 
 int miro_gpu_set_trace_chaining(miro_gpu_ctx* ctx, int on) {

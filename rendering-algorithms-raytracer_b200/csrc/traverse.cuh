@@ -401,7 +401,7 @@ __device__ __forceinline__ float hit_alpha(const AlphaData& A, uint32_t prim, fl
 
 // Leaf phase.  Returns true when an ANY query has found its occluder.
 template <bool ANY, bool COUNT, bool ALPHA>
-__device__ __forceinline__ bool intersect_leaf(const DeviceScene& s, Lane& L, TraversalStack& st, const float4* __restrict__ rays,
+__device__ __forceinline__ bool intersect_leaf(const DeviceScene& s, Lane& L, TraversalStack& st, const float4* __restrict__ rays, const uint32_t ray_f4,
                                                uint32_t& n_tris, uint32_t& n_insts) {
     const uint32_t u = (uint32_t)L.cur;
     const uint32_t kind = (u >> 29) & 3u;
@@ -446,7 +446,7 @@ __device__ __forceinline__ bool intersect_leaf(const DeviceScene& s, Lane& L, Tr
         const int4 meta = __ldg(reinterpret_cast<const int4*>(m + 3));
         if (COUNT) ++n_insts;
         // the world-space ray is not kept in registers: instance entry / exit re-read it (L2-resident, rare)
-        const float4 w0 = __ldg(rays + (size_t)L.ray_idx * 3), w1 = __ldg(rays + (size_t)L.ray_idx * 3 + 1);
+        const float4 w0 = __ldg(rays + (size_t)L.ray_idx * ray_f4), w1 = __ldg(rays + (size_t)L.ray_idx * ray_f4 + 1);
         const float wox = w0.x, woy = w0.y, woz = w0.z, wdx = w1.x, wdy = w1.y, wdz = w1.z;
         // o' = M^-1 [o 1], d' = M^-1 [d 0]  (src/ProxyObject.cpp:78-79; affine, so w = 1)
         L.set_ray(r0.x * wox + r0.y * woy + r0.z * woz + r0.w, r1.x * wox + r1.y * woy + r1.z * woz + r1.w, r2.x * wox + r2.y * woy + r2.z * woz + r2.w,

@@ -11,7 +11,16 @@ from . import capi
 RAY_DTYPE = np.dtype([("o", np.float32, 3), ("tmin", np.float32), ("d", np.float32, 3), ("tmax", np.float32),
                       ("time", np.float32), ("flags", np.uint32), ("user", np.uint32, 2)])
 HIT_DTYPE = np.dtype([("t", np.float32), ("a", np.float32), ("b", np.float32), ("prim", np.int32), ("inst", np.int32)])
-assert RAY_DTYPE.itemsize == 48 and HIT_DTYPE.itemsize == 20
+RAY32_DTYPE = np.dtype([("o", np.float32, 3), ("tmin", np.float32), ("d", np.float32, 3), ("tmax", np.float32)])      # miro_gpu_ray32
+assert RAY_DTYPE.itemsize == 48 and HIT_DTYPE.itemsize == 20 and RAY32_DTYPE.itemsize == 32
+
+
+def pack_rays(rays):
+    """miro_gpu_ray records -> miro_gpu_ray32 (drops time / flags / user words: static scenes)."""
+    r = np.empty(len(rays), RAY32_DTYPE)
+    for k in ("o", "tmin", "d", "tmax"):
+        r[k] = rays[k]
+    return r
 
 
 class MiroError(RuntimeError):
@@ -150,6 +159,19 @@ class MiroScene:
         rays = np.ascontiguousarray(rays, RAY_DTYPE)
         bits = np.zeros((len(rays) + 31) // 32, np.uint32)
         self._gpu_check(self.L.miro_gpu_trace_any(self.ctx, _ptr(rays), len(rays), _ptr(bits)), "trace_any")
+        return np.unpackbits(bits.view(np.uint8), bitorder="little")[:len(rays)].astype(bool)
+
+    def trace_closest_packed(self, rays):
+        """32-byte rays (pack_rays): miro_gpu_trace_closest_packed — the same hits as trace_closest of the same rays at time 0."""
+        rays = np.ascontiguousarray(rays, RAY32_DTYPE)
+        hits = np.empty(len(rays), HIT_DTYPE)
+        self._gpu_check(self.L.miro_gpu_trace_closest_packed(self.ctx, _ptr(rays), len(rays), _ptr(hits)), "trace_closest_packed")
+        return hits
+
+    def trace_any_packed(self, rays):
+        rays = np.ascontiguousarray(rays, RAY32_DTYPE)
+        bits = np.zeros((len(rays) + 31) // 32, np.uint32)
+        self._gpu_check(self.L.miro_gpu_trace_any_packed(self.ctx, _ptr(rays), len(rays), _ptr(bits)), "trace_any_packed")
         return np.unpackbits(bits.view(np.uint8), bitorder="little")[:len(rays)].astype(bool)
 
     def trace_closest_device(self, d_rays_ptr, n, d_hits_ptr):

@@ -228,3 +228,20 @@ def test_host_pointer_pipeline_settings_do_not_change_results(tmp_path):
         env = dict(os.environ, MIRO_GPU_CHUNK=str(chunk), MIRO_GPU_KSTREAMS=str(ks))
         p = subprocess.run([sys.executable, "-c", child], env=env, capture_output=True, text=True, timeout=300)
         assert p.returncode == 0 and "ok" in p.stdout, (chunk, ks, p.stdout[-500:], p.stderr[-1500:])
+
+
+@pytest.mark.parametrize("name", ["c1_cornell", "c2_explosion", "c5_mb_instances"])
+def test_packed_rays_give_the_hits_of_time_zero(name):
+    """miro_gpu_trace_closest_packed / _any_packed (32-byte rays): bit-identical to the 48-byte calls with time = 0, also on a
+    scene with instances (the world ray is re-read at instance entry / exit) and motion-blur triangles."""
+    fx = helpers.Fixture(helpers.fixture_path(name))
+    sc = fx.scene().attach(0)
+    rays = fx.rays.copy(); rays["time"] = 0.0
+    want = sc.trace_closest(rays); want_occ = sc.trace_any(rays)
+    got = sc.trace_closest_packed(mb.pack_rays(rays)); got_occ = sc.trace_any_packed(mb.pack_rays(rays))
+    assert got.tobytes() == want.tobytes() and (got_occ == want_occ).all()
+    assert (want["prim"] >= 0).mean() > 0.3
+    # ragged sizes and the empty batch
+    for n in (0, 1, 33, 1000):
+        assert sc.trace_closest_packed(mb.pack_rays(rays[:n])).tobytes() == want[:n].tobytes()
+    sc.close()
