@@ -530,7 +530,7 @@ bool Scene::preCalc() {
                     if (!appendTriangle(bo, q.index, q.lo, q.hi)) return false;
                     bprims.push_back(q);
                 }
-                const int32_t root = build_wide_bvh(bprims, m_flat.nodes, order);
+                const int32_t root = build_wide_bvh(bprims, m_flat.nodes, order, nullptr, m_srcTris.data());
                 std::vector<float> lo(3), hi(3);
                 refBounds(m_flat, m_srcTris, order[MIRO_GPU_KIND_TRI], root, lo.data(), hi.data());
                 blasInfo[o.m_blas] = std::make_pair(root, std::make_pair(lo, hi));
@@ -575,7 +575,7 @@ bool Scene::preCalc() {
         // hand the triangles over in object order; miro_gpu_upload_scene builds an LBVH over them on the GPU
         m_flat.root = MIRO_GPU_ROOT_BUILD_ON_DEVICE;
         for (const BuildPrim& bp : top) order[MIRO_GPU_KIND_TRI].push_back(bp.index);
-    } else m_flat.root = build_wide_bvh(top, m_flat.nodes, order, &m_flat.top_stats);
+    } else m_flat.root = build_wide_bvh(top, m_flat.nodes, order, &m_flat.top_stats, m_srcTris.data());
 
     // gather primitives into leaf order
     m_flat.tris.resize(order[0].size()); m_flat.mbtris.resize(order[1].size()); m_flat.instances.resize(order[2].size());

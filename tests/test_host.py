@@ -24,8 +24,10 @@ def leaf_fields(ref):
     return (u >> 29) & 3, ((u >> 26) & 7) + 1, u & ((1 << 26) - 1)
 
 
-def walk(d, nodes, child, tris, ref, lo, hi, seen, depth=0):
-    """Every leaf range is inside its parent's box; every triangle is referenced exactly once."""
+def walk(d, nodes, child, tris, ref, lo, hi, seen, depth=0, inside=True):
+    """Every child box is inside its parent's box.  Object splits only (inside=True): every triangle of a leaf lies inside the
+    leaf's box.  With spatial splits a leaf holds the part of a triangle that lies inside its box: the triangle's box must at
+    least overlap it."""
     if ref == capi.CHILD_EMPTY:
         return 0
     if ref < 0:
@@ -35,7 +37,10 @@ def walk(d, nodes, child, tris, ref, lo, hi, seen, depth=0):
             for i in range(first, first + count):
                 seen[i] += 1
                 v = tris[i].reshape(3, 4)[:, :3]
-                assert (v.min(0) >= lo - 1e-6).all() and (v.max(0) <= hi + 1e-6).all()
+                if inside:
+                    assert (v.min(0) >= lo - 1e-6).all() and (v.max(0) <= hi + 1e-6).all()
+                else:
+                    assert (v.max(0) >= lo - 1e-6).all() and (v.min(0) <= hi + 1e-6).all()
         return depth
     n = nodes[ref]
     best = depth
@@ -46,25 +51,32 @@ def walk(d, nodes, child, tris, ref, lo, hi, seen, depth=0):
         clo = np.array([n[0 + i], n[4 + i], n[8 + i]]); chi = np.array([n[12 + i], n[16 + i], n[20 + i]])
         assert (clo <= chi).all()
         assert (clo >= lo - 1e-6).all() and (chi <= hi + 1e-6).all()
-        best = max(best, walk(d, nodes, child, tris, c, clo, chi, seen, depth + 1))
+        best = max(best, walk(d, nodes, child, tris, c, clo, chi, seen, depth + 1, inside))
     return best
 
 
 @pytest.mark.parametrize("scene", ["c1_cornell", "c2_explosion"])
-def test_flatten_invariants(scene):
+@pytest.mark.parametrize("spatial", [False, True])
+def test_flatten_invariants(scene, spatial, monkeypatch):
+    """spatial=False: object splits only (MIRO_BVH_SPATIAL=0) — the flattening is a permutation of the source triangles.
+    spatial=True (the default build): spatial splits may reference a triangle from several leaves (at most 2x the source
+    count); every source triangle is still referenced, and every copy carries its (mesh, tri) identity."""
+    if not spatial:
+        monkeypatch.setenv("MIRO_BVH_SPATIAL", "0")
     fx = helpers.Fixture(helpers.fixture_path(scene))
     sc = fx.scene()
     d, nodes, child, tris = flat(sc)
-    assert d.n_tris == sum(len(fx.mesh(k)["vidx"]) for k in range(len(fx.names)))
+    n_src = sum(len(fx.mesh(k)["vidx"]) for k in range(len(fx.names)))
+    assert d.n_tris == n_src if not spatial else n_src <= d.n_tris <= 2 * n_src
     seen = np.zeros(d.n_tris, np.int64)
     big = np.float32(3e38)
-    depth = walk(d, nodes, child, tris, d.root, -np.full(3, big), np.full(3, big), seen)
-    assert (seen == 1).all()          # flattening round trip: every triangle appears in exactly one leaf
+    depth = walk(d, nodes, child, tris, d.root, -np.full(3, big), np.full(3, big), seen, inside=not spatial)
+    assert (seen == 1).all()          # every leaf slot belongs to exactly one leaf
     st = sc.bvh_stats()
     assert st["nodes"] == d.n_nodes and st["max_depth"] >= depth >= 1
-    # (mesh, tri) identity is a bijection onto the source triangles
+    # (mesh, tri) identity maps ONTO the source triangles (a bijection without spatial splits)
     mesh_of, tri_of, _ = sc.prim_table()
-    assert len(set(zip(mesh_of.tolist(), tri_of.tolist()))) == d.n_tris
+    assert len(set(zip(mesh_of.tolist(), tri_of.tolist()))) == n_src
     # leaf-ordered vertices equal the source mesh's vertices
     m = fx.mesh(0)
     k = np.nonzero(mesh_of == 0)[0][:500]

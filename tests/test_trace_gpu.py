@@ -82,7 +82,7 @@ def test_edge_cases(loaded):
     r["d"][:, 0] = 0.0
     d = r["d"]; d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-20); r["d"] = d
     g = sc.trace_closest(r); o, _ = helpers.oracle_trace_closest(sc, r)
-    assert (g["prim"] == o["prim"]).mean() >= 0.95
+    assert helpers.same_primitive(sc, g, o).mean() >= 0.95
     r = fx.rays[:64].copy(); r["tmax"] = r["tmin"]
     assert (sc.trace_closest(r)["prim"] == -1).all()
 
@@ -121,7 +121,8 @@ def test_full_size_batches_against_reference(name):
     assert ((near["prim"] < 0) | (near["t"] < r["tmax"]))[h].all()
     r["tmax"][h] = hits["t"][h] * (1 + 1e-4)
     again = sc.trace_closest(r)
-    assert (again["prim"][h] == hits["prim"][h]).mean() > 0.9999 and np.array_equal(again["t"][h][again["prim"][h] == hits["prim"][h]], hits["t"][h][again["prim"][h] == hits["prim"][h]])
+    same = helpers.same_primitive(sc, again, hits)      # the same triangle, possibly through another of its leaf copies (spatial splits)
+    assert same[h].mean() > 0.9999 and np.array_equal(again["t"][h & same], hits["t"][h & same])
     sc.close()
 
 
@@ -143,7 +144,7 @@ def test_forty_thousand_instances():
     rays["time"] = rng.uniform(0, 1, n).astype(np.float32)
     g = sc.trace_closest(rays)
     oh, _ = helpers.oracle_trace_closest(sc, rays)
-    same = (g["prim"] == oh["prim"]) & (g["inst"] == oh["inst"])
+    same = helpers.same_primitive(sc, g, oh) & (g["inst"] == oh["inst"])
     hit = g["prim"] >= 0
     print("40k instances: hit frac %.3f id match %.6f" % (hit.mean(), same.mean()))
     assert hit.mean() > 0.2 and same.mean() >= 0.9995
