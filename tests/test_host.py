@@ -63,6 +63,8 @@ def test_flatten_invariants(scene, spatial, monkeypatch):
     count); every source triangle is still referenced, and every copy carries its (mesh, tri) identity."""
     if not spatial:
         monkeypatch.setenv("MIRO_BVH_SPATIAL", "0")
+    else:
+        monkeypatch.setenv("MIRO_BVH_SPATIAL_MIN", "0")       # also on the 36-triangle Cornell box (the default skips tiny scenes)
     fx = helpers.Fixture(helpers.fixture_path(scene))
     sc = fx.scene()
     d, nodes, child, tris = flat(sc)
