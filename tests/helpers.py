@@ -256,10 +256,15 @@ def same_primitive(sc, a, b):
     """Boolean array: hit records a and b name the same SOURCE primitive (or both miss).  Spatial splits of the host builder
     store a triangle once per leaf that references it, so two traversal orders may report different copies of one triangle;
     identity is (mesh ordinal, triangle index), as it is against the reference."""
-    mesh_of, tri_of, _ = sc.prim_table()
+    mesh_of, tri_of, inst_ord = sc.prim_table()
     def ident(h):
         p = h["prim"].astype(np.int64); ok = p >= 0
         out = np.full(len(p), -1, np.int64)
         out[ok] = mesh_of[p[ok]] * (1 << 32) + tri_of[p[ok]]
         return out
-    return ident(a) == ident(b)
+    def instance(h):        # an instance is entered through several records (braiding): compare ordinals, not record indices
+        i = h["inst"].astype(np.int64); ok = i >= 0
+        out = np.full(len(i), -1, np.int64)
+        out[ok] = inst_ord[i[ok]]
+        return out
+    return (ident(a) == ident(b)) & (instance(a) == instance(b))
