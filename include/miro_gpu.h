@@ -166,7 +166,10 @@ typedef struct miro_gpu_light {     /* 64 bytes */
     float noise_threshold;          /* Light::m_noiseThreshold */
     uint32_t cast_shadows;
     int32_t texture;                /* dome: light map texture index */
-    uint32_t reserved;
+    uint32_t full_shadows;          /* 0: Light::m_fastShadows (the default, src/Light.h:16) — a shadow ray is an any-hit query.
+                                       1: setFastShadows(false), the "full method" of src/PointLight.cpp:49-70, RectangleLight.cpp:93-118,
+                                       DomeLight.cpp:123-146: the ray is walked hit by hit and attenuated by the refractAmt of every
+                                       surface it enters (was `reserved`, must-be-zero, up to ABI v2: same layout) */
 } miro_gpu_light;
 
 /* ---- textures (reference: src/Texture.cpp:12-125; float texels, row-major, already linearised) */

@@ -211,6 +211,28 @@ static surf surface_at(const octx* c, const oray2* r, const miro_gpu_hit* h) {  
     return o;
 }
 
+/* The "full method" of the shadow test, Light::setFastShadows(false) (RectangleLight.cpp:93-118, DomeLight.cpp:123-146): the ray is
+ * walked hit by hit; a surface whose INTERPOLATED normal (HitInfo::getInterpolatedNormal, Ray.cpp:52-66: object space, not
+ * transformed by a proxy) faces the ray multiplies the visibility by its material's refractAmt.  Kept as the reference has it:
+ * sampleHit is never reset, so the previous segment's hit distance is the next segment's tMax. */
+static float full_shadow(octx* c, v3 from, v3 dir, float time, float first_tmax, float distance) {
+    const miro_gpu_scene_desc* s = c->s;
+    float attenuate = 1.0f, traversed = 0.0f, hit_t = first_tmax;
+    v3 o = from;
+    miro_gpu_hit h;
+    for (int guard = 0; traversed < distance && attenuate > O_EPS && guard < 4096; ++guard) {
+        if (trace(c, o, dir, time, O_EPS, hit_t, &h)) {
+            const miro_gpu_prim* pr = &s->prims[h.prim];
+            const float a = h.a, b = h.b, cc = 1.0f - a - b;
+            const float *n0 = s->normals + (size_t)pr->n[0] * 3, *n1 = s->normals + (size_t)pr->n[1] * 3, *n2 = s->normals + (size_t)pr->n[2] * 3;
+            const v3 N = normalize(V(n0[0] * cc + n1[0] * a + n2[0] * b, n0[1] * cc + n1[1] * a + n2[1] * b, n0[2] * cc + n1[2] * a + n2[2] * b));
+            if (dot(N, scl(dir, -1.f)) > 0.0f) attenuate *= s->materials[pr->material].refract_amt;
+            o = add(o, scl(dir, h.t)); traversed += h.t; hit_t = h.t;
+        } else traversed = distance;
+    }
+    return attenuate;
+}
+
 /* ---- lights: one call = one Light::sampleLight ---------------------------------------------------------------- */
 static v3 sample_light(octx* c, uint32_t li, v3 from, v3 normal, float time, v3 rVec, float* outSpec, int isSecondary, uint32_t pass, const raddr* addr) {
     const miro_gpu_light* L = &c->s->lights[li];
@@ -225,7 +247,8 @@ static v3 sample_light(octx* c, uint32_t li, v3 from, v3 normal, float time, v3 
         falloff = 1.0f / falloff;
         l = scl(l, distanceRecip); nDotL *= distanceRecip;
         float attenuate = 1.0f;
-        if (L->cast_shadows && trace(c, from, l, time, 0.001f, distance, &sh)) attenuate = 0.0f;
+        /* full method (PointLight.cpp:49-70): `sampleHit.t = distance; while (sampleHit.t < distance)` never runs: no shadow at all */
+        if (L->cast_shadows && !L->full_shadows && trace(c, from, l, time, 0.001f, distance, &sh)) attenuate = 0.0f;
         attenuate *= nDotL;
         const float rl = dot(rVec, l);
         *outSpec = (rl > 0.f ? rl : 0.f) * attenuate;
@@ -246,7 +269,8 @@ static v3 sample_light(octx* c, uint32_t li, v3 from, v3 normal, float time, v3 
                 const float distance = sqrtf(falloff), distanceRecip = 1.0f / distance;
                 falloff = 1.0f / falloff;
                 dir = scl(dir, distanceRecip);
-                if (L->cast_shadows && trace(c, from, dir, time, O_EPS, distance - O_EPS, &sh)) attenuate = 0.0f;
+                if (L->cast_shadows && L->full_shadows) attenuate = full_shadow(c, from, dir, time, distance - O_EPS, distance);
+                else if (L->cast_shadows && trace(c, from, dir, time, O_EPS, distance - O_EPS, &sh)) attenuate = 0.0f;
             } else attenuate = 0.0f;
             const float e = L->power * falloff * O_1_4PI;
             samplesDone++; samplesDoneRecip = 1.0f / (float)samplesDone;
@@ -285,7 +309,8 @@ static v3 sample_light(octx* c, uint32_t li, v3 from, v3 normal, float time, v3 
             const float pdf = (pdfs[0] * pdfs[1]) / (O_2_PI2 * sinTheta);
             const v3 imageSample = tex_lookup_dir(tex, direction);
             attenuate = 1.0f;
-            if (trace(c, from, direction, time, O_EPS, MIRO_GPU_TMAX, &sh)) attenuate = 0.0f;
+            if (L->full_shadows) attenuate = full_shadow(c, from, direction, time, MIRO_GPU_TMAX, MIRO_GPU_TMAX);
+            else if (trace(c, from, direction, time, O_EPS, MIRO_GPU_TMAX, &sh)) attenuate = 0.0f;
             E = scl(imageSample, L->power / pdf);
             if (!(pdf > 0.f) || isinf(pdf) || isnan(pdf)) E = V(0, 0, 0);
         }

@@ -204,6 +204,7 @@ void loadScene(const std::string& file) {
                     if (k == "pos") l->setPosition(read3(ss));
                     else if (k == "power") { float f; ss >> f; l->setPower(f); }
                     else if (k == "shadows") { int v; ss >> v; l->setCastShadows(v != 0); }
+                    else if (k == "fastshadows") { int v; ss >> v; l->setFastShadows(v != 0); }
                     else die("point light: unknown key " + k);
                 }
                 g_scene->addLight(l);
@@ -218,6 +219,7 @@ void loadScene(const std::string& file) {
                     else if (k == "samples") { int n; ss >> n; l->setSamples(n); }
                     else if (k == "noise") { float f; ss >> f; l->setNoiseThreshold(f); }
                     else if (k == "shadows") { int v; ss >> v; l->setCastShadows(v != 0); }
+                    else if (k == "fastshadows") { int v; ss >> v; l->setFastShadows(v != 0); }
                     else die("rect light: unknown key " + k);
                 }
                 // same call order as the scene functions: setPower, then setVertices (assignment2.h:404-405)
@@ -230,6 +232,7 @@ void loadScene(const std::string& file) {
                     else if (k == "power") { float f; ss >> f; l->setPower(f); }
                     else if (k == "samples") { int n; ss >> n; l->setSamples(n); }
                     else if (k == "noise") { float f; ss >> f; l->setNoiseThreshold(f); }
+                    else if (k == "fastshadows") { int v; ss >> v; l->setFastShadows(v != 0); }
                     else die("dome light: unknown key " + k);
                 }
                 g_scene->addLight(l);

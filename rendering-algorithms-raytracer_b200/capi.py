@@ -64,7 +64,7 @@ class Material(C.Structure):
 class Light(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("p0", C.c_float * 3), ("p1", C.c_float * 3), ("p2", C.c_float * 3),
                 ("power", C.c_float), ("num_samples", C.c_int32), ("noise_threshold", C.c_float),
-                ("cast_shadows", C.c_uint32), ("texture", C.c_int32), ("reserved", C.c_uint32)]
+                ("cast_shadows", C.c_uint32), ("texture", C.c_int32), ("full_shadows", C.c_uint32)]
 
 
 class Texture(C.Structure):

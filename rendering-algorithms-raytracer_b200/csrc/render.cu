@@ -64,6 +64,7 @@ struct RenderParamsDev {
     uint32_t next_cap;          // capacity of the continuation-ray queues (3x the wave when a material disperses)
     int local_paths;            // paths per camera sample traced by THIS call (sample sharding), path = k * path_stride + path_first
     int path_first, path_stride;
+    uint32_t full_shadows;      // some light uses the "full" shadow method (Light::setFastShadows(false)): its shadow rays go to the walk queue
 };
 
 struct Queues {
@@ -74,7 +75,10 @@ struct Queues {
     float4* q_ior[2];      // 2 x float4 per ray: the IOR history (only allocated when a material reflects / refracts)
     // shadow queue and light-loop slots
     miro_gpu_ray* sh_rays; float4* sh_E; Slot* slots;
-    // device counters: [0] next bounce count, [1] shadow count, [2] slot count, [3] next active-pixel count, [4..7] spare
+    // shadow rays of lights with the "full" shadow method (walked hit by hit, k_walk_shadows); allocated only when such a light exists
+    miro_gpu_ray* ws_rays; float4* ws_E;
+    // device counters: [0] next bounce count, [1] shadow count, [2] slot count, [3] next active-pixel count, [4] bounce count being
+    // traced, [5] dropped continuation rays, [6] walked-shadow count, [7] spare
     uint32_t* counts;
     size_t cap_cs, cap_paths, cap_shadow, cap_slots;
 };
@@ -86,7 +90,7 @@ struct RenderState {
     cudaStream_t aux = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::vector<void*> allocs;
-    size_t key_paths = 0, key_shadow_per_path = 0, key_slots_per_path = 0, key_next_mult = 1; bool key_ior = false;
+    size_t key_paths = 0, key_shadow_per_path = 0, key_slots_per_path = 0, key_next_mult = 1; bool key_ior = false, key_walk = false;
     // frame buffers
     float4* level_sum = nullptr; float4* result = nullptr; uint32_t* active[2] = {nullptr, nullptr};
     float* rgb_dev = nullptr; size_t frame_pixels = 0;
@@ -146,6 +150,12 @@ __device__ __forceinline__ void for_each_light_loop(const DeviceShading& sh, boo
         for (uint32_t li = 0; li < sh.n_lights; ++li) f(li, 2u, secondary, false);
 }
 
+// Light::m_fastShadows == false: rectangle (when it casts shadows at all) and dome lights walk their shadow rays hit by hit;
+// a point light's loop `sampleHit.t = distance; while (sampleHit.t < distance)` never runs (PointLight.cpp:39,52) — it casts no shadow.
+__device__ __forceinline__ bool light_walks(const miro_gpu_light& l) {
+    return l.full_shadows && (l.kind == MIRO_GPU_LIGHT_DOME || (l.kind == MIRO_GPU_LIGHT_RECT && l.cast_shadows));
+}
+
 template <bool PRIMARY>
 __global__ void __launch_bounds__(SHADE_BLOCK)
 k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q, uint32_t n_static, const uint32_t* __restrict__ d_count,
@@ -165,7 +175,7 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
         uint32_t bounce_flags = 0;
         IorStack ior; ior.init_camera();
         ShadeCtx c{};
-        int n_shadow = 0, n_slots = 0;
+        int n_shadow = 0, n_slots = 0, n_walk = 0;
         RandAddr addr{};
         if (active) {
             const uint32_t ri = PRIMARY ? idx / (uint32_t)P.local_paths : idx;
@@ -311,7 +321,7 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
                 if (diffuse) for_each_light_loop(sh, pt_last, blinn, c.is_secondary, translucent, [&](uint32_t li, uint32_t pass, bool secondary_, bool with_spec) {
                     int lit = 0;
                     light_loop(sh, li, c.P, pass == 2u ? -c.N : c.N, with_spec ? c.rVec : f3(0, 0, 0), secondary_, pass, addr, [&](const LightSample&) { ++lit; });
-                    if (lit) { n_shadow += lit; ++n_slots; }
+                    if (lit) { if (P.full_shadows && light_walks(sh.lights[li])) n_walk += lit; else n_shadow += lit; ++n_slots; }
                 });
             }
         }
@@ -332,6 +342,13 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
         b_shadow = __shfl_sync(0xffffffffu, b_shadow, 31) + s_shadow - (uint32_t)n_shadow;
         b_slots = __shfl_sync(0xffffffffu, b_slots, 31) + s_slots - (uint32_t)n_slots;
         b_next = __shfl_sync(0xffffffffu, b_next, 31) + s_next - n_next;
+        uint32_t b_walk = 0;
+        if (P.full_shadows) {          // uniform: the walk queue exists only in scenes with such a light
+            uint32_t s_walk = (uint32_t)n_walk;
+            for (int off = 1; off < 32; off <<= 1) { const uint32_t a = __shfl_up_sync(0xffffffffu, s_walk, off); if ((int)lane >= off) s_walk += a; }
+            if (lane == 31 && s_walk) b_walk = atomicAdd(q.counts + 6, s_walk);
+            b_walk = __shfl_sync(0xffffffffu, b_walk, 31) + s_walk - (uint32_t)n_walk;
+        }
         if (!active) continue;
         // ------------------------------------------------------------------ phase 3: emit
         if (n_next && b_next + n_next > P.next_cap) { atomicAdd(q.counts + 5, n_next); }      // queue full: reported as an error by the host
@@ -364,14 +381,24 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
             }
         }
         if (n_slots == 0) continue;
-        if (b_shadow + (uint32_t)n_shadow > shadow_cap || b_slots + (uint32_t)n_slots > slot_cap) continue;   // cannot happen: capacities are worst case
-        uint32_t w_shadow = b_shadow, w_slot = b_slots;
+        if (b_shadow + (uint32_t)n_shadow > shadow_cap || b_slots + (uint32_t)n_slots > slot_cap || b_walk + (uint32_t)n_walk > shadow_cap) continue;   // cannot happen: capacities are worst case
+        uint32_t w_shadow = b_shadow, w_slot = b_slots, w_walk = b_walk;
         for_each_light_loop(sh, pt_last, blinn, c.is_secondary, translucent, [&](uint32_t li, uint32_t pass, bool secondary, bool with_spec) {
             const uint32_t slot = w_slot;
             int lit = 0;
-            const bool shadows = sh.lights[li].cast_shadows != 0;
+            const bool walk = P.full_shadows && light_walks(sh.lights[li]);
+            const bool shadows = sh.lights[li].cast_shadows != 0 && !sh.lights[li].full_shadows;      // full method without a walk: no shadow (see light_walks)
             const float ray_time = pass == 2u ? .001f : c.time;           // the translucency loop passes .001f as the time (Blinn.cpp:232)
             const int done = light_loop(sh, li, c.P, pass == 2u ? -c.N : c.N, with_spec ? c.rVec : f3(0, 0, 0), secondary, pass, addr, [&](const LightSample& ls) {
+                if (walk) {
+                    float4* o4 = reinterpret_cast<float4*>(q.ws_rays + w_walk);
+                    __stcs(o4 + 0, make_float4(c.P.x, c.P.y, c.P.z, ls.tmin));
+                    __stcs(o4 + 1, make_float4(ls.dir.x, ls.dir.y, ls.dir.z, ls.tmax));
+                    __stcs(o4 + 2, make_float4(ray_time, 0.f, __uint_as_float(slot), ls.dist));
+                    __stcs(q.ws_E + w_walk, make_float4(ls.E.x, ls.E.y, ls.E.z, ls.spec));
+                    ++w_walk; ++lit;
+                    return;
+                }
                 float4* o4 = reinterpret_cast<float4*>(q.sh_rays + w_shadow);
                 // a light that casts no shadows gets an empty interval: never occluded
                 __stcs(o4 + 0, make_float4(c.P.x, c.P.y, c.P.z, shadows ? ls.tmin : 1.f));
@@ -390,6 +417,49 @@ k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q,
                 ++w_slot;
             }
         });
+    }
+}
+
+// The "full" shadow method (Light::setFastShadows(false); RectangleLight.cpp:93-118, DomeLight.cpp:123-146): one thread walks one
+// shadow ray hit by hit.  A surface whose INTERPOLATED normal faces the ray (HitInfo::getInterpolatedNormal, Ray.cpp:52-66: object
+// space, not transformed by a proxy) multiplies the visibility by its material's refractAmt; the walk ends when the light is
+// reached, nothing is hit, or the visibility falls to epsilon.  Kept as the reference has it: sampleHit is never reset, so the
+// previous segment's hit distance is the next segment's tMax.  The sample then enters its light loop's accumulator scaled by
+// the visibility, as the any-hit kernel's epilogue does with 0 / 1.
+template <bool ALPHA>
+__global__ void __launch_bounds__(TRACE_BLOCK)
+k_walk_shadows(DeviceScene sc, DeviceShading sh, const miro_gpu_ray* __restrict__ rays, const float4* __restrict__ sample_E,
+               const uint32_t* __restrict__ d_count, uint32_t cap, float4* __restrict__ slots, TraceCounters* __restrict__ ctr) {
+    __shared__ unsigned long long stack[SMEM_STACK * TRACE_BLOCK];
+    unsigned long long overflow[LMEM_STACK];
+    TraversalStack st; st.init(stack + threadIdx.x, overflow);
+    const uint32_t n = min(*d_count, cap);
+    for (uint32_t i = blockIdx.x * TRACE_BLOCK + threadIdx.x; i < n; i += gridDim.x * TRACE_BLOCK) {
+        const float4* rp = reinterpret_cast<const float4*>(rays + i);
+        const float4 r0 = __ldcs(rp), r1 = __ldcs(rp + 1), r2 = __ldcs(rp + 2);
+        float3x o = f3(r0.x, r0.y, r0.z);
+        const float3x d = f3(r1.x, r1.y, r1.z);
+        const float distance = r2.w;
+        float attenuate = 1.0f, traversed = 0.0f;
+        uint32_t segments = 0;
+        Lane L; L.ray_idx = i; L.done = false; L.tmin = r0.w; L.time = r2.x; L.hit.t = r1.w;
+        for (int guard = 0; traversed < distance && attenuate > kEps && guard < 4096; ++guard) {
+            trace_closest_thread<ALPHA>(sc, L, st, o.x, o.y, o.z, d.x, d.y, d.z);      // tMax = L.hit.t, carried over from the previous segment
+            ++segments;
+            if (L.hit.prim < 0) { traversed = distance; break; }
+            const miro_gpu_prim* pr = sh.prims + L.hit.prim;
+            const float a = L.hit.a, b = L.hit.b, cc = 1.0f - a - b;
+            const float* n0 = sh.normals + (size_t)__ldg(&pr->n[0]) * 3; const float* n1 = sh.normals + (size_t)__ldg(&pr->n[1]) * 3; const float* n2 = sh.normals + (size_t)__ldg(&pr->n[2]) * 3;
+            const float3x N = normalize3(f3(__ldg(n0) * cc + __ldg(n1) * a + __ldg(n2) * b, __ldg(n0 + 1) * cc + __ldg(n1 + 1) * a + __ldg(n2 + 1) * b,
+                                            __ldg(n0 + 2) * cc + __ldg(n1 + 2) * a + __ldg(n2 + 2) * b));
+            if (dot3(N, -d) > 0.0f) attenuate *= sh.materials[__ldg(&pr->material)].refract_amt;
+            o = o + L.hit.t * d; traversed += L.hit.t;
+        }
+        if (segments) atomicAdd(&ctr->rays_closest, (unsigned long long)segments);      // every segment is one Scene::trace call
+        if (attenuate != 0.0f) {
+            const float4 E = __ldcs(sample_E + i);
+            atomicAdd(slots + (size_t)__float_as_uint(r2.z) * 4, make_float4(E.x * attenuate, E.y * attenuate, E.z * attenuate, E.w * attenuate));
+        }
     }
 }
 
@@ -492,8 +562,8 @@ static cudaError_t qalloc(RenderState* st, T** p, size_t n) {
     return e;
 }
 
-static int ensure_queues(miro_gpu_ctx* ctx, RenderState* st, size_t paths, size_t cs, size_t shadow_per_path, size_t slots_per_path, bool with_ior, size_t next_mult) {
-    if (st->key_next_mult == next_mult && st->key_paths == paths && st->q[0].cap_cs >= cs && st->key_shadow_per_path == shadow_per_path && st->key_slots_per_path == slots_per_path && st->key_ior == with_ior) return MIRO_GPU_OK;
+static int ensure_queues(miro_gpu_ctx* ctx, RenderState* st, size_t paths, size_t cs, size_t shadow_per_path, size_t slots_per_path, bool with_ior, size_t next_mult, bool with_walk) {
+    if (st->key_walk == with_walk && st->key_next_mult == next_mult && st->key_paths == paths && st->q[0].cap_cs >= cs && st->key_shadow_per_path == shadow_per_path && st->key_slots_per_path == slots_per_path && st->key_ior == with_ior) return MIRO_GPU_OK;
     free_queues(st);
     for (int set = 0; set < 2; ++set) {
     Queues& q = st->q[set];
@@ -508,10 +578,11 @@ static int ensure_queues(miro_gpu_ctx* ctx, RenderState* st, size_t paths, size_
     MIRO_CUDA(ctx, qalloc(st, &q.q_hits, q.cap_paths));
     MIRO_CUDA(ctx, qalloc(st, &q.sh_rays, q.cap_shadow));
     MIRO_CUDA(ctx, qalloc(st, &q.sh_E, q.cap_shadow));
+    if (with_walk) { MIRO_CUDA(ctx, qalloc(st, &q.ws_rays, q.cap_shadow)); MIRO_CUDA(ctx, qalloc(st, &q.ws_E, q.cap_shadow)); }
     MIRO_CUDA(ctx, qalloc(st, &q.slots, q.cap_slots));
     MIRO_CUDA(ctx, qalloc(st, &q.counts, (size_t)8));
     }
-    st->key_next_mult = next_mult; st->key_paths = paths; st->key_shadow_per_path = shadow_per_path; st->key_slots_per_path = slots_per_path; st->key_ior = with_ior;
+    st->key_next_mult = next_mult; st->key_paths = paths; st->key_shadow_per_path = shadow_per_path; st->key_slots_per_path = slots_per_path; st->key_ior = with_ior; st->key_walk = with_walk;
     return MIRO_GPU_OK;
 }
 
@@ -597,13 +668,15 @@ extern "C" int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, co
     for (const miro_gpu_material& m : ctx->host_materials) if (m.kind == MIRO_GPU_MAT_BLINN && m.translucency > 0.01f) any_translucent = true;
     const size_t loops = (rp->path_trace ? 2 : 1) + (any_translucent ? 1 : 0);
     const size_t shadow_per_path = std::max<size_t>(1, loops * light_samples), slots_per_path = std::max<size_t>(1, loops * ctx->host_lights.size());
-    const size_t bytes_per_path = next_mult * (2 * (48 + 16 + (P.has_specular ? 32 : 0)) + 20 + shadow_per_path * 64 + slots_per_path * 64) + (48 + 20);
+    P.full_shadows = 0;
+    for (const miro_gpu_light& l : ctx->host_lights) if (l.full_shadows && (l.kind == MIRO_GPU_LIGHT_DOME || (l.kind == MIRO_GPU_LIGHT_RECT && l.cast_shadows))) P.full_shadows = 1;
+    const size_t bytes_per_path = next_mult * (2 * (48 + 16 + (P.has_specular ? 32 : 0)) + 20 + shadow_per_path * 64 * (P.full_shadows ? 2 : 1) + slots_per_path * 64) + (48 + 20);
     size_t paths = std::min<size_t>(WAVE_PATHS_MAX, std::max<size_t>(WAVE_BYTES_BUDGET / 2 / bytes_per_path, (size_t)rp->num_paths));
     const size_t frame_paths = pixels * (size_t)max_sub * max_sub * rp->num_paths;
     paths = std::min(paths, frame_paths);
     paths = std::max<size_t>((paths / rp->num_paths) * rp->num_paths, (size_t)rp->num_paths);
     const size_t wave_cs = paths / rp->num_paths;
-    if ((rc = ensure_queues(ctx, st, paths, wave_cs, shadow_per_path, slots_per_path, P.has_specular != 0, next_mult))) return rc;
+    if ((rc = ensure_queues(ctx, st, paths, wave_cs, shadow_per_path, slots_per_path, P.has_specular != 0, next_mult, P.full_shadows != 0))) return rc;
     P.next_cap = (uint32_t)(paths * next_mult);
     cudaStream_t s = ctx->stream;
     struct Restore { miro_gpu_ctx* c; cudaStream_t s; ~Restore() { c->stream = s; c->work_lane = 0; } } restore{ctx, s};      // also on error returns
@@ -655,6 +728,7 @@ extern "C" int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, co
             ctx->launches++;
             launch_trace_closest(ctx, q.cs_rays, n_cs, nullptr, q.cs_hits);
             MIRO_CUDA(ctx, cudaMemsetAsync(q.counts, 0, 3 * sizeof(uint32_t), ws));
+            if (P.full_shadows) MIRO_CUDA(ctx, cudaMemsetAsync(q.counts + 6, 0, sizeof(uint32_t), ws));
             const size_t n_threads = (size_t)n_cs * P.local_paths;
             k_shade<true><<<std::min(grid_for(n_threads, SHADE_BLOCK), kPersistentGrid * 4), SHADE_BLOCK, 0, ws>>>(
                 ctx->scene, ctx->shading, P, q, 0, (uint32_t)n_threads, nullptr, st->level_sum, (uint32_t)q.cap_shadow, (uint32_t)q.cap_slots);
@@ -663,12 +737,18 @@ extern "C" int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, co
             for (int depth = 0; depth <= last_depth; ++depth) {
                 // shadow rays of the vertices at `depth`, then the per-loop resolve
                 launch_trace_shadow(ctx, q.sh_rays, q.cap_shadow, q.counts + 1, q.sh_E, reinterpret_cast<float4*>(q.slots));
+                if (P.full_shadows) {
+                    if (ctx->has_alpha) k_walk_shadows<true><<<kPersistentGrid, TRACE_BLOCK, 0, ws>>>(ctx->scene, ctx->shading, q.ws_rays, q.ws_E, q.counts + 6, (uint32_t)q.cap_shadow, reinterpret_cast<float4*>(q.slots), ctx->d_counters);
+                    else k_walk_shadows<false><<<kPersistentGrid, TRACE_BLOCK, 0, ws>>>(ctx->scene, ctx->shading, q.ws_rays, q.ws_E, q.counts + 6, (uint32_t)q.cap_shadow, reinterpret_cast<float4*>(q.slots), ctx->d_counters);
+                    ctx->launches++;
+                }
                 k_resolve_slots<<<kPersistentGrid, SHADE_BLOCK, 0, ws>>>(q.slots, q.counts + 2, st->level_sum);
                 ctx->launches++;
                 if (depth == last_depth) break;
                 // bounce rays spawned at `depth` -> vertices at depth + 1
                 MIRO_CUDA(ctx, cudaMemcpyAsync(q.counts + 4, q.counts + 0, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ws));
                 MIRO_CUDA(ctx, cudaMemsetAsync(q.counts, 0, 3 * sizeof(uint32_t), ws));
+            if (P.full_shadows) MIRO_CUDA(ctx, cudaMemsetAsync(q.counts + 6, 0, sizeof(uint32_t), ws));
                 launch_trace_closest(ctx, q.q_rays[in_q], q.cap_paths, q.counts + 4, q.q_hits);
                 k_shade<false><<<kPersistentGrid * 4, SHADE_BLOCK, 0, ws>>>(ctx->scene, ctx->shading, P, q, in_q, 0, q.counts + 4, st->level_sum,
                                                                            (uint32_t)q.cap_shadow, (uint32_t)q.cap_slots);

@@ -239,6 +239,7 @@ struct IorStack {
 struct LightSample {
     float3x dir;        // unit direction towards the light sample
     float tmin, tmax;   // shadow-ray interval
+    float dist;         // distance to the light sample (the walk length of the "full" shadow method; MIRO_GPU_TMAX for the dome)
     float3x E;          // irradiance of the sample if unoccluded (already times the cosine where the reference applies it)
     float spec;         // specular lobe input of the sample if unoccluded
     bool lit;           // false: contributes nothing (back-facing); no shadow ray
@@ -259,7 +260,7 @@ __device__ inline int light_loop(const DeviceShading& sh, uint32_t li, float3x f
             const float d2 = dot3(L, L);
             const float distRecip = rsqrtf(d2), falloff = 1.0f / d2, distance = 1.0f / distRecip;
             L = L * distRecip; nDotL *= distRecip;
-            LightSample s; s.dir = L; s.tmin = 0.001f; s.tmax = distance; s.lit = true;
+            LightSample s; s.dir = L; s.tmin = 0.001f; s.tmax = distance; s.dist = distance; s.lit = true;
             const float att = nDotL;                                    // "attenuate *= nDotL": the cosine
             const float e = power * falloff * k1_4PI * att;
             s.E = f3(e, e, e); s.spec = fmaxf(0.f, dot3(rVec, L)) * att;
@@ -281,7 +282,7 @@ __device__ inline int light_loop(const DeviceShading& sh, uint32_t li, float3x f
                 const float d2 = dot3(dir, dir);
                 const float distRecip = rsqrtf(d2); falloff = 1.0f / d2; const float distance = 1.0f / distRecip;
                 dir = dir * distRecip;
-                s.lit = true; s.dir = dir; s.tmin = kEps; s.tmax = distance - kEps;
+                s.lit = true; s.dir = dir; s.tmin = kEps; s.tmax = distance - kEps; s.dist = distance;
                 s.spec = fmaxf(0.f, dot3(rVec, dir));
             }
             const float e = power * falloff * k1_4PI;                   // no cosine at the surface (reference behaviour)
@@ -310,7 +311,7 @@ __device__ inline int light_loop(const DeviceShading& sh, uint32_t li, float3x f
                 const float cosT = __ldg(D.cos_v + v), sinT = __ldg(D.sin_v + v), sinP = __ldg(D.sin_u + u), cosP = __ldg(D.cos_u + u);
                 const float3x dir = f3(-sinT * cosP, -cosT, -sinT * sinP);
                 if (dot3(normal, dir) < 0.0f) continue;
-                s.lit = true; s.dir = dir; s.tmin = kEps; s.tmax = MIRO_GPU_TMAX;
+                s.lit = true; s.dir = dir; s.tmin = kEps; s.tmax = MIRO_GPU_TMAX; s.dist = MIRO_GPU_TMAX;
                 E4 = __ldg(D.cell_E + cell);
             }
         }

@@ -399,6 +399,23 @@ __device__ __forceinline__ float hit_alpha(const AlphaData& A, uint32_t prim, fl
     return q1 * (1.0f - dy) + q2 * dy;
 }
 
+// Instance leaf {first, count}: the lane enters instance `first` with the world-space ray (wo, wd) moved into its object space and
+// defers the others; a marker on the stack restores the world-space ray when the instance's sub-tree is exhausted.
+__device__ __forceinline__ void enter_instance(const DeviceScene& s, Lane& L, TraversalStack& st, uint32_t first, uint32_t count,
+                                               float wox, float woy, float woz, float wdx, float wdy, float wdz) {
+    const int ninf = (int)0x80000000;
+    if (count > 1u) st.push(MIRO_GPU_LEAF(MIRO_GPU_KIND_INST, first + 1u, count - 1u), ninf);
+    st.push(STACK_SENTINEL, ninf);
+    const float4* m = s.insts + (size_t)first * 4;
+    const float4 r0 = __ldg(m), r1 = __ldg(m + 1), r2 = __ldg(m + 2);
+    const int4 meta = __ldg(reinterpret_cast<const int4*>(m + 3));
+    // o' = M^-1 [o 1], d' = M^-1 [d 0]  (src/ProxyObject.cpp:78-79; affine, so w = 1)
+    L.set_ray(r0.x * wox + r0.y * woy + r0.z * woz + r0.w, r1.x * wox + r1.y * woy + r1.z * woz + r1.w, r2.x * wox + r2.y * woy + r2.z * woz + r2.w,
+            r0.x * wdx + r0.y * wdy + r0.z * wdz, r1.x * wdx + r1.y * wdy + r1.z * wdz, r2.x * wdx + r2.y * wdy + r2.z * wdz);
+    L.cur_inst = (int32_t)first;
+    L.cur = meta.x;
+}
+
 // Leaf phase.  Returns true when an ANY query has found its occluder.
 template <bool ANY, bool COUNT, bool ALPHA>
 __device__ __forceinline__ bool intersect_leaf(const DeviceScene& s, Lane& L, TraversalStack& st, const float4* __restrict__ rays, const uint32_t ray_f4,
@@ -438,25 +455,36 @@ __device__ __forceinline__ bool intersect_leaf(const DeviceScene& s, Lane& L, Tr
             }
         }
     } else {   // MIRO_GPU_KIND_INST: enter the first instance, defer the others
-        const int ninf = (int)0x80000000;
-        if (count > 1u) st.push(MIRO_GPU_LEAF(MIRO_GPU_KIND_INST, first + 1u, count - 1u), ninf);
-        st.push(STACK_SENTINEL, ninf);
-        const float4* m = s.insts + (size_t)first * 4;
-        const float4 r0 = __ldg(m), r1 = __ldg(m + 1), r2 = __ldg(m + 2);
-        const int4 meta = __ldg(reinterpret_cast<const int4*>(m + 3));
-        if (COUNT) ++n_insts;
         // the world-space ray is not kept in registers: instance entry / exit re-read it (L2-resident, rare)
         const float4 w0 = __ldg(rays + (size_t)L.ray_idx * ray_f4), w1 = __ldg(rays + (size_t)L.ray_idx * ray_f4 + 1);
-        const float wox = w0.x, woy = w0.y, woz = w0.z, wdx = w1.x, wdy = w1.y, wdz = w1.z;
-        // o' = M^-1 [o 1], d' = M^-1 [d 0]  (src/ProxyObject.cpp:78-79; affine, so w = 1)
-        L.set_ray(r0.x * wox + r0.y * woy + r0.z * woz + r0.w, r1.x * wox + r1.y * woy + r1.z * woz + r1.w, r2.x * wox + r2.y * woy + r2.z * woz + r2.w,
-                r0.x * wdx + r0.y * wdy + r0.z * wdz, r1.x * wdx + r1.y * wdy + r1.z * wdz, r2.x * wdx + r2.y * wdy + r2.z * wdz);
-        L.cur_inst = (int32_t)first;
-        L.cur = meta.x;
+        if (COUNT) ++n_insts;
+        enter_instance(s, L, st, first, count, w0.x, w0.y, w0.z, w1.x, w1.y, w1.z);
         return false;
     }
     L.cur = MIRO_GPU_CHILD_EMPTY;
     return false;
+}
+
+// One thread walks one ray to its closest hit, without warp cooperation — for the renderer's rare in-kernel queries (the "full"
+// shadow method re-traces from every hit point, render.cu).  (wo, wd) is the world-space ray; L.tmin / L.time / L.hit.t (= tMax)
+// are set by the caller.  Same node step, leaf step and instance handling as the persistent-warp kernel.
+template <bool ALPHA>
+__device__ inline void trace_closest_thread(const DeviceScene& s, Lane& L, TraversalStack& st, float wox, float woy, float woz, float wdx, float wdy, float wdz) {
+    uint32_t unused = 0;
+    L.set_ray(wox, woy, woz, wdx, wdy, wdz);
+    L.hit.a = L.hit.b = 0.f; L.hit.prim = -1; L.hit.inst = -1;
+    L.cur = s.root; L.cur_inst = -1; st.sp = 0;
+    while (L.cur != MIRO_GPU_CHILD_EMPTY) {
+        if (ref_is_inner(L.cur)) { node_step<false>(s, L, st, unused); continue; }
+        if (L.cur == STACK_SENTINEL) { L.set_ray(wox, woy, woz, wdx, wdy, wdz); L.cur_inst = -1; L.cur = MIRO_GPU_CHILD_EMPTY; }
+        else {
+            const uint32_t u = (uint32_t)L.cur;
+            if (((u >> 29) & 3u) == MIRO_GPU_KIND_INST)
+                enter_instance(s, L, st, u & ((1u << MIRO_GPU_LEAF_INDEX_BITS) - 1u), ((u >> MIRO_GPU_LEAF_INDEX_BITS) & 7u) + 1u, wox, woy, woz, wdx, wdy, wdz);
+            else intersect_leaf<false, false, ALPHA>(s, L, st, nullptr, 0u, unused, unused);
+        }
+        if (L.cur == MIRO_GPU_CHILD_EMPTY) pop_next(L, st);
+    }
 }
 
 }  // namespace miro

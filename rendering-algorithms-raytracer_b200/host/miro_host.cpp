@@ -313,6 +313,7 @@ void PointLight::fill(miro_gpu_light& l) const {
     memset(&l, 0, sizeof(l));
     l.kind = MIRO_GPU_LIGHT_POINT; copy3(l.p0, m_position); l.power = m_power; l.num_samples = 1;
     l.noise_threshold = m_noiseThreshold; l.cast_shadows = m_castShadows ? 1u : 0u; l.texture = -1;
+    l.full_shadows = m_fastShadows ? 0u : 1u;
 }
 void RectangleLight::setPower(float f) {
     Vector3 e0 = m_v2 - m_v1, e1 = m_v3 - m_v1;
@@ -326,11 +327,13 @@ void RectangleLight::fill(miro_gpu_light& l) const {
     memset(&l, 0, sizeof(l));
     l.kind = MIRO_GPU_LIGHT_RECT; copy3(l.p0, m_v1); copy3(l.p1, m_v2); copy3(l.p2, m_v3); l.power = m_power;
     l.num_samples = m_numSamples; l.noise_threshold = m_noiseThreshold; l.cast_shadows = m_castShadows ? 1u : 0u; l.texture = -1;
+    l.full_shadows = m_fastShadows ? 0u : 1u;
 }
 void DomeLight::fill(miro_gpu_light& l) const {
     memset(&l, 0, sizeof(l));
     l.kind = MIRO_GPU_LIGHT_DOME; l.power = m_Gain; l.num_samples = m_numSamples; l.noise_threshold = m_noiseThreshold;
     l.cast_shadows = 1u; l.texture = m_lightMap ? m_lightMap->ordinal : -1;
+    l.full_shadows = m_fastShadows ? 0u : 1u;
 }
 
 Camera::Camera()   // src/Camera.cpp:15-27 (the default fov there is radians-by-mistake; every scene calls setFOV)

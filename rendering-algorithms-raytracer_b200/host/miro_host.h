@@ -158,12 +158,14 @@ public:
     virtual void setPower(float f) { m_power = f; }
     void setSamples(int n) { m_numSamples = n; }
     void setCastShadows(bool c) { m_castShadows = c; }
+    void setFastShadows(bool c) { m_fastShadows = c; }   // src/Light.h:24
     void setNoiseThreshold(float t) { m_noiseThreshold = t; }
     virtual void fill(miro_gpu_light& l) const = 0;
     Vector3 m_color;
     float m_power = 0.f;
     int m_numSamples = 1;
     bool m_castShadows = true;
+    bool m_fastShadows = true;                       // src/Light.h:16
     float m_noiseThreshold = MIRO_GPU_EPSILON;       // src/Light.h:17
 };
 class PointLight : public Light {

@@ -12,9 +12,9 @@
 //   material NAME blinn   [kd ..] [ka ..] [ks ..] [specexp f] [specamt f] [ior f | ior_i i f] [reflect f] [refract f]
 //                         [gloss f] [translucency f] [emit intensity r g b] [colormap TEX] [alphamap TEX] [sampleenv 0|1]
 //                         [normalmap TEX] [specularmap TEX] [reflectmap TEX] [refractmap TEX]
-//   light point [pos x y z] [power p] [shadows 0|1]
-//   light rect  [v1 x y z] [v2 x y z] [v3 x y z] [power p] [samples n] [noise t] [shadows 0|1]
-//   light dome  [tex TEX] [power gain] [samples n] [noise t]
+//   light point [pos x y z] [power p] [shadows 0|1] [fastshadows 0|1]
+//   light rect  [v1 x y z] [v2 x y z] [v3 x y z] [power p] [samples n] [noise t] [shadows 0|1] [fastshadows 0|1]
+//   light dome  [tex TEX] [power gain] [samples n] [noise t] [fastshadows 0|1]        (fastshadows 0 = Light::setFastShadows(false))
 //   mesh NAME file.obj [ctm m11 m12 ... m44]          (row-major)
 //   object MESH MATERIAL                               makeMeshObjs
 //   mbobject MESH_T1 MESH_T2 MATERIAL                  makeMBMeshObjs
@@ -142,6 +142,7 @@ bool loadSceneScript(const char* file, const char* assetRoot, LoadedScene& out, 
                     if (k == "pos") l->setPosition(read3(ss));
                     else if (k == "power") { float f; ss >> f; l->setPower(f); }
                     else if (k == "shadows") { int v; ss >> v; l->setCastShadows(v != 0); }
+                    else if (k == "fastshadows") { int v; ss >> v; l->setFastShadows(v != 0); }
                     else return fail("point light: unknown key " + k);
                 }
                 out.scene->addLight(l);
@@ -156,6 +157,7 @@ bool loadSceneScript(const char* file, const char* assetRoot, LoadedScene& out, 
                     else if (k == "samples") { int n; ss >> n; l->setSamples(n); }
                     else if (k == "noise") { float f; ss >> f; l->setNoiseThreshold(f); }
                     else if (k == "shadows") { int v; ss >> v; l->setCastShadows(v != 0); }
+                    else if (k == "fastshadows") { int v; ss >> v; l->setFastShadows(v != 0); }
                     else return fail("rect light: unknown key " + k);
                 }
                 l->setPower(power); l->setVertices(v1, v2, v3);   // call order of src/assignment2.h:404-405
@@ -167,6 +169,7 @@ bool loadSceneScript(const char* file, const char* assetRoot, LoadedScene& out, 
                     else if (k == "power") { float f; ss >> f; l->setPower(f); }
                     else if (k == "samples") { int n; ss >> n; l->setSamples(n); }
                     else if (k == "noise") { float f; ss >> f; l->setNoiseThreshold(f); }
+                    else if (k == "fastshadows") { int v; ss >> v; l->setFastShadows(v != 0); }
                     else return fail("dome light: unknown key " + k);
                 }
                 if (!l->m_lightMap) return fail("dome light without tex");

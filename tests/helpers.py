@@ -26,9 +26,18 @@ class Fixture:
 
     def __init__(self, path):
         z = np.load(path, allow_pickle=False)
+        self.events = str(z["events"])
+        self.script = str(z["script"])
+        self.radiance = z["radiance"].astype(np.float32) if "radiance" in z.files else None
+        self.radiance_converged = z["radiance_converged"].astype(np.float32) if "radiance_converged" in z.files else None
+        if "overlay_of" in z.files:       # an overlay: its own script and reference images, geometry / textures of another fixture
+            z = np.load(os.path.join(os.path.dirname(path), str(z["overlay_of"]) + ".npz"), allow_pickle=False)
+            self.z = z
+            self.names = [str(n) for n in z["mesh_names"]]
+            self.rays = self.hits = self.ray_index = self.image8 = None
+            return
         self.z = z
         self.names = [str(n) for n in z["mesh_names"]]
-        self.script = str(z["script"])
         self.rays = z["rays"]; self.hits = z["hits"]; self.ray_index = z["ray_index"]
         self.radiance = z["radiance"].astype(np.float32) if "radiance" in z.files else None
         self.image8 = z["image8"] if "image8" in z.files else None

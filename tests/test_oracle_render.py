@@ -26,7 +26,7 @@ def rmse(a, b, clamp=4.0):
 
 
 def ref_rays(fx):
-    return [e for e in json.loads(str(fx.z["events"])) if e["event"] == "render_float"][0]["rays"]
+    return [e for e in json.loads(fx.events) if e["event"] == "render_float"][0]["rays"]
 
 
 def test_c1_deterministic_image_matches_reference():
@@ -43,7 +43,7 @@ def test_c1_deterministic_image_matches_reference():
     sc.close()
 
 
-@pytest.mark.parametrize("name,mean_tol", [("c4_cornell_pt", 0.08), ("c3_dome_pt", 0.02), ("c6_cornell_glass", 0.02), ("c8_dispersion", 0.03)])
+@pytest.mark.parametrize("name,mean_tol", [("c4_cornell_pt", 0.08), ("c3_dome_pt", 0.02), ("c6_cornell_glass", 0.02), ("c8_dispersion", 0.03), ("c10_full_shadows", 0.02), ("c11_dome_full_shadows", 0.02)])
 def test_path_traced_estimator_matches_reference(name, mean_tol):
     """RMSE(oracle_N, ref_converged) <= 1.1 * RMSE(ref_N, ref_converged) at equal spp; mean radiance and ray count agree."""
     fx, sc = load(name)

@@ -46,7 +46,7 @@ def test_c1_image_matches_reference_and_oracle():
     sc.close()
 
 
-@pytest.mark.parametrize("name", ["c4_cornell_pt", "c5_mb_instances", "c6_cornell_glass", "c7_foliage", "c9_texmaps"])
+@pytest.mark.parametrize("name", ["c4_cornell_pt", "c5_mb_instances", "c6_cornell_glass", "c7_foliage", "c9_texmaps", "c10_full_shadows"])
 def test_image_matches_oracle_sample_by_sample(name):
     fx, sc = load(name)
     img = sc.render()
@@ -61,7 +61,7 @@ def test_image_matches_oracle_sample_by_sample(name):
     sc.close()
 
 
-@pytest.mark.parametrize("name,mean_tol", [("c4_cornell_pt", 0.08), ("c3_dome_pt", 0.02), ("c6_cornell_glass", 0.02), ("c8_dispersion", 0.03)])
+@pytest.mark.parametrize("name,mean_tol", [("c4_cornell_pt", 0.08), ("c3_dome_pt", 0.02), ("c6_cornell_glass", 0.02), ("c8_dispersion", 0.03), ("c10_full_shadows", 0.02), ("c11_dome_full_shadows", 0.02)])
 def test_path_traced_estimator_matches_reference(name, mean_tol):
     """RMSE(gpu_N, ref_converged) <= 1.1 * RMSE(ref_N, ref_converged) at equal spp."""
     fx, sc = load(name)
@@ -73,6 +73,30 @@ def test_path_traced_estimator_matches_reference(name, mean_tol):
     assert e_g <= 1.1 * e_r, (e_g, e_r)
     assert abs(np.minimum(img, 4).mean() - np.minimum(conv, 4).mean()) <= mean_tol * np.minimum(conv, 4).mean()
     sc.close()
+
+
+def test_full_shadow_method_under_a_dome_light_matches_oracle():
+    """Light::setFastShadows(false) on a DomeLight (DomeLight.cpp:123-146): shadow rays are walked hit by hit through a
+    half-transparent teapot (refract 0.5).  GPU and oracle draw dome cells differently (alias table vs. CDF inversion), so the
+    images are compared as estimators of each other; the walk must also differ visibly from the any-hit shadows."""
+    path = helpers.fixture_path("c11_dome_full_shadows")
+    if path is None:
+        pytest.skip("fixture c11_dome_full_shadows not generated")
+    fx = helpers.Fixture(path)
+    full = fx.scene().attach(0)
+    fast = fx.scene(script_override=fx.script.replace(" fastshadows 0", "")).attach(0)
+    img_fast, img_full = fast.render(), full.render()
+    oimg, orays = helpers.oracle_render(full)
+    assert np.isfinite(img_full).all()
+    blk = lambda a: np.minimum(a, 4).reshape(32, 8, 32, 8, 3).mean(axis=(1, 3))
+    d_full = np.abs(blk(img_full) - blk(oimg)).mean(); d_fast = np.abs(blk(img_fast) - blk(oimg)).mean()
+    print("dome full shadows: block diff gpu-full/oracle %.4f gpu-fast/oracle %.4f" % (d_full, d_fast), "means", img_full.mean(), oimg.mean(), img_fast.mean())
+    assert abs(np.minimum(img_full, 4).mean() - np.minimum(oimg, 4).mean()) <= 0.02 * np.minimum(oimg, 4).mean()
+    assert img_full.mean() > 1.02 * img_fast.mean()          # light leaks through the teapot
+    assert d_full < 0.6 * d_fast
+    c = full.counters()
+    assert abs(int(c["rays_closest"] + c["rays_any"]) - orays) <= 0.02 * orays
+    fast.close(); full.close()
 
 
 def test_sharded_render_equals_whole():

@@ -42,6 +42,9 @@ SCENES = {
     "c8_dispersion": dict(render=True, stock=False, incoherent=0, threads=1, converged=16),
     "c6_cornell_glass": dict(render=True, stock=False, incoherent=0, threads=1, converged=16),
     "c9_texmaps": dict(render=True, stock=False, incoherent=0, threads=1, converged=16),
+    "c10_full_shadows": dict(render=True, stock=False, incoherent=0, threads=1, converged=32),
+    # same geometry and light map as c3: the committed file holds only the script and the reference's images (overlay of c3_dome_pt)
+    "c11_dome_full_shadows": dict(render=True, stock=False, incoherent=0, threads=1, converged=16, overlay_of="c3_dome_pt"),
 }
 
 
@@ -207,7 +210,11 @@ def run(scene, opt):
     small_img = image8
     if radiance is not None and radiance.shape[0] * radiance.shape[1] > 512 * 512:
         small_rad = None; small_img = None      # large images stay in the full fixture only
-    pack(os.path.join(GOLDEN, scene + ".npz"), meshes, names, text, events, rays[sel], hits[sel], sel, small_rad, small_img, shape, np.float16, textures, extra)
+    if opt.get("overlay_of"):
+        np.savez_compressed(os.path.join(GOLDEN, scene + ".npz"), overlay_of=np.array(opt["overlay_of"]), script=np.array(text), events=np.array(json.dumps(events)),
+                            image_shape=np.array(shape, np.int32), radiance=radiance.astype(np.float16), radiance_converged=extra["radiance_converged"].astype(np.float16))
+    else:
+        pack(os.path.join(GOLDEN, scene + ".npz"), meshes, names, text, events, rays[sel], hits[sel], sel, small_rad, small_img, shape, np.float16, textures, extra)
     print(scene, "primary", n_primary, "total rays", len(rays), "hit fraction %.3f" % (hits["mesh"] >= 0).mean())
 
 
