@@ -134,7 +134,7 @@ k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const
                     L.tmin = r0.w; L.time = PACKED ? 0.f : __ldcs(reinterpret_cast<const float*>(rp + 2));
                     L.hit.t = r1.w; L.hit.a = 0.f; L.hit.b = 0.f; L.hit.prim = -1; L.hit.inst = -1;
                     L.cur = s.root; L.cur_inst = -1; st.sp = 0; L.done = false;
-                    ++c_rays;
+                    c_rays += (r0.w <= r1.w) ? 1u : 0u;      // an empty interval (a light that casts no shadow) is not a Scene::trace call
                 }
                 chunk_next += take;
                 if (idle == 0xffffffffu && take == 0) continue;      // nothing claimed this round: try the next chunk (or leave)
