@@ -145,7 +145,7 @@ k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const
         const bool at_leaf = !L.done && !at_node;
         const int n_node = __popc(__ballot_sync(0xffffffffu, at_node)), n_leaf = __popc(__ballot_sync(0xffffffffu, at_leaf));
         bool finished = false;
-        if (n_node * TRACE_NODE_BIAS_DEN >= n_leaf * TRACE_NODE_BIAS_NUM) {
+        if (n_node * TRACE_NODE_BIAS_DEN >= n_leaf * TRACE_NODE_BIAS_NUM || (TRACE_LEAF_MIN > 0 && n_node > 0 && n_leaf < TRACE_LEAF_MIN)) {
             // ---- node round
             if (at_node) { node_step<COUNT>(s, L, st, c_nodes); finished = L.cur == MIRO_GPU_CHILD_EMPTY; }
         } else if (at_leaf) {

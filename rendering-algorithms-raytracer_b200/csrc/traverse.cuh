@@ -67,7 +67,12 @@ constexpr int TRACE_REFILL = MIRO_TRACE_REFILL;
 #ifndef MIRO_NODE_BIAS_DEN
 #define MIRO_NODE_BIAS_DEN 1
 #endif
-constexpr int TRACE_NODE_BIAS_NUM = MIRO_NODE_BIAS_NUM, TRACE_NODE_BIAS_DEN = MIRO_NODE_BIAS_DEN;   // idle lanes in a warp that trigger a refill from the work counter
+constexpr int TRACE_NODE_BIAS_NUM = MIRO_NODE_BIAS_NUM, TRACE_NODE_BIAS_DEN = MIRO_NODE_BIAS_DEN;
+#ifndef MIRO_LEAF_MIN
+#define MIRO_LEAF_MIN 0
+#endif
+constexpr int TRACE_LEAF_MIN = MIRO_LEAF_MIN;   // tuning knob: while some lane waits at a node, a leaf round needs at least this many lanes (0: the ratio alone decides)
+   // idle lanes in a warp that trigger a refill from the work counter
 constexpr int SMEM_STACK = MIRO_SMEM_STACK;   // per-thread stack entries kept in shared memory
 constexpr int LMEM_STACK = 96 - MIRO_SMEM_STACK;          // overflow entries (local memory, touched only by very deep trees)
 constexpr int32_t STACK_SENTINEL = 0x7ffffffe;   // "leave instance" marker
@@ -115,7 +120,6 @@ __device__ __forceinline__ float safe_rcp_dir(float d) {
     return 1.0f / d;
 }
 
-__device__ __forceinline__ float sel3(float x, float y, float z, int k) { return k == 0 ? x : (k == 1 ? y : z); }
 
 // error-free a*b - c*d (Kahan): relative error <= 1.5 ulp, sign always exact, exactly 0 when the true value is 0
 __device__ __forceinline__ float diff_of_products(float a, float b, float c, float d) {
@@ -125,42 +129,62 @@ __device__ __forceinline__ float diff_of_products(float a, float b, float c, flo
     return __fadd_rn(f, e);
 }
 
+// branch-free float select (the compiler turns chains of ternaries on the dominant axis into divergent branches)
+__device__ __forceinline__ float fsel(bool c, float a, float b) {
+    float r;
+    asm("{ .reg .pred p; setp.ne.b32 p, %3, 0; selp.f32 %0, %1, %2, p; }" : "=f"(r) : "f"(a), "f"(b), "r"((int)c));
+    return r;
+}
+
 struct RaySpace {
     float ox, oy, oz;
     float dx, dy, dz;
     float ix, iy, iz;      // reciprocal direction (slab test)
-    float Sx, Sy, Sz;      // shear / scale of the watertight test
-    int kx, ky, kz;
+    // The watertight test works in a sheared space whose z axis is the ray (Woop, Benthin, Wald 2013): with kz the dominant axis
+    // of the direction, a translated vertex v maps to  x' = v[kz+1] - Sb v[kz],  y' = v[kz+2] - Sc v[kz]  (indices mod 3),
+    // Sb = d[kz+1] / d[kz], Sc = d[kz+2] / d[kz].  The paper also swaps x' and y' when d[kz] < 0 to keep the winding for back-face
+    // culling; this test is two-sided (only the signs' agreement matters, and they are exact), so the swap is dropped.
+    float Sb, Sc;
+    int kz;
 
     __device__ __forceinline__ void set(float ox_, float oy_, float oz_, float dx_, float dy_, float dz_) {
         ox = ox_; oy = oy_; oz = oz_; dx = dx_; dy = dy_; dz = dz_;
         ix = safe_rcp_dir(dx); iy = safe_rcp_dir(dy); iz = safe_rcp_dir(dz);
-        float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
-        kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
-        kx = kz + 1; if (kx == 3) kx = 0;
-        ky = kx + 1; if (ky == 3) ky = 0;
-        float dkz = sel3(dx, dy, dz, kz);
-        if (dkz < 0.0f) { int t = kx; kx = ky; ky = t; }
-        float rz = 1.0f / dkz;
-        Sx = sel3(dx, dy, dz, kx) * rz;
-        Sy = sel3(dx, dy, dz, ky) * rz;
-        Sz = rz;
+        const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+        const bool z0 = (ax > ay) && (ax > az);                 // kz == 0
+        const bool z1 = !(ax > ay) && (ay > az);                // kz == 1; otherwise kz == 2
+        kz = z0 ? 0 : (z1 ? 1 : 2);
+        const float rz = 1.0f / fsel(z0, dx, fsel(z1, dy, dz));
+        Sb = fsel(z0, dy, fsel(z1, dz, dx)) * rz;
+        Sc = fsel(z0, dz, fsel(z1, dx, dy)) * rz;
     }
 };
+
+// The three translated vertices of a triangle rotated into the ray's axis order: (a, b, c) = (v[kz], v[kz+1], v[kz+2]).  One
+// block of predicated selects (2 setp + 18 selp): as C++ ternaries this compiled to ~48 instructions of divergent branches per
+// triangle test, 15 % of all instructions the traversal kernel issued.
+__device__ __forceinline__ void rotate_to_ray_axes(int kz, float& ax, float& ay, float& az, float& bx, float& by, float& bz, float& cx, float& cy, float& cz) {
+    float a0, b0, c0, a1, b1, c1, a2, b2, c2;
+    asm("{ .reg .pred p0, p1; .reg .f32 t;\n\t"
+        "setp.eq.s32 p0, %18, 0; setp.eq.s32 p1, %18, 1;\n\t"
+        "selp.f32 t, %10, %11, p1; selp.f32 %0, %9, t, p0; selp.f32 t, %11, %9, p1; selp.f32 %1, %10, t, p0; selp.f32 t, %9, %10, p1; selp.f32 %2, %11, t, p0;\n\t"
+        "selp.f32 t, %13, %14, p1; selp.f32 %3, %12, t, p0; selp.f32 t, %14, %12, p1; selp.f32 %4, %13, t, p0; selp.f32 t, %12, %13, p1; selp.f32 %5, %14, t, p0;\n\t"
+        "selp.f32 t, %16, %17, p1; selp.f32 %6, %15, t, p0; selp.f32 t, %17, %15, p1; selp.f32 %7, %16, t, p0; selp.f32 t, %15, %16, p1; selp.f32 %8, %17, t, p0; }"
+        : "=f"(a0), "=f"(b0), "=f"(c0), "=f"(a1), "=f"(b1), "=f"(c1), "=f"(a2), "=f"(b2), "=f"(c2)
+        : "f"(ax), "f"(ay), "f"(az), "f"(bx), "f"(by), "f"(bz), "f"(cx), "f"(cy), "f"(cz), "r"(kz));
+    ax = a0; ay = b0; az = c0; bx = a1; by = b1; bz = c1; cx = a2; cy = b2; cz = c2;
+}
 
 // Watertight two-sided ray/triangle test.  Returns true and updates (t,a,b) when tmin <= t < tmax.
 __device__ __forceinline__ bool intersect_tri(const RaySpace& r, float tmin, float tmax,
                                               float4 p0, float4 p1, float4 p2, float& t_out, float& a_out, float& b_out) {
-    const float Ax_ = p0.x - r.ox, Ay_ = p0.y - r.oy, Az_ = p0.z - r.oz;
-    const float Bx_ = p1.x - r.ox, By_ = p1.y - r.oy, Bz_ = p1.z - r.oz;
-    const float Cx_ = p2.x - r.ox, Cy_ = p2.y - r.oy, Cz_ = p2.z - r.oz;
-    const float Akz = sel3(Ax_, Ay_, Az_, r.kz), Bkz = sel3(Bx_, By_, Bz_, r.kz), Ckz = sel3(Cx_, Cy_, Cz_, r.kz);
-    const float Ax = __fmaf_rn(-r.Sx, Akz, sel3(Ax_, Ay_, Az_, r.kx));
-    const float Ay = __fmaf_rn(-r.Sy, Akz, sel3(Ax_, Ay_, Az_, r.ky));
-    const float Bx = __fmaf_rn(-r.Sx, Bkz, sel3(Bx_, By_, Bz_, r.kx));
-    const float By = __fmaf_rn(-r.Sy, Bkz, sel3(Bx_, By_, Bz_, r.ky));
-    const float Cx = __fmaf_rn(-r.Sx, Ckz, sel3(Cx_, Cy_, Cz_, r.kx));
-    const float Cy = __fmaf_rn(-r.Sy, Ckz, sel3(Cx_, Cy_, Cz_, r.ky));
+    float Aa = p0.x - r.ox, Ab = p0.y - r.oy, Ac = p0.z - r.oz;
+    float Ba = p1.x - r.ox, Bb = p1.y - r.oy, Bc = p1.z - r.oz;
+    float Ca = p2.x - r.ox, Cb = p2.y - r.oy, Cc = p2.z - r.oz;
+    rotate_to_ray_axes(r.kz, Aa, Ab, Ac, Ba, Bb, Bc, Ca, Cb, Cc);      // (a, b, c) = components along kz, kz+1, kz+2
+    const float Ax = __fmaf_rn(-r.Sb, Aa, Ab), Ay = __fmaf_rn(-r.Sc, Aa, Ac);
+    const float Bx = __fmaf_rn(-r.Sb, Ba, Bb), By = __fmaf_rn(-r.Sc, Ba, Bc);
+    const float Cx = __fmaf_rn(-r.Sb, Ca, Cb), Cy = __fmaf_rn(-r.Sc, Ca, Cc);
     const float U = diff_of_products(Cx, By, Cy, Bx);
     const float V = diff_of_products(Ax, Cy, Ay, Cx);
     const float W = diff_of_products(Bx, Ay, By, Ax);
