@@ -114,10 +114,20 @@ struct HitRec {
     int32_t prim, inst;
 };
 
+// branch-free float select (the compiler turns chains of ternaries on the dominant axis into divergent branches)
+__device__ __forceinline__ float fsel(bool c, float a, float b) {
+    float r;
+    asm("{ .reg .pred p; setp.ne.b32 p, %3, 0; selp.f32 %0, %1, %2, p; }" : "=f"(r) : "f"(a), "f"(b), "r"((int)c));
+    return r;
+}
+
 __device__ __forceinline__ float safe_rcp_dir(float d) {
-    // src/Ray.h:79-90: 1/d, with d == 0 mapped to +-MIRO_TMAX by the sign of the IEEE quotient
-    if (d == 0.0f) return (__float_as_uint(d) >> 31) ? -MIRO_GPU_TMAX : MIRO_GPU_TMAX;
-    return 1.0f / d;
+    // The reciprocal direction only feeds the (conservative) slab test: one MUFU.RCP (<= 1 ulp) instead of the correctly rounded
+    // reciprocal with its slow path, branch-free.  Components below 1e-12 in magnitude (0 included) get the reference's +-MIRO_TMAX
+    // (src/Ray.h:79-90); the slab test's widening (node_step) covers the reciprocal's error.
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    return fsel(fabsf(d) < 1.0e-12f, copysignf(MIRO_GPU_TMAX, d), r);
 }
 
 
@@ -127,13 +137,6 @@ __device__ __forceinline__ float diff_of_products(float a, float b, float c, flo
     float e = __fmaf_rn(-c, d, w);
     float f = __fmaf_rn(a, b, -w);
     return __fadd_rn(f, e);
-}
-
-// branch-free float select (the compiler turns chains of ternaries on the dominant axis into divergent branches)
-__device__ __forceinline__ float fsel(bool c, float a, float b) {
-    float r;
-    asm("{ .reg .pred p; setp.ne.b32 p, %3, 0; selp.f32 %0, %1, %2, p; }" : "=f"(r) : "f"(a), "f"(b), "r"((int)c));
-    return r;
 }
 
 struct RaySpace {
@@ -154,7 +157,7 @@ struct RaySpace {
         const bool z0 = (ax > ay) && (ax > az);                 // kz == 0
         const bool z1 = !(ax > ay) && (ay > az);                // kz == 1; otherwise kz == 2
         kz = z0 ? 0 : (z1 ? 1 : 2);
-        const float rz = 1.0f / fsel(z0, dx, fsel(z1, dy, dz));
+        const float rz = __frcp_rn(fsel(z0, dx, fsel(z1, dy, dz)));
         Sb = fsel(z0, dy, fsel(z1, dz, dx)) * rz;
         Sc = fsel(z0, dz, fsel(z1, dx, dy)) * rz;
     }
@@ -270,7 +273,6 @@ __device__ __forceinline__ bool ref_is_inner(int32_t ref) { return ref >= 0 && r
 // One ray slot of a persistent warp.
 struct Lane {
     RaySpace r;          // current-space ray (world, or object space inside an instance)
-    float oix, oiy, oiz; // origin * reciprocal direction (slab test in FMA form)
     float tmin, time;
     HitRec hit;          // hit.t = current tmax
     int32_t cur;         // node / leaf reference being processed, or MIRO_GPU_CHILD_EMPTY
@@ -279,7 +281,6 @@ struct Lane {
     bool done;           // slot is empty
     __device__ __forceinline__ void set_ray(float ox, float oy, float oz, float dx, float dy, float dz) {
         r.set(ox, oy, oz, dx, dy, dz);
-        oix = ox * r.ix; oiy = oy * r.iy; oiz = oz * r.iz;
     }
 };
 
@@ -350,9 +351,11 @@ __device__ __forceinline__ void node_step(const DeviceScene& s, Lane& L, Travers
     if (COUNT) ++n_nodes;
     const uint32_t ex = __float_as_uint(h0.w);
     // per axis: t(q) = q * (step / d) + (p - o) / d
-    const float ax = __uint_as_float((ex & 0xffu) << 23) * L.r.ix, bx = __fmaf_rn(h0.x, L.r.ix, -L.oix);
-    const float ay = __uint_as_float((ex & 0xff00u) << 15) * L.r.iy, by = __fmaf_rn(h0.y, L.r.iy, -L.oiy);
-    const float az = __uint_as_float((ex & 0xff0000u) << 7) * L.r.iz, bz = __fmaf_rn(h0.z, L.r.iz, -L.oiz);
+    // (p - o) / d: the subtraction first, so every error of t is RELATIVE (a few ulp, covered by the widened far bound) — the
+    // FMA form p/d - o/d loses absolute accuracy when |o/d| is large against t — and three registers fewer per lane
+    const float ax = __uint_as_float((ex & 0xffu) << 23) * L.r.ix, bx = (h0.x - L.r.ox) * L.r.ix;
+    const float ay = __uint_as_float((ex & 0xff00u) << 15) * L.r.iy, by = (h0.y - L.r.oy) * L.r.iy;
+    const float az = __uint_as_float((ex & 0xff0000u) << 7) * L.r.iz, bz = (h0.z - L.r.oz) * L.r.iz;
     // near / far planes by the sign of the ray direction (the same for all four children): whole-word selects, so the
     // per-child test needs no min/max of plane pairs
     const uint32_t lx = __float_as_uint(q0.x), ly = __float_as_uint(q0.y), lz = __float_as_uint(q0.z);
@@ -364,10 +367,11 @@ __device__ __forceinline__ void node_step(const DeviceScene& s, Lane& L, Travers
     const int INF_KEY = 0x7fffffff;
     const float tmax = L.hit.t;
     int k0, k1, k2, k3;
+#define MIRO_SLAB_WIDEN 1.0000008f      /* ~7 ulp: reciprocal 1, step/d 0.5, p - o 0.5, product 0.5, fma 0.5 on each of the two bounds */
 #define MIRO_BYTE(W, C) ((float)(((W) >> (8 * (C))) & 0xffu))
 #define MIRO_SLAB(C, CH, KEY) { \
     const float tn = fmaxf(fmaxf(__fmaf_rn(MIRO_BYTE(nx, C), ax, bx), __fmaf_rn(MIRO_BYTE(ny, C), ay, by)), fmaxf(__fmaf_rn(MIRO_BYTE(nz, C), az, bz), L.tmin)); \
-    const float tf = fminf(fminf(__fmaf_rn(MIRO_BYTE(fx, C), ax, bx), __fmaf_rn(MIRO_BYTE(fy, C), ay, by)), fminf(__fmaf_rn(MIRO_BYTE(fz, C), az, bz), tmax)) * 1.0000003f; \
+    const float tf = fminf(fminf(__fmaf_rn(MIRO_BYTE(fx, C), ax, bx), __fmaf_rn(MIRO_BYTE(fy, C), ay, by)), fminf(__fmaf_rn(MIRO_BYTE(fz, C), az, bz), tmax)) * MIRO_SLAB_WIDEN; \
     KEY = (tn <= tf && __float_as_int(CH) != MIRO_GPU_CHILD_EMPTY) ? ((float_key(tn) & ~3) | C) : INF_KEY; }
     MIRO_SLAB(0, chf.x, k0) MIRO_SLAB(1, chf.y, k1) MIRO_SLAB(2, chf.z, k2) MIRO_SLAB(3, chf.w, k3)
 #undef MIRO_SLAB
