@@ -80,7 +80,7 @@ k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const
     uint32_t c_nodes = 0, c_tris = 0, c_insts = 0, c_rays = 0;
     uint32_t chunk_next = 0, chunk_end = 0;      // warp-uniform: the warp's claimed range of ray indices
     bool exhausted = false;                      // warp-uniform: the global counter has run past n
-    Lane L; L.done = true; L.cur = MIRO_GPU_CHILD_EMPTY; L.ray_idx = 0; L.cur_inst = -1; L.tmin = 0.f; L.time = 0.f;
+    Lane L; L.cur = MIRO_GPU_CHILD_EMPTY; L.ray_idx = 0; L.cur_inst = -1; L.tmin = 0.f; L.time = 0.f;
     L.hit.t = 0.f; L.hit.a = L.hit.b = 0.f; L.hit.prim = -1; L.hit.inst = -1;
     L.set_ray(0.f, 0.f, 0.f, 0.f, 0.f, 1.f);
     unsigned long long overflow[LMEM_STACK];
@@ -98,13 +98,16 @@ k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const
             __stcs(reinterpret_cast<int*>(o) + 3, L.hit.prim); __stcs(reinterpret_cast<int*>(o) + 4, hit ? L.hit.inst : -1);
         }
     };
-    bool pending = false;      // the slot's ray has finished; its result is written (with the other idle lanes) at the next refill
+    // A slot is idle when its `cur` is EMPTY.  pending: the slot holds a ray whose result has not been written yet — it is written
+    // (with the other idle lanes, converged) at the next refill, not when the ray finishes (divergent).
+    bool pending = false;
 
     while (true) {
         // ---- refill: idle slots write their results, then take the next rays of the warp's chunk
-        const uint32_t idle = __ballot_sync(0xffffffffu, L.done);
-        if (__popc(idle) >= TRACE_REFILL || (exhausted && idle == 0xffffffffu)) {
-            if (pending) { write_result(); pending = false; }
+        const uint32_t idle = __ballot_sync(0xffffffffu, L.cur == MIRO_GPU_CHILD_EMPTY);
+        int n_idle = __popc(idle);
+        if (n_idle >= TRACE_REFILL || (exhausted && idle == 0xffffffffu)) {
+            if (pending && L.cur == MIRO_GPU_CHILD_EMPTY) { write_result(); pending = false; }
             if (exhausted) { if (idle == 0xffffffffu) break; }
             else {
                 if (chunk_next == chunk_end) {
@@ -126,24 +129,24 @@ k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const
                 }
                 const uint32_t take = min((uint32_t)__popc(idle), chunk_end - chunk_next);
                 const uint32_t rank = __popc(idle & lt_mask);
-                if (L.done && rank < take) {
+                if (L.cur == MIRO_GPU_CHILD_EMPTY && rank < take) {
                     L.ray_idx = chunk_next + rank;
                     const float4* rp = rays + (size_t)L.ray_idx * RAY_F4;
                     const float4 r0 = __ldcs(rp), r1 = __ldcs(rp + 1);
                     L.set_ray(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
                     L.tmin = r0.w; L.time = PACKED ? 0.f : __ldcs(reinterpret_cast<const float*>(rp + 2));
                     L.hit.t = r1.w; L.hit.a = 0.f; L.hit.b = 0.f; L.hit.prim = -1; L.hit.inst = -1;
-                    L.cur = s.root; L.cur_inst = -1; st.sp = 0; L.done = false;
+                    L.cur = s.root; L.cur_inst = -1; st.sp = 0; pending = true;
                     c_rays += (r0.w <= r1.w) ? 1u : 0u;      // an empty interval (a light that casts no shadow) is not a Scene::trace call
                 }
-                chunk_next += take;
+                chunk_next += take; n_idle -= (int)take;
                 if (idle == 0xffffffffu && take == 0) continue;      // nothing claimed this round: try the next chunk (or leave)
             }
         }
         // ---- vote: a live lane waits either at an inner node or at a leaf (leaf reference / instance-exit marker)
-        const bool at_node = !L.done && ref_is_inner(L.cur);
-        const bool at_leaf = !L.done && !at_node;
-        const int n_node = __popc(__ballot_sync(0xffffffffu, at_node)), n_leaf = __popc(__ballot_sync(0xffffffffu, at_leaf));
+        const bool at_node = ref_is_inner(L.cur);
+        const bool at_leaf = !at_node && L.cur != MIRO_GPU_CHILD_EMPTY;
+        const int n_node = __popc(__ballot_sync(0xffffffffu, at_node)), n_leaf = 32 - n_idle - n_node;
         bool finished = false;
         if (n_node * TRACE_NODE_BIAS_DEN >= n_leaf * TRACE_NODE_BIAS_NUM || (TRACE_LEAF_MIN > 0 && n_node > 0 && n_leaf < TRACE_LEAF_MIN)) {
             // ---- node round
@@ -157,7 +160,7 @@ k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const
             } else finished = intersect_leaf<ANY, COUNT, ALPHA>(s, L, st, rays, RAY_F4, c_tris, c_insts);     // true: any-hit found its occluder
             if (!finished && L.cur == MIRO_GPU_CHILD_EMPTY) { pop_next(L, st); finished = L.cur == MIRO_GPU_CHILD_EMPTY; }
         }
-        if (finished) { L.done = true; pending = true; }
+        if (finished) L.cur = MIRO_GPU_CHILD_EMPTY;      // (an any-hit query that found its occluder stops with work left)
     }
     // counters: warp-reduce then one atomic per warp
     unsigned long long v_rays = c_rays, v_nodes = c_nodes, v_tris = c_tris, v_insts = c_insts;

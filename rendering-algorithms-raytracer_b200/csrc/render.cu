@@ -442,7 +442,7 @@ k_walk_shadows(DeviceScene sc, DeviceShading sh, const miro_gpu_ray* __restrict_
         const float distance = r2.w;
         float attenuate = 1.0f, traversed = 0.0f;
         uint32_t segments = 0;
-        Lane L; L.ray_idx = i; L.done = false; L.tmin = r0.w; L.time = r2.x; L.hit.t = r1.w;
+        Lane L; L.ray_idx = i; L.tmin = r0.w; L.time = r2.x; L.hit.t = r1.w;
         for (int guard = 0; traversed < distance && attenuate > kEps && guard < 4096; ++guard) {
             trace_closest_thread<ALPHA>(sc, L, st, o.x, o.y, o.z, d.x, d.y, d.z);      // tMax = L.hit.t, carried over from the previous segment
             ++segments;

@@ -268,7 +268,8 @@ __device__ __forceinline__ void sts_if(int cond, uint32_t addr, int ref, int key
     asm volatile("{ .reg .pred q; setp.ne.b32 q, %3, 0; @q st.shared.v2.b32 [%0], {%1, %2}; }" :: "r"(addr), "r"(ref), "r"(key), "r"(cond) : "memory");
 }
 
-__device__ __forceinline__ bool ref_is_inner(int32_t ref) { return ref >= 0 && ref != MIRO_GPU_CHILD_EMPTY && ref != STACK_SENTINEL; }
+// inner-node references are 0 .. 0x7ffffffd; the instance-exit marker, EMPTY and the leaf references (bit 31) lie above
+__device__ __forceinline__ bool ref_is_inner(int32_t ref) { return (uint32_t)ref < (uint32_t)STACK_SENTINEL; }
 
 // One ray slot of a persistent warp.
 struct Lane {
@@ -278,7 +279,6 @@ struct Lane {
     int32_t cur;         // node / leaf reference being processed, or MIRO_GPU_CHILD_EMPTY
     int32_t cur_inst;
     uint32_t ray_idx;
-    bool done;           // slot is empty
     __device__ __forceinline__ void set_ray(float ox, float oy, float oz, float dx, float dy, float dz) {
         r.set(ox, oy, oz, dx, dy, dz);
     }
