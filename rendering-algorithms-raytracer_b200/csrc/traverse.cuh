@@ -17,8 +17,8 @@
 //     a node step (4 slab tests, sort, push) or a leaf step (<= 4 triangles / instance entry) —
 //     so both code paths run with most lanes active instead of a while-while loop whose inner
 //     loop runs at the length of the slowest lane (measured: 5.5 of 32 lanes in the node test);
-//   * 128-byte BVH4 nodes fetched with seven 16-byte vector loads through the read-only path (the
-//     whole tree lives in the 126 MB L2; hot top levels in L1);
+//   * 64-byte quantized BVH4 nodes (re-encoded from the 128-byte ABI node at upload) fetched with two 32-byte vector loads
+//     through the read-only path (the whole tree lives in the 126 MB L2; hot top levels in L1);
 //   * children are visited nearest-first (4-element sorting network) and the deferred ones go
 //     to a per-thread stack in SHARED memory laid out [entry][lane] (conflict-free, "warp
 //     coherent"); entries carry their entry distance so popped sub-trees behind the current
@@ -179,6 +179,10 @@ __device__ __forceinline__ void rotate_to_ray_axes(int kz, float& ax, float& ay,
 }
 
 // Watertight two-sided ray/triangle test.  Returns true and updates (t,a,b) when tmin <= t < tmax.
+// T_ONLY (any-hit queries without alpha maps): the caller only asks WHETHER the crossing lies in [tmin, tmax), so the distance is
+// taken from the edge functions themselves and the reference-order Moller-Trumbore block (53 instructions run by 2 of 32 lanes,
+// 8 % of a shadow launch) is skipped; a, b are not produced.
+template <bool T_ONLY = false>
 __device__ __forceinline__ bool intersect_tri(const RaySpace& r, float tmin, float tmax,
                                               float4 p0, float4 p1, float4 p2, float& t_out, float& a_out, float& b_out) {
     float Aa = p0.x - r.ox, Ab = p0.y - r.oy, Ac = p0.z - r.oz;
@@ -194,6 +198,16 @@ __device__ __forceinline__ bool intersect_tri(const RaySpace& r, float tmin, flo
     if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
     const float det = U + V + W;
     if (det == 0.0f) return false;
+    if (T_ONLY) {
+        // t = (U A + V B + W C)[kz] / (det d[kz]): the barycentric mean of the vertices' distances along the dominant axis
+        const float dkz = fsel(r.kz == 0, r.dx, fsel(r.kz == 1, r.dy, r.dz));
+        float inv;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(det * dkz));
+        const float t = __fmaf_rn(U, Aa, __fmaf_rn(V, Ba, W * Ca)) * inv;
+        if (!(t >= tmin && t < tmax)) return false;
+        t_out = t; a_out = 0.f; b_out = 0.f;
+        return true;
+    }
     // The ray passes through the triangle (decided watertight, above).  Distance and barycentrics are then
     // evaluated with the reference's Moller-Trumbore expressions in the reference's operation order
     // (src/BVH.cpp:1343-1369; SoADot = x*x' + (y*y' + z*z'), no FMA contraction), so t, a, b agree with it
@@ -458,7 +472,7 @@ __device__ __forceinline__ bool intersect_leaf(const DeviceScene& s, Lane& L, Tr
             const float4 p0 = __ldg(t), p1 = __ldg(t + 1), p2 = __ldg(t + 2);
             if (COUNT) ++n_tris;
             float ht, ha, hb;
-            if (intersect_tri(L.r, L.tmin, L.hit.t, p0, p1, p2, ht, ha, hb) && (!ALPHA || hit_alpha(s.alpha, first + i, ha, hb) >= 0.5f)) {
+            if (intersect_tri<ANY && !ALPHA>(L.r, L.tmin, L.hit.t, p0, p1, p2, ht, ha, hb) && (!ALPHA || hit_alpha(s.alpha, first + i, ha, hb) >= 0.5f)) {
                 L.hit.t = ht; L.hit.a = ha; L.hit.b = hb;
                 L.hit.prim = (int32_t)(first + i); L.hit.inst = L.cur_inst;
                 if (ANY) return true;
@@ -476,7 +490,7 @@ __device__ __forceinline__ bool intersect_leaf(const DeviceScene& s, Lane& L, Tr
             p1.x = w1 * b1.x + w0 * a1.x; p1.y = w1 * b1.y + w0 * a1.y; p1.z = w1 * b1.z + w0 * a1.z;
             p2.x = w1 * b2.x + w0 * a2.x; p2.y = w1 * b2.y + w0 * a2.y; p2.z = w1 * b2.z + w0 * a2.z;
             float ht, ha, hb;
-            if (intersect_tri(L.r, L.tmin, L.hit.t, p0, p1, p2, ht, ha, hb) && (!ALPHA || hit_alpha(s.alpha, s.n_tris + first + i, ha, hb) >= 0.5f)) {
+            if (intersect_tri<ANY && !ALPHA>(L.r, L.tmin, L.hit.t, p0, p1, p2, ht, ha, hb) && (!ALPHA || hit_alpha(s.alpha, s.n_tris + first + i, ha, hb) >= 0.5f)) {
                 L.hit.t = ht; L.hit.a = ha; L.hit.b = hb;
                 L.hit.prim = (int32_t)(s.n_tris + first + i); L.hit.inst = L.cur_inst;
                 if (ANY) return true;
