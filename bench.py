@@ -250,6 +250,8 @@ def main():
     bind_to_gpu_numa_node(local)
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's version banner goes to stdout, which carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     sc = fx.scene().attach(local)
     cam = sc.camera()
