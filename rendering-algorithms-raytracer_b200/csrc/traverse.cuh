@@ -178,6 +178,31 @@ __device__ __forceinline__ void rotate_to_ray_axes(int kz, float& ax, float& ay,
     ax = a0; ay = b0; az = c0; bx = a1; by = b1; bz = c1; cx = a2; cy = b2; cz = c2;
 }
 
+// Distance and barycentrics of a crossing the watertight test has accepted, evaluated with the reference's Moller-Trumbore
+// expressions in the reference's operation order (src/BVH.cpp:1343-1369; SoADot = x*x' + (y*y' + z*z'), no FMA contraction), so
+// t, a, b agree with it to rounding instead of differing by the conditioning of two different algorithms on sliver triangles.
+// a, b are clamped to the triangle (inside by the edge test: only the rounding residue is cut).  False: degenerate (det == 0).
+__device__ __forceinline__ bool moller_trumbore_reference(const RaySpace& r, float4 p0, float4 p1, float4 p2, float& t_out, float& a_out, float& b_out) {
+    const float e0x = __fsub_rn(p1.x, p0.x), e0y = __fsub_rn(p1.y, p0.y), e0z = __fsub_rn(p1.z, p0.z);
+    const float e1x = __fsub_rn(p2.x, p0.x), e1y = __fsub_rn(p2.y, p0.y), e1z = __fsub_rn(p2.z, p0.z);
+    const float px = __fsub_rn(__fmul_rn(r.dy, e1z), __fmul_rn(r.dz, e1y));
+    const float py = -__fsub_rn(__fmul_rn(r.dx, e1z), __fmul_rn(r.dz, e1x));
+    const float pz = __fsub_rn(__fmul_rn(r.dx, e1y), __fmul_rn(r.dy, e1x));
+    const float mdet = __fadd_rn(__fmul_rn(e0x, px), __fadd_rn(__fmul_rn(e0y, py), __fmul_rn(e0z, pz)));
+    if (mdet == 0.0f) return false;
+    const float inv = __frcp_rn(mdet);
+    const float tx = __fsub_rn(r.ox, p0.x), ty = __fsub_rn(r.oy, p0.y), tz = __fsub_rn(r.oz, p0.z);
+    const float qx = __fsub_rn(__fmul_rn(ty, e0z), __fmul_rn(tz, e0y));
+    const float qy = -__fsub_rn(__fmul_rn(tx, e0z), __fmul_rn(tz, e0x));
+    const float qz = __fsub_rn(__fmul_rn(tx, e0y), __fmul_rn(ty, e0x));
+    t_out = __fmul_rn(inv, __fadd_rn(__fmul_rn(e1x, qx), __fadd_rn(__fmul_rn(e1y, qy), __fmul_rn(e1z, qz))));
+    const float a = __fmul_rn(inv, __fadd_rn(__fmul_rn(tx, px), __fadd_rn(__fmul_rn(ty, py), __fmul_rn(tz, pz))));
+    const float b = __fmul_rn(inv, __fadd_rn(__fmul_rn(r.dx, qx), __fadd_rn(__fmul_rn(r.dy, qy), __fmul_rn(r.dz, qz))));
+    a_out = fminf(fmaxf(a, 0.0f), 1.0f);
+    b_out = fminf(fmaxf(b, 0.0f), 1.0f - a_out);
+    return true;
+}
+
 // Watertight two-sided ray/triangle test.  Returns true and updates (t,a,b) when tmin <= t < tmax.
 // T_ONLY (any-hit queries without alpha maps): the caller only asks WHETHER the crossing lies in [tmin, tmax), so the distance is
 // taken from the edge functions themselves and the reference-order Moller-Trumbore block (53 instructions run by 2 of 32 lanes,
@@ -208,29 +233,10 @@ __device__ __forceinline__ bool intersect_tri(const RaySpace& r, float tmin, flo
         t_out = t; a_out = 0.f; b_out = 0.f;
         return true;
     }
-    // The ray passes through the triangle (decided watertight, above).  Distance and barycentrics are then
-    // evaluated with the reference's Moller-Trumbore expressions in the reference's operation order
-    // (src/BVH.cpp:1343-1369; SoADot = x*x' + (y*y' + z*z'), no FMA contraction), so t, a, b agree with it
-    // to rounding instead of differing by the conditioning of two different algorithms on sliver triangles.
-    const float e0x = __fsub_rn(p1.x, p0.x), e0y = __fsub_rn(p1.y, p0.y), e0z = __fsub_rn(p1.z, p0.z);
-    const float e1x = __fsub_rn(p2.x, p0.x), e1y = __fsub_rn(p2.y, p0.y), e1z = __fsub_rn(p2.z, p0.z);
-    const float px = __fsub_rn(__fmul_rn(r.dy, e1z), __fmul_rn(r.dz, e1y));
-    const float py = -__fsub_rn(__fmul_rn(r.dx, e1z), __fmul_rn(r.dz, e1x));
-    const float pz = __fsub_rn(__fmul_rn(r.dx, e1y), __fmul_rn(r.dy, e1x));
-    const float mdet = __fadd_rn(__fmul_rn(e0x, px), __fadd_rn(__fmul_rn(e0y, py), __fmul_rn(e0z, pz)));
-    if (mdet == 0.0f) return false;
-    const float inv = __frcp_rn(mdet);
-    const float tx = __fsub_rn(r.ox, p0.x), ty = __fsub_rn(r.oy, p0.y), tz = __fsub_rn(r.oz, p0.z);
-    const float qx = __fsub_rn(__fmul_rn(ty, e0z), __fmul_rn(tz, e0y));
-    const float qy = -__fsub_rn(__fmul_rn(tx, e0z), __fmul_rn(tz, e0x));
-    const float qz = __fsub_rn(__fmul_rn(tx, e0y), __fmul_rn(ty, e0x));
-    const float t = __fmul_rn(inv, __fadd_rn(__fmul_rn(e1x, qx), __fadd_rn(__fmul_rn(e1y, qy), __fmul_rn(e1z, qz))));
+    float t, a, b;
+    if (!moller_trumbore_reference(r, p0, p1, p2, t, a, b)) return false;
     if (!(t >= tmin && t < tmax)) return false;
-    const float a = __fmul_rn(inv, __fadd_rn(__fmul_rn(tx, px), __fadd_rn(__fmul_rn(ty, py), __fmul_rn(tz, pz))));
-    const float b = __fmul_rn(inv, __fadd_rn(__fmul_rn(r.dx, qx), __fadd_rn(__fmul_rn(r.dy, qy), __fmul_rn(r.dz, qz))));
-    t_out = t;
-    a_out = fminf(fmaxf(a, 0.0f), 1.0f);     // inside by the edge test: clamp the rounding residue
-    b_out = fminf(fmaxf(b, 0.0f), 1.0f - a_out);
+    t_out = t; a_out = a; b_out = b;
     return true;
 }
 
