@@ -153,6 +153,18 @@ def test_specular_material_fields_travel_in_the_desc():
     sc.close()
 
 
+def test_light_shadow_flags_travel_in_the_desc():
+    # Light::setCastShadows / setFastShadows (src/Light.h:22-24): script keys `shadows`, `fastshadows`; defaults cast + fast
+    sc = _script_scene("material m lambert kd .5 .5 .5\nlight point pos 0 1 0 power 1\nlight point pos 0 2 0 power 1 shadows 0 fastshadows 0\n"
+                       "light rect v1 0 3 0 v2 1 3 0 v3 0 3 1 power 2 samples 3 fastshadows 0\nmesh a a.obj\nobject a m\n", {"a": QUAD})
+    d = sc.desc()
+    assert d.n_lights == 3
+    assert (d.lights[0].cast_shadows, d.lights[0].full_shadows) == (1, 0)
+    assert (d.lights[1].cast_shadows, d.lights[1].full_shadows) == (0, 1)
+    assert (d.lights[2].kind, d.lights[2].cast_shadows, d.lights[2].full_shadows, d.lights[2].num_samples) == (1, 1, 1, 3)
+    sc.close()
+
+
 def test_tangent_frame_and_texture_maps_travel_in_the_desc(tmp_path):
     """TriangleMesh::preCalc (src/TriangleMesh.cpp:107-150): per NORMAL index, the reference's tangent made orthogonal to the
     normal, bitangent = cross(tangent, normal); a triangle with a degenerate uv mapping writes nothing; meshes without uvs
