@@ -2,9 +2,13 @@
 #include "miro_bvh.h"
 #include <math.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <float.h>
 #include <algorithm>
+#include <atomic>
+#include <future>
 #include <numeric>
+#include <thread>
 
 namespace miro {
 namespace {
@@ -17,6 +21,9 @@ static uint32_t kMaxLeaf = MIRO_GPU_MAX_LEAF;   // tuning aid: MIRO_BVH_MAX_LEAF
 static float kTraversalCost = 1.0f;      // one binary split level, in units of one triangle test (tunable: MIRO_BVH_TRAVERSAL_COST)
 constexpr float kPrimCost = 1.0f;
 static double kSpatialBudget = 1.0;      // extra references spatial splits may create, as a fraction of the primitive count (MIRO_BVH_SPATIAL; 0: object splits only)
+// Sub-trees of at least this many references are built as parallel tasks (MIRO_BVH_PARALLEL_MIN; 0: sequential build).  The tree does
+// not depend on the number of threads: WHETHER a node's children run concurrently is decided by its reference count alone.
+static size_t kParallelMin = 8192;
 
 struct Box {
     float lo[3], hi[3];
@@ -55,16 +62,24 @@ struct Ref {
 struct Builder {
     const std::vector<BuildPrim>& prims;
     const miro_gpu_tri* tri_verts;   // vertices of the static triangles (indexed by BuildPrim::index), or NULL: no spatial splits
+    // Node and leaf-slot storage is allocated up front and handed out by atomic counters, so concurrently built sub-trees never
+    // move each other's nodes.  (Where a node ends up in `bn` depends on timing; the tree it belongs to does not — the collapse
+    // walks child links and assigns the final order.)
     std::vector<BinNode> bn;
-    std::vector<uint32_t> leaf_prims;     // primitive (index into prims) of every leaf slot, leaves contiguous
-    uint32_t max_depth = 0;
-    size_t extra_refs = 0, extra_budget = 0;
+    std::vector<uint32_t> leaf_prims;     // primitive (index into prims) of every leaf slot, a leaf's slots contiguous
+    std::atomic<uint32_t> bn_next{0}, leaf_next{0};
+    std::atomic<uint32_t> max_depth{0};
+    std::atomic<size_t> extra_refs{0};
+    size_t extra_budget = 0;
     float root_area = 1.f;
 
     Builder(const std::vector<BuildPrim>& p, const miro_gpu_tri* tv) : prims(p), tri_verts(tv) {
-        bn.reserve(p.size() ? 2 * p.size() : 1);
         extra_budget = tv ? (size_t)(kSpatialBudget * (double)p.size()) : 0;
+        const size_t max_refs = p.size() + extra_budget + 16;      // every split that adds references is paid from the budget
+        bn.resize(2 * max_refs);
+        leaf_prims.resize(max_refs);
     }
+    void note_depth(uint32_t d) { uint32_t cur = max_depth.load(std::memory_order_relaxed); while (d > cur && !max_depth.compare_exchange_weak(cur, d, std::memory_order_relaxed)) {} }
 
     static float centroid(const Ref& r, int axis) { return 0.5f * (r.box.lo[axis] + r.box.hi[axis]); }
 
@@ -78,8 +93,9 @@ struct Builder {
     }
 
     int32_t make_leaf(int32_t me, const std::vector<Ref>& refs) {
-        bn[me].first = (uint32_t)leaf_prims.size(); bn[me].count = (uint32_t)refs.size();
-        for (const Ref& r : refs) leaf_prims.push_back(r.prim);
+        const uint32_t first = leaf_next.fetch_add((uint32_t)refs.size(), std::memory_order_relaxed);
+        bn[me].first = first; bn[me].count = (uint32_t)refs.size();
+        for (size_t i = 0; i < refs.size(); ++i) leaf_prims[first + i] = refs[i].prim;
         return me;
     }
 
@@ -118,11 +134,12 @@ struct Builder {
 
     // `budget`: extra references this sub-tree may still create (in: its share; out: what it did not use).  The share is handed
     // down in proportion to the children's reference counts and what the left child leaves goes to the right one, so the depth-
-    // first recursion does not spend the whole allowance in the first corner of the scene it visits.
+    // first recursion does not spend the whole allowance in the first corner of the scene it visits.  Children of a node with
+    // at least kParallelMin references are built concurrently, each with its own share (nothing is handed across).
     int32_t build(std::vector<Ref>& refs, uint32_t depth, size_t& budget) {
-        max_depth = std::max(max_depth, depth);
-        const int32_t me = (int32_t)bn.size();
-        bn.emplace_back();
+        note_depth(depth);
+        const int32_t me = (int32_t)bn_next.fetch_add(1u, std::memory_order_relaxed);
+        if ((size_t)me >= bn.size()) { fprintf(stderr, "miro_bvh: node storage exhausted (internal invariant)\n"); abort(); }
         const uint32_t count = (uint32_t)refs.size();
         Box box; box.reset();
         Box cbox; cbox.reset();
@@ -223,7 +240,7 @@ struct Builder {
                     }
                 }
                 have_split = !left.empty() && !right.empty() && left.size() < count && right.size() < count;
-                if (have_split) { const size_t used = left.size() + right.size() - count; extra_refs += used; budget -= std::min(budget, used); }
+                if (have_split) { const size_t used = left.size() + right.size() - count; extra_refs.fetch_add(used, std::memory_order_relaxed); budget -= std::min(budget, used); }
                 else { left.clear(); right.clear(); }
             }
             if (!have_split && best_axis >= 0 && depth < 40) {   // beyond 40 levels fall through to balanced median splits
@@ -250,6 +267,15 @@ struct Builder {
         const size_t nl = left.size(), nr = right.size();
         size_t b_left = (size_t)((double)budget * (double)nl / (double)(nl + nr));
         const size_t rest = budget - b_left;
+        if (kParallelMin > 0 && count >= kParallelMin && depth < 7) {      // at most 2^7 tasks; the rule depends on the node alone
+            size_t b_right = rest;
+            std::future<int32_t> lf = std::async(std::launch::async, [&]() { return build(left, depth + 1, b_left); });
+            const int32_t r = build(right, depth + 1, b_right);
+            const int32_t l = lf.get();
+            budget = b_left + b_right;
+            bn[me].left = l; bn[me].right = r;
+            return me;
+        }
         const int32_t l = build(left, depth + 1, b_left);
         std::vector<Ref>().swap(left);
         size_t b_right = rest + b_left;          // its own share plus what the left sub-tree did not use
@@ -324,6 +350,7 @@ int32_t build_wide_bvh(const std::vector<BuildPrim>& prims, std::vector<miro_gpu
     if (const char* e = getenv("MIRO_BVH_BINS")) { const int v = atoi(e); if (v >= 4 && v <= kMaxBins) kBins = v; }
     if (const char* e = getenv("MIRO_BVH_ALPHA")) { const float v = (float)atof(e); if (v >= 0.f) kSpatialAlpha = v; }
     if (const char* e = getenv("MIRO_BVH_SPATIAL")) { const double v = atof(e); if (v >= 0.0 && v <= 4.0) kSpatialBudget = v; }
+    if (const char* e = getenv("MIRO_BVH_PARALLEL_MIN")) { const long v = atol(e); if (v >= 0) kParallelMin = (size_t)v; }
     // scenes of a few hundred triangles gain nothing from spatial splits (measured: the Cornell box renders 3 % slower with them)
     Builder b(prims, (kSpatialBudget > 0.0 && prims.size() >= kSpatialMinPrims) ? tri_verts : nullptr);
     std::vector<Ref> refs(prims.size());
@@ -335,7 +362,7 @@ int32_t build_wide_bvh(const std::vector<BuildPrim>& prims, std::vector<miro_gpu
     const int32_t root = b.build(refs, 0, budget);
     Collapser c{b, nodes, order, BvhStats()};
     const int32_t ref = c.emit(root, 0);
-    c.st.references = (uint32_t)b.leaf_prims.size();
+    c.st.references = b.leaf_next.load();
     if (stats) *stats = c.st;
     return ref;
 }
