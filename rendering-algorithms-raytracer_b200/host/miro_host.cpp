@@ -5,6 +5,7 @@
 #include <string.h>
 #include <float.h>
 #include <algorithm>
+#include <chrono>
 #include <map>
 
 namespace miro {
@@ -522,6 +523,13 @@ static void collectSubTrees(const FlatScene& f, int32_t ref, const float* box, i
 }
 
 bool Scene::preCalc() {
+    // MIRO_HOST_TIMING=1: phases of the scene hand-off on stderr (diagnostic)
+    static const bool timing = getenv("MIRO_HOST_TIMING") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (timing) fprintf(stderr, "[miro_host] preCalc %-28s %8.1f ms since start\n", what,
+                            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
+    };
     m_error.clear();
     m_flat = FlatScene();
     meshes.clear(); m_materialList.clear(); m_textureList.clear();
@@ -605,6 +613,7 @@ bool Scene::preCalc() {
         }
         top.push_back(bp);
     }
+    lap("primitives gathered");
     bool onDevice = m_buildOnDevice;
     for (const BuildPrim& bp : top) if (bp.kind != MIRO_GPU_KIND_TRI) onDevice = false;
     if (onDevice) {
@@ -613,6 +622,7 @@ bool Scene::preCalc() {
         for (const BuildPrim& bp : top) order[MIRO_GPU_KIND_TRI].push_back(bp.index);
     } else m_flat.root = build_wide_bvh(top, m_flat.nodes, order, &m_flat.top_stats, m_srcTris.data());
 
+    lap("acceleration structure built");
     // gather primitives into leaf order
     m_flat.tris.resize(order[0].size()); m_flat.mbtris.resize(order[1].size()); m_flat.instances.resize(order[2].size());
     m_flat.prims.resize(order[0].size() + order[1].size());
@@ -623,6 +633,7 @@ bool Scene::preCalc() {
         m_flat.instances[i] = m_srcInst[order[2][i]];
         memcpy(&m_flat.inst_nxf[i * 9], &m_srcInstNxf[(size_t)order[2][i] * 9], 9 * sizeof(float));
     }
+    lap("leaf-order arrays");
     // lights / env (textures they use must get ordinals before the texture table is emitted)
     for (Light* l : m_lights) if (DomeLight* d = dynamic_cast<DomeLight*>(l)) textureOrdinal(d->m_lightMap);
     m_flat.env_map = textureOrdinal(m_envMap);
