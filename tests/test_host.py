@@ -87,6 +87,27 @@ def test_flatten_invariants(scene, spatial, monkeypatch):
     sc.close()
 
 
+def test_parallel_build_is_deterministic_and_valid(monkeypatch):
+    """Sub-trees of >= MIRO_BVH_PARALLEL_MIN references are built as concurrent tasks; whether a node's children run concurrently
+    depends on the node alone, so two builds (any thread timing) give byte-identical node and triangle arrays."""
+    monkeypatch.setenv("MIRO_BVH_PARALLEL_MIN", "1024")       # many tasks
+    fx = helpers.Fixture(helpers.fixture_path("c2_explosion"))
+    builds = []
+    for _ in range(2):
+        sc = fx.scene()
+        d, nodes, child, tris = flat(sc)
+        builds.append((d.root, nodes.copy(), child.copy(), tris.copy(), sc.bvh_stats()))
+        seen = np.zeros(d.n_tris, np.int64)
+        big = np.float32(3e38)
+        walk(d, nodes, child, tris, d.root, -np.full(3, big), np.full(3, big), seen, inside=False)
+        assert (seen == 1).all()
+        sc.close()
+    a, b = builds
+    assert a[0] == b[0] and a[4] == b[4]
+    u = lambda x: x.view(np.uint32)      # compare bit patterns: child references read as floats are NaNs
+    assert np.array_equal(u(a[1]), u(b[1])) and np.array_equal(a[2], b[2]) and np.array_equal(u(a[3]), u(b[3]))
+
+
 def _script_scene(text, meshes=None):
     sc = mb.MiroScene()
     for name, (v, f) in (meshes or {}).items():
