@@ -50,7 +50,7 @@ grep -q 'const Matrix4x4 &t' "$B/ProxyObject.h" && grep -q 'const Matrix4x4& t' 
   && grep -q -- '-Y %d +X %d' "$B/hdrloader.cpp" && grep -q 'g_miro_trace_calls' "$B/Scene.cpp" \
   || { echo "a reference patch did not apply" >&2; exit 4; }
 CXX=${MIRO_CXX:-/usr/bin/g++}   # the image exports CXX=/opt/gcc/bin/g++, which has no libgomp.spec
-FLAGS="-std=gnu++14 -fpermissive -w -fopenmp -msse4.1 -O3 -include $HERE/shim/shim.h -I$HERE/shim -I$B"
+FLAGS="-std=gnu++14 -fpermissive -w -fopenmp -msse4.1 -O3 -include $HERE/shim/shim.h -I$HERE/shim -I$B -I$HERE/../include"
 objs=""
 pids=""
 for f in "$B"/*.cpp; do
@@ -61,6 +61,6 @@ done
 $CXX $FLAGS -c "$HERE/ref_harness.cpp" -o "$B/ref_harness.o" &
 pids="$pids $!"
 for p in $pids; do wait "$p"; done
-$CXX -fopenmp -O3 $objs "$B/ref_harness.o" -o "$OUT/miro_ref" -lm
+$CXX -fopenmp -O3 $objs "$B/ref_harness.o" -o "$OUT/miro_ref" -lm -ldl
 rm -rf "$B"
 echo "built $OUT/miro_ref"

@@ -50,6 +50,8 @@
 #include <fstream>
 #include <cstdio>
 #include <cstdint>
+#include <dlfcn.h>
+#include "miro_gpu.h"      // include/miro_gpu.h: the C ABI the --render-gpu glue binds (dlopen, no link-time dependency)
 
 unsigned long long g_miro_trace_calls[32 * 16] = {0};
 void ParseFile(FILE*) {}
@@ -452,10 +454,162 @@ void dumpQBVH(const std::string& path) {
     fclose(f);
 }
 
+// --render-gpu FILE --gpu-lib LIB: the binding of INTEGRATION.md made real.  The reference's OWN scene — its Object list, its
+// materials and lights as the scene code set them up, and its OWN QBVH (BVH.cpp:100-389) — is flattened into a
+// miro_gpu_scene_desc, handed to libmiro_gpu.so (loaded with dlopen: this harness has no link-time dependency on CUDA) through
+// miro_gpu_upload_scene, and Scene::raytraceImage's float radiance comes back from miro_gpu_render.  Scope of this glue:
+// plain Objects (static triangles), Lambert / Blinn without texture maps, point and rectangle lights — what the c1 / c2 / c4 /
+// c6 / c8 / c10 scene scripts use; anything else stops with a message.
+struct GpuFlat {
+    std::vector<miro_gpu_node> nodes; std::vector<miro_gpu_tri> tris; std::vector<miro_gpu_prim> prims;
+    std::vector<float> normals, uvs;
+    std::map<TriangleMesh*, std::pair<uint32_t, uint32_t> > meshBase;      // first normal / first uv of a mesh
+    std::vector<miro_gpu_material> materials; std::map<const Material*, uint32_t> matOrdinal;
+};
+uint32_t gpuMaterial(const Material* m, GpuFlat& f) {
+    if (f.matOrdinal.count(m)) return f.matOrdinal[m];
+    if (m->m_colorMap || m->m_alphaMap || m->m_normalMap || m->m_specularMap || m->m_reflectMap || m->m_refractMap) die("--render-gpu: texture maps are outside this glue's scope");
+    miro_gpu_material g; memset(&g, 0, sizeof(g));
+    g.color_map = g.alpha_map = g.normal_map = g.specular_map = g.reflect_map = g.refract_map = -1;
+    g.translucency = m->m_translucency; g.sample_env = m->m_sampleEnv ? 1u : 0u; g.disperse = m->m_disperse ? 1u : 0u; g.spec_gloss = 1.0f;
+    if (const Blinn* b = dynamic_cast<const Blinn*>(m)) {
+        g.kind = MIRO_GPU_MAT_BLINN;
+        g.kd[0] = b->m_kd.x; g.kd[1] = b->m_kd.y; g.kd[2] = b->m_kd.z; g.ka[0] = b->m_ka.x; g.ka[1] = b->m_ka.y; g.ka[2] = b->m_ka.z;
+        g.ks[0] = b->m_ks.x; g.ks[1] = b->m_ks.y; g.ks[2] = b->m_ks.z;
+        g.spec_exp = b->m_specExp; g.spec_amt = b->m_specAmt; g.emit_intensity = b->m_lightEmitted;
+        g.le[0] = b->m_Le.x; g.le[1] = b->m_Le.y; g.le[2] = b->m_Le.z;
+        g.reflect_amt = b->m_reflectAmt; g.refract_amt = b->m_refractAmt; g.spec_gloss = b->m_specGloss;
+        g.ior[0] = b->m_ior[0]; g.ior[1] = b->m_ior[1]; g.ior[2] = b->m_ior[2];
+    } else if (const Lambert* l = dynamic_cast<const Lambert*>(m)) {
+        g.kind = MIRO_GPU_MAT_LAMBERT;
+        g.kd[0] = l->m_kd.x; g.kd[1] = l->m_kd.y; g.kd[2] = l->m_kd.z; g.ka[0] = l->m_ka.x; g.ka[1] = l->m_ka.y; g.ka[2] = l->m_ka.z;
+    } else die("--render-gpu: unknown material class");
+    const uint32_t k = (uint32_t)f.materials.size(); f.materials.push_back(g); f.matOrdinal[m] = k;
+    return k;
+}
+void gpuAppendTriangle(const Object* o, GpuFlat& f) {
+    if (o->m_objectType != OBJECT) die("--render-gpu: motion-blur objects and proxies are outside this glue's scope");
+    TriangleMesh* m = o->m_mesh;
+    if (!f.meshBase.count(m)) {                  // the mesh's normals / uvs are appended once (counts: highest index used)
+        uint32_t maxn = 0, maxt = 0;
+        for (u_int i = 0; i < m->m_numTris; i++) {
+            maxn = std::max(maxn, std::max(m->m_normalIndices[i].x, std::max(m->m_normalIndices[i].y, m->m_normalIndices[i].z)));
+            if (m->m_texCoordIndices) maxt = std::max(maxt, std::max(m->m_texCoordIndices[i].x, std::max(m->m_texCoordIndices[i].y, m->m_texCoordIndices[i].z)));
+        }
+        f.meshBase[m] = std::make_pair((uint32_t)(f.normals.size() / 3), (uint32_t)(f.uvs.size() / 2));
+        for (uint32_t i = 0; i <= maxn; i++) { f.normals.push_back(m->m_normals[i].x); f.normals.push_back(m->m_normals[i].y); f.normals.push_back(m->m_normals[i].z); }
+        if (m->m_texCoordIndices) for (uint32_t i = 0; i <= maxt; i++) { f.uvs.push_back(m->m_texCoords[i].x); f.uvs.push_back(m->m_texCoords[i].y); }
+    }
+    const std::pair<uint32_t, uint32_t> base = f.meshBase[m];
+    const TriangleMesh::TupleI3 vi = m->m_vertexIndices[o->m_index], ni = m->m_normalIndices[o->m_index];
+    miro_gpu_tri t; memset(&t, 0, sizeof(t));
+    const Vector3 &a = m->m_vertices[vi.x], &b = m->m_vertices[vi.y], &c = m->m_vertices[vi.z];
+    t.v0[0] = a.x; t.v0[1] = a.y; t.v0[2] = a.z; t.v1[0] = b.x; t.v1[1] = b.y; t.v1[2] = b.z; t.v2[0] = c.x; t.v2[1] = c.y; t.v2[2] = c.z;
+    miro_gpu_prim p; memset(&p, 0, sizeof(p));
+    p.n[0] = base.first + ni.x; p.n[1] = base.first + ni.y; p.n[2] = base.first + ni.z;
+    if (m->m_texCoordIndices) { const TriangleMesh::TupleI3 ti = m->m_texCoordIndices[o->m_index]; p.uv[0] = base.second + ti.x; p.uv[1] = base.second + ti.y; p.uv[2] = base.second + ti.z; }
+    else p.uv[0] = p.uv[1] = p.uv[2] = 0xffffffffu;
+    p.material = gpuMaterial(o->m_material, f);
+    p.mesh = g_meshOrdinal.count(m) ? (uint32_t)g_meshOrdinal[m] : 0u; p.tri = o->m_index;
+    f.tris.push_back(t); f.prims.push_back(p);
+}
+int32_t gpuFlattenQ(const QBVH_Node* n, GpuFlat& f) {               // QBVH_Node, BVH.h:89-104 -> miro_gpu_node, 1:1
+    const int32_t me = (int32_t)f.nodes.size(); f.nodes.push_back(miro_gpu_node());
+    miro_gpu_node out; memset(&out, 0, sizeof(out));
+    memcpy(out.lo_x, n->bbMinX, 16); memcpy(out.lo_y, n->bbMinY, 16); memcpy(out.lo_z, n->bbMinZ, 16);
+    memcpy(out.hi_x, n->bbMaxX, 16); memcpy(out.hi_y, n->bbMaxY, 16); memcpy(out.hi_z, n->bbMaxZ, 16);
+    for (int i = 0; i < 4; i++) {
+        out.child[i] = MIRO_GPU_CHILD_EMPTY;
+        if (n->flagsIsLeaf[i]) {                                     // one TriCache4 packet (BVH.cpp:64-98): its lanes, contiguously
+            const BVH_Node::TriCache4* tc = n->triCaches[i];
+            const uint32_t first = (uint32_t)f.tris.size(); uint32_t count = 0;
+            for (int k = 0; k < 4; k++) if (tc->tris[k]) { gpuAppendTriangle(tc->tris[k], f); ++count; }
+            if (count) out.child[i] = MIRO_GPU_LEAF(MIRO_GPU_KIND_TRI, first, count);
+        } else if (n->flagsIsValid[i]) out.child[i] = gpuFlattenQ(n->Children[i], f);
+    }
+    f.nodes[me] = out;
+    return me;
+}
+double renderGPU(const std::string& out, const std::string& libPath) {
+    void* lib = dlopen(libPath.c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (!lib) die(std::string("--render-gpu: cannot load ") + libPath + ": " + dlerror());
+    // LIB is libmiro_gpu.so (the product).  For checking THIS GLUE where there is no GPU, LIB may also be the CPU oracle
+    // (oracle/_build/libmiro_oracle.so exports oracle_render(desc, camera, params, rgb, mask)): same description, same image path.
+    typedef uint64_t (*oracle_render_fn)(const miro_gpu_scene_desc*, const miro_gpu_camera*, const miro_gpu_render_params*, float*, const uint8_t*);
+    oracle_render_fn p_oracle_render = (oracle_render_fn)dlsym(lib, "oracle_render");
+    #define GPU_SYM(name) decltype(&name) p_##name = (decltype(&name))dlsym(lib, #name); if (!p_##name && !p_oracle_render) die("--render-gpu: symbol " #name " missing")
+    GPU_SYM(miro_gpu_create); GPU_SYM(miro_gpu_destroy); GPU_SYM(miro_gpu_last_error); GPU_SYM(miro_gpu_abi_version);
+    GPU_SYM(miro_gpu_upload_scene); GPU_SYM(miro_gpu_render); GPU_SYM(miro_gpu_get_counters);
+    #undef GPU_SYM
+    // ---- Scene::preCalc() has run (loadScene); flatten what it built
+    GpuFlat f;
+    const int32_t root = gpuFlattenQ(g_scene->m_bvh.m_baseQNode, f);
+    std::vector<miro_gpu_light> lights;
+    const Lights* ls = g_scene->lights();
+    for (size_t i = 0; i < ls->size(); i++) {
+        const Light* l = (*ls)[i];
+        miro_gpu_light g; memset(&g, 0, sizeof(g));
+        g.num_samples = l->m_numSamples; g.noise_threshold = l->m_noiseThreshold; g.cast_shadows = l->m_castShadows ? 1u : 0u;
+        g.full_shadows = l->m_fastShadows ? 0u : 1u; g.texture = -1; g.power = l->m_power;
+        if (const PointLight* pl = dynamic_cast<const PointLight*>(l)) {
+            g.kind = MIRO_GPU_LIGHT_POINT; g.p0[0] = pl->m_position.x; g.p0[1] = pl->m_position.y; g.p0[2] = pl->m_position.z;
+        } else if (const RectangleLight* rl = dynamic_cast<const RectangleLight*>(l)) {
+            g.kind = MIRO_GPU_LIGHT_RECT;           // m_power already carries setPower's 1 / area (RectangleLight.cpp:39)
+            g.p0[0] = rl->m_v1.x; g.p0[1] = rl->m_v1.y; g.p0[2] = rl->m_v1.z; g.p1[0] = rl->m_v2.x; g.p1[1] = rl->m_v2.y; g.p1[2] = rl->m_v2.z;
+            g.p2[0] = rl->m_v3.x; g.p2[1] = rl->m_v3.y; g.p2[2] = rl->m_v3.z;
+        } else die("--render-gpu: dome lights are outside this glue's scope");
+        lights.push_back(g);
+    }
+    if (g_scene->m_envMap) die("--render-gpu: environment maps are outside this glue's scope");
+    miro_gpu_scene_desc d; memset(&d, 0, sizeof(d));
+    d.abi_version = p_miro_gpu_abi_version ? (uint32_t)p_miro_gpu_abi_version() : (uint32_t)MIRO_GPU_ABI_VERSION;
+    d.nodes = f.nodes.data(); d.n_nodes = (uint32_t)f.nodes.size(); d.root = root;
+    d.tris = f.tris.data(); d.n_tris = (uint32_t)f.tris.size(); d.prims = f.prims.data();
+    d.normals = f.normals.data(); d.n_normals = (uint32_t)(f.normals.size() / 3);
+    d.uvs = f.uvs.empty() ? NULL : f.uvs.data(); d.n_uvs = (uint32_t)(f.uvs.size() / 2);
+    d.materials = f.materials.data(); d.n_materials = (uint32_t)f.materials.size();
+    d.lights = lights.empty() ? NULL : lights.data(); d.n_lights = (uint32_t)lights.size();
+    d.env_map = -1; d.env_exposure = g_scene->m_envExposure;
+    d.bg_color[0] = g_scene->m_BGColor.x; d.bg_color[1] = g_scene->m_BGColor.y; d.bg_color[2] = g_scene->m_BGColor.z;
+    miro_gpu_ctx* ctx = NULL;
+    if (!p_oracle_render) {
+        if (p_miro_gpu_create(&ctx, 0)) die(std::string("miro_gpu_create: ") + p_miro_gpu_last_error(NULL));
+        if (p_miro_gpu_upload_scene(ctx, &d)) die(std::string("miro_gpu_upload_scene: ") + p_miro_gpu_last_error(ctx));
+    }
+    // ---- Scene::raytraceImage(Camera*, Image*) (Scene.cpp:86-217)
+    Camera* cam = g_camera;
+    miro_gpu_camera c; memset(&c, 0, sizeof(c));
+    c.eye[0] = cam->eye().x; c.eye[1] = cam->eye().y; c.eye[2] = cam->eye().z;
+    c.view_dir[0] = cam->viewDir().x; c.view_dir[1] = cam->viewDir().y; c.view_dir[2] = cam->viewDir().z;
+    c.up[0] = cam->up().x; c.up[1] = cam->up().y; c.up[2] = cam->up().z;
+    c.fov_deg = cam->fov(); c.focus_plane = cam->focusPlane(); c.aperture = cam->aperture(); c.shutter_speed = cam->shutterSpeed();
+    miro_gpu_render_params rp; memset(&rp, 0, sizeof(rp));
+    rp.width = g_image->width(); rp.height = g_image->height();
+    rp.min_subdivs = g_scene->m_minSubdivs; rp.max_subdivs = g_scene->m_maxSubdivs; rp.noise_threshold = g_scene->m_noiseThreshold;
+    rp.num_paths = g_scene->m_numPaths; rp.max_bounces = g_scene->m_maxBounces; rp.path_trace = g_scene->m_pathTrace ? 1u : 0u;
+    rp.sample_env = g_scene->m_sampleLightFromEnv ? 1u : 0u; rp.seed = 3163513; rp.shard_index = 0; rp.shard_count = 1;
+    std::vector<float> rgb((size_t)rp.width * rp.height * 3);
+    const double t0 = omp_get_wtime();
+    unsigned long long rays = 0;
+    if (p_oracle_render) rays = p_oracle_render(&d, &c, &rp, rgb.data(), NULL);
+    else if (p_miro_gpu_render(ctx, &c, &rp, rgb.data())) die(std::string("miro_gpu_render: ") + p_miro_gpu_last_error(ctx));
+    const double t1 = omp_get_wtime();
+    for (int y = 0; y < rp.height; ++y) for (int x = 0; x < rp.width; ++x) {      // row 0 = bottom, as Image expects
+        const float* q = &rgb[((size_t)y * rp.width + x) * 3];
+        g_image->setPixel(x, y, Vector3(q[0], q[1], q[2]));                       // Image::Map: clamp + gamma LUT
+    }
+    if (ctx) { miro_gpu_counters ctr; memset(&ctr, 0, sizeof(ctr)); p_miro_gpu_get_counters(ctx, &ctr); rays = ctr.rays_closest + ctr.rays_any; }
+    fprintf(stderr, "{\"event\":\"render_gpu\",\"rays\":%llu,\"seconds\":%.6f,\"nodes\":%zu,\"tris\":%zu,\"materials\":%zu,\"lights\":%zu,\"width\":%d,\"height\":%d}\n",
+            rays, t1 - t0, f.nodes.size(), f.tris.size(), f.materials.size(), lights.size(), rp.width, rp.height);
+    if (!out.empty()) writeVec(out, rgb);
+    if (ctx) p_miro_gpu_destroy(ctx);
+    return t1 - t0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
-    std::string scene, dumpPrim, traceIn, traceOut, floatOut, ppmOut, meshDir, qbvhOut, texDir;
+    std::string scene, dumpPrim, traceIn, traceOut, floatOut, ppmOut, meshDir, qbvhOut, texDir, gpuOut, gpuLib, gpuPpm;
     int threads = 1, repeat = 1, warmup = 0; bool stock = false, doFloat = false;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -473,6 +627,9 @@ int main(int argc, char** argv) {
         else if (a == "--dump-meshes") meshDir = NEXT();
         else if (a == "--dump-qbvh") qbvhOut = NEXT();
         else if (a == "--dump-textures") texDir = NEXT();
+        else if (a == "--render-gpu") gpuOut = NEXT();
+        else if (a == "--gpu-lib") gpuLib = NEXT();
+        else if (a == "--gpu-ppm") gpuPpm = NEXT();
         else die("unknown argument " + a);
     }
     if (scene.empty()) die("usage: miro_ref --scene S.miro [--assets DIR] [--threads N] [--dump-primary F] [--trace RAYS --hits F] [--render-float F] [--render-stock F.ppm] [--dump-meshes DIR] [--dump-qbvh F]");
@@ -489,6 +646,11 @@ int main(int argc, char** argv) {
     if (!qbvhOut.empty()) dumpQBVH(qbvhOut);
     if (!texDir.empty()) dumpTextures(texDir);
     if (!dumpPrim.empty()) dumpPrimary(dumpPrim);
+    if (!gpuOut.empty()) {
+        if (gpuLib.empty()) die("--render-gpu needs --gpu-lib path/to/libmiro_gpu.so");
+        renderGPU(gpuOut, gpuLib);
+        if (!gpuPpm.empty()) g_image->writePPM((char*)gpuPpm.c_str());
+    }
     if (!traceIn.empty()) {
         resetTraceCalls();
         double s = traceRays(traceIn, traceOut, threads, repeat, warmup);

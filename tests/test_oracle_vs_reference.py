@@ -74,3 +74,29 @@ def test_oracle_on_the_references_own_tree_is_exact(name):
     assert st["hard"] == 0 and st["ties"] <= 8, st
     assert st["id_match"] >= 0.9997, st
     assert st["frac_t_within"] >= 0.9999, st
+
+
+def test_reference_binding_glue_through_the_oracle(tmp_path):
+    """The --render-gpu glue of oracle/ref_harness.cpp (the binding INTEGRATION.md describes: the reference's own objects,
+    materials, lights and QBVH flattened into a miro_gpu_scene_desc) checked without a GPU: pointed at the CPU oracle's
+    oracle_render instead of libmiro_gpu.so, the description it builds must render the reference's own image."""
+    import os, subprocess
+    exe = os.path.join(helpers.ROOT, "oracle", "_ref", "miro_ref")
+    if not os.path.exists(exe):
+        pytest.skip("reference binary not built (oracle/_ref)")
+    fx = helpers.Fixture(helpers.fixture_path("c1_cornell"))
+    sp = helpers.write_obj_scene(fx, str(tmp_path))
+    out = tmp_path / "glue.f32"
+    p = subprocess.run([exe, "--scene", sp, "--assets", str(tmp_path), "--render-gpu", str(out), "--gpu-lib", helpers.ORACLE_LIB],
+                       stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr
+    H, W = fx.radiance.shape[:2]
+    img = np.fromfile(out, np.float32).reshape(H, W, 3)
+    err = np.abs(img - fx.radiance).max(axis=2)
+    assert (err <= 2e-3 * np.maximum(fx.radiance.max(axis=2), 1e-3) + 1e-4).mean() > 0.998
+    # and the product refuses to pretend: without a CUDA device the same call through libmiro_gpu.so fails loudly
+    import torch
+    if not torch.cuda.is_available():
+        lib = os.path.join(helpers.ROOT, "rendering-algorithms-raytracer_b200", "libmiro_gpu.so")
+        q = subprocess.run([exe, "--scene", sp, "--assets", str(tmp_path), "--render-gpu", str(out), "--gpu-lib", lib], stderr=subprocess.PIPE, text=True)
+        assert q.returncode != 0 and "no CUDA device" in q.stderr

@@ -254,3 +254,30 @@ def test_headless_cli_writes_the_reference_ppm(tmp_path):
     img = np.frombuffer(raw[3], np.uint8).reshape(h, w, 3)[::-1]       # PPM rows are top-down
     d8 = np.abs(img.astype(int) - fx.image8.astype(int)).max(axis=2)
     assert (d8 <= 1).mean() > 0.998
+
+
+def test_reference_binding_renders_the_references_own_scene_on_the_gpu(tmp_path):
+    """INTEGRATION.md made real: the UNMODIFIED reference (oracle/_ref/miro_ref) loads the scene with its own loaders, builds its
+    own QBVH, and its --render-gpu glue flattens the reference's objects / materials / lights / tree into a
+    miro_gpu_scene_desc and calls libmiro_gpu.so (dlopen) for Scene::raytraceImage.  The float radiance must be the
+    reference's own CPU render (golden fixture), and the 8-bit image through the reference's Image::Map its stock render."""
+    import os, subprocess
+    exe = os.path.join(helpers.ROOT, "oracle", "_ref", "miro_ref")
+    lib = os.path.join(helpers.ROOT, "rendering-algorithms-raytracer_b200", "libmiro_gpu.so")
+    if not os.path.exists(exe):
+        pytest.skip("reference binary not built (oracle/_ref)")
+    fx = helpers.Fixture(helpers.fixture_path("c1_cornell"))
+    sp = helpers.write_obj_scene(fx, str(tmp_path))
+    out, ppm = tmp_path / "gpu.f32", tmp_path / "gpu.ppm"
+    p = subprocess.run([exe, "--scene", sp, "--assets", str(tmp_path), "--render-gpu", str(out), "--gpu-lib", lib, "--gpu-ppm", str(ppm)],
+                       stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr
+    assert '"event":"render_gpu"' in p.stderr
+    H, W = fx.radiance.shape[:2]
+    img = np.fromfile(out, np.float32).reshape(H, W, 3)
+    ok = pixel_agreement(img, fx.radiance)               # float16 fixture; the rest: crack / tie pixels of the reference
+    print("reference binding: gpu vs reference radiance agreement", ok.mean())
+    assert ok.mean() > 0.998
+    raw = open(ppm, "rb").read().split(b"\n", 3)
+    img8 = np.frombuffer(raw[3], np.uint8).reshape(H, W, 3)[::-1]
+    assert (np.abs(img8.astype(int) - fx.image8.astype(int)).max(axis=2) <= 1).mean() > 0.998
