@@ -457,23 +457,42 @@ void dumpQBVH(const std::string& path) {
 // --render-gpu FILE --gpu-lib LIB: the binding of INTEGRATION.md made real.  The reference's OWN scene — its Object list, its
 // materials and lights as the scene code set them up, and its OWN QBVH (BVH.cpp:100-389) — is flattened into a
 // miro_gpu_scene_desc, handed to libmiro_gpu.so (loaded with dlopen: this harness has no link-time dependency on CUDA) through
-// miro_gpu_upload_scene, and Scene::raytraceImage's float radiance comes back from miro_gpu_render.  Scope of this glue:
-// plain Objects (static triangles), Lambert / Blinn without texture maps, point and rectangle lights — what the c1 / c2 / c4 /
-// c6 / c8 / c10 scene scripts use; anything else stops with a message.
+// miro_gpu_upload_scene, and Scene::raytraceImage's float radiance comes back from miro_gpu_render.  Covers what the reference's
+// scene code can build: Objects, MBObjects, ProxyObjects (one level, shared bottom-level trees), Lambert / Blinn with their
+// texture maps, point / rectangle / dome lights, the environment map.
 struct GpuFlat {
-    std::vector<miro_gpu_node> nodes; std::vector<miro_gpu_tri> tris; std::vector<miro_gpu_prim> prims;
-    std::vector<float> normals, uvs;
+    std::vector<miro_gpu_node> nodes; std::vector<miro_gpu_tri> tris; std::vector<miro_gpu_mbtri> mb; std::vector<miro_gpu_instance> inst;
+    std::vector<miro_gpu_prim> prims, mbprims;
+    std::vector<float> normals, tangents, bitangents, uvs, nxf;
+    bool anyTangents;
     std::map<TriangleMesh*, std::pair<uint32_t, uint32_t> > meshBase;      // first normal / first uv of a mesh
     std::vector<miro_gpu_material> materials; std::map<const Material*, uint32_t> matOrdinal;
+    std::vector<miro_gpu_texture> textures; std::map<const Texture*, int32_t> texOrdinal;
+    std::map<const BVH*, int32_t> blasRoot;
+    GpuFlat() : anyTangents(false) {}
 };
+int32_t gpuFlattenQ(const QBVH_Node* n, GpuFlat& f);
+int32_t gpuTexture(const Texture* t, GpuFlat& f) {              // RawImage::m_rawData: float texels, row-major (borrowed, not copied)
+    if (!t) return -1;
+    if (f.texOrdinal.count(t)) return f.texOrdinal[t];
+    const RawImage* im = t->m_image;
+    miro_gpu_texture g; memset(&g, 0, sizeof(g));
+    g.texels = im->m_rawData; g.width = im->m_width; g.height = im->m_height;
+    g.channels = im->m_imageType == GRAYSCALE ? 1 : (im->m_imageType == RGBA ? 4 : 3);
+    const int32_t k = (int32_t)f.textures.size(); f.textures.push_back(g); f.texOrdinal[t] = k;
+    return k;
+}
 uint32_t gpuMaterial(const Material* m, GpuFlat& f) {
     if (f.matOrdinal.count(m)) return f.matOrdinal[m];
-    if (m->m_colorMap || m->m_alphaMap || m->m_normalMap || m->m_specularMap || m->m_reflectMap || m->m_refractMap) die("--render-gpu: texture maps are outside this glue's scope");
     miro_gpu_material g; memset(&g, 0, sizeof(g));
-    g.color_map = g.alpha_map = g.normal_map = g.specular_map = g.reflect_map = g.refract_map = -1;
+    g.color_map = gpuTexture(m->m_colorMap, f); g.alpha_map = gpuTexture(m->m_alphaMap, f);
+    g.normal_map = g.specular_map = g.reflect_map = g.refract_map = -1;
     g.translucency = m->m_translucency; g.sample_env = m->m_sampleEnv ? 1u : 0u; g.disperse = m->m_disperse ? 1u : 0u; g.spec_gloss = 1.0f;
+    g.refract_amt = m->m_refractAmt;                              // Material's member: the full shadow method reads it of any material
     if (const Blinn* b = dynamic_cast<const Blinn*>(m)) {
         g.kind = MIRO_GPU_MAT_BLINN;
+        g.normal_map = gpuTexture(m->m_normalMap, f); g.specular_map = gpuTexture(m->m_specularMap, f);
+        g.reflect_map = gpuTexture(m->m_reflectMap, f); g.refract_map = gpuTexture(m->m_refractMap, f);
         g.kd[0] = b->m_kd.x; g.kd[1] = b->m_kd.y; g.kd[2] = b->m_kd.z; g.ka[0] = b->m_ka.x; g.ka[1] = b->m_ka.y; g.ka[2] = b->m_ka.z;
         g.ks[0] = b->m_ks.x; g.ks[1] = b->m_ks.y; g.ks[2] = b->m_ks.z;
         g.spec_exp = b->m_specExp; g.spec_amt = b->m_specAmt; g.emit_intensity = b->m_lightEmitted;
@@ -481,38 +500,67 @@ uint32_t gpuMaterial(const Material* m, GpuFlat& f) {
         g.reflect_amt = b->m_reflectAmt; g.refract_amt = b->m_refractAmt; g.spec_gloss = b->m_specGloss;
         g.ior[0] = b->m_ior[0]; g.ior[1] = b->m_ior[1]; g.ior[2] = b->m_ior[2];
     } else if (const Lambert* l = dynamic_cast<const Lambert*>(m)) {
-        g.kind = MIRO_GPU_MAT_LAMBERT;
+        g.kind = MIRO_GPU_MAT_LAMBERT;                             // Lambert::shade reads the colour map only (Lambert.cpp:19-53)
+        g.refract_amt = 0.f;                                       // (the reference leaves Material::m_refractAmt of a Lambert uninitialised)
         g.kd[0] = l->m_kd.x; g.kd[1] = l->m_kd.y; g.kd[2] = l->m_kd.z; g.ka[0] = l->m_ka.x; g.ka[1] = l->m_ka.y; g.ka[2] = l->m_ka.z;
     } else die("--render-gpu: unknown material class");
     const uint32_t k = (uint32_t)f.materials.size(); f.materials.push_back(g); f.matOrdinal[m] = k;
     return k;
 }
-void gpuAppendTriangle(const Object* o, GpuFlat& f) {
-    if (o->m_objectType != OBJECT) die("--render-gpu: motion-blur objects and proxies are outside this glue's scope");
+miro_gpu_tri gpuTri(const TriangleMesh* m, u_int i) {
+    const TriangleMesh::TupleI3 vi = m->m_vertexIndices[i];
+    miro_gpu_tri t; memset(&t, 0, sizeof(t));
+    const Vector3 &a = m->m_vertices[vi.x], &b = m->m_vertices[vi.y], &c = m->m_vertices[vi.z];
+    t.v0[0] = a.x; t.v0[1] = a.y; t.v0[2] = a.z; t.v1[0] = b.x; t.v1[1] = b.y; t.v1[2] = b.z; t.v2[0] = c.x; t.v2[1] = c.y; t.v2[2] = c.z;
+    return t;
+}
+// One Object of the reference -> its place in the description (INTEGRATION.md's appendPrimitive).
+void gpuAppendPrimitive(const Object* o, GpuFlat& f) {
+    if (o->m_objectType == PROXY_OBJECT) {
+        const ProxyObject* p = static_cast<const ProxyObject*>(o);
+        if (!f.blasRoot.count(p->m_BVH)) f.blasRoot[p->m_BVH] = gpuFlattenQ(p->m_BVH->m_baseQNode, f);      // the shared bottom-level tree, once
+        const ProxyMatrix& M = p->getMatrix();
+        miro_gpu_instance in; memset(&in, 0, sizeof(in));
+        const Matrix4x4& I = M.m_inverse; const Matrix4x4& T = M.m_invTranspose;
+        const float inv[12] = {I.m11, I.m12, I.m13, I.m14, I.m21, I.m22, I.m23, I.m24, I.m31, I.m32, I.m33, I.m34};
+        memcpy(in.inv, inv, sizeof(inv)); in.blas_root = f.blasRoot[p->m_BVH];
+        const float nx[9] = {T.m11, T.m12, T.m13, T.m21, T.m22, T.m23, T.m31, T.m32, T.m33};
+        f.nxf.insert(f.nxf.end(), nx, nx + 9);
+        f.inst.push_back(in);
+        return;
+    }
     TriangleMesh* m = o->m_mesh;
-    if (!f.meshBase.count(m)) {                  // the mesh's normals / uvs are appended once (counts: highest index used)
+    if (!f.meshBase.count(m)) {                  // the mesh's normals (tangents, bitangents) / uvs are appended once (counts: highest index used)
         uint32_t maxn = 0, maxt = 0;
         for (u_int i = 0; i < m->m_numTris; i++) {
             maxn = std::max(maxn, std::max(m->m_normalIndices[i].x, std::max(m->m_normalIndices[i].y, m->m_normalIndices[i].z)));
             if (m->m_texCoordIndices) maxt = std::max(maxt, std::max(m->m_texCoordIndices[i].x, std::max(m->m_texCoordIndices[i].y, m->m_texCoordIndices[i].z)));
         }
         f.meshBase[m] = std::make_pair((uint32_t)(f.normals.size() / 3), (uint32_t)(f.uvs.size() / 2));
-        for (uint32_t i = 0; i <= maxn; i++) { f.normals.push_back(m->m_normals[i].x); f.normals.push_back(m->m_normals[i].y); f.normals.push_back(m->m_normals[i].z); }
+        const bool tb = m->m_texCoordIndices && m->m_tangents && m->m_biTangents;      // TriangleMesh::preCalc fills them for meshes with uvs
+        if (tb) f.anyTangents = true;
+        for (uint32_t i = 0; i <= maxn; i++) {
+            f.normals.push_back(m->m_normals[i].x); f.normals.push_back(m->m_normals[i].y); f.normals.push_back(m->m_normals[i].z);
+            f.tangents.push_back(tb ? m->m_tangents[i].x : 0.f); f.tangents.push_back(tb ? m->m_tangents[i].y : 0.f); f.tangents.push_back(tb ? m->m_tangents[i].z : 0.f);
+            f.bitangents.push_back(tb ? m->m_biTangents[i].x : 0.f); f.bitangents.push_back(tb ? m->m_biTangents[i].y : 0.f); f.bitangents.push_back(tb ? m->m_biTangents[i].z : 0.f);
+        }
         if (m->m_texCoordIndices) for (uint32_t i = 0; i <= maxt; i++) { f.uvs.push_back(m->m_texCoords[i].x); f.uvs.push_back(m->m_texCoords[i].y); }
     }
     const std::pair<uint32_t, uint32_t> base = f.meshBase[m];
-    const TriangleMesh::TupleI3 vi = m->m_vertexIndices[o->m_index], ni = m->m_normalIndices[o->m_index];
-    miro_gpu_tri t; memset(&t, 0, sizeof(t));
-    const Vector3 &a = m->m_vertices[vi.x], &b = m->m_vertices[vi.y], &c = m->m_vertices[vi.z];
-    t.v0[0] = a.x; t.v0[1] = a.y; t.v0[2] = a.z; t.v1[0] = b.x; t.v1[1] = b.y; t.v1[2] = b.z; t.v2[0] = c.x; t.v2[1] = c.y; t.v2[2] = c.z;
+    const TriangleMesh::TupleI3 ni = m->m_normalIndices[o->m_index];
     miro_gpu_prim p; memset(&p, 0, sizeof(p));
     p.n[0] = base.first + ni.x; p.n[1] = base.first + ni.y; p.n[2] = base.first + ni.z;
     if (m->m_texCoordIndices) { const TriangleMesh::TupleI3 ti = m->m_texCoordIndices[o->m_index]; p.uv[0] = base.second + ti.x; p.uv[1] = base.second + ti.y; p.uv[2] = base.second + ti.z; }
     else p.uv[0] = p.uv[1] = p.uv[2] = 0xffffffffu;
     p.material = gpuMaterial(o->m_material, f);
     p.mesh = g_meshOrdinal.count(m) ? (uint32_t)g_meshOrdinal[m] : 0u; p.tri = o->m_index;
-    f.tris.push_back(t); f.prims.push_back(p);
+    if (o->m_objectType == MB_OBJECT) {          // both poses; shading attributes come from the first mesh (Ray.cpp:12-25)
+        const MBObject* mbo = static_cast<const MBObject*>(o);
+        miro_gpu_mbtri t; t.pose[0] = gpuTri(m, o->m_index); t.pose[1] = gpuTri(mbo->m_mesh_t2, o->m_index);
+        f.mb.push_back(t); f.mbprims.push_back(p);
+    } else { f.tris.push_back(gpuTri(m, o->m_index)); f.prims.push_back(p); }
 }
+uint32_t gpuKind(const Object* o) { return o->m_objectType == MB_OBJECT ? MIRO_GPU_KIND_MBTRI : (o->m_objectType == PROXY_OBJECT ? MIRO_GPU_KIND_INST : MIRO_GPU_KIND_TRI); }
 int32_t gpuFlattenQ(const QBVH_Node* n, GpuFlat& f) {               // QBVH_Node, BVH.h:89-104 -> miro_gpu_node, 1:1
     const int32_t me = (int32_t)f.nodes.size(); f.nodes.push_back(miro_gpu_node());
     miro_gpu_node out; memset(&out, 0, sizeof(out));
@@ -520,11 +568,28 @@ int32_t gpuFlattenQ(const QBVH_Node* n, GpuFlat& f) {               // QBVH_Node
     memcpy(out.hi_x, n->bbMaxX, 16); memcpy(out.hi_y, n->bbMaxY, 16); memcpy(out.hi_z, n->bbMaxZ, 16);
     for (int i = 0; i < 4; i++) {
         out.child[i] = MIRO_GPU_CHILD_EMPTY;
-        if (n->flagsIsLeaf[i]) {                                     // one TriCache4 packet (BVH.cpp:64-98): its lanes, contiguously
+        if (n->flagsIsLeaf[i]) {
+            // One TriCache4 packet (BVH.cpp:64-98).  Its lanes may mix Objects, MBObjects and ProxyObjects; a leaf of the ABI holds one
+            // kind, so a mixed packet becomes a small node of homogeneous leaves that all carry the packet's box.
             const BVH_Node::TriCache4* tc = n->triCaches[i];
-            const uint32_t first = (uint32_t)f.tris.size(); uint32_t count = 0;
-            for (int k = 0; k < 4; k++) if (tc->tris[k]) { gpuAppendTriangle(tc->tris[k], f); ++count; }
-            if (count) out.child[i] = MIRO_GPU_LEAF(MIRO_GPU_KIND_TRI, first, count);
+            int32_t refs[3]; int nrefs = 0;
+            for (uint32_t kind = 0; kind < 3; kind++) {
+                const uint32_t first = kind == MIRO_GPU_KIND_TRI ? (uint32_t)f.tris.size() : kind == MIRO_GPU_KIND_MBTRI ? (uint32_t)f.mb.size() : (uint32_t)f.inst.size();
+                uint32_t count = 0;
+                for (int k = 0; k < 4; k++) if (tc->tris[k] && gpuKind(tc->tris[k]) == kind) { gpuAppendPrimitive(tc->tris[k], f); ++count; }
+                if (count) refs[nrefs++] = MIRO_GPU_LEAF(kind, first, count);
+            }
+            if (nrefs == 1) out.child[i] = refs[0];
+            else if (nrefs > 1) {
+                const int32_t mid = (int32_t)f.nodes.size(); f.nodes.push_back(miro_gpu_node());
+                miro_gpu_node m; memset(&m, 0, sizeof(m));
+                for (int k = 0; k < 4; k++) {
+                    m.child[k] = k < nrefs ? refs[k] : MIRO_GPU_CHILD_EMPTY;
+                    m.lo_x[k] = n->bbMinX[i]; m.lo_y[k] = n->bbMinY[i]; m.lo_z[k] = n->bbMinZ[i];
+                    m.hi_x[k] = n->bbMaxX[i]; m.hi_y[k] = n->bbMaxY[i]; m.hi_z[k] = n->bbMaxZ[i];
+                }
+                f.nodes[mid] = m; out.child[i] = mid;
+            }
         } else if (n->flagsIsValid[i]) out.child[i] = gpuFlattenQ(n->Children[i], f);
     }
     f.nodes[me] = out;
@@ -557,19 +622,26 @@ double renderGPU(const std::string& out, const std::string& libPath) {
             g.kind = MIRO_GPU_LIGHT_RECT;           // m_power already carries setPower's 1 / area (RectangleLight.cpp:39)
             g.p0[0] = rl->m_v1.x; g.p0[1] = rl->m_v1.y; g.p0[2] = rl->m_v1.z; g.p1[0] = rl->m_v2.x; g.p1[1] = rl->m_v2.y; g.p1[2] = rl->m_v2.z;
             g.p2[0] = rl->m_v3.x; g.p2[1] = rl->m_v3.y; g.p2[2] = rl->m_v3.z;
-        } else die("--render-gpu: dome lights are outside this glue's scope");
+        } else if (const DomeLight* dl = dynamic_cast<const DomeLight*>(l)) {
+            g.kind = MIRO_GPU_LIGHT_DOME; g.power = dl->m_Gain; g.texture = gpuTexture(dl->m_lightMap, f); g.cast_shadows = 1u;
+        } else die("--render-gpu: unknown light class");
         lights.push_back(g);
     }
-    if (g_scene->m_envMap) die("--render-gpu: environment maps are outside this glue's scope");
     miro_gpu_scene_desc d; memset(&d, 0, sizeof(d));
     d.abi_version = p_miro_gpu_abi_version ? (uint32_t)p_miro_gpu_abi_version() : (uint32_t)MIRO_GPU_ABI_VERSION;
     d.nodes = f.nodes.data(); d.n_nodes = (uint32_t)f.nodes.size(); d.root = root;
-    d.tris = f.tris.data(); d.n_tris = (uint32_t)f.tris.size(); d.prims = f.prims.data();
+    f.prims.insert(f.prims.end(), f.mbprims.begin(), f.mbprims.end());      // prims[n_tris ..) describe the motion-blur triangles
+    d.tris = f.tris.empty() ? NULL : f.tris.data(); d.n_tris = (uint32_t)f.tris.size(); d.prims = f.prims.data();
+    d.mbtris = f.mb.empty() ? NULL : f.mb.data(); d.n_mbtris = (uint32_t)f.mb.size();
+    d.instances = f.inst.empty() ? NULL : f.inst.data(); d.n_instances = (uint32_t)f.inst.size();
+    d.inst_normal_xform = f.nxf.empty() ? NULL : f.nxf.data();
+    d.tangents = f.anyTangents ? f.tangents.data() : NULL; d.bitangents = f.anyTangents ? f.bitangents.data() : NULL;
     d.normals = f.normals.data(); d.n_normals = (uint32_t)(f.normals.size() / 3);
     d.uvs = f.uvs.empty() ? NULL : f.uvs.data(); d.n_uvs = (uint32_t)(f.uvs.size() / 2);
     d.materials = f.materials.data(); d.n_materials = (uint32_t)f.materials.size();
     d.lights = lights.empty() ? NULL : lights.data(); d.n_lights = (uint32_t)lights.size();
-    d.env_map = -1; d.env_exposure = g_scene->m_envExposure;
+    d.env_map = gpuTexture(g_scene->m_envMap, f); d.env_exposure = g_scene->m_envExposure;
+    d.textures = f.textures.empty() ? NULL : f.textures.data(); d.n_textures = (uint32_t)f.textures.size();
     d.bg_color[0] = g_scene->m_BGColor.x; d.bg_color[1] = g_scene->m_BGColor.y; d.bg_color[2] = g_scene->m_BGColor.z;
     miro_gpu_ctx* ctx = NULL;
     if (!p_oracle_render) {

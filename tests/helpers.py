@@ -158,21 +158,37 @@ def oracle_render(scene, params=None, camera=None, mask=None):
 
 
 def write_obj_scene(fx, tmp):
-    """Materialise the fixture's geometry as OBJ + script so the reference binary can load it with its own loader."""
+    """Materialise the fixture's geometry as OBJ + script so the reference binary can load it with its own loader (positions,
+    and normals / texture coordinates with their own index triples where the mesh has them)."""
     script = fx.script
     for k, name in enumerate(fx.names):
         m = fx.mesh(k)
         path = os.path.join(tmp, name + ".obj")
+        has_n = len(m["normals"]) > 0 and not np.array_equal(m["nidx"], np.arange(3 * len(m["vidx"]), dtype=np.uint32).reshape(-1, 3))
+        has_t = m["uvs"] is not None
         with open(path, "w") as f:
             for v in m["vertices"]:
                 f.write("v %.9g %.9g %.9g\n" % tuple(v))
-            for t in m["vidx"]:
-                f.write("f %d %d %d\n" % (t[0] + 1, t[1] + 1, t[2] + 1))
+            if has_t:
+                for t in m["uvs"]:
+                    f.write("vt %.9g %.9g\n" % tuple(t))
+            if has_n:
+                for n in m["normals"]:
+                    f.write("vn %.9g %.9g %.9g\n" % tuple(n))
+            for i, t in enumerate(m["vidx"]):
+                if has_n and has_t:
+                    f.write("f %d/%d/%d %d/%d/%d %d/%d/%d\n" % tuple(x for j in range(3) for x in (t[j] + 1, m["tidx"][i][j] + 1, m["nidx"][i][j] + 1)))
+                elif has_n:
+                    f.write("f %d//%d %d//%d %d//%d\n" % tuple(x for j in range(3) for x in (t[j] + 1, m["nidx"][i][j] + 1)))
+                elif has_t:
+                    f.write("f %d/%d %d/%d %d/%d\n" % tuple(x for j in range(3) for x in (t[j] + 1, m["tidx"][i][j] + 1)))
+                else:
+                    f.write("f %d %d %d\n" % (t[0] + 1, t[1] + 1, t[2] + 1))
         lines = []
         for line in script.splitlines():
             tok = line.split()
             if len(tok) >= 3 and tok[0] == "mesh" and tok[1] == name:
-                line = "mesh %s %s" % (name, path)
+                line = "mesh %s %s" % (name, path) + ("" if len(tok) == 3 else " " + " ".join(tok[3:]))
             lines.append(line)
         script = "\n".join(lines) + "\n"
     sp = os.path.join(tmp, "scene.miro")

@@ -100,3 +100,29 @@ def test_reference_binding_glue_through_the_oracle(tmp_path):
         lib = os.path.join(helpers.ROOT, "rendering-algorithms-raytracer_b200", "libmiro_gpu.so")
         q = subprocess.run([exe, "--scene", sp, "--assets", str(tmp_path), "--render-gpu", str(out), "--gpu-lib", lib], stderr=subprocess.PIPE, text=True)
         assert q.returncode != 0 and "no CUDA device" in q.stderr
+
+
+@pytest.mark.parametrize("scene,block_tol", [("c5_mb_instances", 0.01), ("c7_foliage", 0.004), ("c9_texmaps", 0.03)])
+def test_reference_binding_glue_covers_the_reference_object_model(scene, block_tol, tmp_path):
+    """The same glue on scenes with MBObjects + ProxyObjects (shared bottom-level trees, mixed TriCache4 packets), alpha-mapped
+    foliage, and normal / specular / reflect / refract maps with the tangent frame: the description built from the reference's
+    own objects, rendered by the CPU oracle, against the reference's own render of the same process (same Scene::trace count,
+    same image up to the random numbers).  Needs the reference's asset tree (this container only)."""
+    import json, os, subprocess
+    exe = os.path.join(helpers.ROOT, "oracle", "_ref", "miro_ref")
+    assets = os.environ.get("MIRO_REFERENCE_ROOT", "/root/reference")
+    if not os.path.exists(exe) or not os.path.isdir(os.path.join(assets, "Models")):
+        pytest.skip("reference binary or asset tree not present")
+    script = os.path.join(helpers.ROOT, "tests", "scenes", scene + ".miro")
+    glue, ref = tmp_path / "glue.f32", tmp_path / "ref.f32"
+    p = subprocess.run([exe, "--scene", script, "--assets", assets, "--render-gpu", str(glue), "--gpu-lib", helpers.ORACLE_LIB, "--render-float", str(ref)],
+                       stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr
+    ev = {e["event"]: e for e in (json.loads(l) for l in p.stderr.splitlines() if l.startswith("{"))}
+    assert abs(ev["render_gpu"]["rays"] - ev["render_float"]["rays"]) <= 2e-3 * ev["render_float"]["rays"]
+    W, H = ev["render_float"]["width"], ev["render_float"]["height"]
+    a = np.fromfile(glue, np.float32).reshape(H, W, 3); b = np.fromfile(ref, np.float32).reshape(H, W, 3)
+    blk = lambda x: np.minimum(x, 4).reshape(32, H // 32, 32, W // 32, 3).mean(axis=(1, 3))
+    print(scene, "means", a.mean(), b.mean(), "block diff", np.abs(blk(a) - blk(b)).mean())
+    assert abs(np.minimum(a, 4).mean() - np.minimum(b, 4).mean()) <= 0.01 * np.minimum(b, 4).mean()
+    assert np.abs(blk(a) - blk(b)).mean() < block_tol

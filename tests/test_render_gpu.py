@@ -281,3 +281,30 @@ def test_reference_binding_renders_the_references_own_scene_on_the_gpu(tmp_path)
     raw = open(ppm, "rb").read().split(b"\n", 3)
     img8 = np.frombuffer(raw[3], np.uint8).reshape(H, W, 3)[::-1]
     assert (np.abs(img8.astype(int) - fx.image8.astype(int)).max(axis=2) <= 1).mean() > 0.998
+
+
+def test_reference_binding_renders_motion_blur_and_instances_on_the_gpu(tmp_path):
+    """The same binding on c5: MBObjects and 961 ProxyObjects sharing one bottom-level tree, mixed TriCache4 packets — the
+    reference's own object model flattened by the glue, rendered by libmiro_gpu.so; compared with the reference's CPU render as
+    in test_oracle_render.py (the jittered camera samples draw different random numbers)."""
+    import json, os, subprocess
+    exe = os.path.join(helpers.ROOT, "oracle", "_ref", "miro_ref")
+    lib = os.path.join(helpers.ROOT, "rendering-algorithms-raytracer_b200", "libmiro_gpu.so")
+    if not os.path.exists(exe):
+        pytest.skip("reference binary not built (oracle/_ref)")
+    fx = helpers.Fixture(helpers.fixture_path("c5_mb_instances"))
+    sp = helpers.write_obj_scene(fx, str(tmp_path))
+    out = tmp_path / "gpu.f32"
+    p = subprocess.run([exe, "--scene", sp, "--assets", str(tmp_path), "--render-gpu", str(out), "--gpu-lib", lib], stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr
+    ev = [json.loads(l) for l in p.stderr.splitlines() if l.startswith("{")]
+    ref_rays = [e for e in json.loads(fx.events) if e["event"] == "render_float"][0]["rays"]
+    gpu = [e for e in ev if e["event"] == "render_gpu"][0]
+    assert abs(gpu["rays"] - ref_rays) <= 0.01 * ref_rays
+    H, W = fx.radiance.shape[:2]
+    img = np.fromfile(out, np.float32).reshape(H, W, 3)
+    ref = fx.radiance
+    blk = lambda a: a.reshape(32, 8, 32, 8, 3).mean(axis=(1, 3))
+    print("reference binding c5: means", img.mean(), ref.mean(), "block diff", np.abs(blk(img) - blk(ref)).mean())
+    assert abs(img.mean() - ref.mean()) <= 0.02 * ref.mean()
+    assert np.abs(blk(img) - blk(ref)).mean() < 0.01
