@@ -101,6 +101,28 @@ def test_full_shadow_method_under_a_dome_light_matches_oracle():
     fast.close(); full.close()
 
 
+def test_full_shadow_method_through_alpha_cutouts_matches_oracle():
+    """The shadow walk (k_walk_shadows, one thread per ray) in a scene WITH alpha maps — its traversal evaluates the cut-outs like
+    the persistent-warp kernels — through half-transparent leaves (refract 0.4), rectangle light with two samples per loop."""
+    fx = helpers.Fixture(helpers.fixture_path("c7_foliage"))
+    script = fx.script.replace("light point pos 15 60 -40 power 60000", "light rect v1 10 60 -40 v2 20 60 -40 v3 10 60 -30 power 60000 samples 2 fastshadows 0")
+    script = script.replace("translucency 0.6 colormap", "translucency 0.6 refract 0.4 reflect 0 colormap")
+    assert script != fx.script
+    sc = fx.scene(script_override=script).attach(0)
+    fast = fx.scene(script_override=script.replace(" fastshadows 0", "")).attach(0)
+    img, img_fast = sc.render(), fast.render()
+    oimg, orays = helpers.oracle_render(sc)
+    ok = pixel_agreement(img, oimg, rel=5e-3, ab=1e-3)
+    print("full shadows through alpha cut-outs: agreement", ok.mean(), "means", img.mean(), oimg.mean(), "any-hit method", img_fast.mean())
+    assert np.isfinite(img).all() and ok.mean() > 0.97
+    assert abs(img.mean() - oimg.mean()) <= 0.01 * oimg.mean()
+    c, cf = sc.counters(), fast.counters()
+    assert abs(int(c["rays_closest"] + c["rays_any"]) - orays) <= 5e-3 * orays
+    assert int(c["rays_closest"] + c["rays_any"]) > 1.05 * int(cf["rays_closest"] + cf["rays_any"])      # the walk re-traces from every hit
+    assert img.mean() > img_fast.mean()                  # and some light passes the leaves
+    sc.close(); fast.close()
+
+
 def test_sharded_render_equals_whole():
     """Buckets b % shard_count == shard_index; the union of the shards is the whole image (RNG keyed by pixel)."""
     fx, sc = load("c4_cornell_pt")
