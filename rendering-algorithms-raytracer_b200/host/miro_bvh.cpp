@@ -6,6 +6,7 @@
 #include <float.h>
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <future>
 #include <numeric>
 #include <thread>
@@ -359,9 +360,14 @@ int32_t build_wide_bvh(const std::vector<BuildPrim>& prims, std::vector<miro_gpu
         for (int k = 0; k < 3; ++k) { refs[i].box.lo[k] = prims[i].lo[k]; refs[i].box.hi[k] = prims[i].hi[k]; }
     }
     size_t budget = b.extra_budget;
+    static const bool timing = getenv("MIRO_HOST_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     const int32_t root = b.build(refs, 0, budget);
+    const auto t1 = std::chrono::steady_clock::now();
     Collapser c{b, nodes, order, BvhStats()};
     const int32_t ref = c.emit(root, 0);
+    if (timing) fprintf(stderr, "[miro_host] build_wide_bvh %zu prims: binary build %.1f ms, collapse %.1f ms\n", prims.size(),
+                        std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
     c.st.references = b.leaf_next.load();
     if (stats) *stats = c.st;
     return ref;
