@@ -165,7 +165,7 @@ struct Builder {
         if (!have_split) {
             const float parent_area = std::max(box.area(), 1e-30f);
             // ---- object split: binned SAH over the three axes
-            float best_cost = FLT_MAX; int best_axis = -1, best_bin = -1;
+            float best_cost = FLT_MAX; int best_axis = -1, best_bin = -1; uint32_t best_nl = 0, best_nr = 0;
             Box best_lbox, best_rbox; best_lbox.reset(); best_rbox.reset();
             for (int axis = 0; axis < 3; ++axis) {
                 const float lo = cbox.lo[axis], ext = cbox.hi[axis] - cbox.lo[axis];
@@ -186,7 +186,7 @@ struct Builder {
                     acc.grow(bb[b]); cnt += bc[b];
                     if (cnt == 0 || right_cnt[b + 1] == 0) continue;
                     const float cost = kTraversalCost + kPrimCost * (acc.area() * cnt + right_box[b + 1].area() * right_cnt[b + 1]) / parent_area;
-                    if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; best_lbox = acc; best_rbox = right_box[b + 1]; }
+                    if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; best_lbox = acc; best_rbox = right_box[b + 1]; best_nl = cnt; best_nr = right_cnt[b + 1]; }
                 }
             }
             // ---- spatial split: only where the object split's children overlap noticeably (relative to the ROOT's area)
@@ -246,6 +246,7 @@ struct Builder {
             }
             if (!have_split && best_axis >= 0 && depth < 40) {   // beyond 40 levels fall through to balanced median splits
                 const float lo = cbox.lo[best_axis], scale = kBins / (cbox.hi[best_axis] - cbox.lo[best_axis]);
+                left.reserve(best_nl); right.reserve(best_nr);      // the winning bin boundary's counts: no regrowth while partitioning
                 for (const Ref& r : refs) {
                     int b = (int)((centroid(r, best_axis) - lo) * scale);
                     b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
