@@ -384,10 +384,13 @@ def main():
     if rank == 0:
         dom = int(np.argmax(launch_ms))
         kernel_names = ["k_trace<closest> primary", "k_trace<closest> incoherent", "k_trace<any> shadow"]
-        traffic = None
+        traffic = l2_bytes = l1_bytes = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):      # dram__bytes_read+write per launch from the committed ncu --set full capture
-            traffic = json.load(open(tp)).get("per_launch_dram_bytes", {}).get(kernel_names[dom])
+        if os.path.exists(tp):      # per launch, from the committed ncu --set full capture: DRAM read+write, L2 sectors, L1 global-load sectors
+            tj = json.load(open(tp))
+            traffic = tj.get("per_launch_dram_bytes", {}).get(kernel_names[dom])
+            l2_bytes = tj.get("per_launch_l2_bytes", {}).get(kernel_names[dom])
+            l1_bytes = tj.get("per_launch_l1_global_load_bytes", {}).get(kernel_names[dom])
         achieved = per_launch[dom]["bytes"] / (launch_ms[dom] * 1e-3) * 1e-9
         line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -401,7 +404,8 @@ def main():
                                "ray_format": "miro_gpu_ray32, 32 B (static scenes: no time / flags words); identical hits asserted"},
                 "roofline": {"bound": "hbm", "kernel": kernel_names[dom],
                              "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": peak_src,
-                             "traffic": traffic, "algorithmic_bytes_per_launch": per_launch[dom]["bytes"],
+                             "traffic": traffic, "l2_traffic": l2_bytes, "l1_global_load_traffic": l1_bytes,
+                             "algorithmic_bytes_per_launch": per_launch[dom]["bytes"],
                              "nodes_per_ray": per_launch[dom]["nodes"] / N_BATCH, "tris_per_ray": per_launch[dom]["tris"] / N_BATCH,
                              "launch_ms": launch_ms[dom], "share_of_step": launch_ms[dom] / sum(launch_ms),
                              "all_launches": [{"kernel": kernel_names[i], "ms": launch_ms[i], "Mrays_per_s": N_BATCH / launch_ms[i] * 1e-3,
