@@ -116,7 +116,7 @@ def trace_events(root, bounds, child, tris, rays, max_events=256):
     return events, ne, best
 
 
-def simulate(events, ne, pool=32, refill=8, rays_per_warp=4096, bias=(1, 1), width=32):
+def simulate(events, ne, pool=32, refill=8, rays_per_warp=4096, bias=(1, 1), width=32, both_min=0):
     """One persistent warp per block of `rays_per_warp` consecutive rays, all warps simulated at once.  pool: ray slots per warp
     (32 = the kernel; more = a shared-memory pool from which each round picks up to `width` rays of the majority phase)."""
     n = len(ne) // rays_per_warp * rays_per_warp
@@ -144,15 +144,18 @@ def simulate(events, ne, pool=32, refill=8, rays_per_warp=4096, bias=(1, 1), wid
         n_node = at_node.sum(1); n_leaf = at_leaf.sum(1)
         node_round = (n_node * bias[1] >= n_leaf * bias[0]) & (n_node + n_leaf > 0)
         leaf_round = ~node_round & (n_leaf > 0)
+        if both_min > 0:      # a round runs BOTH steps when each phase has at least both_min lanes waiting (node lanes first, then the lanes that were at a leaf)
+            both = (n_node >= both_min) & (n_leaf >= both_min)
+            node_round |= both; leaf_round |= both
         # pick up to `width` slots of the chosen phase (lowest slot index first)
-        chosen = np.where(node_round[:, None], at_node, np.where(leaf_round[:, None], at_leaf, False))
+        chosen = (node_round[:, None] & at_node) | (leaf_round[:, None] & at_leaf)
         if pool > width:
             rank = np.cumsum(chosen, axis=1)
             chosen &= rank <= width
         k = chosen.sum(1)
         st["rounds"] += int((k > 0).sum())
-        st["node_rounds"] += int(node_round.sum()); st["node_lanes"] += int(k[node_round].sum())
-        st["leaf_rounds"] += int(leaf_round.sum()); st["leaf_lanes"] += int(k[leaf_round].sum())
+        st["node_rounds"] += int(node_round.sum()); st["node_lanes"] += int((chosen & at_node).sum())
+        st["leaf_rounds"] += int(leaf_round.sum()); st["leaf_lanes"] += int((chosen & at_leaf).sum())
         lv = np.where(chosen & leaf_round[:, None], ev, 0)
         cnt = np.where(lv >= 2, (lv - 2) >> 4, 0); msk = np.where(lv >= 2, (lv - 2) & 15, 0)
         st["tri_iters"] += int(cnt.max(1).sum()); st["tri_lane_iters"] += int(cnt.sum())
@@ -191,7 +194,9 @@ def main():
     rows = [("kernel as shipped: 32 slots, refill at 8", dict()),
             ("refill at 4", dict(refill=4)), ("refill at 16", dict(refill=16)),
             ("pool of 48 rays, 32 per round", dict(pool=48)), ("pool of 64 rays, 32 per round", dict(pool=64)),
-            ("pool of 96 rays, 32 per round", dict(pool=96))]
+            ("pool of 96 rays, 32 per round", dict(pool=96)),
+            ("both steps per round when each phase has >= 1", dict(both_min=1)), ("... >= 4", dict(both_min=4)),
+            ("... >= 8", dict(both_min=8)), ("... >= 12", dict(both_min=12))]
     print("%-44s %9s %9s %6s %6s %6s %6s" % ("policy", "instr/ray", "rounds/ray", "node", "leaf", "tri", "MT"))
     for name, kw in rows:
         p = price(simulate(events, ne, **kw))
