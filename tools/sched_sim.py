@@ -116,6 +116,28 @@ def trace_events(root, bounds, child, tris, rays, max_events=256):
     return events, ne, best
 
 
+RESOLVE = 1 << 20      # event code of a deferred Moller-Trumbore evaluation (third phase)
+
+
+def with_resolve_events(events, ne):
+    """Every accepted candidate of a leaf step becomes an event of its own, after the leaf step: the model of a third scheduling
+    phase in which the lanes that hold a candidate evaluate it together."""
+    n, m = events.shape
+    out = np.zeros((n, 2 * m), np.int32); pos = np.zeros(n, np.int64)
+    for j in range(int(ne.max())):
+        e = events[:, j]
+        act = j < ne
+        leaf = act & (e >= 2)
+        k = np.where(leaf, ((e - 2) & 15), 0)
+        acc = ((k & 1) + ((k >> 1) & 1) + ((k >> 2) & 1) + ((k >> 3) & 1))
+        rows = np.nonzero(act)[0]
+        out[rows, pos[rows]] = np.where(leaf[rows], e[rows] - k[rows], e[rows]); pos[rows] += 1
+        for t in range(1, 5):
+            r = np.nonzero(acc >= t)[0]
+            out[r, pos[r]] = RESOLVE; pos[r] += 1
+    return out, pos
+
+
 def simulate(events, ne, pool=32, refill=8, rays_per_warp=4096, bias=(1, 1), width=32, both_min=0):
     """One persistent warp per block of `rays_per_warp` consecutive rays, all warps simulated at once.  pool: ray slots per warp
     (32 = the kernel; more = a shared-memory pool from which each round picks up to `width` rays of the majority phase)."""
@@ -140,15 +162,16 @@ def simulate(events, ne, pool=32, refill=8, rays_per_warp=4096, bias=(1, 1), wid
         if not live.any():
             break
         ev = np.where(live, events[np.maximum(slot_ray, 0), slot_pos], 0)
-        at_node = ev == 1; at_leaf = ev >= 2
-        n_node = at_node.sum(1); n_leaf = at_leaf.sum(1)
-        node_round = (n_node * bias[1] >= n_leaf * bias[0]) & (n_node + n_leaf > 0)
-        leaf_round = ~node_round & (n_leaf > 0)
+        at_node = ev == 1; at_leaf = (ev >= 2) & (ev < RESOLVE); at_res = ev == RESOLVE
+        n_node = at_node.sum(1); n_leaf = at_leaf.sum(1); n_res = at_res.sum(1)
+        res_round = (n_res > n_node) & (n_res > n_leaf)          # third phase: only when it is the largest group
+        node_round = ~res_round & (n_node * bias[1] >= n_leaf * bias[0]) & (n_node + n_leaf > 0)
+        leaf_round = ~res_round & ~node_round & (n_leaf > 0)
         if both_min > 0:      # a round runs BOTH steps when each phase has at least both_min lanes waiting (node lanes first, then the lanes that were at a leaf)
             both = (n_node >= both_min) & (n_leaf >= both_min)
             node_round |= both; leaf_round |= both
         # pick up to `width` slots of the chosen phase (lowest slot index first)
-        chosen = (node_round[:, None] & at_node) | (leaf_round[:, None] & at_leaf)
+        chosen = (node_round[:, None] & at_node) | (leaf_round[:, None] & at_leaf) | (res_round[:, None] & at_res)
         if pool > width:
             rank = np.cumsum(chosen, axis=1)
             chosen &= rank <= width
@@ -156,7 +179,9 @@ def simulate(events, ne, pool=32, refill=8, rays_per_warp=4096, bias=(1, 1), wid
         st["rounds"] += int((k > 0).sum())
         st["node_rounds"] += int(node_round.sum()); st["node_lanes"] += int((chosen & at_node).sum())
         st["leaf_rounds"] += int(leaf_round.sum()); st["leaf_lanes"] += int((chosen & at_leaf).sum())
-        lv = np.where(chosen & leaf_round[:, None], ev, 0)
+        kr = (chosen & at_res).sum(1)
+        st["mt_execs"] += int((kr > 0).sum()); st["mt_lanes"] += int(kr.sum())
+        lv = np.where(chosen & at_leaf & leaf_round[:, None], ev, 0)
         cnt = np.where(lv >= 2, (lv - 2) >> 4, 0); msk = np.where(lv >= 2, (lv - 2) & 15, 0)
         st["tri_iters"] += int(cnt.max(1).sum()); st["tri_lane_iters"] += int(cnt.sum())
         for i in range(4):
@@ -195,11 +220,14 @@ def main():
             ("refill at 4", dict(refill=4)), ("refill at 16", dict(refill=16)),
             ("pool of 48 rays, 32 per round", dict(pool=48)), ("pool of 64 rays, 32 per round", dict(pool=64)),
             ("pool of 96 rays, 32 per round", dict(pool=96)),
+            ("32 slots + resolve phase", dict(resolve=True)), ("pool of 64 + resolve phase", dict(pool=64, resolve=True)),
             ("both steps per round when each phase has >= 1", dict(both_min=1)), ("... >= 4", dict(both_min=4)),
             ("... >= 8", dict(both_min=8)), ("... >= 12", dict(both_min=12))]
     print("%-44s %9s %9s %6s %6s %6s %6s" % ("policy", "instr/ray", "rounds/ray", "node", "leaf", "tri", "MT"))
+    ev3, ne3 = with_resolve_events(events, ne)
     for name, kw in rows:
-        p = price(simulate(events, ne, **kw))
+        kw = dict(kw)
+        p = price(simulate(ev3, ne3, **kw) if kw.pop("resolve", False) else simulate(events, ne, **kw))
         print("%-44s %9.1f %9.3f %6.1f %6.1f %6.1f %6.2f" % (name, p["instr_per_ray"], p["rounds_per_ray"], p["node_lanes"], p["leaf_lanes"], p["tri_lanes"], p["mt_lanes"]))
 
 
