@@ -82,7 +82,7 @@ def trace_events(root, bounds, child, tris, rays, max_events=256):
             u = cur[l] & 0xffffffff
             count = ((u >> 26) & 7) + 1; first = u & ((1 << 26) - 1)
             acc_mask = np.zeros(len(l), np.int64)
-            for i in range(4):
+            for i in range(int(count.max())):
                 m = count > i
                 rows = l[m]
                 tv = tris[first[m] + i]
@@ -96,7 +96,7 @@ def trace_events(root, bounds, child, tris, rays, max_events=256):
                 best[rows[ok]] = tt[ok]
                 sub = np.nonzero(m)[0][ok]
                 acc_mask[sub] |= (1 << i)
-            events[l, ne[l]] = 2 + count * 16 + acc_mask; ne[l] += 1
+            events[l, ne[l]] = 2 + count * 16 + (acc_mask & 15); ne[l] += 1      # (accepted candidates beyond the 4th of a leaf are not priced)
             cur[l] = EMPTY
         # ---- pop (culled by entry distance)
         need = idx[cur[idx] == EMPTY]
