@@ -123,7 +123,7 @@ __global__ void k_fit(const float4* __restrict__ tris_sorted, int n, BinTree t, 
         for (int k = 0; k < 2; ++k) {
             float clo[3], chi[3], ccost;
             if (c[k] < 0) {
-                const float4* p = tris_sorted + 3 * (size_t)(~c[k]);
+                const float4* p = tris_sorted + TRI_F4 * (size_t)(~c[k]);
                 clo[0] = fminf(p[0].x, fminf(p[1].x, p[2].x)); clo[1] = fminf(p[0].y, fminf(p[1].y, p[2].y)); clo[2] = fminf(p[0].z, fminf(p[1].z, p[2].z));
                 chi[0] = fmaxf(p[0].x, fmaxf(p[1].x, p[2].x)); chi[1] = fmaxf(p[0].y, fmaxf(p[1].y, p[2].y)); chi[2] = fmaxf(p[0].z, fmaxf(p[1].z, p[2].z));
                 ccost = 1.f;
@@ -153,7 +153,8 @@ __global__ void k_gather_tris(const float4* __restrict__ in, const uint32_t* __r
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const size_t s = (size_t)perm[i] * 3;
-    out[3 * (size_t)i] = in[s]; out[3 * (size_t)i + 1] = in[s + 1]; out[3 * (size_t)i + 2] = in[s + 2];
+    float4* o = out + TRI_F4 * (size_t)i;       // 64-byte device records (traverse.cuh)
+    o[0] = in[s]; o[1] = in[s + 1]; o[2] = in[s + 2]; o[3] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 __global__ void k_gather_prims(const miro_gpu_prim* __restrict__ in, const uint32_t* __restrict__ perm, uint32_t n, miro_gpu_prim* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -193,7 +194,7 @@ __global__ void k_collapse(BinTree t, const float4* __restrict__ tris_sorted, co
         int first, count;
         if (c < 0) {
             first = ~c; count = 1;
-            const float4* p = tris_sorted + 3 * (size_t)first;
+            const float4* p = tris_sorted + TRI_F4 * (size_t)first;
             lo[0] = fminf(p[0].x, fminf(p[1].x, p[2].x)); lo[1] = fminf(p[0].y, fminf(p[1].y, p[2].y)); lo[2] = fminf(p[0].z, fminf(p[1].z, p[2].z));
             hi[0] = fmaxf(p[0].x, fmaxf(p[1].x, p[2].x)); hi[1] = fmaxf(p[0].y, fmaxf(p[1].y, p[2].y)); hi[2] = fmaxf(p[0].z, fmaxf(p[1].z, p[2].z));
         } else {
@@ -228,13 +229,14 @@ int build_lbvh_on_device(miro_gpu_ctx* ctx, const float4* d_tris_in, uint32_t n,
     cudaStream_t s = ctx->stream;
     auto keep = [&](void* p) { ctx->scene_allocs.push_back(p); };
     float4* tris_sorted = nullptr; uint32_t* perm = nullptr; DeviceNode* nodes = nullptr;
-    MIRO_CUDA(ctx, cudaMalloc((void**)&tris_sorted, (size_t)std::max<uint32_t>(n, 1) * 48)); keep(tris_sorted);
+    MIRO_CUDA(ctx, cudaMalloc((void**)&tris_sorted, (size_t)std::max<uint32_t>(n, 1) * TRI_F4 * sizeof(float4))); keep(tris_sorted);
     MIRO_CUDA(ctx, cudaMalloc((void**)&perm, (size_t)std::max<uint32_t>(n, 1) * 4)); keep(perm);
     *out_tris = tris_sorted; *out_perm = perm;
     const int B = 256;
     auto grid = [&](size_t k) { return (unsigned)((k + B - 1) / B); };
     if (n <= MIRO_GPU_MAX_LEAF) {        // the whole scene is one leaf (cf. src/BVH.cpp:118-132)
-        MIRO_CUDA(ctx, cudaMemcpyAsync(tris_sorted, d_tris_in, (size_t)n * 48, cudaMemcpyDeviceToDevice, s));
+        MIRO_CUDA(ctx, cudaMemsetAsync(tris_sorted, 0, (size_t)std::max<uint32_t>(n, 1) * TRI_F4 * sizeof(float4), s));
+        if (n) MIRO_CUDA(ctx, cudaMemcpy2DAsync(tris_sorted, TRI_F4 * sizeof(float4), d_tris_in, 48, 48, n, cudaMemcpyDeviceToDevice, s));      // 48-byte ABI records -> 64-byte device records
         std::vector<uint32_t> id(n); for (uint32_t i = 0; i < n; ++i) id[i] = i;
         MIRO_CUDA(ctx, cudaMemcpyAsync(perm, id.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
         MIRO_CUDA(ctx, cudaStreamSynchronize(s));

@@ -62,7 +62,7 @@ void drain_timing(miro_gpu_ctx* ctx) {
 // MODE: 0 closest hit -> hit records; 1 any hit -> one bit per ray; 2 any hit -> the unoccluded ray's light sample
 // (sample_E[i] = E.rgb, specular input) is added to the accumulator of its light loop (slot index in ray.user0).
 enum { TRACE_CLOSEST = 0, TRACE_ANY_BITS = 1, TRACE_ANY_ACCUM = 2 };
-constexpr int WORK_RING = 8;      // pairs of work counters per lane; launch k of a lane uses pair k % WORK_RING and re-arms it when its last block leaves
+constexpr int WORK_RING = 32;     // pairs of work counters per lane; launch k of a lane uses pair k % WORK_RING and re-arms it when its last block leaves
 constexpr int WORK_LANES = 4;     // lanes = streams a caller may spread traversal launches over (miro_gpu_ctx::work_lane)
 
 // PACKED: rays are miro_gpu_ray32 records (two 16-byte words: o, tmin | d, tmax; time = 0) instead of miro_gpu_ray (three).
@@ -180,10 +180,9 @@ k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const
     __syncthreads();
     if (threadIdx.x == 0) {
         // chained launches: no block of this launch retires before the launch chained in front of it has completed and
-        // flushed (a no-op without the launch attribute).  A block waiting here still holds its SM slot and a grid fills
-        // the SMs (launch bounds = resident blocks), so only about two consecutive launches ever coexist — the ring of
-        // WORK_RING work-counter pairs cannot wrap onto a live launch, and "this launch is complete" implies "all
-        // earlier ones are".
+        // flushed (a no-op without the launch attribute), so "this launch is complete" implies "all earlier ones are".
+        // A block waiting here still holds its SM slot; the host breaks the chain every WORK_RING - 1 launches
+        // (launch_trace), so the ring of work-counter pairs cannot wrap onto a live launch.
         asm volatile("griddepcontrol.wait;" ::: "memory");
         __threadfence();
         if (atomicAdd(work + 1, 1u) == gridDim.x - 1) { work[0] = 0; work[1] = 0; __threadfence(); }      // this launch's own pair (ring of pairs)
@@ -232,12 +231,19 @@ static void launch_trace(miro_gpu_ctx* ctx, const void* d_rays, size_t n, const 
     // caller has switched trace chaining on (miro_gpu_set_trace_chaining: it vouches that the inputs do not depend on work
     // enqueued since the previous trace call), the launch carries the programmatic-dependent-launch attribute: the tail of
     // launch k, where warps drain their last rays at falling occupancy, overlaps the start of launch k+1.
-    uint32_t* work = ctx->d_work + 2 * ((size_t)ctx->work_lane * WORK_RING + ctx->work_slot[ctx->work_lane]++ % WORK_RING);
+    const uint64_t slot = ctx->work_slot[ctx->work_lane]++;
+    uint32_t* work = ctx->d_work + 2 * ((size_t)ctx->work_lane * WORK_RING + slot % WORK_RING);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TRACE_BLOCK); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = (ctx->chain_traces && ctx->in_api_trace) ? 1 : 0;
+    // The chain is broken at every (WORK_RING - 1)-th launch of a lane (that launch waits for the complete end of everything
+    // before it, as an unchained one does): short launches pass their launch_dependents point almost at once and park at
+    // griddepcontrol.wait while still resident, so without the break any number of them could be live behind one long launch
+    // and launch k + WORK_RING would claim rays from the not yet re-armed counter pair of launch k.  With the break at most
+    // WORK_RING - 1 consecutive launches of a lane are ever live together.
+    const bool chained = ctx->chain_traces && ctx->in_api_trace && (slot % (WORK_RING - 1)) != 0;
+    cfg.attrs = attr; cfg.numAttrs = chained ? 1 : 0;
 #define MIRO_LAUNCH(COUNT, ALPHA) cudaLaunchKernelEx(&cfg, k_trace<MODE, COUNT, ALPHA, PACKED>, ctx->scene, r, (uint32_t)n, d_count, chunk, d_hits, d_bits, d_E, d_slots, ctx->d_counters, work)
     if (ctx->has_alpha) { if (ctx->counting) MIRO_LAUNCH(true, true); else MIRO_LAUNCH(false, true); }
     else { if (ctx->counting) MIRO_LAUNCH(true, false); else MIRO_LAUNCH(false, false); }
@@ -358,24 +364,32 @@ static int upload_array(miro_gpu_ctx* ctx, const T* host, size_t n, const T** de
     return MIRO_GPU_OK;
 }
 
-// depth of the (sub)tree behind a child-style reference; -1 on a malformed tree
-static int tree_depth(const miro_gpu_scene_desc* d, int32_t ref, int level, std::string& err) {
+// Depth of the (sub)tree behind a child-style reference; -1 on a malformed tree.  memo[node] caches the depth of a node's
+// sub-tree (-2: not visited, -3: on the current path, i.e. a cycle), so shared sub-trees — every instance of one bottom-level
+// tree — and DAG-shaped input cost one visit per node.  in_blas: the walk is below an instance; the reference has ONE level
+// of instancing (a ProxyObject's BVH holds plain Objects, src/ProxyObject.cpp:131-166) and so has the traversal kernel.
+static int tree_depth(const miro_gpu_scene_desc* d, int32_t ref, int level, bool in_blas, std::vector<int>& memo, std::string& err, int& code) {
     if (ref == MIRO_GPU_CHILD_EMPTY) return 0;
     if (ref < 0) {
         uint32_t u = (uint32_t)ref, kind = (u >> 29) & 3u, count = ((u >> MIRO_GPU_LEAF_INDEX_BITS) & 7u) + 1u, first = u & ((1u << MIRO_GPU_LEAF_INDEX_BITS) - 1u);
         uint32_t limit = kind == MIRO_GPU_KIND_TRI ? d->n_tris : kind == MIRO_GPU_KIND_MBTRI ? d->n_mbtris : kind == MIRO_GPU_KIND_INST ? d->n_instances : 0;
         if (kind > 2 || first + count > limit) { err = "leaf reference out of range"; return -1; }
+        if (kind == MIRO_GPU_KIND_INST && in_blas) { err = "instance inside an instanced tree (one level of instancing, as the reference)"; code = MIRO_GPU_EUNSUPPORTED; return -1; }
         return 0;
     }
     if ((uint32_t)ref >= d->n_nodes) { err = "child node index out of range"; return -1; }
-    if (level > 64) { err = "BVH deeper than 64 levels (cycle?)"; return -1; }
+    if (level > 64) { err = "BVH deeper than 64 levels"; return -1; }
+    int& m = memo[(size_t)ref];
+    if (m == -3) { err = "cycle in the node array"; return -1; }
+    if (m >= 0) return m;
+    m = -3;
     int best = 0;
     for (int i = 0; i < 4; ++i) {
-        int c = tree_depth(d, d->nodes[ref].child[i], level + 1, err);
+        int c = tree_depth(d, d->nodes[ref].child[i], level + 1, in_blas, memo, err, code);
         if (c < 0) return -1;
         best = std::max(best, c);
     }
-    return best + 1;
+    return memo[(size_t)ref] = best + 1;
 }
 
 extern "C" {
@@ -391,14 +405,20 @@ int miro_gpu_upload_scene(miro_gpu_ctx* ctx, const miro_gpu_scene_desc* d) {
     const bool device_build = d->root == MIRO_GPU_ROOT_BUILD_ON_DEVICE;
     if (device_build && (d->n_mbtris || d->n_instances || d->n_nodes))
         return set_error(ctx, MIRO_GPU_EUNSUPPORTED, "device BVH build handles static triangles only (no motion-blur triangles, instances or host nodes)");
-    // validate the trees and bound the traversal stack: <= 3 pushes per level, + 2 for an instance hop
+    if ((d->n_materials && !d->materials) || (d->n_lights && !d->lights) || (d->n_textures && !d->textures) || (d->n_normals && !d->normals) || (d->n_uvs && !d->uvs))
+        return set_error(ctx, MIRO_GPU_EINVAL, "scene desc: NULL material / light / texture / normal / uv array with non-zero count");
+    // validate the trees and bound the traversal stack: <= 3 pushes per level, + 2 for an instance hop.  The top-level walk
+    // and the bottom-level walks keep separate memos: a node reached both ways would be an instance's tree containing an
+    // instance, or the top level entering a bottom-level tree directly — the second is legal, the first is reported.
     std::string err;
-    int top = device_build ? 0 : tree_depth(d, d->root, 0, err);
-    if (top < 0) return set_error(ctx, MIRO_GPU_EINVAL, "scene desc: " + err);
+    int code = MIRO_GPU_EINVAL;
+    std::vector<int> memo_top(d->n_nodes, -2), memo_blas(d->n_nodes, -2);
+    int top = device_build ? 0 : tree_depth(d, d->root, 0, false, memo_top, err, code);
+    if (top < 0) return set_error(ctx, code, "scene desc: " + err);
     int blas = 0;
     for (uint32_t i = 0; i < d->n_instances; ++i) {
-        int b = tree_depth(d, d->instances[i].blas_root, 0, err);
-        if (b < 0) return set_error(ctx, MIRO_GPU_EINVAL, "scene desc: instance " + std::to_string(i) + ": " + err);
+        int b = tree_depth(d, d->instances[i].blas_root, 0, true, memo_blas, err, code);
+        if (b < 0) return set_error(ctx, code, "scene desc: instance " + std::to_string(i) + ": " + err);
         blas = std::max(blas, b);
     }
     if (3 * top + 2 + 3 * blas > SMEM_STACK + LMEM_STACK)
@@ -411,8 +431,14 @@ int miro_gpu_upload_scene(miro_gpu_ctx* ctx, const miro_gpu_scene_desc* d) {
         if (m.normal_map >= (int32_t)d->n_textures || m.specular_map >= (int32_t)d->n_textures || m.reflect_map >= (int32_t)d->n_textures ||
             m.refract_map >= (int32_t)d->n_textures) return set_error(ctx, MIRO_GPU_EINVAL, "material normal/specular/reflect/refract map out of range");
     }
-    for (uint32_t i = 0; i < d->n_tris + d->n_mbtris && d->prims; ++i)
-        if (d->prims[i].material >= d->n_materials) return set_error(ctx, MIRO_GPU_EINVAL, "prim material out of range");
+    for (uint32_t i = 0; i < d->n_tris + d->n_mbtris && d->prims; ++i) {
+        const miro_gpu_prim& pr = d->prims[i];
+        if (pr.material >= d->n_materials) return set_error(ctx, MIRO_GPU_EINVAL, "prim material out of range");
+        for (int k = 0; k < 3; ++k) {
+            if (pr.n[k] >= d->n_normals) return set_error(ctx, MIRO_GPU_EINVAL, "prim " + std::to_string(i) + ": normal index out of range");
+            if (pr.uv[k] != 0xffffffffu && pr.uv[k] >= d->n_uvs) return set_error(ctx, MIRO_GPU_EINVAL, "prim " + std::to_string(i) + ": uv index out of range");
+        }
+    }
 
     MIRO_CUDA(ctx, cudaSetDevice(ctx->device));
     MIRO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -434,7 +460,15 @@ int miro_gpu_upload_scene(miro_gpu_ctx* ctx, const miro_gpu_scene_desc* d) {
         std::vector<DeviceNode> cnodes(d->n_nodes);          // 128-byte ABI nodes -> 64-byte device nodes (traverse.cuh)
         for (uint32_t i = 0; i < d->n_nodes; ++i) cnodes[i] = compress_node(d->nodes[i]);
         if ((rc = upload_array(ctx, cnodes.data(), cnodes.size(), &dn))) return rc;
-        if ((rc = upload_array(ctx, d->tris, d->n_tris, &dt))) return rc;
+        // 48-byte ABI triangles -> 64-byte aligned device records (traverse.cuh, TRI_F4)
+        struct Tri64 { miro_gpu_tri t; uint32_t pad[4]; };
+        static_assert(sizeof(Tri64) == TRI_F4 * sizeof(float4), "device triangle record");
+        std::vector<Tri64> ctris(d->n_tris);
+        for (uint32_t i = 0; i < d->n_tris; ++i) { ctris[i].t = d->tris[i]; ctris[i].pad[0] = ctris[i].pad[1] = ctris[i].pad[2] = ctris[i].pad[3] = 0; }
+        const Tri64* dt64;
+        if ((rc = upload_array(ctx, ctris.data(), ctris.size(), &dt64))) return rc;
+        MIRO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the staging vectors go out of scope
+        dt = reinterpret_cast<const miro_gpu_tri*>(dt64);
     }
     if ((rc = upload_array(ctx, d->mbtris, d->n_mbtris, &dm))) return rc;
     if ((rc = upload_array(ctx, d->instances, d->n_instances, &di))) return rc;

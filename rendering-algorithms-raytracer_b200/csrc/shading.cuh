@@ -167,7 +167,7 @@ __device__ inline Surface surface_at(const DeviceScene& sc, const DeviceShading&
     const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(pr) + 1);   // uv[1..2], material, mesh
     s.material = q1.z;
     // geometric normal from pose-1 vertices (MB objects shade with mesh 1, src/Ray.cpp:12-19)
-    const float4* tv = (uint32_t)prim < sc.n_tris ? sc.tris + (size_t)prim * 3 : sc.mbtris + (size_t)((uint32_t)prim - sc.n_tris) * 6;
+    const float4* tv = (uint32_t)prim < sc.n_tris ? sc.tris + (size_t)prim * TRI_F4 : sc.mbtris + (size_t)((uint32_t)prim - sc.n_tris) * 6;
     const float4 p0 = __ldg(tv), p1 = __ldg(tv + 1), p2 = __ldg(tv + 2);
     const float3x e0 = f3(p1.x - p0.x, p1.y - p0.y, p1.z - p0.z), e1 = f3(p2.x - p0.x, p2.y - p0.y, p2.z - p0.z);
     s.geoN = normalize3(cross3(e0, e1));

@@ -90,8 +90,8 @@ struct AlphaData {
 struct DeviceScene {
     AlphaData alpha;
     const float4* nodes;     // DeviceNode: 4 x float4 per node (the 64-byte compressed form, see compress_node)
-    const float4* tris;      // 3 x float4 per triangle
-    const float4* mbtris;    // 6 x float4 per motion-blur triangle
+    const float4* tris;      // TRI_F4 x float4 per triangle (64-byte records: v0, v1, v2, pad), leaf order
+    const float4* mbtris;    // 6 x float4 per motion-blur triangle (96 bytes: three 32-byte loads)
     const float4* insts;     // 4 x float4 per instance
     int32_t root;
     uint32_t n_tris;
@@ -103,6 +103,16 @@ struct DeviceScene {
 __device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+
+// Device triangle record: the 48-byte ABI triangle (three float4 vertices) padded to 64 bytes and 64-byte aligned, so a test
+// fetches it with ONE 32-byte and ONE 16-byte load out of one 128-byte line and exactly two 32-byte sectors (the 48-byte stride
+// needed three 16-byte loads — L1 wavefronts are per lane and per load for divergent addresses — and every fourth triangle
+// straddled two lines; ncu: L1 sector traffic 1.23 x algorithmic).  The kernel still reads 48 bytes per test.
+constexpr int TRI_F4 = 4;
+__device__ __forceinline__ void load_tri(const float4* __restrict__ t, float4& p0, float4& p1, float4& p2) {
+    ldg256(t, p0, p1);
+    p2 = __ldg(t + 2);
 }
 
 struct TraceCounters {
@@ -316,15 +326,19 @@ __device__ __forceinline__ void pop_next(Lane& L, TraversalStack& st) {
 
 // Device node: the 128-byte ABI node (include/miro_gpu.h) is re-encoded at upload into 64 bytes — the traversal kernels
 // are bound by L1 data-pipe wavefronts, which for divergent loads scale with the BYTES each lane fetches:
-//   word 0..2   p = min corner of the union of the children's boxes (float)
-//   word 3      biased power-of-two exponents of the per-axis grid step: ex | ey << 8 | ez << 16 (step = 2^(e-127))
+//   word 0..2   p = grid origin, a little below the min corner of the union of the children's boxes (float)
+//   word 3      biased power-of-two exponents of 2^15 x the per-axis grid step: ex | ey << 8 | ez << 16 (step = 2^(e-142))
 //   word 4..7   child references (as in miro_gpu_node)
 //   word 8..10  lower bounds of the 4 children on x, y, z: one byte per child, grid units, rounded DOWN
 //   word 11..13 upper bounds, rounded UP            word 14..15 unused
-// A child's box only ever grows (by less than one grid step = extent/255 per side), so no hit is lost; the
-// uncompressed node would only have culled a few more candidates.
+// A child's box only ever grows (by less than 1 + 2/32 grid steps = extent/240 per side), so no hit is lost; the
+// uncompressed node would only have culled a few more candidates.  Every quantized plane keeps a MARGIN of >= 1/32 grid step
+// to the true box (NODE_GRID_MARGIN): that margin is what absorbs the absolute rounding error of the slab arithmetic in
+// node_step (see there), so the boxes stay conservative for every ray, not only up to rounding.
 struct DeviceNode { uint32_t w[16]; };
 static_assert(sizeof(DeviceNode) == 64, "DeviceNode layout");
+constexpr double NODE_GRID_MARGIN = 1.0 / 32.0;
+constexpr int NODE_EXP_SHIFT = 15;        // word 3 stores the exponent of 2^15 * step: node_step decodes a byte q as 1 + q * 2^-15
 
 __host__ __device__ inline DeviceNode compress_node(const miro_gpu_node& n) {
     DeviceNode o;
@@ -335,24 +349,34 @@ __host__ __device__ inline DeviceNode compress_node(const miro_gpu_node& n) {
         float pmin = 3.0e38f, pmax = -3.0e38f;
         for (int c = 0; c < 4; ++c) if (n.child[c] != MIRO_GPU_CHILD_EMPTY) { pmin = fminf(pmin, lo[k][c]); pmax = fmaxf(pmax, hi[k][c]); }
         if (!(pmin <= pmax)) { pmin = 0.f; pmax = 0.f; }
-        // smallest power of two step with p + 255 * step >= pmax (evaluated in double: exact for these operands)
+        // grid: origin p0 (a float at or below pmin - margin), step = the smallest power of two with
+        // p0 + 255 * step >= pmax + margin, margin = step / 32.  Evaluated in double (exact for these operands).
+        float p0 = pmin;
         int e = 1;
-        const double ext = (double)pmax - (double)pmin;
-        if (ext > 0.0) { int ex; frexp(ext / 255.0, &ex); e = ex + 126; e = e < 1 ? 1 : (e > 254 ? 254 : e); }    // 2^(ex-1) <= ext/255 < 2^ex
-        while (e < 254 && 255.0 * ldexp(1.0, e - 127) < ext) ++e;
-        const double step = ldexp(1.0, e - 127);
+        double step = 0.0;
+        for (int iter = 0; iter < 8; ++iter) {
+            const double ext = ((double)pmax - (double)p0) * (1.0 + 1.0 / 64.0);
+            e = 1;
+            if (ext > 0.0) { int ex; frexp(ext / 254.0, &ex); e = ex + 126; e = e < 1 ? 1 : (e > 230 ? 230 : e); }    // 2^(ex-1) <= ext/254 < 2^ex
+            while (e < 230 && 254.0 * ldexp(1.0, e - 127) < ext) ++e;
+            step = ldexp(1.0, e - 127);
+            if ((double)pmin - (double)p0 >= step * NODE_GRID_MARGIN) break;
+            // lower the origin by ~step/16 (at least one float below) and size the grid again
+            const float want = (float)((double)pmin - step * (1.0 / 16.0));
+            p0 = want < p0 ? want : nextafterf(p0, -3.0e38f);
+        }
         uint32_t qlo = 0, qhi = 0;
         for (int c = 0; c < 4; ++c) {
             uint32_t a = 255u, b = 0u;                     // empty slot: never consulted (its reference is EMPTY)
             if (n.child[c] != MIRO_GPU_CHILD_EMPTY) {
-                double fa = floor(((double)lo[k][c] - (double)pmin) / step), fb = ceil(((double)hi[k][c] - (double)pmin) / step);
+                double fa = floor(((double)lo[k][c] - (double)p0) / step - NODE_GRID_MARGIN), fb = ceil(((double)hi[k][c] - (double)p0) / step + NODE_GRID_MARGIN);
                 fa = fa < 0.0 ? 0.0 : (fa > 255.0 ? 255.0 : fa); fb = fb < 0.0 ? 0.0 : (fb > 255.0 ? 255.0 : fb);
                 a = (uint32_t)fa; b = (uint32_t)fb;
             }
             qlo |= a << (8 * c); qhi |= b << (8 * c);
         }
-        union { float f; uint32_t u; } cv; cv.f = pmin; o.w[k] = cv.u;
-        o.w[3] |= (uint32_t)e << (8 * k);
+        union { float f; uint32_t u; } cv; cv.f = p0; o.w[k] = cv.u;
+        o.w[3] |= (uint32_t)(e + NODE_EXP_SHIFT) << (8 * k);
         o.w[8 + k] = qlo; o.w[11 + k] = qhi;
     }
     for (int c = 0; c < 4; ++c) o.w[4 + c] = (uint32_t)n.child[c];
@@ -360,9 +384,19 @@ __host__ __device__ inline DeviceNode compress_node(const miro_gpu_node& n) {
 }
 
 // Node step: test the four children of inner node `cur`, continue with the nearest, defer the others (far to near).
-// Straight-line code: two 32-byte loads, byte -> float conversions, slab tests in FMA form (grid unit * step/d +
-// (p - o)/d), a 5-comparator sorting network on integer keys (entry distance with the child slot in its two low
-// mantissa bits — truncation only makes an entry look nearer, which is conservative for culling), predicated pushes.
+// Straight-line code: two 32-byte loads, byte -> float by ONE byte permute each, slab tests in FMA form, a 5-comparator sorting
+// network on integer keys (entry distance with the child slot in its two low mantissa bits — truncation only makes an entry look
+// nearer, which is conservative for culling), predicated pushes.
+//
+// Decoding a bound: the byte q is dropped into the mantissa of 1.0f (PRMT: bits 8..15), f = 1 + q 2^-15, and the plane's
+// distance is  t = f A + B  with  A = 2^15 step / d  (the node stores the exponent of 2^15 step)  and  B = (p - o) / d - A.
+// Kernel versions up to v11 converted the 24 bytes with I2F.U8, which runs on the quarter-rate XU pipe: ncu showed that pipe
+// 78 % (incoherent) to 93 % (primary rays) busy — the bound of the whole kernel, hidden behind a 65 % issue utilisation.
+//
+// Error budget (what keeps the test conservative): relative errors of t (reciprocal 1 ulp, p - o, products, FMA: < 8 ulp on
+// the near and the far bound together) are covered by widening the far bound by MIRO_SLAB_WIDEN; the absolute error of B —
+// rounded at the magnitude of A = 2^15 grid steps of t, i.e. <= 2^-9 grid step — is covered by the >= 1/32 grid step every
+// quantized plane keeps to the true box (compress_node, NODE_GRID_MARGIN).
 template <bool COUNT>
 __device__ __forceinline__ void node_step(const DeviceScene& s, Lane& L, TraversalStack& st, uint32_t& n_nodes) {
     const float4* n = s.nodes + (size_t)L.cur * 4;
@@ -370,12 +404,9 @@ __device__ __forceinline__ void node_step(const DeviceScene& s, Lane& L, Travers
     ldg256(n + 0, h0, chf); ldg256(n + 2, q0, q1);
     if (COUNT) ++n_nodes;
     const uint32_t ex = __float_as_uint(h0.w);
-    // per axis: t(q) = q * (step / d) + (p - o) / d
-    // (p - o) / d: the subtraction first, so every error of t is RELATIVE (a few ulp, covered by the widened far bound) — the
-    // FMA form p/d - o/d loses absolute accuracy when |o/d| is large against t — and three registers fewer per lane
-    const float ax = __uint_as_float((ex & 0xffu) << 23) * L.r.ix, bx = (h0.x - L.r.ox) * L.r.ix;
-    const float ay = __uint_as_float((ex & 0xff00u) << 15) * L.r.iy, by = (h0.y - L.r.oy) * L.r.iy;
-    const float az = __uint_as_float((ex & 0xff0000u) << 7) * L.r.iz, bz = (h0.z - L.r.oz) * L.r.iz;
+    const float ax = __uint_as_float((ex & 0xffu) << 23) * L.r.ix, bx = __fmaf_rn(h0.x - L.r.ox, L.r.ix, -ax);
+    const float ay = __uint_as_float((ex & 0xff00u) << 15) * L.r.iy, by = __fmaf_rn(h0.y - L.r.oy, L.r.iy, -ay);
+    const float az = __uint_as_float((ex & 0xff0000u) << 7) * L.r.iz, bz = __fmaf_rn(h0.z - L.r.oz, L.r.iz, -az);
     // near / far planes by the sign of the ray direction (the same for all four children): whole-word selects, so the
     // per-child test needs no min/max of plane pairs
     const uint32_t lx = __float_as_uint(q0.x), ly = __float_as_uint(q0.y), lz = __float_as_uint(q0.z);
@@ -387,11 +418,12 @@ __device__ __forceinline__ void node_step(const DeviceScene& s, Lane& L, Travers
     const int INF_KEY = 0x7fffffff;
     const float tmax = L.hit.t;
     int k0, k1, k2, k3;
-#define MIRO_SLAB_WIDEN 1.0000008f      /* ~7 ulp: reciprocal 1, step/d 0.5, p - o 0.5, product 0.5, fma 0.5 on each of the two bounds */
-#define MIRO_BYTE(W, C) ((float)(((W) >> (8 * (C))) & 0xffu))
+#define MIRO_SLAB_WIDEN 1.6e-6f      /* relative: ~13 ulp, the near and the far bound's rounding together (see above) */
+#define MIRO_BYTE(W, C) __uint_as_float(__byte_perm((W), 0x3f800000u, 0x7604u | ((C) << 4)))      /* 1 + q 2^-15 */
 #define MIRO_SLAB(C, CH, KEY) { \
     const float tn = fmaxf(fmaxf(__fmaf_rn(MIRO_BYTE(nx, C), ax, bx), __fmaf_rn(MIRO_BYTE(ny, C), ay, by)), fmaxf(__fmaf_rn(MIRO_BYTE(nz, C), az, bz), L.tmin)); \
-    const float tf = fminf(fminf(__fmaf_rn(MIRO_BYTE(fx, C), ax, bx), __fmaf_rn(MIRO_BYTE(fy, C), ay, by)), fminf(__fmaf_rn(MIRO_BYTE(fz, C), az, bz), tmax)) * MIRO_SLAB_WIDEN; \
+    const float tf0 = fminf(fminf(__fmaf_rn(MIRO_BYTE(fx, C), ax, bx), __fmaf_rn(MIRO_BYTE(fy, C), ay, by)), fminf(__fmaf_rn(MIRO_BYTE(fz, C), az, bz), tmax)); \
+    const float tf = __fmaf_rn(fabsf(tf0), MIRO_SLAB_WIDEN, tf0); \
     KEY = (tn <= tf && __float_as_int(CH) != MIRO_GPU_CHILD_EMPTY) ? ((float_key(tn) & ~3) | C) : INF_KEY; }
     MIRO_SLAB(0, chf.x, k0) MIRO_SLAB(1, chf.y, k1) MIRO_SLAB(2, chf.z, k2) MIRO_SLAB(3, chf.w, k3)
 #undef MIRO_SLAB
@@ -474,8 +506,8 @@ __device__ __forceinline__ bool intersect_leaf(const DeviceScene& s, Lane& L, Tr
     const uint32_t first = u & ((1u << MIRO_GPU_LEAF_INDEX_BITS) - 1u);
     if (kind == MIRO_GPU_KIND_TRI) {
         for (uint32_t i = 0; i < count; ++i) {
-            const float4* t = s.tris + (size_t)(first + i) * 3;
-            const float4 p0 = __ldg(t), p1 = __ldg(t + 1), p2 = __ldg(t + 2);
+            float4 p0, p1, p2;
+            load_tri(s.tris + (size_t)(first + i) * TRI_F4, p0, p1, p2);
             if (COUNT) ++n_tris;
             float ht, ha, hb;
             if (intersect_tri<ANY && !ALPHA>(L.r, L.tmin, L.hit.t, p0, p1, p2, ht, ha, hb) && (!ALPHA || hit_alpha(s.alpha, first + i, ha, hb) >= 0.5f)) {
@@ -488,8 +520,8 @@ __device__ __forceinline__ bool intersect_leaf(const DeviceScene& s, Lane& L, Tr
         const float w1 = L.time, w0 = 1.0f - L.time;    // src/BVH.cpp:1323-1334
         for (uint32_t i = 0; i < count; ++i) {
             const float4* t = s.mbtris + (size_t)(first + i) * 6;
-            const float4 a0 = __ldg(t), a1 = __ldg(t + 1), a2 = __ldg(t + 2);
-            const float4 b0 = __ldg(t + 3), b1 = __ldg(t + 4), b2 = __ldg(t + 5);
+            float4 a0, a1, a2, b0, b1, b2;
+            ldg256(t, a0, a1); ldg256(t + 2, a2, b0); ldg256(t + 4, b1, b2);
             if (COUNT) ++n_tris;
             float4 p0, p1, p2;
             p0.x = w1 * b0.x + w0 * a0.x; p0.y = w1 * b0.y + w0 * a0.y; p0.z = w1 * b0.z + w0 * a0.z;

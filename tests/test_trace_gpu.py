@@ -168,6 +168,43 @@ def test_gpu_traces_the_references_own_tree(name):
     sc.close()
 
 
+def test_many_short_chained_launches_behind_a_long_one():
+    """The ring of work counters must not wrap onto a live launch: one long launch followed by 80 chained 1 K-ray launches
+    into distinct buffers (short launches pass their launch_dependents point at once and stay resident, waiting for the
+    long one) — every one of them must have traced its rays, and stale any-hit words must have been cleared."""
+    import torch
+    fx = helpers.Fixture(helpers.fixture_path("c2_explosion"))
+    sc = fx.scene().attach(0)
+    rays = fx.rays
+    n = len(rays)
+    big = np.tile(rays, 64)                                     # ~2 M rays
+    want = sc.trace_closest(rays); want_occ = sc.trace_any(rays)
+    d_big = torch.from_numpy(big.view(np.uint8).reshape(len(big), -1)).cuda()
+    d_rays = torch.from_numpy(rays.view(np.uint8).reshape(n, -1)).cuda()
+    big_hits = torch.empty((len(big), 20), dtype=torch.uint8, device="cuda")
+    m = 1024
+    stream = torch.cuda.Stream(); sc.set_stream(stream.cuda_stream)
+    hits = [torch.full((m, 20), 0xff, dtype=torch.uint8, device="cuda") for _ in range(40)]
+    bits = [torch.full((m // 32,), -1, dtype=torch.int32, device="cuda") for _ in range(40)]
+    torch.cuda.synchronize()
+    sc.set_trace_chaining(True)
+    sc.trace_closest_device(d_big.data_ptr(), len(big), big_hits.data_ptr())
+    for k in range(40):
+        off = (k * m) % (n - m)
+        sc.trace_closest_device(d_rays.data_ptr() + off * 48, m, hits[k].data_ptr())
+        sc.trace_any_device(d_rays.data_ptr() + off * 48, m, bits[k].data_ptr())
+    stream.synchronize()
+    sc.set_trace_chaining(False); sc.set_stream(None)
+    assert big_hits[:n].cpu().numpy().view(mb.HIT_DTYPE).reshape(-1).tobytes() == want.tobytes()
+    for k in range(40):
+        off = (k * m) % (n - m)
+        h = hits[k].cpu().numpy().view(mb.HIT_DTYPE).reshape(-1)
+        assert h.tobytes() == want[off:off + m].tobytes(), k
+        occ = np.unpackbits(bits[k].cpu().numpy().view(np.uint8), bitorder="little")[:m].astype(bool)
+        assert (occ == want_occ[off:off + m]).all(), k
+    sc.close()
+
+
 def test_chained_launches_give_identical_results():
     """miro_gpu_set_trace_chaining: consecutive *_device launches overlap (programmatic dependent launch); results must be
     those of unchained launches, also when many short launches follow each other and result words are cleared in-kernel."""
