@@ -57,6 +57,7 @@ struct DeviceBuffer {
 };
 
 struct EventPair { cudaEvent_t a, b; bool trace; };
+struct PoolScratch { unsigned long long* ptr = nullptr; size_t entries = 0; };      // stack overflow of the pool kernel's slots
 
 }  // namespace miro
 
@@ -88,6 +89,9 @@ struct miro_gpu_ctx {
                                                 // several streams give every stream its own lane (launches of one lane are
                                                 // stream-ordered or PDL-chained, so a ring never wraps onto a live launch)
     int build_levels = 0;                       // depth of the last device-built wide tree
+    int stack_need = 0;                         // deepest traversal stack the uploaded trees can ask for (entries)
+    int trace_kernel = MIRO_GPU_KERNEL_WARP;    // miro_gpu_set_trace_kernel
+    miro::PoolScratch pool_ovf[4];              // per work lane
     std::vector<miro::EventPair> events;        // pending (not yet summed) timing pairs
     std::vector<miro::EventPair> event_pool;
     double trace_ms = 0.0, total_ms = 0.0;

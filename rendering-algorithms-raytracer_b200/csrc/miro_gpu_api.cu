@@ -10,6 +10,7 @@
 #include <vector>
 #include "context.cuh"
 #include "dome.cuh"
+#include "trace_pool.cuh"
 
 using namespace miro;
 
@@ -84,7 +85,7 @@ k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const
     L.hit.t = 0.f; L.hit.a = L.hit.b = 0.f; L.hit.prim = -1; L.hit.inst = -1;
     L.set_ray(0.f, 0.f, 0.f, 0.f, 0.f, 1.f);
     unsigned long long overflow[LMEM_STACK];
-    TraversalStack st; st.init(stack + threadIdx.x, overflow);
+    TraversalStack st; st.init(stack + threadIdx.x, overflow, LMEM_STACK);
 
     auto write_result = [&]() {
         const uint32_t i = L.ray_idx;
@@ -214,6 +215,50 @@ static int trace_grid(miro_gpu_ctx* ctx, size_t n) {
     return (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->sm_count * v, blocks_needed));
 }
 
+// Pool kernel (trace_pool.cuh): grid = SMs x resident blocks, dynamic shared memory = the warps' pools; the per-slot stack
+// overflow scratch (global memory; one per work lane, because launches of different lanes run concurrently) is sized from the
+// depth of the uploaded trees and allocated on first use.
+template <int MODE, bool PACKED>
+static cudaError_t launch_trace_pool(miro_gpu_ctx* ctx, const cudaLaunchConfig_t& base_cfg, const float4* r, size_t n, const uint32_t* d_count, uint32_t chunk,
+                                     miro_gpu_hit* d_hits, uint32_t* d_bits, const float4* d_E, float4* d_slots, uint32_t* work) {
+    static int per_sm[4] = {0, 0, 0, 0};
+    int& v = per_sm[(ctx->counting ? 1 : 0) + (ctx->has_alpha ? 2 : 0)];
+#define MIRO_POOL_KERNEL(COUNT, ALPHA) k_trace_pool<MODE, COUNT, ALPHA, PACKED>
+#define MIRO_POOL_DISPATCH(WHAT) \
+    if (ctx->has_alpha) { if (ctx->counting) { WHAT(true, true); } else { WHAT(false, true); } } \
+    else { if (ctx->counting) { WHAT(true, false); } else { WHAT(false, false); } }
+    if (v == 0) {
+#define MIRO_POOL_SETUP(COUNT, ALPHA) \
+        cudaFuncSetAttribute(MIRO_POOL_KERNEL(COUNT, ALPHA), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POOL_SMEM_BYTES); \
+        cudaFuncSetAttribute(MIRO_POOL_KERNEL(COUNT, ALPHA), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, MIRO_POOL_KERNEL(COUNT, ALPHA), POOL_BLOCK, POOL_SMEM_BYTES)
+        MIRO_POOL_DISPATCH(MIRO_POOL_SETUP)
+#undef MIRO_POOL_SETUP
+        if (v <= 0) v = 1;
+    }
+    const int full_grid = ctx->sm_count * v;
+    const size_t blocks_needed = (n + POOL_WARPS * POOL_SLOTS - 1) / (POOL_WARPS * POOL_SLOTS);
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)full_grid, blocks_needed));
+    const int cap = std::max(0, ctx->stack_need - POOL_STACK);
+    const size_t need = (size_t)full_grid * POOL_WARPS * POOL_SLOTS * (size_t)cap;
+    PoolScratch& sc = ctx->pool_ovf[ctx->work_lane];
+    if (need > sc.entries) {
+        if (sc.ptr) { cudaStreamSynchronize(ctx->stream); cudaFree(sc.ptr); sc.ptr = nullptr; sc.entries = 0; }
+        cudaError_t e = cudaMalloc((void**)&sc.ptr, need * sizeof(unsigned long long));
+        if (e != cudaSuccess) return e;
+        sc.entries = need;
+    }
+    cudaLaunchConfig_t cfg = base_cfg;
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(POOL_BLOCK); cfg.dynamicSmemBytes = POOL_SMEM_BYTES;
+    cudaError_t e = cudaSuccess;
+#define MIRO_POOL_LAUNCH(COUNT, ALPHA) e = cudaLaunchKernelEx(&cfg, MIRO_POOL_KERNEL(COUNT, ALPHA), ctx->scene, r, (uint32_t)n, d_count, chunk, d_hits, d_bits, d_E, d_slots, ctx->d_counters, work, sc.ptr, cap)
+    MIRO_POOL_DISPATCH(MIRO_POOL_LAUNCH)
+#undef MIRO_POOL_LAUNCH
+#undef MIRO_POOL_DISPATCH
+#undef MIRO_POOL_KERNEL
+    return e;
+}
+
 template <int MODE, bool PACKED = false>
 static void launch_trace(miro_gpu_ctx* ctx, const void* d_rays, size_t n, const uint32_t* d_count, miro_gpu_hit* d_hits, uint32_t* d_bits,
                          const float4* d_E, float4* d_slots) {
@@ -226,6 +271,7 @@ static void launch_trace(miro_gpu_ctx* ctx, const void* d_rays, size_t n, const 
 #else
     const uint32_t chunk = 32u;
 #endif
+    static_assert(MODE != TRACE_ANY_BITS || true, "");
     const float4* r = reinterpret_cast<const float4*>(d_rays);
     // Every launch has its own pair of work counters out of a ring, so consecutive traversal launches can overlap.  When the
     // caller has switched trace chaining on (miro_gpu_set_trace_chaining: it vouches that the inputs do not depend on work
@@ -244,11 +290,17 @@ static void launch_trace(miro_gpu_ctx* ctx, const void* d_rays, size_t n, const 
     // WORK_RING - 1 consecutive launches of a lane are ever live together.
     const bool chained = ctx->chain_traces && ctx->in_api_trace && (slot % (WORK_RING - 1)) != 0;
     cfg.attrs = attr; cfg.numAttrs = chained ? 1 : 0;
+    ctx->launches++;
+    if (ctx->trace_kernel == MIRO_GPU_KERNEL_POOL) {
+        static_assert(TRACE_CLOSEST == POOL_TRACE_CLOSEST && TRACE_ANY_BITS == POOL_TRACE_ANY_BITS && TRACE_ANY_ACCUM == POOL_TRACE_ANY_ACCUM, "mode numbering");
+        const cudaError_t e = launch_trace_pool<MODE, PACKED>(ctx, cfg, r, n, d_count, chunk, d_hits, d_bits, d_E, d_slots, work);
+        if (e != cudaSuccess) ctx->error = std::string("pool traversal launch: ") + cudaGetErrorString(e);      // surfaces through the caller's cudaGetLastError check
+        return;
+    }
 #define MIRO_LAUNCH(COUNT, ALPHA) cudaLaunchKernelEx(&cfg, k_trace<MODE, COUNT, ALPHA, PACKED>, ctx->scene, r, (uint32_t)n, d_count, chunk, d_hits, d_bits, d_E, d_slots, ctx->d_counters, work)
     if (ctx->has_alpha) { if (ctx->counting) MIRO_LAUNCH(true, true); else MIRO_LAUNCH(false, true); }
     else { if (ctx->counting) MIRO_LAUNCH(true, false); else MIRO_LAUNCH(false, false); }
 #undef MIRO_LAUNCH
-    ctx->launches++;
 }
 void launch_trace_closest(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, const uint32_t* d_count, miro_gpu_hit* d_hits) {
     launch_trace<TRACE_CLOSEST>(ctx, d_rays, n, d_count, d_hits, nullptr, nullptr, nullptr);
@@ -311,6 +363,7 @@ int miro_gpu_create(miro_gpu_ctx** out, int device_id) {
     if ((e = cudaMalloc((void**)&ctx->d_work, 2 * WORK_RING * WORK_LANES * sizeof(uint32_t))) != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaMalloc(work counter)"); }
     cudaMemset(ctx->d_work, 0, 2 * WORK_RING * WORK_LANES * sizeof(uint32_t));
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char* k = getenv("MIRO_GPU_TRACE_KERNEL")) ctx->trace_kernel = strcmp(k, "pool") == 0 ? MIRO_GPU_KERNEL_POOL : MIRO_GPU_KERNEL_WARP;
     // the traversal kernels keep their stacks in shared memory and want the rest of the 256 KB as L1
     *out = ctx;
     return MIRO_GPU_OK;
@@ -333,6 +386,7 @@ void miro_gpu_destroy(miro_gpu_ctx* ctx) {
     ctx->d_rays.release(); ctx->d_hits.release(); ctx->d_bits.release();
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_work) cudaFree(ctx->d_work);
+    for (PoolScratch& sc : ctx->pool_ovf) if (sc.ptr) cudaFree(sc.ptr);
     for (cudaEvent_t e : ctx->pipe_events) cudaEventDestroy(e);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
@@ -423,6 +477,7 @@ int miro_gpu_upload_scene(miro_gpu_ctx* ctx, const miro_gpu_scene_desc* d) {
     }
     if (3 * top + 2 + 3 * blas > SMEM_STACK + LMEM_STACK)
         return set_error(ctx, MIRO_GPU_EUNSUPPORTED, "BVH too deep for the traversal stack (top " + std::to_string(top) + ", instanced " + std::to_string(blas) + " levels)");
+    int stack_need = 3 * top + 2 + 3 * blas;
     for (uint32_t i = 0; i < d->n_materials; ++i) {
         const miro_gpu_material& m = d->materials[i];
         if (m.kind > MIRO_GPU_MAT_BLINN) return set_error(ctx, MIRO_GPU_EINVAL, "unknown material kind");
@@ -455,6 +510,7 @@ int miro_gpu_upload_scene(miro_gpu_ctx* ctx, const miro_gpu_scene_desc* d) {
         if ((rc = build_lbvh_on_device(ctx, reinterpret_cast<const float4*>(d_in), d->n_tris, &dn, &n_nodes, &root, &sorted, &d_perm))) return rc;
         dt = reinterpret_cast<const miro_gpu_tri*>(sorted);
         if (3 * ctx->build_levels + 2 > SMEM_STACK + LMEM_STACK) return set_error(ctx, MIRO_GPU_EUNSUPPORTED, "device-built BVH too deep for the traversal stack");
+        stack_need = 3 * ctx->build_levels + 2;
         ctx->n_nodes = n_nodes;
     } else {
         std::vector<DeviceNode> cnodes(d->n_nodes);          // 128-byte ABI nodes -> 64-byte device nodes (traverse.cuh)
@@ -480,6 +536,7 @@ int miro_gpu_upload_scene(miro_gpu_ctx* ctx, const miro_gpu_scene_desc* d) {
     ctx->scene.n_tris = d->n_tris;
     ctx->scene.prim_map = d_perm;
     if (!device_build) ctx->n_nodes = d->n_nodes;
+    ctx->stack_need = stack_need;
     ctx->n_tris = d->n_tris; ctx->n_mbtris = d->n_mbtris; ctx->n_insts = d->n_instances;
 
     DeviceShading& sh = ctx->shading;
@@ -680,6 +737,15 @@ int miro_gpu_trace_closest_packed(miro_gpu_ctx* ctx, const miro_gpu_ray32* rays,
 int miro_gpu_trace_any_packed(miro_gpu_ctx* ctx, const miro_gpu_ray32* rays, size_t n, uint32_t* occluded_bits) {
     if (ctx && n && !occluded_bits) return set_error(ctx, MIRO_GPU_EINVAL, "NULL ray/bit buffer");
     return trace_host(ctx, rays, n, nullptr, occluded_bits, true);
+}
+
+int miro_gpu_set_trace_kernel(miro_gpu_ctx* ctx, int kind) {
+    if (!ctx) return MIRO_GPU_EINVAL;
+    if (kind != MIRO_GPU_KERNEL_WARP && kind != MIRO_GPU_KERNEL_POOL) return set_error(ctx, MIRO_GPU_EINVAL, "miro_gpu_set_trace_kernel: unknown kernel");
+    MIRO_CUDA(ctx, cudaSetDevice(ctx->device));
+    MIRO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->trace_kernel = kind;
+    return MIRO_GPU_OK;
 }
 
 int miro_gpu_set_trace_chaining(miro_gpu_ctx* ctx, int on) {

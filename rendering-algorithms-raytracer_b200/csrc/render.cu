@@ -432,7 +432,7 @@ k_walk_shadows(DeviceScene sc, DeviceShading sh, const miro_gpu_ray* __restrict_
                const uint32_t* __restrict__ d_count, uint32_t cap, float4* __restrict__ slots, TraceCounters* __restrict__ ctr) {
     __shared__ unsigned long long stack[SMEM_STACK * TRACE_BLOCK];
     unsigned long long overflow[LMEM_STACK];
-    TraversalStack st; st.init(stack + threadIdx.x, overflow);
+    TraversalStack st; st.init(stack + threadIdx.x, overflow, LMEM_STACK);
     const uint32_t n = min(*d_count, cap);
     for (uint32_t i = blockIdx.x * TRACE_BLOCK + threadIdx.x; i < n; i += gridDim.x * TRACE_BLOCK) {
         const float4* rp = reinterpret_cast<const float4*>(rays + i);

@@ -255,34 +255,41 @@ __device__ __forceinline__ int float_key(float f) { const int i = __float_as_int
 
 struct StackEntry { int32_t ref; int key; };     // key: float_key(entry distance), low bits cleared (never later than the truth)
 
-// Per-lane traversal stack.  Entries are {reference, entry distance}; the first SMEM_STACK of them live in SHARED
-// memory laid out [entry][lane] (conflict free), addressed with explicit 32-bit shared addresses (ld/st.shared — a
-// generic pointer here made the compiler emit generic LD/ST plus a stack pointer in local memory).  Deeper entries
-// (very deep trees only; depth is validated at upload) overflow into a local-memory array behind one rarely taken branch.
-struct TraversalStack {
-    uint32_t base;                       // shared address of entry 0 of this lane
-    unsigned long long* overflow;        // LMEM_STACK entries of local memory
+// Per-ray traversal stack.  Entries are {reference, entry distance}; the first NSMEM of them live in SHARED memory with a
+// fixed byte STRIDE between consecutive entries of one stack — [entry][lane] for the persistent-warp kernel, [entry][slot] for
+// the pool kernel: conflict free when the lanes of a warp address distinct columns —, addressed with explicit 32-bit shared
+// addresses (ld/st.shared — a generic pointer here made the compiler emit generic LD/ST plus a stack pointer in local memory).
+// Deeper entries (very deep trees only; depth is validated at upload) overflow into `overflow` (local memory of the lane, or a
+// per-slot scratch in global memory for the pool kernel, whose rays change lanes) behind one rarely taken branch.
+template <uint32_t STRIDE_, int NSMEM_>
+struct TraversalStackT {
+    static constexpr uint32_t STRIDE = STRIDE_;
+    static constexpr int NSMEM = NSMEM_;
+    uint32_t base;                       // shared address of entry 0 of this stack
+    unsigned long long* overflow;        // `cap` further entries
+    int cap;
     int sp;
-    __device__ __forceinline__ void init(unsigned long long* smem_lane, unsigned long long* lmem) {
-        base = (uint32_t)__cvta_generic_to_shared(smem_lane); overflow = lmem; sp = 0;
+    __device__ __forceinline__ void init(unsigned long long* smem_entry0, unsigned long long* ovf, int ovf_cap) {
+        base = (uint32_t)__cvta_generic_to_shared(smem_entry0); overflow = ovf; cap = ovf_cap; sp = 0;
     }
     __device__ __forceinline__ void store(int slot, int32_t ref, int key) {
-        if (slot < SMEM_STACK)
-            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" :: "r"(base + (uint32_t)slot * (TRACE_BLOCK * 8u)), "r"(ref), "r"(key) : "memory");
-        else if (slot - SMEM_STACK < LMEM_STACK)
-            overflow[slot - SMEM_STACK] = ((unsigned long long)(uint32_t)key << 32) | (uint32_t)ref;
+        if (slot < NSMEM)
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" :: "r"(base + (uint32_t)slot * STRIDE), "r"(ref), "r"(key) : "memory");
+        else if (slot - NSMEM < cap)
+            overflow[slot - NSMEM] = ((unsigned long long)(uint32_t)key << 32) | (uint32_t)ref;
     }
     __device__ __forceinline__ void push(int32_t ref, int key) { store(sp, ref, key); ++sp; }
     __device__ __forceinline__ StackEntry pop() {
         --sp;
         StackEntry e;
-        if (sp < SMEM_STACK)
-            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(e.ref), "=r"(e.key) : "r"(base + (uint32_t)sp * (TRACE_BLOCK * 8u)) : "memory");
-        else if (sp - SMEM_STACK < LMEM_STACK) { const unsigned long long v = overflow[sp - SMEM_STACK]; e.ref = (int32_t)(uint32_t)v; e.key = (int)(uint32_t)(v >> 32); }
+        if (sp < NSMEM)
+            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(e.ref), "=r"(e.key) : "r"(base + (uint32_t)sp * STRIDE) : "memory");
+        else if (sp - NSMEM < cap) { const unsigned long long v = overflow[sp - NSMEM]; e.ref = (int32_t)(uint32_t)v; e.key = (int)(uint32_t)(v >> 32); }
         else { e.ref = MIRO_GPU_CHILD_EMPTY; e.key = 0x7fffffff; }
         return e;
     }
 };
+using TraversalStack = TraversalStackT<TRACE_BLOCK * 8u, SMEM_STACK>;      // the persistent-warp kernel: [entry][lane of the block]
 
 // four-way select by a 2-bit slot index, forced to predicated selects (the compiler turns the ternary chain into branches)
 __device__ __forceinline__ int sel4(int sl, int a, int b, int c, int d) {
@@ -315,7 +322,8 @@ struct Lane {
 };
 
 // Pops the next candidate that can still beat the current hit; `cur` = MIRO_GPU_CHILD_EMPTY when the stack runs dry.
-__device__ __forceinline__ void pop_next(Lane& L, TraversalStack& st) {
+template <class ST>
+__device__ __forceinline__ void pop_next(Lane& L, ST& st) {
     L.cur = MIRO_GPU_CHILD_EMPTY;
     const int limit = float_key(L.hit.t);
     while (st.sp > 0) {
@@ -327,7 +335,7 @@ __device__ __forceinline__ void pop_next(Lane& L, TraversalStack& st) {
 // Device node: the 128-byte ABI node (include/miro_gpu.h) is re-encoded at upload into 64 bytes — the traversal kernels
 // are bound by L1 data-pipe wavefronts, which for divergent loads scale with the BYTES each lane fetches:
 //   word 0..2   p = grid origin, a little below the min corner of the union of the children's boxes (float)
-//   word 3      biased power-of-two exponents of 2^15 x the per-axis grid step: ex | ey << 8 | ez << 16 (step = 2^(e-142))
+//   word 3      biased power-of-two exponents of the per-axis grid step: ex | ey << 8 | ez << 16 (step = 2^(e-127))
 //   word 4..7   child references (as in miro_gpu_node)
 //   word 8..10  lower bounds of the 4 children on x, y, z: one byte per child, grid units, rounded DOWN
 //   word 11..13 upper bounds, rounded UP            word 14..15 unused
@@ -338,7 +346,6 @@ __device__ __forceinline__ void pop_next(Lane& L, TraversalStack& st) {
 struct DeviceNode { uint32_t w[16]; };
 static_assert(sizeof(DeviceNode) == 64, "DeviceNode layout");
 constexpr double NODE_GRID_MARGIN = 1.0 / 32.0;
-constexpr int NODE_EXP_SHIFT = 15;        // word 3 stores the exponent of 2^15 * step: node_step decodes a byte q as 1 + q * 2^-15
 
 __host__ __device__ inline DeviceNode compress_node(const miro_gpu_node& n) {
     DeviceNode o;
@@ -355,10 +362,10 @@ __host__ __device__ inline DeviceNode compress_node(const miro_gpu_node& n) {
         int e = 1;
         double step = 0.0;
         for (int iter = 0; iter < 8; ++iter) {
-            const double ext = ((double)pmax - (double)p0) * (1.0 + 1.0 / 64.0);
+            const double ext = (double)pmax - (double)p0;
             e = 1;
-            if (ext > 0.0) { int ex; frexp(ext / 254.0, &ex); e = ex + 126; e = e < 1 ? 1 : (e > 230 ? 230 : e); }    // 2^(ex-1) <= ext/254 < 2^ex
-            while (e < 230 && 254.0 * ldexp(1.0, e - 127) < ext) ++e;
+            if (ext > 0.0) { int ex; frexp(ext / 255.0, &ex); e = ex + 126; e = e < 1 ? 1 : (e > 254 ? 254 : e); }    // 2^(ex-1) <= ext/255 < 2^ex
+            while (e < 254 && (255.0 - NODE_GRID_MARGIN) * ldexp(1.0, e - 127) < ext) ++e;
             step = ldexp(1.0, e - 127);
             if ((double)pmin - (double)p0 >= step * NODE_GRID_MARGIN) break;
             // lower the origin by ~step/16 (at least one float below) and size the grid again
@@ -376,7 +383,7 @@ __host__ __device__ inline DeviceNode compress_node(const miro_gpu_node& n) {
             qlo |= a << (8 * c); qhi |= b << (8 * c);
         }
         union { float f; uint32_t u; } cv; cv.f = p0; o.w[k] = cv.u;
-        o.w[3] |= (uint32_t)(e + NODE_EXP_SHIFT) << (8 * k);
+        o.w[3] |= (uint32_t)e << (8 * k);
         o.w[8 + k] = qlo; o.w[11 + k] = qhi;
     }
     for (int c = 0; c < 4; ++c) o.w[4 + c] = (uint32_t)n.child[c];
@@ -384,29 +391,27 @@ __host__ __device__ inline DeviceNode compress_node(const miro_gpu_node& n) {
 }
 
 // Node step: test the four children of inner node `cur`, continue with the nearest, defer the others (far to near).
-// Straight-line code: two 32-byte loads, byte -> float by ONE byte permute each, slab tests in FMA form, a 5-comparator sorting
-// network on integer keys (entry distance with the child slot in its two low mantissa bits — truncation only makes an entry look
-// nearer, which is conservative for culling), predicated pushes.
+// Straight-line code: two 32-byte loads, byte -> float conversions (I2F.U8: the XU pipe, which nothing else here uses — decoding
+// the bytes with PRMT into a float's mantissa instead was measured in round 2 and is slower, because it moves 24 instructions per
+// step onto the ALU pipe, the busiest one at ~60 %), slab tests in FMA form (grid unit * step/d + (p - o)/d), a 5-comparator
+// sorting network on integer keys (entry distance with the child slot in its two low mantissa bits — truncation only makes an
+// entry look nearer, which is conservative for culling), predicated pushes.
 //
-// Decoding a bound: the byte q is dropped into the mantissa of 1.0f (PRMT: bits 8..15), f = 1 + q 2^-15, and the plane's
-// distance is  t = f A + B  with  A = 2^15 step / d  (the node stores the exponent of 2^15 step)  and  B = (p - o) / d - A.
-// Kernel versions up to v11 converted the 24 bytes with I2F.U8, which runs on the quarter-rate XU pipe: ncu showed that pipe
-// 78 % (incoherent) to 93 % (primary rays) busy — the bound of the whole kernel, hidden behind a 65 % issue utilisation.
-//
-// Error budget (what keeps the test conservative): relative errors of t (reciprocal 1 ulp, p - o, products, FMA: < 8 ulp on
-// the near and the far bound together) are covered by widening the far bound by MIRO_SLAB_WIDEN; the absolute error of B —
-// rounded at the magnitude of A = 2^15 grid steps of t, i.e. <= 2^-9 grid step — is covered by the >= 1/32 grid step every
-// quantized plane keeps to the true box (compress_node, NODE_GRID_MARGIN).
-template <bool COUNT>
-__device__ __forceinline__ void node_step(const DeviceScene& s, Lane& L, TraversalStack& st, uint32_t& n_nodes) {
+// Error budget (what keeps the test conservative): the relative errors of t (reciprocal 1 ulp, p - o, products, FMA: < 8 ulp
+// on the near and the far bound together) are covered by widening the far bound by MIRO_SLAB_WIDEN; what is absolute — the
+// rounding of (p - o)/d when the plane is much nearer than the grid origin, <= 2^-23 x 255 grid steps of t — is covered by the
+// >= 1/32 grid step every quantized plane keeps to the true box (compress_node, NODE_GRID_MARGIN).
+template <bool COUNT, class ST>
+__device__ __forceinline__ void node_step(const DeviceScene& s, Lane& L, ST& st, uint32_t& n_nodes) {
     const float4* n = s.nodes + (size_t)L.cur * 4;
     float4 h0, chf, q0, q1;
     ldg256(n + 0, h0, chf); ldg256(n + 2, q0, q1);
     if (COUNT) ++n_nodes;
     const uint32_t ex = __float_as_uint(h0.w);
-    const float ax = __uint_as_float((ex & 0xffu) << 23) * L.r.ix, bx = __fmaf_rn(h0.x - L.r.ox, L.r.ix, -ax);
-    const float ay = __uint_as_float((ex & 0xff00u) << 15) * L.r.iy, by = __fmaf_rn(h0.y - L.r.oy, L.r.iy, -ay);
-    const float az = __uint_as_float((ex & 0xff0000u) << 7) * L.r.iz, bz = __fmaf_rn(h0.z - L.r.oz, L.r.iz, -az);
+    // per axis: t(q) = q * (step / d) + (p - o) / d   (the subtraction first, so the error of the second term is relative to it)
+    const float ax = __uint_as_float((ex & 0xffu) << 23) * L.r.ix, bx = (h0.x - L.r.ox) * L.r.ix;
+    const float ay = __uint_as_float((ex & 0xff00u) << 15) * L.r.iy, by = (h0.y - L.r.oy) * L.r.iy;
+    const float az = __uint_as_float((ex & 0xff0000u) << 7) * L.r.iz, bz = (h0.z - L.r.oz) * L.r.iz;
     // near / far planes by the sign of the ray direction (the same for all four children): whole-word selects, so the
     // per-child test needs no min/max of plane pairs
     const uint32_t lx = __float_as_uint(q0.x), ly = __float_as_uint(q0.y), lz = __float_as_uint(q0.z);
@@ -419,7 +424,7 @@ __device__ __forceinline__ void node_step(const DeviceScene& s, Lane& L, Travers
     const float tmax = L.hit.t;
     int k0, k1, k2, k3;
 #define MIRO_SLAB_WIDEN 1.6e-6f      /* relative: ~13 ulp, the near and the far bound's rounding together (see above) */
-#define MIRO_BYTE(W, C) __uint_as_float(__byte_perm((W), 0x3f800000u, 0x7604u | ((C) << 4)))      /* 1 + q 2^-15 */
+#define MIRO_BYTE(W, C) ((float)(((W) >> (8 * (C))) & 0xffu))
 #define MIRO_SLAB(C, CH, KEY) { \
     const float tn = fmaxf(fmaxf(__fmaf_rn(MIRO_BYTE(nx, C), ax, bx), __fmaf_rn(MIRO_BYTE(ny, C), ay, by)), fmaxf(__fmaf_rn(MIRO_BYTE(nz, C), az, bz), L.tmin)); \
     const float tf0 = fminf(fminf(__fmaf_rn(MIRO_BYTE(fx, C), ax, bx), __fmaf_rn(MIRO_BYTE(fy, C), ay, by)), fminf(__fmaf_rn(MIRO_BYTE(fz, C), az, bz), tmax)); \
@@ -436,11 +441,11 @@ __device__ __forceinline__ void node_step(const DeviceScene& s, Lane& L, Travers
     const int hits = (k0 != INF_KEY) + (k1 != INF_KEY) + (k2 != INF_KEY) + (k3 != INF_KEY);
     // deferred children go on the stack far to near: k3 (if hit) lowest, k1 on top
     const int sp = st.sp;
-    if (sp + 3 <= SMEM_STACK) {          // the usual case: three predicated shared stores, no branches
-        const uint32_t a0 = st.base + (uint32_t)sp * (TRACE_BLOCK * 8u);
+    if (sp + 3 <= ST::NSMEM) {          // the usual case: three predicated shared stores, no branches
+        const uint32_t a0 = st.base + (uint32_t)sp * ST::STRIDE;
         sts_if(hits > 3, a0, child_of(k3), k3 & ~3);
-        sts_if(hits > 2, a0 + (uint32_t)(hits - 3) * (TRACE_BLOCK * 8u), child_of(k2), k2 & ~3);
-        sts_if(hits > 1, a0 + (uint32_t)(hits - 2) * (TRACE_BLOCK * 8u), child_of(k1), k1 & ~3);
+        sts_if(hits > 2, a0 + (uint32_t)(hits - 3) * ST::STRIDE, child_of(k2), k2 & ~3);
+        sts_if(hits > 1, a0 + (uint32_t)(hits - 2) * ST::STRIDE, child_of(k1), k1 & ~3);
     } else {
         if (hits > 3) st.store(sp, child_of(k3), k3 & ~3);
         if (hits > 2) st.store(sp + hits - 3, child_of(k2), k2 & ~3);
@@ -481,7 +486,8 @@ __device__ __forceinline__ float hit_alpha(const AlphaData& A, uint32_t prim, fl
 
 // Instance leaf {first, count}: the lane enters instance `first` with the world-space ray (wo, wd) moved into its object space and
 // defers the others; a marker on the stack restores the world-space ray when the instance's sub-tree is exhausted.
-__device__ __forceinline__ void enter_instance(const DeviceScene& s, Lane& L, TraversalStack& st, uint32_t first, uint32_t count,
+template <class ST>
+__device__ __forceinline__ void enter_instance(const DeviceScene& s, Lane& L, ST& st, uint32_t first, uint32_t count,
                                                float wox, float woy, float woz, float wdx, float wdy, float wdz) {
     const int ninf = (int)0x80000000;
     if (count > 1u) st.push(MIRO_GPU_LEAF(MIRO_GPU_KIND_INST, first + 1u, count - 1u), ninf);
@@ -497,8 +503,8 @@ __device__ __forceinline__ void enter_instance(const DeviceScene& s, Lane& L, Tr
 }
 
 // Leaf phase.  Returns true when an ANY query has found its occluder.
-template <bool ANY, bool COUNT, bool ALPHA>
-__device__ __forceinline__ bool intersect_leaf(const DeviceScene& s, Lane& L, TraversalStack& st, const float4* __restrict__ rays, const uint32_t ray_f4,
+template <bool ANY, bool COUNT, bool ALPHA, class ST>
+__device__ __forceinline__ bool intersect_leaf(const DeviceScene& s, Lane& L, ST& st, const float4* __restrict__ rays, const uint32_t ray_f4,
                                                uint32_t& n_tris, uint32_t& n_insts) {
     const uint32_t u = (uint32_t)L.cur;
     const uint32_t kind = (u >> 29) & 3u;

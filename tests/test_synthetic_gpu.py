@@ -75,9 +75,11 @@ def test_soup_matches_oracle(n, clustered, size):
     sc.close()
 
 
-def test_deep_tree_uses_the_stack_overflow_path():
-    """A chain of nested shells: every ray crosses dozens of overlapping boxes, so the per-lane stack grows past the 16
-    shared-memory entries into the local-memory overflow."""
+@pytest.mark.parametrize("kernel", ["warp", "pool"])
+def test_deep_tree_uses_the_stack_overflow_path(kernel):
+    """A chain of nested shells: every ray crosses dozens of overlapping boxes, so the per-ray stack grows past its
+    shared-memory entries (16 / 12) into the overflow (local memory of the lane / the pool kernel's per-slot scratch in global
+    memory)."""
     rng = np.random.default_rng(3)
     tris = []
     for k in range(1, 300):                           # concentric octahedron shells
@@ -87,6 +89,7 @@ def test_deep_tree_uses_the_stack_overflow_path():
             tris.append(p[[a, b, c]])
     v = np.concatenate(tris).astype(np.float32); f = np.arange(len(v), dtype=np.uint32).reshape(-1, 3)
     sc = scene_of(v, f).attach(0)
+    sc.set_trace_kernel(kernel)
     o = rng.normal(size=(20000, 3)); o = 5.0 * o / np.linalg.norm(o, axis=1, keepdims=True)
     tgt = rng.uniform(-0.5, 0.5, (20000, 3))
     d = tgt - o; d /= np.linalg.norm(d, axis=1, keepdims=True)

@@ -10,13 +10,34 @@ pytestmark = pytest.mark.gpu
 SCENES = ["c1_cornell", "c2_explosion", "c5_mb_instances", "c7_foliage"]      # c7: alpha cut-outs inside Scene::trace
 
 
-@pytest.fixture(scope="module", params=SCENES)
+KERNELS = ["warp", "pool"]      # miro_gpu_set_trace_kernel: both traversal kernels must give the reference's hits
+
+
+@pytest.fixture(scope="module", params=[(s, k) for s in SCENES for k in KERNELS], ids=lambda p: "%s-%s" % p)
 def loaded(request):
-    path = helpers.fixture_path(request.param)
+    name, kernel = request.param
+    path = helpers.fixture_path(name)
     fx = helpers.Fixture(path)
     sc = fx.scene().attach(0)
-    yield request.param, fx, sc
+    sc.set_trace_kernel(kernel)
+    yield name, fx, sc
     sc.close()
+
+
+def test_pool_kernel_gives_the_warp_kernels_hits():
+    """The two traversal kernels visit nodes in the same per-ray order, so their hit records are byte-identical (closest hits;
+    occlusion bits likewise), on a static scene and on motion blur + instances; the pool kernel's stack overflow scratch
+    (global memory, per slot) is exercised by the deep-tree test in test_synthetic_gpu.py."""
+    for name in ("c2_explosion", "c5_mb_instances", "c7_foliage"):
+        fx = helpers.Fixture(helpers.fixture_path(name))
+        sc = fx.scene().attach(0)
+        sc.set_trace_kernel("warp"); a = sc.trace_closest(fx.rays); oa = sc.trace_any(fx.rays)
+        sc.set_trace_kernel("pool"); b = sc.trace_closest(fx.rays); ob = sc.trace_any(fx.rays)
+        assert a.tobytes() == b.tobytes(), name
+        assert (oa == ob).all(), name
+        for n in (1, 31, 33, 63, 65, 127, 129, 1000):
+            assert sc.trace_closest(fx.rays[:n]).tobytes() == a[:n].tobytes(), (name, n)
+        sc.close()
 
 
 def test_closest_hit_matches_reference(loaded):
@@ -93,16 +114,43 @@ def test_determinism(loaded):
     assert a.tobytes() == b.tobytes()
 
 
+def full_size_batch(name):
+    """BASELINE-size rays and the reference's hits for them.  The cached full fixture (oracle/_ref/fixtures, written by
+    tools/make_fixtures.py where /root/reference exists) when present; otherwise the rays are generated here — pinhole rays at
+    the pixel centres of the script's image at 1920x1080 + 1 Mi seeded incoherent rays with random times — and the reference
+    binary (oracle/_ref/miro_ref, which travels to the GPU box) traces them ON THE SPOT, single-threaded, on the committed
+    fixture's geometry."""
+    import reference_arm as ra
+    path = helpers.fixture_path(name, full=True)
+    if path is not None:
+        fx = helpers.Fixture(path)
+        return fx, fx.rays, fx.hits
+    if not ra.have_reference():
+        pytest.skip("neither the full-size fixture nor the reference binary is present")
+    fx = helpers.Fixture(helpers.fixture_path(name))
+    cam = ra.script_camera(fx.script)
+    prim = ra.primary_rays(cam, 1920, 1080)
+    lo, hi = fx.bounds()
+    if name == "c5_mb_instances":      # the instanced field is much larger than its meshes: shoot where the camera rays go
+        far = prim["o"] + 60.0 * prim["d"]
+        lo, hi = np.minimum(lo, far.min(0)), np.maximum(hi, far.max(0))
+    inco = ra.incoherent_rays(lo, hi, 1 << 20, 0x5EED, times=True)
+    rays = np.concatenate([prim, inco])
+    return fx, rays, helpers.reference_hits(fx, rays)
+
+
 @pytest.mark.parametrize("name", ["c2_explosion", "c5_mb_instances"])
 def test_full_size_batches_against_reference(name):
-    """BASELINE-size batches (1920x1080 primary + 1 Mi incoherent rays) against the reference's recorded hits, when the
-    full fixture (oracle/_ref/fixtures, generated here, travels with the snapshot) is present; plus size-independent
-    properties: any-hit == closest-hit-as-boolean, shortening tmax to just before / after the hit flips occlusion."""
-    path = helpers.fixture_path(name, full=True)
-    if path is None:
-        pytest.skip("full-size fixture not present")
-    fx = helpers.Fixture(path)
+    """BASELINE-size batches (1920x1080 primary + 1 Mi incoherent rays) against the reference's hits for the same rays (see
+    full_size_batch), through both traversal kernels; plus size-independent properties: any-hit == closest-hit-as-boolean,
+    shortening tmax to just before / after the hit flips occlusion."""
+    fx, rays, ref_hits = full_size_batch(name)
+    fx.rays, fx.hits = rays, ref_hits
     sc = fx.scene().attach(0)
+    sc.set_trace_kernel("pool")
+    pool_hits = sc.trace_closest(fx.rays)
+    sc.set_trace_kernel("warp")
+    assert sc.trace_closest(fx.rays).tobytes() == pool_hits.tobytes()
     hits = sc.trace_closest(fx.rays)
     st = helpers.compare_hits(sc, hits, fx.hits, t_rel=1e-5, rays=fx.rays)
     print(name, len(fx.rays), {k: v for k, v in st.items() if k != "hard_idx"})
