@@ -110,7 +110,12 @@ typedef struct miro_gpu_mbtri {     /* 96 bytes: pose 1 (time 0) and pose 2 (tim
 typedef struct miro_gpu_instance {  /* 64 bytes: what traversal needs of a ProxyObject */
     float inv[12];                  /* rows 0..2 of M^-1 (row-major 3x4), src/ProxyObject.cpp:78-79 */
     int32_t blas_root;              /* node index of the instanced BVH's root */
-    uint32_t reserved[3];
+    uint32_t ordinal;               /* caller's ProxyObject ordinal (reported back by the host layer, not interpreted) */
+    float w_recip;                  /* what Matrix4x4::multiplyAndDivideByW multiplies the transformed origin by
+                                       (src/Matrix4x4.h:728-741): recipps(w), w = row 4 of the inverse . [o 1] — for an
+                                       affine matrix the inverse's m44 as Matrix4x4::invert rounds it (often 1 - 2^-24) —,
+                                       i.e. rcpps(w) + one Newton step ON THE HOST'S SSE UNIT; 0 = not supplied, treated as 1 */
+    uint32_t reserved;
 } miro_gpu_instance;
 
 /* Shading record of one primitive; prims[0..n_tris) describe tris[], prims[n_tris..n_tris+n_mbtris)
@@ -246,8 +251,9 @@ typedef struct miro_gpu_counters {
 
 typedef struct miro_gpu_ctx miro_gpu_ctx;
 
-/* Create a context on one CUDA device (device_id as in cudaSetDevice).  One context per GPU; a
- * multi-GPU job is one process per GPU (torch.distributed / NCCL combine the frame buffers). */
+/* Create a context on one CUDA device (device_id as in cudaSetDevice).  One context per GPU.  Several GPUs are driven either by
+ * one process per GPU (torch.distributed: NCCL combines the frame buffers, bench.py) or by ONE caller through a group
+ * (miro_gpu_group_*, below). */
 int miro_gpu_create(miro_gpu_ctx** out, int device_id);
 void miro_gpu_destroy(miro_gpu_ctx* ctx);
 const char* miro_gpu_last_error(const miro_gpu_ctx* ctx);   /* ctx may be NULL: last create() error */
@@ -309,6 +315,33 @@ int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, const miro_gp
 int miro_gpu_enable_counting(miro_gpu_ctx* ctx, int enable);
 int miro_gpu_get_counters(miro_gpu_ctx* ctx, miro_gpu_counters* out);
 int miro_gpu_reset_counters(miro_gpu_ctx* ctx);
+
+/* ---- several GPUs behind one caller ("one ctx owns 1..8 GPUs"; replaces the OpenMP bucket loop of
+ * Scene::raytraceImage, src/Scene.cpp:160-175, across devices).  A group holds one context per listed device (the same device
+ * may be listed twice: two contexts on one GPU).  The scene is replicated; miro_gpu_group_render deals the frame's 32x32
+ * buckets (MIRO_GPU_SHARD_BUCKETS: bucket b of the reference's bucket order to member b % n — any configuration) or the paths of
+ * every camera sample (MIRO_GPU_SHARD_SAMPLES: path p to member p % n — path-traced configurations with min_subdivs ==
+ * max_subdivs) to the members, and combines the members' frames on the first device with one kernel that reads the others'
+ * memory over NVLink peer access (staged by cudaMemcpyPeerAsync where peer access is unavailable).  Random numbers are keyed by
+ * (pixel, sample, path), so the frame equals the single-GPU frame (bit for bit with bucket sharding).  rgb_out: host pointer,
+ * or device pointer on the first device.  The trace calls split the batch into contiguous parts, one per member (host
+ * pointers; no exchange).  A group is used from one host thread at a time; it fans out to one worker thread per member
+ * for the duration of a call. */
+typedef struct miro_gpu_group miro_gpu_group;
+#define MIRO_GPU_SHARD_BUCKETS 0
+#define MIRO_GPU_SHARD_SAMPLES 1
+int miro_gpu_group_create(miro_gpu_group** out, const int* device_ids, int n_devices);
+void miro_gpu_group_destroy(miro_gpu_group* g);
+int miro_gpu_group_size(const miro_gpu_group* g);
+miro_gpu_ctx* miro_gpu_group_ctx(miro_gpu_group* g, int i);          /* member i's context (counters, kernel selection, ...) */
+const char* miro_gpu_group_last_error(const miro_gpu_group* g);
+int miro_gpu_group_peer_access(const miro_gpu_group* g, int i);      /* 1: the first member reads member i's frame directly */
+int miro_gpu_group_upload_scene(miro_gpu_group* g, const miro_gpu_scene_desc* desc);
+int miro_gpu_group_render(miro_gpu_group* g, const miro_gpu_camera* cam, const miro_gpu_render_params* params, int sharding, float* rgb_out);
+int miro_gpu_group_trace_closest(miro_gpu_group* g, const miro_gpu_ray* rays, size_t n, miro_gpu_hit* hits);
+int miro_gpu_group_trace_any(miro_gpu_group* g, const miro_gpu_ray* rays, size_t n, uint32_t* occluded_bits);
+int miro_gpu_group_get_counters(miro_gpu_group* g, miro_gpu_counters* out);      /* sums over members (times: the slowest member) */
+int miro_gpu_group_reset_counters(miro_gpu_group* g);
 
 #ifdef __cplusplus
 }

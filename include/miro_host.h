@@ -31,6 +31,13 @@ int miro_host_get_render_params(const miro_host_scene* s, miro_gpu_render_params
 int miro_host_bvh_stats(const miro_host_scene* s, uint32_t* nodes, uint32_t* leaves, uint32_t* max_depth, double* sah_cost);
 /* Scene::attach: create the GPU context on `device` and upload.  Fails loudly without a GPU. */
 int miro_host_attach(miro_host_scene* s, int device);
+/* The same over several GPUs of one box (miro_gpu_group_*, include/miro_gpu.h): the scene is replicated, miro_host_raytrace_image
+ * deals the frame's buckets (sample_sharding != 0: the paths of every camera sample) to the devices and combines the frame on
+ * the first; miro_host_trace / _trace_any (Scene::trace, src/Scene.h:32, batched) split their batch over the devices. */
+int miro_host_attach_devices(miro_host_scene* s, const int* device_ids, int n_devices, int sample_sharding);
+miro_gpu_group* miro_host_group(miro_host_scene* s);
+int miro_host_trace(miro_host_scene* s, const miro_gpu_ray* rays, size_t n, miro_gpu_hit* hits);
+int miro_host_trace_any(miro_host_scene* s, const miro_gpu_ray* rays, size_t n, uint32_t* occluded_bits);
 miro_gpu_ctx* miro_host_ctx(miro_host_scene* s);
 /* Scene::raytraceImage: rgb = width*height*3 floats (row 0 = bottom); rgb8 (optional) = Image::Map'ed bytes. */
 int miro_host_raytrace_image(miro_host_scene* s, float* rgb, unsigned char* rgb8, int shard_index, int shard_count);

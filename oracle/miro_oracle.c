@@ -109,8 +109,10 @@ static int intersect_leaf(const miro_gpu_scene_desc* s, int32_t ref, const oray*
             float no[3], nd[3];
             for (int k = 0; k < 3; ++k) {
                 const float* m = &in->inv[4 * k];
-                no[k] = m[0] * r->o[0] + m[1] * r->o[1] + m[2] * r->o[2] + m[3];
-                nd[k] = m[0] * r->d[0] + m[1] * r->d[1] + m[2] * r->d[2];
+                /* src/Matrix4x4.h:728-733 (dpps over [o 1]: (p0 + p1) + (p2 + p3), times recipps(w), w = 1) and :699-701 */
+                const float wr = in->w_recip == 0.f ? 1.0f : in->w_recip;
+                no[k] = ((m[0] * r->o[0] + m[1] * r->o[1]) + (m[2] * r->o[2] + m[3])) * wr;
+                nd[k] = (m[0] * r->d[0] + m[1] * r->d[1]) + m[2] * r->d[2];
             }
             oray nr; ray_set(&nr, no, nd, r->time);
             ohit nh = *hit;   /* newHit.t = result.t */

@@ -327,29 +327,52 @@ void dumpPrimary(const std::string& out) {
     writeVec(out, rays);
 }
 
-// --trace: Scene::trace (Scene.cpp:295) over a caller-supplied ray buffer.
-double g_traceMean = 0.0;       // mean seconds over the timed repeats of the last traceRays call
-double traceRays(const std::string& in, const std::string& out, int threads, int repeat, int warmup) {
-    std::vector<RayRec> rays = readVec<RayRec>(in);
-    std::vector<RefHit> hits(rays.size());
+// --trace: Scene::trace (Scene.cpp:295) over a caller-supplied ray buffer.  Timed passes run on `threads` OpenMP threads; the
+// hit records that are written come from one more, SINGLE-threaded pass when threads > 1 — concurrent traversals corrupt each
+// other through QBVH_Node::boxHit, a mutable member of the shared node (BVH.h:101, BVH.cpp:413,1151), so only a
+// single-threaded pass yields the reference's true answers.
+double g_traceMean = 0.0;       // mean seconds over the timed repeats of the last traceBatch call
+void tracePass(const std::vector<RayRec>& rays, std::vector<RefHit>& hits, int threads) {
+    #pragma omp parallel for schedule(dynamic, 1024) num_threads(threads)
+    for (long i = 0; i < (long)rays.size(); i++) {
+        unsigned tid = omp_get_thread_num();
+        const RayRec& q = rays[i];
+        Ray r(tid, Vector3(q.ox, q.oy, q.oz), Vector3(q.dx, q.dy, q.dz), q.time);
+        HitInfo h; h.t = q.tmax;
+        bool hit = g_scene->trace(tid, h, r, q.tmin);
+        hits[i] = toRefHit(hit, h);
+    }
+}
+double traceBatch(const std::vector<RayRec>& rays, std::vector<RefHit>& hits, int threads, int repeat, int warmup, bool wantHits) {
+    hits.resize(rays.size());
     double best = 1e30, sum = 0.0;
     for (int it = -warmup; it < repeat; ++it) {
         double t0 = omp_get_wtime();
-        #pragma omp parallel for schedule(dynamic, 1024) num_threads(threads)
-        for (long i = 0; i < (long)rays.size(); i++) {
-            unsigned tid = omp_get_thread_num();
-            const RayRec& q = rays[i];
-            Ray r(tid, Vector3(q.ox, q.oy, q.oz), Vector3(q.dx, q.dy, q.dz), q.time);
-            HitInfo h; h.t = q.tmax;
-            bool hit = g_scene->trace(tid, h, r, q.tmin);
-            hits[i] = toRefHit(hit, h);
-        }
+        tracePass(rays, hits, threads);
         double t1 = omp_get_wtime();
         if (it >= 0) { if (t1 - t0 < best) best = t1 - t0; sum += t1 - t0; }
     }
     g_traceMean = sum / (repeat > 0 ? repeat : 1);
-    if (!out.empty()) writeVec(out, hits);
+    if (wantHits && threads > 1) tracePass(rays, hits, 1);
     return best;
+}
+
+// --shadow-light X Y Z FIRST COUNT: the shadow rays PointLight::sampleLight would cast (PointLight.cpp:20-48) from the hits of
+// rays [FIRST, FIRST + COUNT) of the traced batch towards a point light — from the hit point, or from the ray origin for a miss;
+// tMin = epsilon, tMax = the distance to the light — traced as a second timed batch.
+void shadowRaysFromHits(const std::vector<RayRec>& rays, const std::vector<RefHit>& hits, size_t first, size_t count, const float light[3],
+                        std::vector<RayRec>& out) {
+    out.clear();
+    for (size_t i = first; i < first + count && i < rays.size(); i++) {
+        const RayRec& q = rays[i];
+        const float t = hits[i].mesh >= 0 ? hits[i].t : 0.0f;
+        RayRec s = q;
+        s.ox = q.ox + t * q.dx; s.oy = q.oy + t * q.dy; s.oz = q.oz + t * q.dz;
+        const float lx = light[0] - s.ox, ly = light[1] - s.oy, lz = light[2] - s.oz;
+        const float dist = sqrtf(lx * lx + ly * ly + lz * lz), inv = 1.0f / (dist > 1e-20f ? dist : 1e-20f);
+        s.dx = lx * inv; s.dy = ly * inv; s.dz = lz * inv; s.tmin = epsilon; s.tmax = dist;
+        out.push_back(s);
+    }
 }
 
 // --render-float: the reference's per-pixel entry point (Scene.cpp:252 adaptiveSampleScene) over
@@ -524,6 +547,7 @@ void gpuAppendPrimitive(const Object* o, GpuFlat& f) {
         const Matrix4x4& I = M.m_inverse; const Matrix4x4& T = M.m_invTranspose;
         const float inv[12] = {I.m11, I.m12, I.m13, I.m14, I.m21, I.m22, I.m23, I.m24, I.m31, I.m32, I.m33, I.m34};
         memcpy(in.inv, inv, sizeof(inv)); in.blas_root = f.blasRoot[p->m_BVH];
+        { __attribute__((aligned(16))) float one[4] = {I.m44, I.m44, I.m44, I.m44}; __attribute__((aligned(16))) float r[4]; storeps(recipps(loadps(one)), r); in.w_recip = r[0]; }      // what multiplyAndDivideByW multiplies by: w = m44 for an affine matrix
         const float nx[9] = {T.m11, T.m12, T.m13, T.m21, T.m22, T.m23, T.m31, T.m32, T.m33};
         f.nxf.insert(f.nxf.end(), nx, nx + 9);
         f.inst.push_back(in);
@@ -681,8 +705,9 @@ double renderGPU(const std::string& out, const std::string& libPath) {
 }  // namespace
 
 int main(int argc, char** argv) {
-    std::string scene, dumpPrim, traceIn, traceOut, floatOut, ppmOut, meshDir, qbvhOut, texDir, gpuOut, gpuLib, gpuPpm;
-    int threads = 1, repeat = 1, warmup = 0; bool stock = false, doFloat = false;
+    std::string scene, dumpPrim, traceIn, traceOut, floatOut, ppmOut, meshDir, qbvhOut, texDir, gpuOut, gpuLib, gpuPpm, shadowRaysOut, shadowHitsOut;
+    int threads = 1, repeat = 1, warmup = 0; bool stock = false, doFloat = false, doShadow = false;
+    float shadowLight[3] = {0, 0, 0}; size_t shadowFirst = 0, shadowCount = 0;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         #define NEXT() (i + 1 < argc ? std::string(argv[++i]) : (die("missing value for " + a), std::string()))
@@ -694,6 +719,10 @@ int main(int argc, char** argv) {
         else if (a == "--dump-primary") dumpPrim = NEXT();
         else if (a == "--trace") { traceIn = NEXT(); }
         else if (a == "--hits") traceOut = NEXT();
+        else if (a == "--shadow-light") { doShadow = true; for (int k = 0; k < 3; k++) shadowLight[k] = (float)atof(NEXT().c_str());
+                                          shadowFirst = (size_t)atoll(NEXT().c_str()); shadowCount = (size_t)atoll(NEXT().c_str()); }
+        else if (a == "--shadow-rays") shadowRaysOut = NEXT();
+        else if (a == "--shadow-hits") shadowHitsOut = NEXT();
         else if (a == "--render-float") { doFloat = true; floatOut = NEXT(); }
         else if (a == "--render-stock") { stock = true; ppmOut = NEXT(); }
         else if (a == "--dump-meshes") meshDir = NEXT();
@@ -725,10 +754,23 @@ int main(int argc, char** argv) {
     }
     if (!traceIn.empty()) {
         resetTraceCalls();
-        double s = traceRays(traceIn, traceOut, threads, repeat, warmup);
-        unsigned long long n = traceCalls() / (unsigned long long)(repeat + warmup);
+        std::vector<RayRec> rays = readVec<RayRec>(traceIn);
+        std::vector<RefHit> hits;
+        double s = traceBatch(rays, hits, threads, repeat, warmup, !traceOut.empty() || doShadow);
+        double mean = g_traceMean;
+        if (!traceOut.empty()) writeVec(traceOut, hits);
+        unsigned long long n = rays.size();
         fprintf(stderr, "{\"event\":\"trace\",\"rays\":%llu,\"seconds\":%.6f,\"mean_seconds\":%.6f,\"mrays_per_s\":%.4f,\"threads\":%d,\"repeat\":%d,\"warmup\":%d}\n",
-                n, s, g_traceMean, n / s * 1e-6, threads, repeat, warmup);
+                n, s, mean, n / s * 1e-6, threads, repeat, warmup);
+        if (doShadow) {
+            std::vector<RayRec> srays; std::vector<RefHit> shits;
+            shadowRaysFromHits(rays, hits, shadowFirst, shadowCount, shadowLight, srays);
+            double ss = traceBatch(srays, shits, threads, repeat, warmup, !shadowHitsOut.empty());
+            if (!shadowRaysOut.empty()) writeVec(shadowRaysOut, srays);
+            if (!shadowHitsOut.empty()) writeVec(shadowHitsOut, shits);
+            fprintf(stderr, "{\"event\":\"shadow\",\"rays\":%zu,\"seconds\":%.6f,\"mean_seconds\":%.6f,\"mrays_per_s\":%.4f,\"threads\":%d}\n",
+                    srays.size(), ss, g_traceMean, srays.size() / ss * 1e-6, threads);
+        }
     }
     if (doFloat) {
         resetTraceCalls();

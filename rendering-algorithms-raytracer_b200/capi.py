@@ -45,7 +45,7 @@ class MBTri(C.Structure):
 
 
 class Instance(C.Structure):
-    _fields_ = [("inv", C.c_float * 12), ("blas_root", C.c_int32), ("reserved", C.c_uint32 * 3)]
+    _fields_ = [("inv", C.c_float * 12), ("blas_root", C.c_int32), ("ordinal", C.c_uint32), ("w_recip", C.c_float), ("reserved", C.c_uint32)]
 
 
 class Prim(C.Structure):
@@ -112,10 +112,14 @@ class Counters(C.Structure):
 GPU_SYMBOLS = ["miro_gpu_create", "miro_gpu_destroy", "miro_gpu_last_error", "miro_gpu_abi_version", "miro_gpu_sizeof", "miro_gpu_set_stream", "miro_gpu_set_trace_chaining", "miro_gpu_set_trace_kernel",
                "miro_gpu_upload_scene", "miro_gpu_trace_closest", "miro_gpu_trace_any", "miro_gpu_trace_closest_packed", "miro_gpu_trace_any_packed", "miro_gpu_trace_closest_device",
                "miro_gpu_trace_any_device", "miro_gpu_render", "miro_gpu_enable_counting", "miro_gpu_get_counters",
-               "miro_gpu_reset_counters"]
+               "miro_gpu_reset_counters",
+               "miro_gpu_group_create", "miro_gpu_group_destroy", "miro_gpu_group_size", "miro_gpu_group_ctx", "miro_gpu_group_last_error", "miro_gpu_group_peer_access",
+               "miro_gpu_group_upload_scene", "miro_gpu_group_render", "miro_gpu_group_trace_closest", "miro_gpu_group_trace_any", "miro_gpu_group_get_counters",
+               "miro_gpu_group_reset_counters"]
 HOST_SYMBOLS = ["miro_host_new", "miro_host_free", "miro_host_error", "miro_host_preload_mesh", "miro_host_preload_image",
                 "miro_host_load_script", "miro_host_get_desc", "miro_host_get_camera", "miro_host_get_render_params",
-                "miro_host_bvh_stats", "miro_host_attach", "miro_host_ctx", "miro_host_raytrace_image", "miro_host_write_ppm"]
+                "miro_host_bvh_stats", "miro_host_attach", "miro_host_attach_devices", "miro_host_group", "miro_host_trace", "miro_host_trace_any",
+                "miro_host_ctx", "miro_host_raytrace_image", "miro_host_write_ppm"]
 
 _lib = None
 
@@ -157,6 +161,22 @@ def lib():
     L.miro_host_bvh_stats.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(C.c_double)]; L.miro_host_bvh_stats.restype = i32
     L.miro_host_attach.argtypes = [vp, i32]; L.miro_host_attach.restype = i32
     L.miro_host_ctx.argtypes = [vp]; L.miro_host_ctx.restype = vp
+    L.miro_host_attach_devices.argtypes = [vp, C.POINTER(i32), i32, i32]; L.miro_host_attach_devices.restype = i32
+    L.miro_host_group.argtypes = [vp]; L.miro_host_group.restype = vp
+    L.miro_host_trace.argtypes = [vp, vp, sz, vp]; L.miro_host_trace.restype = i32
+    L.miro_host_trace_any.argtypes = [vp, vp, sz, vp]; L.miro_host_trace_any.restype = i32
+    L.miro_gpu_group_create.argtypes = [C.POINTER(vp), C.POINTER(i32), i32]; L.miro_gpu_group_create.restype = i32
+    L.miro_gpu_group_destroy.argtypes = [vp]; L.miro_gpu_group_destroy.restype = None
+    L.miro_gpu_group_size.argtypes = [vp]; L.miro_gpu_group_size.restype = i32
+    L.miro_gpu_group_ctx.argtypes = [vp, i32]; L.miro_gpu_group_ctx.restype = vp
+    L.miro_gpu_group_last_error.argtypes = [vp]; L.miro_gpu_group_last_error.restype = cp
+    L.miro_gpu_group_peer_access.argtypes = [vp, i32]; L.miro_gpu_group_peer_access.restype = i32
+    L.miro_gpu_group_upload_scene.argtypes = [vp, C.POINTER(SceneDesc)]; L.miro_gpu_group_upload_scene.restype = i32
+    L.miro_gpu_group_render.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), i32, vp]; L.miro_gpu_group_render.restype = i32
+    L.miro_gpu_group_trace_closest.argtypes = [vp, vp, sz, vp]; L.miro_gpu_group_trace_closest.restype = i32
+    L.miro_gpu_group_trace_any.argtypes = [vp, vp, sz, vp]; L.miro_gpu_group_trace_any.restype = i32
+    L.miro_gpu_group_get_counters.argtypes = [vp, C.POINTER(Counters)]; L.miro_gpu_group_get_counters.restype = i32
+    L.miro_gpu_group_reset_counters.argtypes = [vp]; L.miro_gpu_group_reset_counters.restype = i32
     L.miro_host_raytrace_image.argtypes = [vp, vp, vp, i32, i32]; L.miro_host_raytrace_image.restype = i32
     L.miro_host_write_ppm.argtypes = [vp, cp]; L.miro_host_write_ppm.restype = i32
     _lib = L

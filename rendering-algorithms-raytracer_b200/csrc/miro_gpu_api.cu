@@ -292,7 +292,7 @@ static void launch_trace(miro_gpu_ctx* ctx, const void* d_rays, size_t n, const 
     cfg.attrs = attr; cfg.numAttrs = chained ? 1 : 0;
     ctx->launches++;
     if (ctx->trace_kernel == MIRO_GPU_KERNEL_POOL) {
-        static_assert(TRACE_CLOSEST == POOL_TRACE_CLOSEST && TRACE_ANY_BITS == POOL_TRACE_ANY_BITS && TRACE_ANY_ACCUM == POOL_TRACE_ANY_ACCUM, "mode numbering");
+        static_assert((int)TRACE_CLOSEST == (int)POOL_TRACE_CLOSEST && (int)TRACE_ANY_BITS == (int)POOL_TRACE_ANY_BITS && (int)TRACE_ANY_ACCUM == (int)POOL_TRACE_ANY_ACCUM, "mode numbering");
         const cudaError_t e = launch_trace_pool<MODE, PACKED>(ctx, cfg, r, n, d_count, chunk, d_hits, d_bits, d_E, d_slots, work);
         if (e != cudaSuccess) ctx->error = std::string("pool traversal launch: ") + cudaGetErrorString(e);      // surfaces through the caller's cudaGetLastError check
         return;

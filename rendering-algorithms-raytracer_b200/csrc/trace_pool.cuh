@@ -41,7 +41,7 @@ constexpr int POOL_BLOCK = MIRO_POOL_BLOCK;            // threads per block
 constexpr int POOL_WARPS = POOL_BLOCK / 32;
 constexpr int POOL_MIN_BLOCKS = MIRO_POOL_MIN_BLOCKS;  // resident blocks per SM the kernel is compiled for
 constexpr int POOL_REFILL = MIRO_POOL_REFILL;          // idle slots that trigger a refill
-static_assert(POOL_SLOTS == 64, "two slots per lane");
+static_assert(POOL_SLOTS > 32 && POOL_SLOTS <= 64, "lane l owns slot l and, when it exists, slot l + 32");
 
 enum PoolField {
     F_OX, F_OY, F_OZ, F_IX, F_IY, F_IZ, F_TMIN, F_T, F_CUR, F_SP,                         // what a node step reads
@@ -73,8 +73,9 @@ k_trace_pool(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, 
     uint32_t chunk_next = 0, chunk_end = 0;
     bool exhausted = false;
     bool pending_lo = false, pending_hi = false;       // the owned slot holds a ray whose result has not been written
+    const bool has_hi = lane + 32u < (uint32_t)POOL_SLOTS;      // pools of fewer than 64 slots: the upper lanes own one slot only
     S[F_CUR * POOL_SLOTS + lane] = (uint32_t)MIRO_GPU_CHILD_EMPTY;
-    S[F_CUR * POOL_SLOTS + 32 + lane] = (uint32_t)MIRO_GPU_CHILD_EMPTY;
+    if (has_hi) S[F_CUR * POOL_SLOTS + 32 + lane] = (uint32_t)MIRO_GPU_CHILD_EMPTY;
     __syncwarp();
 
     auto write_result = [&](uint32_t slot) {
@@ -102,9 +103,9 @@ k_trace_pool(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, 
 
     while (true) {
         // ---- the owner's view of its two slots
-        int cur_lo = (int)S[F_CUR * POOL_SLOTS + lane], cur_hi = (int)S[F_CUR * POOL_SLOTS + 32 + lane];
+        int cur_lo = (int)S[F_CUR * POOL_SLOTS + lane], cur_hi = has_hi ? (int)S[F_CUR * POOL_SLOTS + 32 + lane] : MIRO_GPU_CHILD_EMPTY;
         const uint32_t idle_lo = __ballot_sync(0xffffffffu, cur_lo == MIRO_GPU_CHILD_EMPTY);
-        const uint32_t idle_hi = __ballot_sync(0xffffffffu, cur_hi == MIRO_GPU_CHILD_EMPTY);
+        const uint32_t idle_hi = __ballot_sync(0xffffffffu, has_hi && cur_hi == MIRO_GPU_CHILD_EMPTY);
         const int n_idle = __popc(idle_lo) + __popc(idle_hi);
         if (n_idle >= POOL_REFILL || (exhausted && n_idle == POOL_SLOTS)) {
             // results of finished rays leave here, converged, not when each ray finishes

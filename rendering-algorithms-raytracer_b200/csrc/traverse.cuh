@@ -73,6 +73,12 @@ constexpr int TRACE_NODE_BIAS_NUM = MIRO_NODE_BIAS_NUM, TRACE_NODE_BIAS_DEN = MI
 #endif
 constexpr int TRACE_LEAF_MIN = MIRO_LEAF_MIN;   // tuning knob: while some lane waits at a node, a leaf round needs at least this many lanes (0: the ratio alone decides)
    // idle lanes in a warp that trigger a refill from the work counter
+// Byte -> float decode of the quantized node bounds.  0: all 24 planes by I2F.U8 (the quarter-rate XU pipe); 1: the 12 far planes by
+// one byte permute each (PRMT drops the byte into the mantissa of 1.0f: ALU pipe), the 12 near planes by I2F — splits the decode
+// over two pipes; 2: all 24 by PRMT (measured slower than 0 in round 2: the ALU pipe becomes the bound).
+#ifndef MIRO_PRMT_PLANES
+#define MIRO_PRMT_PLANES 0
+#endif
 constexpr int SMEM_STACK = MIRO_SMEM_STACK;   // per-thread stack entries kept in shared memory
 constexpr int LMEM_STACK = 96 - MIRO_SMEM_STACK;          // overflow entries (local memory, touched only by very deep trees)
 constexpr int32_t STACK_SENTINEL = 0x7ffffffe;   // "leave instance" marker
@@ -425,12 +431,27 @@ __device__ __forceinline__ void node_step(const DeviceScene& s, Lane& L, ST& st,
     int k0, k1, k2, k3;
 #define MIRO_SLAB_WIDEN 1.6e-6f      /* relative: ~13 ulp, the near and the far bound's rounding together (see above) */
 #define MIRO_BYTE(W, C) ((float)(((W) >> (8 * (C))) & 0xffu))
+#if MIRO_PRMT_PLANES
+    // PRMT decode (see MIRO_PRMT_PLANES): f = 1 + q 2^-15, t = f A + B with A = 2^15 a, B = b - A
+    const float Ax = ax * 32768.0f, Bx = __fsub_rn(bx, Ax), Ay = ay * 32768.0f, By = __fsub_rn(by, Ay), Az = az * 32768.0f, Bz = __fsub_rn(bz, Az);
+#define MIRO_BYTE_P(W, C) __uint_as_float(__byte_perm((W), 0x3f800000u, 0x7604u | ((C) << 4)))
+#define MIRO_FAR(W, C, K) __fmaf_rn(MIRO_BYTE_P(W, C), A##K, B##K)
+#else
+#define MIRO_FAR(W, C, K) __fmaf_rn(MIRO_BYTE(W, C), a##K, b##K)
+#endif
+#if MIRO_PRMT_PLANES == 2
+#define MIRO_NEAR(W, C, K) __fmaf_rn(MIRO_BYTE_P(W, C), A##K, B##K)
+#else
+#define MIRO_NEAR(W, C, K) __fmaf_rn(MIRO_BYTE(W, C), a##K, b##K)
+#endif
 #define MIRO_SLAB(C, CH, KEY) { \
-    const float tn = fmaxf(fmaxf(__fmaf_rn(MIRO_BYTE(nx, C), ax, bx), __fmaf_rn(MIRO_BYTE(ny, C), ay, by)), fmaxf(__fmaf_rn(MIRO_BYTE(nz, C), az, bz), L.tmin)); \
-    const float tf0 = fminf(fminf(__fmaf_rn(MIRO_BYTE(fx, C), ax, bx), __fmaf_rn(MIRO_BYTE(fy, C), ay, by)), fminf(__fmaf_rn(MIRO_BYTE(fz, C), az, bz), tmax)); \
+    const float tn = fmaxf(fmaxf(MIRO_NEAR(nx, C, x), MIRO_NEAR(ny, C, y)), fmaxf(MIRO_NEAR(nz, C, z), L.tmin)); \
+    const float tf0 = fminf(fminf(MIRO_FAR(fx, C, x), MIRO_FAR(fy, C, y)), fminf(MIRO_FAR(fz, C, z), tmax)); \
     const float tf = __fmaf_rn(fabsf(tf0), MIRO_SLAB_WIDEN, tf0); \
     KEY = (tn <= tf && __float_as_int(CH) != MIRO_GPU_CHILD_EMPTY) ? ((float_key(tn) & ~3) | C) : INF_KEY; }
     MIRO_SLAB(0, chf.x, k0) MIRO_SLAB(1, chf.y, k1) MIRO_SLAB(2, chf.z, k2) MIRO_SLAB(3, chf.w, k3)
+#undef MIRO_NEAR
+#undef MIRO_FAR
 #undef MIRO_SLAB
 #undef MIRO_BYTE
 #define MIRO_KSWAP(a, b) { const int lo_ = min(a, b), hi_ = max(a, b); a = lo_; b = hi_; }
@@ -495,9 +516,17 @@ __device__ __forceinline__ void enter_instance(const DeviceScene& s, Lane& L, ST
     const float4* m = s.insts + (size_t)first * 4;
     const float4 r0 = __ldg(m), r1 = __ldg(m + 1), r2 = __ldg(m + 2);
     const int4 meta = __ldg(reinterpret_cast<const int4*>(m + 3));
-    // o' = M^-1 [o 1], d' = M^-1 [d 0]  (src/ProxyObject.cpp:78-79; affine, so w = 1)
-    L.set_ray(r0.x * wox + r0.y * woy + r0.z * woz + r0.w, r1.x * wox + r1.y * woy + r1.z * woz + r1.w, r2.x * wox + r2.y * woy + r2.z * woz + r2.w,
-            r0.x * wdx + r0.y * wdy + r0.z * wdz, r1.x * wdx + r1.y * wdy + r1.z * wdz, r2.x * wdx + r2.y * wdy + r2.z * wdz);
+    // o' = (M^-1 [o 1]) * wRecip, d' = M^-1 [d 0]  (src/ProxyObject.cpp:78-79) in the REFERENCE's rounding, so the object-space ray —
+    // and with it t, a, b of an instanced hit — is the reference's to the last bit instead of differing by ulp(|o|):
+    //   origin    dpps over [o 1] (src/Matrix4x4.h:728-733): the four products rounded, summed as (p0 + p1) + (p2 + p3), then
+    //             multiplied by recipps(w), w = 1 for an affine matrix (miro_gpu_instance::w_recip, evaluated by the host);
+    //   direction scalar code (src/Matrix4x4.h:699-701): (m0 dx + m1 dy) + m2 dz, no contraction.
+    const float wr = meta.z == 0 ? 1.0f : __int_as_float(meta.z);
+#define MIRO_ROW_POINT(R) __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(R.x, wox), __fmul_rn(R.y, woy)), __fadd_rn(__fmul_rn(R.z, woz), R.w)), wr)
+#define MIRO_ROW_VECTOR(R) __fadd_rn(__fadd_rn(__fmul_rn(R.x, wdx), __fmul_rn(R.y, wdy)), __fmul_rn(R.z, wdz))
+    L.set_ray(MIRO_ROW_POINT(r0), MIRO_ROW_POINT(r1), MIRO_ROW_POINT(r2), MIRO_ROW_VECTOR(r0), MIRO_ROW_VECTOR(r1), MIRO_ROW_VECTOR(r2));
+#undef MIRO_ROW_POINT
+#undef MIRO_ROW_VECTOR
     L.cur_inst = (int32_t)first;
     L.cur = meta.x;
 }
@@ -523,16 +552,19 @@ __device__ __forceinline__ bool intersect_leaf(const DeviceScene& s, Lane& L, ST
             }
         }
     } else if (kind == MIRO_GPU_KIND_MBTRI) {
-        const float w1 = L.time, w0 = 1.0f - L.time;    // src/BVH.cpp:1323-1334
+        const float w1 = L.time, w0 = __fsub_rn(1.0f, L.time);    // src/BVH.cpp:1320-1321
         for (uint32_t i = 0; i < count; ++i) {
             const float4* t = s.mbtris + (size_t)(first + i) * 6;
             float4 a0, a1, a2, b0, b1, b2;
             ldg256(t, a0, a1); ldg256(t + 2, a2, b0); ldg256(t + 4, b1, b2);
             if (COUNT) ++n_tris;
             float4 p0, p1, p2;
-            p0.x = w1 * b0.x + w0 * a0.x; p0.y = w1 * b0.y + w0 * a0.y; p0.z = w1 * b0.z + w0 * a0.z;
-            p1.x = w1 * b1.x + w0 * a1.x; p1.y = w1 * b1.y + w0 * a1.y; p1.z = w1 * b1.z + w0 * a1.z;
-            p2.x = w1 * b2.x + w0 * a2.x; p2.y = w1 * b2.y + w0 * a2.y; p2.z = w1 * b2.z + w0 * a2.z;
+            // time * pose2 + (1 - time) * pose1 with both products rounded (src/BVH.cpp:1327-1335 is scalar code without contraction)
+#define MIRO_LERP(B, A) __fadd_rn(__fmul_rn(w1, B), __fmul_rn(w0, A))
+            p0.x = MIRO_LERP(b0.x, a0.x); p0.y = MIRO_LERP(b0.y, a0.y); p0.z = MIRO_LERP(b0.z, a0.z);
+            p1.x = MIRO_LERP(b1.x, a1.x); p1.y = MIRO_LERP(b1.y, a1.y); p1.z = MIRO_LERP(b1.z, a1.z);
+            p2.x = MIRO_LERP(b2.x, a2.x); p2.y = MIRO_LERP(b2.y, a2.y); p2.z = MIRO_LERP(b2.z, a2.z);
+#undef MIRO_LERP
             float ht, ha, hb;
             if (intersect_tri<ANY && !ALPHA>(L.r, L.tmin, L.hit.t, p0, p1, p2, ht, ha, hb) && (!ALPHA || hit_alpha(s.alpha, s.n_tris + first + i, ha, hb) >= 0.5f)) {
                 L.hit.t = ht; L.hit.a = ha; L.hit.b = hb;

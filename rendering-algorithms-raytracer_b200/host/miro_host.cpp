@@ -7,8 +7,18 @@
 #include <algorithm>
 #include <chrono>
 #include <map>
+#include <xmmintrin.h>
 
 namespace miro {
+
+float referenceRecip(float w) {
+    volatile float wv = w;                             // not a compile-time constant: the instruction itself must run
+    const __m128 v = _mm_set1_ps(wv);
+    const __m128 x0 = _mm_rcp_ps(v);
+    // src/SSE.h:85: 2 * x0 - val * (x0 * x0)
+    const __m128 r = _mm_sub_ps(_mm_mul_ps(_mm_set1_ps(2.0f), x0), _mm_mul_ps(v, _mm_mul_ps(x0, x0)));
+    return _mm_cvtss_f32(r);
+}
 
 // =====================================================================================  meshes
 void TriangleMesh::computeTangents(std::vector<Vector3>& tangents, std::vector<Vector3>& bitangents) const {
@@ -397,7 +407,7 @@ miro_gpu_scene_desc FlatScene::desc() const {
 }
 
 Scene::Scene() {}
-Scene::~Scene() { if (m_ctx) miro_gpu_destroy(m_ctx); }
+Scene::~Scene() { if (m_group) miro_gpu_group_destroy(m_group); if (m_ctx) miro_gpu_destroy(m_ctx); }
 
 int Scene::meshOrdinal(TriangleMesh* m) {
     if (m->ordinal < 0) {
@@ -581,13 +591,16 @@ bool Scene::preCalc() {
             }
             if (!o.m_transform.isAffine()) { m_error = "ProxyObject transform is not affine (projective instances are outside the supported scope)"; return false; }
             Matrix4x4 inv;
-            if (!o.m_transform.inverted(inv)) { m_error = "ProxyObject transform is singular"; return false; }
+            if (!o.m_transform.invertedAsReference(inv)) { m_error = "ProxyObject transform is singular"; return false; }
             const Matrix4x4 it = inv.transposed();
             const uint32_t ordinal = proxyOrdinal++;
+            // w = row 4 of the inverse . [o 1]: for an affine matrix rows 4's first three entries are (signed) zeros, so w is the
+            // inverse's m44 — which Matrix4x4::invert leaves at sd44 * detInv, often 1 - 2^-24 rather than 1
+            const float wRecip = referenceRecip(inv.at(3, 3));
             for (const auto& sub : blasSubs[o.m_blas]) {
                 miro_gpu_instance in; memset(&in, 0, sizeof(in));
                 for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) in.inv[4 * r + c] = inv.at(r, c);
-                in.blas_root = sub.first.ref; in.reserved[0] = ordinal;
+                in.blas_root = sub.first.ref; in.ordinal = ordinal; in.w_recip = wRecip;
                 for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) m_srcInstNxf.push_back(it.at(r, c));
                 // world bounds: the transformed corners of the sub-tree's sub-boxes (cf. ProxyObject::getAABB, src/ProxyObject.cpp:16-44,
                 // which transforms the single root box)
@@ -663,6 +676,18 @@ bool Scene::attach(int device_id) {
     return true;
 }
 
+bool Scene::attachDevices(const int* device_ids, int n) {
+    if (m_ctx) { miro_gpu_destroy(m_ctx); m_ctx = nullptr; }
+    if (!m_group) {
+        int rc = miro_gpu_group_create(&m_group, device_ids, n);
+        if (rc) { m_error = std::string("miro_gpu_group_create: ") + miro_gpu_last_error(nullptr); m_group = nullptr; return false; }
+    }
+    miro_gpu_scene_desc d = m_flat.desc();
+    int rc = miro_gpu_group_upload_scene(m_group, &d);
+    if (rc) { m_error = std::string("miro_gpu_group_upload_scene: ") + miro_gpu_group_last_error(m_group); return false; }
+    return true;
+}
+
 void Scene::renderParams(const Image* img, miro_gpu_render_params& p) const {
     memset(&p, 0, sizeof(p));
     p.width = img->width(); p.height = img->height();
@@ -672,12 +697,18 @@ void Scene::renderParams(const Image* img, miro_gpu_render_params& p) const {
 }
 
 bool Scene::raytraceImage(const Camera* cam, Image* img, int shard_index, int shard_count) {
-    if (!m_ctx) { m_error = "raytraceImage: scene is not attached to a GPU (there is no CPU renderer)"; return false; }
+    if (!m_ctx && !m_group) { m_error = "raytraceImage: scene is not attached to a GPU (there is no CPU renderer)"; return false; }
     miro_gpu_camera c; cam->fill(c);
     miro_gpu_render_params p; renderParams(img, p);
-    p.shard_index = shard_index; p.shard_count = shard_count;
-    int rc = miro_gpu_render(m_ctx, &c, &p, img->m_radiance.data());
-    if (rc) { m_error = std::string("miro_gpu_render: ") + miro_gpu_last_error(m_ctx); return false; }
+    if (m_group) {
+        if (shard_count > 1) { m_error = "raytraceImage: a scene attached to several devices shards the frame itself"; return false; }
+        int rc = miro_gpu_group_render(m_group, &c, &p, m_sampleSharding ? MIRO_GPU_SHARD_SAMPLES : MIRO_GPU_SHARD_BUCKETS, img->m_radiance.data());
+        if (rc) { m_error = std::string("miro_gpu_group_render: ") + miro_gpu_group_last_error(m_group); return false; }
+    } else {
+        p.shard_index = shard_index; p.shard_count = shard_count;
+        int rc = miro_gpu_render(m_ctx, &c, &p, img->m_radiance.data());
+        if (rc) { m_error = std::string("miro_gpu_render: ") + miro_gpu_last_error(m_ctx); return false; }
+    }
     const int w = img->width(), h = img->height();
     for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) {
         const float* q = &img->m_radiance[((size_t)y * w + x) * 3];
@@ -687,12 +718,22 @@ bool Scene::raytraceImage(const Camera* cam, Image* img, int shard_index, int sh
 }
 
 bool Scene::trace(const miro_gpu_ray* rays, size_t n, miro_gpu_hit* hits) {
+    if (m_group) {
+        int rc = miro_gpu_group_trace_closest(m_group, rays, n, hits);
+        if (rc) { m_error = std::string("miro_gpu_group_trace_closest: ") + miro_gpu_group_last_error(m_group); return false; }
+        return true;
+    }
     if (!m_ctx) { m_error = "trace: scene is not attached to a GPU (there is no CPU tracer)"; return false; }
     int rc = miro_gpu_trace_closest(m_ctx, rays, n, hits);
     if (rc) { m_error = std::string("miro_gpu_trace_closest: ") + miro_gpu_last_error(m_ctx); return false; }
     return true;
 }
 bool Scene::traceAny(const miro_gpu_ray* rays, size_t n, uint32_t* bits) {
+    if (m_group) {
+        int rc = miro_gpu_group_trace_any(m_group, rays, n, bits);
+        if (rc) { m_error = std::string("miro_gpu_group_trace_any: ") + miro_gpu_group_last_error(m_group); return false; }
+        return true;
+    }
     if (!m_ctx) { m_error = "traceAny: scene is not attached to a GPU (there is no CPU tracer)"; return false; }
     int rc = miro_gpu_trace_any(m_ctx, rays, n, bits);
     if (rc) { m_error = std::string("miro_gpu_trace_any: ") + miro_gpu_last_error(m_ctx); return false; }

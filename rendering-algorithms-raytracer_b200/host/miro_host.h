@@ -277,7 +277,12 @@ public:
 
     // GPU side.  attach() creates the device context (one per process/GPU) and uploads the flattened scene.
     bool attach(int device_id = 0);
-    miro_gpu_ctx* context() const { return m_ctx; }
+    // The same over several GPUs of one box (miro_gpu_group_*): the scene is replicated, raytraceImage() deals the frame's buckets
+    // (or, with setSampleSharding(true), the paths of every camera sample) to the devices, trace() / traceAny() split their batch.
+    bool attachDevices(const int* device_ids, int n);
+    void setSampleSharding(bool on) { m_sampleSharding = on; }
+    miro_gpu_group* group() const { return m_group; }
+    miro_gpu_ctx* context() const { return m_group ? miro_gpu_group_ctx(m_group, 0) : m_ctx; }
     // Scene::raytraceImage (src/Scene.cpp:86-217): float radiance into img->m_radiance and 8-bit pixels via Image::setPixel.
     bool raytraceImage(const Camera* cam, Image* img, int shard_index = 0, int shard_count = 1);
     // Scene::trace (src/Scene.cpp:295-298), batched.
@@ -315,6 +320,8 @@ protected:
     std::vector<miro_gpu_instance> m_srcInst; std::vector<float> m_srcInstNxf;
     std::vector<uint32_t> m_meshNormalBase, m_meshUvBase;
     miro_gpu_ctx* m_ctx = nullptr;
+    miro_gpu_group* m_group = nullptr;
+    bool m_sampleSharding = false;
     std::string m_error;
 };
 

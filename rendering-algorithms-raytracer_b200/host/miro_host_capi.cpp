@@ -81,6 +81,23 @@ int miro_host_attach(miro_host_scene* s, int device) {
     if (!s->loaded.scene->attach(device)) { s->error = s->loaded.scene->lastError(); return MIRO_GPU_ECUDA; }
     return MIRO_GPU_OK;
 }
+int miro_host_attach_devices(miro_host_scene* s, const int* device_ids, int n_devices, int sample_sharding) {
+    if (!s || !s->ready || !device_ids || n_devices < 1) return MIRO_GPU_EINVAL;
+    s->loaded.scene->setSampleSharding(sample_sharding != 0);
+    if (!s->loaded.scene->attachDevices(device_ids, n_devices)) { s->error = s->loaded.scene->lastError(); return MIRO_GPU_ECUDA; }
+    return MIRO_GPU_OK;
+}
+miro_gpu_group* miro_host_group(miro_host_scene* s) { return (s && s->ready) ? s->loaded.scene->group() : nullptr; }
+int miro_host_trace(miro_host_scene* s, const miro_gpu_ray* rays, size_t n, miro_gpu_hit* hits) {
+    if (!s || !s->ready) return MIRO_GPU_EINVAL;
+    if (!s->loaded.scene->trace(rays, n, hits)) { s->error = s->loaded.scene->lastError(); return MIRO_GPU_ECUDA; }
+    return MIRO_GPU_OK;
+}
+int miro_host_trace_any(miro_host_scene* s, const miro_gpu_ray* rays, size_t n, uint32_t* occluded_bits) {
+    if (!s || !s->ready) return MIRO_GPU_EINVAL;
+    if (!s->loaded.scene->traceAny(rays, n, occluded_bits)) { s->error = s->loaded.scene->lastError(); return MIRO_GPU_ECUDA; }
+    return MIRO_GPU_OK;
+}
 miro_gpu_ctx* miro_host_ctx(miro_host_scene* s) { return (s && s->ready) ? s->loaded.scene->context() : nullptr; }
 
 int miro_host_raytrace_image(miro_host_scene* s, float* rgb, unsigned char* rgb8, int shard_index, int shard_count) {

@@ -53,6 +53,11 @@ struct Matrix4x4 {
     bool isAffine() const { return m[12] == 0.f && m[13] == 0.f && m[14] == 0.f && m[15] == 1.f; }
     // general inverse (double precision cofactors); returns false when singular
     bool inverted(Matrix4x4& out) const;
+    // the inverse with the ROUNDING of the reference's Matrix4x4::invert (src/Matrix4x4.h:354-411): single-precision cofactor
+    // expansion over 2x2 and 3x3 sub-determinants, evaluated left to right.  A ProxyObject's object-space ray is
+    // M^-1 applied to the world-space ray (src/ProxyObject.cpp:78-79); for hit distances to agree with the reference to the
+    // last bits the matrix entries must be the reference's, not a better inverse.  (Compiled with -ffp-contract=off.)
+    bool invertedAsReference(Matrix4x4& out) const;
     Vector3 transformPoint(const Vector3& p) const {   // multiplyAndDivideByW, src/Matrix4x4.h:714-749
         float w = at(3, 0) * p.x + at(3, 1) * p.y + at(3, 2) * p.z + at(3, 3);
         float iw = 1.0f / w;
@@ -110,5 +115,31 @@ inline bool Matrix4x4::inverted(Matrix4x4& out) const {
     for (int i = 0; i < 16; ++i) out.m[i] = (float)(inv[i] * det);
     return true;
 }
+
+inline bool Matrix4x4::invertedAsReference(Matrix4x4& out) const {
+    // minor2(r, s, c, e): rows r < s, columns c < e (0-based) of *this
+    auto minor2 = [&](int r, int s, int c, int e) { return at(r, c) * at(s, e) - at(r, e) * at(s, c); };
+    // minor3(i, j): the sub-determinant without row i and column j, expanded along its first remaining row over the 2x2
+    // minors of its last two rows: first term minus second plus third, in that order
+    auto minor3 = [&](int i, int j) {
+        int rows[3], cols[3];
+        for (int k = 0, n = 0; k < 4; ++k) if (k != i) rows[n++] = k;
+        for (int k = 0, n = 0; k < 4; ++k) if (k != j) cols[n++] = k;
+        const int r = rows[0], p = rows[1], q = rows[2];
+        return at(r, cols[0]) * minor2(p, q, cols[1], cols[2]) - at(r, cols[1]) * minor2(p, q, cols[0], cols[2]) + at(r, cols[2]) * minor2(p, q, cols[0], cols[1]);
+    };
+    float sd[4][4];
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) sd[i][j] = minor3(i, j);
+    const float det = at(0, 0) * sd[0][0] - at(0, 1) * sd[0][1] + at(0, 2) * sd[0][2] - at(0, 3) * sd[0][3];
+    if (det == 0.0f) return false;
+    const float detInv = (float)(1.0 / (double)det);
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) out.at(i, j) = (((i + j) & 1) ? -sd[j][i] : sd[j][i]) * detInv;
+    return true;
+}
+
+// What the reference multiplies a transformed point by (Matrix4x4::multiplyAndDivideByW, src/Matrix4x4.h:728-733):
+// recipps(w) = rcpps(w) refined by one Newton step (src/SSE.h:81-86) — evaluated on THIS host's SSE unit, because the
+// table behind rcpps differs between CPU vendors and the reference running on this host would use this host's.
+float referenceRecip(float w);
 
 }  // namespace miro

@@ -140,6 +140,25 @@ class MiroScene:
         self.attached = True
         return self
 
+    def attach_devices(self, devices, sample_sharding=False):
+        """One caller, several GPUs (miro_gpu_group_*): render() shards the frame over `devices` and combines it on the first;
+        trace_closest() / trace_any() split their batch.  The same device may be listed twice."""
+        ids = (C.c_int * len(devices))(*devices)
+        self._check(self.L.miro_host_attach_devices(self.h, ids, len(devices), 1 if sample_sharding else 0), "attach_devices")
+        self.attached = True
+        return self
+
+    @property
+    def group(self):
+        return self.L.miro_host_group(self.h)
+
+    def group_counters(self):
+        c = capi.Counters()
+        rc = self.L.miro_gpu_group_get_counters(self.group, C.byref(c))
+        if rc != 0:
+            raise MiroError("group_get_counters failed: " + self.L.miro_gpu_group_last_error(self.group).decode())
+        return {k: getattr(c, k) for k, _ in capi.Counters._fields_}
+
     @property
     def ctx(self):
         return self.L.miro_host_ctx(self.h)
@@ -152,12 +171,18 @@ class MiroScene:
         """Host buffers in, host buffers out (H2D + kernel + D2H inside the call)."""
         rays = np.ascontiguousarray(rays, RAY_DTYPE)
         hits = np.empty(len(rays), HIT_DTYPE)
+        if self.group:
+            self._check(self.L.miro_host_trace(self.h, _ptr(rays), len(rays), _ptr(hits)), "trace (group)")
+            return hits
         self._gpu_check(self.L.miro_gpu_trace_closest(self.ctx, _ptr(rays), len(rays), _ptr(hits)), "trace_closest")
         return hits
 
     def trace_any(self, rays):
         rays = np.ascontiguousarray(rays, RAY_DTYPE)
         bits = np.zeros((len(rays) + 31) // 32, np.uint32)
+        if self.group:
+            self._check(self.L.miro_host_trace_any(self.h, _ptr(rays), len(rays), _ptr(bits)), "trace_any (group)")
+            return np.unpackbits(bits.view(np.uint8), bitorder="little")[:len(rays)].astype(bool)
         self._gpu_check(self.L.miro_gpu_trace_any(self.ctx, _ptr(rays), len(rays), _ptr(bits)), "trace_any")
         return np.unpackbits(bits.view(np.uint8), bitorder="little")[:len(rays)].astype(bool)
 

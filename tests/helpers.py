@@ -78,6 +78,14 @@ def compare_hits(scene, hits, ref, t_rel=1e-5, edge_eps=1e-4, rays=None):
     return ra.compare_with_reference(mesh, tri, proxy, hits["t"], hits["a"], hits["b"], ref, rays=rays, t_rel=t_rel, edge_eps=edge_eps)
 
 
+def adjudicate_hard(fx, scene, hits, ref, st, rays, script=None):
+    """The mismatches compare_hits could not class as ties (st["hard_idx"]) re-computed in float64 on both sides' triangles
+    (reference_arm.adjudicate_mismatches).  Returns the class counts; product_missed + unexplained are the true failures."""
+    geom = ra.SceneGeometry(script or fx.script, {n: fx.mesh(k) for k, n in enumerate(fx.names)})
+    mesh, tri, proxy = scene.resolve_hits(hits)
+    return ra.adjudicate_mismatches(geom, rays, st["hard_idx"], mesh, tri, proxy, ref)
+
+
 def reference_hits(fx, rays, threads=1):
     """The reference's own Scene::trace over `rays` on the fixture's scene, run on the spot (oracle/_ref/miro_ref travels to
     the GPU box); the fixture's geometry is REPLACED by what that run loaded (FixtureData.use_meshes), so call this before

@@ -223,12 +223,16 @@ def read_mesh_dump(path):
     return int(ordinal), dict(vertices=v, vidx=vi, normals=n, nidx=ni, uvs=t if nt else None, tidx=ti)
 
 
-def run_reference(fx, rays=None, threads=1, repeat=1, warmup=0, want_hits=False, script=None, extra_args=(), scene_dir=None, dump_meshes=False):
+def run_reference(fx, rays=None, threads=1, repeat=1, warmup=0, want_hits=False, script=None, extra_args=(), scene_dir=None, dump_meshes=False,
+                  shadow=None, extras=None):
     """One run of the unmodified reference behind its headless harness on the fixture's scene: Scene::trace over `rays`
     (timed inside the binary, scene load and BVH::build outside the timed region) and / or whatever `extra_args` ask for.
     Returns (events, hits): the harness's JSON event lines and, with want_hits, the reference's hit records (REFHIT); with
     dump_meshes a third value, {mesh name: mesh dict} — the geometry as the reference holds it after ITS load of the OBJ files
-    (see FixtureData.use_meshes)."""
+    (see FixtureData.use_meshes).  shadow = (light xyz, first, count): after the batch the harness casts PointLight shadow rays
+    from the hits of rays [first, first + count) and traces them as a second timed batch ("shadow" event); `extras` (a dict)
+    receives "shadow_rays" (RAY_DTYPE) and "shadow_hits" (REFHIT).  With threads > 1 the HIT RECORDS still come from a
+    single-threaded pass (the reference's concurrent traversals corrupt each other)."""
     if not have_reference():
         raise FileNotFoundError(REF_BIN)
     with tempfile.TemporaryDirectory() as tmp:
@@ -244,6 +248,10 @@ def run_reference(fx, rays=None, threads=1, repeat=1, warmup=0, want_hits=False,
             cmd += ["--trace", rp]
             if want_hits:
                 cmd += ["--hits", hp]
+            if shadow is not None:
+                light, first, count = shadow
+                cmd += ["--shadow-light"] + ["%.9g" % float(x) for x in light] + [str(int(first)), str(int(count)),
+                        "--shadow-rays", os.path.join(tmp, "shadow.rays"), "--shadow-hits", os.path.join(tmp, "shadow.hits")]
         cmd += list(extra_args)
         md = os.path.join(tmp, "meshdump")
         if dump_meshes:
@@ -254,6 +262,9 @@ def run_reference(fx, rays=None, threads=1, repeat=1, warmup=0, want_hits=False,
             raise RuntimeError("miro_ref failed (%d): %s" % (p.returncode, p.stderr[-2000:]))
         events = [json.loads(l) for l in p.stderr.splitlines() if l.startswith("{")]
         hits = np.fromfile(hp, REFHIT) if (rays is not None and want_hits) else None
+        if shadow is not None and extras is not None:
+            extras["shadow_rays"] = np.fromfile(os.path.join(tmp, "shadow.rays"), RAY_DTYPE)
+            extras["shadow_hits"] = np.fromfile(os.path.join(tmp, "shadow.hits"), REFHIT)
         if dump_meshes:
             meshes = {f[:-5]: read_mesh_dump(os.path.join(md, f))[1] for f in os.listdir(md) if f.endswith(".mesh")}
             return events, hits, meshes
@@ -298,3 +309,80 @@ def compare_with_reference(mesh, tri, proxy, t, a, b, ref, rays=None, t_rel=1e-5
                 max_abs_a=float(np.abs(a - ref["a"])[ok].max()) if ok.any() else 0.0,
                 max_abs_b=float(np.abs(b - ref["b"])[ok].max()) if ok.any() else 0.0,
                 closer=int((~same & g_hit & ((t < ref["t"]) | ~r_hit)).sum()))
+
+
+# ---------------------------------------------------------------------------------------------- float64 adjudication of mismatches
+class SceneGeometry:
+    """Triangles and instance transforms of a scene script by the identities hit records carry (mesh ordinal, triangle index,
+    proxy ordinal), for re-computing single intersections in float64.  meshes: {mesh name: mesh dict}."""
+
+    def __init__(self, script, meshes):
+        self.names = []; self.mb_pair = {}; self.inv = []
+        for line in script.splitlines():
+            t = line.split("#")[0].split()
+            if not t:
+                continue
+            if t[0] == "mesh":
+                self.names.append(t[1])
+            elif t[0] == "mbobject":
+                self.mb_pair[self.names.index(t[1])] = self.names.index(t[2])
+            elif t[0] == "instance":
+                M = np.array([np.float32(x) for x in t[2:18]], np.float64).reshape(4, 4)
+                self.inv.append(np.linalg.inv(M))
+        self.meshes = [meshes[n] for n in self.names]
+
+    def triangle(self, mesh, tri, time):
+        m = self.meshes[mesh]
+        v = m["vertices"][m["vidx"][tri]].astype(np.float64)
+        if mesh in self.mb_pair:      # time * pose2 + (1 - time) * pose1, src/BVH.cpp:1320-1335
+            m2 = self.meshes[self.mb_pair[mesh]]
+            v = float(time) * m2["vertices"][m2["vidx"][tri]].astype(np.float64) + (1.0 - float(time)) * v
+        return v
+
+    def intersect(self, ray, mesh, tri, proxy):
+        """Exact-arithmetic (float64) crossing of `ray` with one triangle: (t, margin) — margin = the smallest barycentric
+        weight (> 0: inside) — or None when the ray is parallel to the plane."""
+        o = ray["o"].astype(np.float64); d = ray["d"].astype(np.float64)
+        if proxy >= 0:
+            Mi = self.inv[proxy]
+            o = Mi[:3, :3] @ o + Mi[:3, 3]; d = Mi[:3, :3] @ d
+        v = self.triangle(mesh, tri, ray["time"])
+        e0, e1 = v[1] - v[0], v[2] - v[0]
+        p = np.cross(d, e1); det = e0 @ p
+        if det == 0.0:
+            return None
+        tv = o - v[0]; a = (tv @ p) / det; q = np.cross(tv, e0); b = (d @ q) / det; t = (e1 @ q) / det
+        return t, min(a, b, 1.0 - a - b)
+
+
+def adjudicate_mismatches(geom, rays, idx, mesh, tri, proxy, ref, margin_eps=1e-6, t_eps=1e-6):
+    """Every id mismatch in `idx` re-computed in float64 on both sides' triangles.  Classes (first match):
+      reference_missed : the product's triangle is truly crossed, clearly inside (margin > margin_eps), within [tmin, tmax), and
+                         NEARER than what the reference reports (or the reference reports a miss) — the reference's traversal
+                         lost a hit (its slab test is not conservative and its triangle test not watertight);
+      product_missed   : the same with the roles swapped — a defect of the product: HARD;
+      coincident       : both crossings are real and their distances agree to t_eps: overlapping / touching surfaces;
+      edge             : the nearer real crossing lies within margin_eps of an edge or vertex of its triangle;
+      unexplained      : anything else: HARD."""
+    out = dict(reference_missed=0, product_missed=0, coincident=0, edge=0, unexplained=0, hard_idx=[])
+    for i in idx:
+        r = rays[i]
+        g = geom.intersect(r, int(mesh[i]), int(tri[i]), int(proxy[i])) if mesh[i] >= 0 else None
+        f = geom.intersect(r, int(ref["mesh"][i]), int(ref["tri"][i]), int(ref["proxy"][i])) if ref["mesh"][i] >= 0 else None
+        ok = lambda x: x is not None and r["tmin"] <= x[0] < r["tmax"] and x[1] > -margin_eps
+        gv, fv = ok(g), ok(f)
+        clear = lambda x: x[1] > margin_eps
+        if gv and fv and abs(g[0] - f[0]) <= t_eps * abs(f[0]):
+            k = "coincident"
+        elif gv and clear(g) and (not fv or g[0] < f[0]):
+            k = "reference_missed"
+        elif fv and clear(f) and (not gv or f[0] < g[0]):
+            k = "product_missed"
+        elif (gv and not clear(g)) or (fv and not clear(f)):
+            k = "edge"
+        else:
+            k = "unexplained"
+        out[k] += 1
+        if k in ("product_missed", "unexplained"):
+            out["hard_idx"].append(int(i))
+    return out

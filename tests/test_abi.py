@@ -53,6 +53,9 @@ def test_no_cpu_fallback_without_a_device():
     rc = L.miro_gpu_create(C.byref(ctx), 0)
     assert rc == capi.ENODEVICE and not ctx.value
     assert b"no CPU fallback" in L.miro_gpu_last_error(None)
+    grp = C.c_void_p()
+    ids = (C.c_int * 2)(0, 1)
+    assert L.miro_gpu_group_create(C.byref(grp), ids, 2) == capi.ENODEVICE and not grp.value      # several GPUs behind one caller: the same
     fx = helpers.Fixture(helpers.fixture_path("c1_cornell"))
     sc = fx.scene()
     with pytest.raises(Exception) as e:

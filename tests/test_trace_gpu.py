@@ -46,12 +46,10 @@ def test_closest_hit_matches_reference(loaded):
     hits = sc.trace_closest(fx.rays)
     st = helpers.compare_hits(sc, hits, fx.hits, t_rel=1e-5, rays=fx.rays)
     print(name, {k: v for k, v in st.items() if k != "hard_idx"})
-    if name == "c5_mb_instances":      # motion blur + instances: t relative to the coordinates involved (helpers.compare_hits)
-        assert st["hard"] <= 3 and st["id_match"] >= 0.999, st
-        assert st["frac_t_within_pos"] >= 0.9999 and st["frac_t_within"] >= 0.97, st
-        return
     # every id mismatch must be an edge/vertex case; C1's symmetric camera puts a whole pixel diagonal exactly on
-    # the shared diagonal of the back wall's two triangles, so its tie count alone exceeds 0.01 % of the rays
+    # the shared diagonal of the back wall's two triangles, so its tie count alone exceeds 0.01 % of the rays.
+    # Motion blur + instances (c5) are held to the same bar since round 2: the object-space ray is built with the reference's
+    # own rounding (enter_instance), so instanced hit distances agree to 2e-7 like all others.
     assert st["hard"] == 0, st
     assert st["id_match"] >= 0.9999 or name == "c1_cornell", st
     assert st["id_match"] >= 0.999, st
@@ -69,9 +67,9 @@ def test_closest_hit_matches_oracle(loaded):
     oref["t"], oref["a"], oref["b"], oref["mesh"], oref["tri"], oref["proxy"] = ohits["t"], ohits["a"], ohits["b"], omesh, otri, oproxy
     st = helpers.compare_hits(sc, hits, oref, rays=fx.rays)
     print(name, {k: v for k, v in st.items() if k != "hard_idx"})
-    assert st["hard"] <= (3 if name == "c5_mb_instances" else 0), st
+    assert st["hard"] == 0, st
     assert st["id_match"] >= 0.999 and st["frac_t_within_pos"] >= 0.9999, st
-    assert st["frac_t_within"] == 1.0 or name == "c5_mb_instances", st
+    assert st["frac_t_within"] == 1.0, st
 
 
 def test_any_hit_matches_closest(loaded):
@@ -154,12 +152,14 @@ def test_full_size_batches_against_reference(name):
     hits = sc.trace_closest(fx.rays)
     st = helpers.compare_hits(sc, hits, fx.hits, t_rel=1e-5, rays=fx.rays)
     print(name, len(fx.rays), {k: v for k, v in st.items() if k != "hard_idx"})
-    assert st["id_match"] >= 0.9999 or name != "c2_explosion", st
-    assert st["id_match"] >= 0.9995, st
-    assert st["hard"] <= 1e-5 * len(fx.rays), st
-    assert st["frac_t_within_pos"] >= 0.9999, st
-    if name == "c2_explosion":
-        assert st["frac_t_within"] >= 0.99999, st
+    # north_star: ids >= 99.99 %, the remainder only ties; t within 1e-5 relative wherever the ids agree
+    assert st["id_match"] >= 0.9999, st
+    assert st["frac_t_within"] == 1.0 and st["max_rel_t"] <= 1e-5, st
+    # what the barycentric heuristic could not class as an edge / equal-distance tie is re-computed in float64 on both sides'
+    # triangles: no ray may remain where the PRODUCT lost a hit or where the two answers cannot be explained
+    adj = helpers.adjudicate_hard(fx, sc, hits, fx.hits, st, fx.rays)
+    print(name, "float64 adjudication of", st["hard"], "unclassed mismatches:", {k: v for k, v in adj.items() if k != "hard_idx"})
+    assert adj["product_missed"] == 0 and adj["unexplained"] == 0, adj
     occ = sc.trace_any(fx.rays)
     assert (occ == (hits["prim"] >= 0)).all()
     h = hits["prim"] >= 0

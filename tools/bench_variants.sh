@@ -1,10 +1,15 @@
 #!/usr/bin/env bash
-# run on the GPU box: bench every build/variants/*.so (and the default lib) and print the three launch times
+# run on the GPU box: bench every build/variants/*.so (tools/tune.sh) under both traversal kernels and print the three launch times
+# usage: tools/bench_variants.sh [warp|pool|both] [lib-name-filter]
+which=${1:-both}; filt=${2:-}
 shopt -s nullglob
-for lib in default build/variants/*.so; do
-  if [ "$lib" = default ]; then unset MIRO_GPU_LIB; else export MIRO_GPU_LIB=$PWD/$lib; fi
-  python bench.py --steps 10 --warmup 3 --no-cpu 2>/dev/null | python -c "
+for lib in build/variants/*$filt*.so; do
+  for k in warp pool; do
+    [ "$which" != both ] && [ "$which" != $k ] && continue
+    case $lib in *pool*) [ $k = warp ] && continue;; esac
+    MIRO_GPU_LIB=$PWD/$lib MIRO_GPU_TRACE_KERNEL=$k python bench.py --steps 10 --warmup 3 --no-cpu --legs c2 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); r=d['roofline']
-print('$lib'.ljust(28), 'Mrays/s %7.1f  ms %s  frac %.3f' % (d['value'], ['%.3f'%x['ms'] for x in r['all_launches']], r['frac']))"
+print('$lib $k'.ljust(48), 'Mrays/s %7.1f  ms %s  frac %.3f' % (d['value'], ['%.3f'%x['ms'] for x in r['all_launches']], r['frac']))"
+  done
 done

@@ -13,7 +13,7 @@ while [ $# -ge 2 ]; do
     /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -ccbin /usr/bin/g++ --compiler-options -fPIC,-ffp-contract=off $flags \
         -c "$PKG/csrc/miro_gpu_api.cu" -o "$tmp/api.o"
     /usr/local/cuda/bin/nvcc -shared -gencode arch=compute_100a,code=sm_100a -ccbin /usr/bin/g++ -o "$ROOT/build/variants/$name.so" "$tmp/api.o" \
-        "$PKG/build/render.o" "$PKG/build/build.o" "$PKG/build/miro_bvh.o" "$PKG/build/miro_host.o" "$PKG/build/miro_script.o" "$PKG/build/miro_host_capi.o"
+        "$PKG/build/render.o" "$PKG/build/build.o" "$PKG/build/multi.o" "$PKG/build/miro_bvh.o" "$PKG/build/miro_host.o" "$PKG/build/miro_script.o" "$PKG/build/miro_host_capi.o"
     rm -rf "$tmp"; echo "built build/variants/$name.so ($flags)"
   ) &
 done
