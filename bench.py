@@ -20,6 +20,7 @@ replicated) and `render_scaling` holds the strong-scaling record of one tile-sha
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--legs c2,big,c5,render] [--no-cpu]
 """
 import argparse
+import ctypes
 import json
 import os
 import re
@@ -419,7 +420,30 @@ def e2e_legs(sc, leg, args, world, barrier):
     pageable = run(L.miro_gpu_trace_closest, L.miro_gpu_trace_any, [p.ctypes.data for p in plain], [h.ctypes.data for h in ph], pb.ctypes.data, 48, max(3, e2e_steps // 2))
     pageable["ray_format"] = "miro_gpu_ray, 48 B, PAGEABLE host buffers (what an unmodified Miro caller holds)"
     assert np.array_equal(ph[1]["prim"], inco_hits["prim"])
-    return e2e, packed, pageable
+    # camera rays made on the device (miro_gpu_trace_primary): a renderer's primary batch needs no upload at all; the other two
+    # batches as packed rays
+    cam = sc.camera()
+
+    def prim_call(ctx, _rays, _n, out):
+        return L.miro_gpu_trace_primary(ctx, ctypes.byref(cam), bw.WIDTH, bw.HEIGHT, 0, out, None)
+
+    def one_dc():
+        prim_call(sc.ctx, None, N_BATCH, hp[0]); L.miro_gpu_trace_closest_packed(sc.ctx, pinned32[1].data_ptr(), N_BATCH, hp[1]); L.miro_gpu_trace_any_packed(sc.ctx, pinned32[2].data_ptr(), N_BATCH, out_bits.data_ptr())
+    for _ in range(2):
+        one_dc()
+    barrier()
+    t0 = time.time()
+    for _ in range(e2e_steps):
+        one_dc()
+    torch.cuda.synchronize()
+    s_dc = time.time() - t0
+    if world > 1:
+        t = torch.tensor([s_dc], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        s_dc = float(t.item())
+    devcam = {"value": 3 * N_BATCH * e2e_steps * world / s_dc * 1e-6, "unit": "Mrays/s", "h2d_bytes_per_step": 2 * N_BATCH * 32, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+              "ray_format": "primary batch: camera rays generated on the device (miro_gpu_trace_primary, hits only travel); incoherent and shadow batches: 32 B packed rays, pinned"}
+    return e2e, packed, pageable, devcam
 
 
 def render_legs(local, with_reference):
@@ -585,11 +609,11 @@ def gpu_main(args, rank, world, local):
             row["cpu_baseline"] = {"value": ref["n"] / ref["seconds_best"] * 1e-6, "unit": "Mrays/s", "cores": ref["threads"], "kind": "reference",
                                    "sample": ref["sample"] + ", best of 3", "scene_load_and_bvh_build_s": ref["build_s"]}
         if name == "c2":
-            e2e, packed, pageable = e2e_legs(sc, leg, args, world, barrier)
+            e2e, packed, pageable, devcam = e2e_legs(sc, leg, args, world, barrier)
             line = {"metric": "Mrays/s", "value": leg["value"], "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                     "ms_per_step": leg["total_ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                     "dtype": "f32", "data": "synthetic", "config": bench_config(w), "clocks": clocks, "gpu_launches": 3 * args.steps,
-                    "e2e": e2e, "e2e_packed": packed, "e2e_pageable": pageable, "host": numa, "sustained": leg["sustained"], "roofline": roof}
+                    "e2e": e2e, "e2e_packed": packed, "e2e_pageable": pageable, "e2e_device_camera": devcam, "host": numa, "sustained": leg["sustained"], "roofline": roof}
             line["roofline"]["frac_abi_node_layout"] = (leg["per_launch"][int(np.argmax(leg["launch_ms"]))]["bytes"] + leg["per_launch"][int(np.argmax(leg["launch_ms"]))]["nodes"] * (128 - NODE_BYTES)) / (max(leg["launch_ms"]) * 1e-3) * 1e-9 / hbm_peak
             line["roofline"]["note"] = ("algorithmic bytes count the SHIPPED 64-byte device node; frac_abi_node_layout counts the 128-byte ABI node as kernel "
                                         "versions <= v4 fetched it (comparable with profiles/bench_r1_v1..v4.json).")

@@ -305,6 +305,13 @@ int miro_gpu_trace_any_device(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, siz
 int miro_gpu_trace_closest_packed(miro_gpu_ctx* ctx, const miro_gpu_ray32* rays, size_t n, miro_gpu_hit* hits);
 int miro_gpu_trace_any_packed(miro_gpu_ctx* ctx, const miro_gpu_ray32* rays, size_t n, uint32_t* occluded_bits);
 
+/* Primary rays made where they are traced: Camera::eyeRayAdaptive at the pixel centres (src/Camera.cpp:116-174 — the level-1 sample of
+ * Scene::adaptiveSampleScene, src/Scene.cpp:254 — with the time sample and lens of miro_gpu_render at the same seed) are generated on
+ * the device and traced; only the hit records travel (20 B per ray instead of 48 B up + 20 B down, and PCIe bounds the
+ * host-pointer calls).  hits[y * width + x], row 0 = bottom; hits: host or device pointer.  d_rays_out: NULL, or a device
+ * buffer of width * height rays that receives the generated rays (origin, direction, tmin = 1e-3, tmax = MIRO_GPU_TMAX, time). */
+int miro_gpu_trace_primary(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, int width, int height, uint64_t seed, miro_gpu_hit* hits, miro_gpu_ray* d_rays_out);
+
 /* Scene::raytraceImage.  rgb_out: width*height*3 floats, row 0 = bottom row (src/Image.cpp:150-151),
  * linear radiance before Image::Map.  rgb_out may be a host or a device pointer. */
 int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, const miro_gpu_render_params* params, float* rgb_out);
@@ -323,7 +330,8 @@ int miro_gpu_reset_counters(miro_gpu_ctx* ctx);
  * every camera sample (MIRO_GPU_SHARD_SAMPLES: path p to member p % n — path-traced configurations with min_subdivs ==
  * max_subdivs) to the members, and combines the members' frames on the first device with one kernel that reads the others'
  * memory over NVLink peer access (staged by cudaMemcpyPeerAsync where peer access is unavailable).  Random numbers are keyed by
- * (pixel, sample, path), so the frame equals the single-GPU frame (bit for bit with bucket sharding).  rgb_out: host pointer,
+ * (pixel, sample, path), so the frame equals the single-GPU frame (to the rounding of a light loop's accumulation order, which also differs between two
+ * single-GPU renders: float atomics).  rgb_out: host pointer,
  * or device pointer on the first device.  The trace calls split the batch into contiguous parts, one per member (host
  * pointers; no exchange).  A group is used from one host thread at a time; it fans out to one worker thread per member
  * for the duration of a call. */

@@ -111,7 +111,7 @@ class Counters(C.Structure):
 # every symbol include/miro_gpu.h and include/miro_host.h declare (checked by tests/test_abi.py)
 GPU_SYMBOLS = ["miro_gpu_create", "miro_gpu_destroy", "miro_gpu_last_error", "miro_gpu_abi_version", "miro_gpu_sizeof", "miro_gpu_set_stream", "miro_gpu_set_trace_chaining", "miro_gpu_set_trace_kernel",
                "miro_gpu_upload_scene", "miro_gpu_trace_closest", "miro_gpu_trace_any", "miro_gpu_trace_closest_packed", "miro_gpu_trace_any_packed", "miro_gpu_trace_closest_device",
-               "miro_gpu_trace_any_device", "miro_gpu_render", "miro_gpu_enable_counting", "miro_gpu_get_counters",
+               "miro_gpu_trace_any_device", "miro_gpu_trace_primary", "miro_gpu_render", "miro_gpu_enable_counting", "miro_gpu_get_counters",
                "miro_gpu_reset_counters",
                "miro_gpu_group_create", "miro_gpu_group_destroy", "miro_gpu_group_size", "miro_gpu_group_ctx", "miro_gpu_group_last_error", "miro_gpu_group_peer_access",
                "miro_gpu_group_upload_scene", "miro_gpu_group_render", "miro_gpu_group_trace_closest", "miro_gpu_group_trace_any", "miro_gpu_group_get_counters",
@@ -143,6 +143,7 @@ def lib():
     for name in ("miro_gpu_trace_closest", "miro_gpu_trace_any", "miro_gpu_trace_closest_device", "miro_gpu_trace_any_device",
                  "miro_gpu_trace_closest_packed", "miro_gpu_trace_any_packed"):
         f = getattr(L, name); f.argtypes = [vp, vp, sz, vp]; f.restype = i32
+    L.miro_gpu_trace_primary.argtypes = [vp, C.POINTER(Camera), i32, i32, C.c_uint64, vp, vp]; L.miro_gpu_trace_primary.restype = i32
     L.miro_gpu_render.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), vp]; L.miro_gpu_render.restype = i32
     L.miro_gpu_enable_counting.argtypes = [vp, i32]; L.miro_gpu_enable_counting.restype = i32
     L.miro_gpu_set_trace_chaining.argtypes = [vp, i32]; L.miro_gpu_set_trace_chaining.restype = i32

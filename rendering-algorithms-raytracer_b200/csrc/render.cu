@@ -96,7 +96,21 @@ struct RenderState {
     float* rgb_dev = nullptr; size_t frame_pixels = 0;
     float* gamma_lut = nullptr;
     uint32_t* h_count = nullptr;       // pinned
+    uint32_t* bucket_first = nullptr;  // per owned bucket: its first position in the shard's pixel list (+ the total at the end)
+    size_t bucket_cap = 0;
 };
+
+// The shard's pixel list in the reference's bucket order (Scene.cpp:160-175: buckets row-major, pixels row-major inside a bucket):
+// one block per owned bucket, its place in the list from a prefix sum over bucket sizes the host makes (a few thousand entries).
+// The frame's pixel list used to be built and uploaded by the host: 8 MB and ~10 ms per 1080p frame, longer than the frame's kernels.
+__global__ void __launch_bounds__(1024)
+k_own_pixels(const uint32_t* __restrict__ bucket_first, int shard_index, int shard_count, int nbx, int W, int H, uint32_t* __restrict__ out) {
+    const int b = shard_index + (int)blockIdx.x * shard_count;
+    const int bx = b % nbx, by = b / nbx;
+    const int bw = min(32, W - bx * 32), bh = min(32, H - by * 32);
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    if (lx < bw && ly < bh) out[bucket_first[blockIdx.x] + (uint32_t)(ly * bw + lx)] = (uint32_t)((by * 32 + ly) * W + bx * 32 + lx);
+}
 
 __device__ __forceinline__ void add_rgb(float4* buf, uint32_t pixel, float3x c) {
     float* p = reinterpret_cast<float*>(buf + pixel);
@@ -115,7 +129,7 @@ k_raygen(DeviceCamera cam, RenderParamsDev P, const uint32_t* __restrict__ activ
     const uint32_t cs = first_cs + i;
     const uint32_t k2 = (uint32_t)(level * level);
     const uint32_t a = cs / k2, s = cs - a * k2;
-    const uint32_t pixel = __ldg(active + a);
+    const uint32_t pixel = active ? __ldg(active + a) : a;      // no list: every pixel of the frame, row-major
     const int x = (int)(pixel % (uint32_t)P.width), y = (int)(pixel / (uint32_t)P.width);
     float minX = 0.5f, maxX = 0.5f, minY = 0.5f, maxY = 0.5f;         // level 1: the pixel centre (Scene.cpp:254)
     if (level > 1) {
@@ -545,7 +559,7 @@ void render_state_free(miro_gpu_ctx* ctx) {
     if (!ctx->render_state) return;
     RenderState* st = static_cast<RenderState*>(ctx->render_state);
     free_queues(st);
-    cudaFree(st->level_sum); cudaFree(st->result); cudaFree(st->active[0]); cudaFree(st->active[1]); cudaFree(st->rgb_dev); cudaFree(st->gamma_lut);
+    cudaFree(st->level_sum); cudaFree(st->result); cudaFree(st->active[0]); cudaFree(st->active[1]); cudaFree(st->rgb_dev); cudaFree(st->gamma_lut); cudaFree(st->bucket_first);
     if (st->h_count) cudaFreeHost(st->h_count);
     if (st->aux) cudaStreamDestroy(st->aux);
     if (st->ev_fork) cudaEventDestroy(st->ev_fork);
@@ -612,11 +626,75 @@ static int ensure_frame(miro_gpu_ctx* ctx, RenderState* st, size_t pixels) {
 }
 
 static inline int grid_for(size_t n, int block) { return (int)std::min<size_t>((n + block - 1) / block, 0x7fffffff); }
-static const int kPersistentGrid = 148 * 8;
+
 
 }  // namespace miro
 
 using namespace miro;
+
+// camera basis (Camera.cpp:123-137) — computed on the host once per frame
+static DeviceCamera make_device_camera(const miro_gpu_camera* cam, int W, int H) {
+    DeviceCamera dc;
+    auto norm = [](float3x a) { const float l = 1.0f / sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); return f3(a.x * l, a.y * l, a.z * l); };
+    const float3x vd = f3(cam->view_dir[0], cam->view_dir[1], cam->view_dir[2]), up = f3(cam->up[0], cam->up[1], cam->up[2]);
+    dc.w = norm(f3(-vd.x, -vd.y, -vd.z));
+    dc.u = norm(cross3(up, dc.w));
+    dc.v = cross3(dc.w, dc.u);
+    dc.eye = f3(cam->eye[0], cam->eye[1], cam->eye[2]);
+    dc.top = tanf(cam->fov_deg * (3.1415926f / 360.0f));
+    dc.right = ((float)W / (float)H) * dc.top;
+    dc.focus_plane = cam->focus_plane; dc.aperture = cam->aperture; dc.shutter = cam->shutter_speed;
+    return dc;
+}
+
+// Primary rays made where they are traced: Camera::eyeRayAdaptive at the pixel centres (Camera.cpp:116-174; the level-1 sample of
+// Scene::adaptiveSampleScene, Scene.cpp:254) generated on the device, traced, and only the 20-byte hit records travel — a third of
+// what miro_gpu_trace_closest moves for the same rays (48 B up + 20 B down per ray over PCIe, which bounds the host-pointer
+// calls).  Pixel order: row-major, row 0 = bottom (hits[y * width + x]); the rays are those miro_gpu_render traces at level 1
+// with the same seed.  hits: host or device pointer.  rays_out (optional, device pointer or NULL): the generated rays.
+extern "C" int miro_gpu_trace_primary(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, int width, int height, uint64_t seed, miro_gpu_hit* hits, miro_gpu_ray* rays_out) {
+    if (!ctx) return MIRO_GPU_EINVAL;
+    if (!cam || !hits) return set_error(ctx, MIRO_GPU_EINVAL, "miro_gpu_trace_primary: NULL argument");
+    if (!ctx->has_scene) return set_error(ctx, MIRO_GPU_ENOSCENE, "trace before upload_scene");
+    if (width <= 0 || height <= 0 || (size_t)width * height > 0x7fffffffu) return set_error(ctx, MIRO_GPU_EINVAL, "bad image size");
+    MIRO_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)width * height;
+    cudaPointerAttributes attr;
+    const bool out_is_device = cudaPointerGetAttributes(&attr, hits) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    if (!rays_out) { MIRO_CUDA(ctx, ctx->d_rays.reserve(n)); }
+    miro_gpu_ray* d_rays = rays_out ? rays_out : ctx->d_rays.ptr;
+    miro_gpu_hit* d_hits = hits;
+    if (!out_is_device) { MIRO_CUDA(ctx, ctx->d_hits.reserve(n)); d_hits = ctx->d_hits.ptr; }
+    if (!ctx->copy_out) MIRO_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    const DeviceCamera dc = make_device_camera(cam, width, height);
+    RenderParamsDev P{};
+    P.width = width; P.height = height; P.num_paths = 1; P.seed = seed;
+    // chunks of rows: the download of chunk k runs while chunk k + 1 is traced
+    const size_t chunk = (size_t)1 << 18;
+    const size_t n_chunks = (n + chunk - 1) / chunk;
+    while (ctx->pipe_events.size() < 2 * n_chunks) { cudaEvent_t e; MIRO_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->pipe_events.push_back(e); }
+    cudaStream_t s = ctx->stream;
+    EventPair tot = begin_timing(ctx, false);
+    for (size_t k = 0; k < n_chunks; ++k) {
+        const size_t off = k * chunk, m = std::min(chunk, n - off);
+        k_raygen<<<grid_for(m, SHADE_BLOCK), SHADE_BLOCK, 0, s>>>(dc, P, nullptr, (uint32_t)off, (uint32_t)m, 1, 0u, d_rays + off);
+        ctx->launches++;
+        EventPair p = begin_timing(ctx, true);
+        launch_trace_closest(ctx, d_rays + off, m, nullptr, d_hits + off);
+        end_timing(ctx, p);
+        if (!out_is_device) {
+            MIRO_CUDA(ctx, cudaEventRecord(ctx->pipe_events[k], s));
+            MIRO_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->pipe_events[k], 0));
+            MIRO_CUDA(ctx, cudaMemcpyAsync(hits + off, d_hits + off, m * sizeof(miro_gpu_hit), cudaMemcpyDeviceToHost, ctx->copy_out));
+        }
+    }
+    end_timing(ctx, tot);
+    MIRO_CUDA(ctx, cudaGetLastError());
+    if (!out_is_device) MIRO_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
+    MIRO_CUDA(ctx, cudaStreamSynchronize(s));
+    return MIRO_GPU_OK;
+}
 
 extern "C" int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, const miro_gpu_render_params* rp, float* rgb_out) {
     if (!ctx) return MIRO_GPU_EINVAL;
@@ -630,24 +708,13 @@ extern "C" int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, co
     if (ctx->shading.n_prims == 0 && (ctx->n_tris || ctx->n_mbtris)) return set_error(ctx, MIRO_GPU_EINVAL, "scene has no shading records (prims)");
     MIRO_CUDA(ctx, cudaSetDevice(ctx->device));
     RenderState* st = state_of(ctx);
+    const int kPersistentGrid = ctx->sm_count * 8;      // the persistent shading / resolve kernels: 8 blocks per SM
     const int W = rp->width, H = rp->height;
     const size_t pixels = (size_t)W * H;
     int rc;
     if ((rc = ensure_frame(ctx, st, pixels))) return rc;
 
-    // ---- camera basis (Camera.cpp:123-137) — computed on the host once per frame
-    DeviceCamera dc;
-    {
-        auto norm = [](float3x a) { const float l = 1.0f / sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); return f3(a.x * l, a.y * l, a.z * l); };
-        const float3x vd = f3(cam->view_dir[0], cam->view_dir[1], cam->view_dir[2]), up = f3(cam->up[0], cam->up[1], cam->up[2]);
-        dc.w = norm(f3(-vd.x, -vd.y, -vd.z));
-        dc.u = norm(cross3(up, dc.w));
-        dc.v = cross3(dc.w, dc.u);
-        dc.eye = f3(cam->eye[0], cam->eye[1], cam->eye[2]);
-        dc.top = tanf(cam->fov_deg * (3.1415926f / 360.0f));
-        dc.right = ((float)W / (float)H) * dc.top;
-        dc.focus_plane = cam->focus_plane; dc.aperture = cam->aperture; dc.shutter = cam->shutter_speed;
-    }
+    const DeviceCamera dc = make_device_camera(cam, W, H);
     RenderParamsDev P;
     P.width = W; P.height = H; P.num_paths = rp->num_paths; P.max_bounces = rp->max_bounces;
     P.path_trace = rp->path_trace; P.sample_env = rp->sample_env; P.seed = rp->seed; P.inv_paths = 1.0f / (float)rp->num_paths;
@@ -682,21 +749,24 @@ extern "C" int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, co
     struct Restore { miro_gpu_ctx* c; cudaStream_t s; ~Restore() { c->stream = s; c->work_lane = 0; } } restore{ctx, s};      // also on error returns
 
     // ---- pixels of this shard: 32x32 buckets in the order of Scene.cpp:160-175, bucket b owned when b % shard_count == shard_index
-    std::vector<uint32_t> own;
-    {
-        const int sc = std::max(1, rp->shard_count), si = rp->shard_index;
-        if (si < 0 || si >= sc) return set_error(ctx, MIRO_GPU_EINVAL, "shard_index out of range");
-        const int nbx = (W + 31) / 32, nby = (H + 31) / 32;
-        own.reserve(pixels / sc + 1024);
-        for (int b = si; b < nbx * nby; b += sc) {
-            const int bx = b % nbx, by = b / nbx;
-            for (int y = by * 32; y < std::min((by + 1) * 32, H); ++y)
-                for (int x = bx * 32; x < std::min((bx + 1) * 32, W); ++x) own.push_back((uint32_t)(y * W + x));
-        }
+    const int shard_n = std::max(1, rp->shard_count), shard_i = rp->shard_index;
+    if (shard_i < 0 || shard_i >= shard_n) return set_error(ctx, MIRO_GPU_EINVAL, "shard_index out of range");
+    const int nbx = (W + 31) / 32, nby = (H + 31) / 32;
+    std::vector<uint32_t> first(1, 0u);                // first[k]: position of owned bucket k's first pixel in the list; back(): the total
+    for (int b = shard_i; b < nbx * nby; b += shard_n) {
+        const int bx = b % nbx, by = b / nbx;
+        first.push_back(first.back() + (uint32_t)(std::min(32, W - bx * 32) * std::min(32, H - by * 32)));
     }
-    uint32_t n_active = (uint32_t)own.size();
+    const uint32_t n_owned = (uint32_t)first.size() - 1, n_own = first.back();
+    if (first.size() > st->bucket_cap) {
+        cudaFree(st->bucket_first); st->bucket_first = nullptr; st->bucket_cap = 0;
+        MIRO_CUDA(ctx, cudaMalloc((void**)&st->bucket_first, first.size() * sizeof(uint32_t)));
+        st->bucket_cap = first.size();
+    }
+    uint32_t n_active = n_own;
     EventPair tot = begin_timing(ctx, false);
-    MIRO_CUDA(ctx, cudaMemcpyAsync(st->active[0], own.data(), own.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    MIRO_CUDA(ctx, cudaMemcpyAsync(st->bucket_first, first.data(), first.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    if (n_owned) { k_own_pixels<<<n_owned, 1024, 0, s>>>(st->bucket_first, shard_i, shard_n, nbx, W, H, st->active[0]); ctx->launches++; }
     MIRO_CUDA(ctx, cudaMemsetAsync(st->level_sum, 0, pixels * sizeof(float4), s));
     MIRO_CUDA(ctx, cudaMemsetAsync(st->q[0].counts + 5, 0, sizeof(uint32_t), s));
     MIRO_CUDA(ctx, cudaMemsetAsync(st->q[1].counts + 5, 0, sizeof(uint32_t), s));
@@ -774,21 +844,27 @@ extern "C" int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, co
     cudaPointerAttributes attr;
     const bool out_is_device = cudaPointerGetAttributes(&attr, rgb_out) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
     cudaGetLastError();
-    MIRO_CUDA(ctx, cudaMemcpyAsync(st->active[cur], own.data(), own.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     float* target = out_is_device ? rgb_out : st->rgb_dev;
-    if (!own.empty()) {
-        k_write_rgb<<<grid_for(own.size(), 256), 256, 0, s>>>(st->active[cur], (uint32_t)own.size(), st->result, target);
-        ctx->launches++;
+    if (n_own) {
+        k_own_pixels<<<n_owned, 1024, 0, s>>>(st->bucket_first, shard_i, shard_n, nbx, W, H, st->active[cur]);
+        k_write_rgb<<<grid_for(n_own, 256), 256, 0, s>>>(st->active[cur], n_own, st->result, target);
+        ctx->launches += 2;
     }
     MIRO_CUDA(ctx, cudaGetLastError());
     if (!out_is_device) {
-        const bool whole = own.size() == pixels;
+        const bool whole = n_own == pixels;
         if (whole) MIRO_CUDA(ctx, cudaMemcpyAsync(rgb_out, st->rgb_dev, pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
         else {
             std::vector<float> tmp(pixels * 3);
             MIRO_CUDA(ctx, cudaMemcpyAsync(tmp.data(), st->rgb_dev, pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
             MIRO_CUDA(ctx, cudaStreamSynchronize(s));
-            for (uint32_t p : own) { rgb_out[(size_t)p * 3] = tmp[(size_t)p * 3]; rgb_out[(size_t)p * 3 + 1] = tmp[(size_t)p * 3 + 1]; rgb_out[(size_t)p * 3 + 2] = tmp[(size_t)p * 3 + 2]; }
+            for (int b = shard_i; b < nbx * nby; b += shard_n) {      // only this shard's pixels reach the caller's frame
+                const int bx = b % nbx, by = b / nbx;
+                for (int y = by * 32; y < std::min((by + 1) * 32, H); ++y) {
+                    const size_t a = ((size_t)y * W + bx * 32) * 3, n = (size_t)(std::min((bx + 1) * 32, W) - bx * 32) * 3;
+                    memcpy(rgb_out + a, tmp.data() + a, n * sizeof(float));
+                }
+            }
         }
     }
     if (any_disperse) {

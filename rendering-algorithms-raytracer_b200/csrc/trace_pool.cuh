@@ -21,21 +21,21 @@
 namespace miro {
 
 #ifndef MIRO_POOL_SLOTS
-#define MIRO_POOL_SLOTS 64
+#define MIRO_POOL_SLOTS 48
 #endif
 #ifndef MIRO_POOL_STACK
-#define MIRO_POOL_STACK 12
+#define MIRO_POOL_STACK 8
 #endif
 #ifndef MIRO_POOL_BLOCK
 #define MIRO_POOL_BLOCK 128
 #endif
 #ifndef MIRO_POOL_MIN_BLOCKS
-#define MIRO_POOL_MIN_BLOCKS 4
+#define MIRO_POOL_MIN_BLOCKS 6
 #endif
 #ifndef MIRO_POOL_REFILL
 #define MIRO_POOL_REFILL 16
 #endif
-constexpr int POOL_SLOTS = MIRO_POOL_SLOTS;            // rays per warp (2 per lane)
+constexpr int POOL_SLOTS = MIRO_POOL_SLOTS;            // rays per warp (33..64; lane l owns slots l and l + 32)
 constexpr int POOL_STACK = MIRO_POOL_STACK;            // stack entries per ray kept in shared memory
 constexpr int POOL_BLOCK = MIRO_POOL_BLOCK;            // threads per block
 constexpr int POOL_WARPS = POOL_BLOCK / 32;

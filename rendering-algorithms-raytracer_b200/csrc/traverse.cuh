@@ -407,12 +407,18 @@ __host__ __device__ inline DeviceNode compress_node(const miro_gpu_node& n) {
 // on the near and the far bound together) are covered by widening the far bound by MIRO_SLAB_WIDEN; what is absolute — the
 // rounding of (p - o)/d when the plane is much nearer than the grid origin, <= 2^-23 x 255 grid steps of t — is covered by the
 // >= 1/32 grid step every quantized plane keeps to the true box (compress_node, NODE_GRID_MARGIN).
-template <bool COUNT, class ST>
-__device__ __forceinline__ void node_step(const DeviceScene& s, Lane& L, ST& st, uint32_t& n_nodes) {
-    const float4* n = s.nodes + (size_t)L.cur * 4;
-    float4 h0, chf, q0, q1;
-    ldg256(n + 0, h0, chf); ldg256(n + 2, q0, q1);
-    if (COUNT) ++n_nodes;
+// The 64 bytes of a device node as the two 32-byte loads deliver them.  node_step = node_fetch + node_test.  (The split served a
+// round-2 variant of the pool kernel that requested a node AND a leaf's first triangle before using either — two steps per round,
+// measured 25 % slower than one: serving every waiting slot at once empties the rounds, the leaf part ran at ~20 lanes.)
+struct NodeData { float4 h0, chf, q0, q1; };
+__device__ __forceinline__ void node_fetch(const DeviceScene& s, int32_t cur, NodeData& d) {
+    const float4* n = s.nodes + (size_t)cur * 4;
+    ldg256(n + 0, d.h0, d.chf); ldg256(n + 2, d.q0, d.q1);
+}
+
+template <class ST>
+__device__ __forceinline__ void node_test(const NodeData& d, Lane& L, ST& st) {
+    const float4 h0 = d.h0, chf = d.chf, q0 = d.q0, q1 = d.q1;
     const uint32_t ex = __float_as_uint(h0.w);
     // per axis: t(q) = q * (step / d) + (p - o) / d   (the subtraction first, so the error of the second term is relative to it)
     const float ax = __uint_as_float((ex & 0xffu) << 23) * L.r.ix, bx = (h0.x - L.r.ox) * L.r.ix;
@@ -475,6 +481,14 @@ __device__ __forceinline__ void node_step(const DeviceScene& s, Lane& L, ST& st,
     st.sp = sp + max(hits - 1, 0);
     if (hits > 0) L.cur = child_of(k0);
     else pop_next(L, st);
+}
+
+template <bool COUNT, class ST>
+__device__ __forceinline__ void node_step(const DeviceScene& s, Lane& L, ST& st, uint32_t& n_nodes) {
+    NodeData d;
+    node_fetch(s, L.cur, d);
+    if (COUNT) ++n_nodes;
+    node_test(d, L, st);
 }
 
 // Texture::getLookupAlpha (src/Texture.cpp:12-41) for the hit (prim, a, b): the bilinearly filtered alpha channel at the

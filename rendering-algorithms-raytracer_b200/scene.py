@@ -199,6 +199,14 @@ class MiroScene:
         self._gpu_check(self.L.miro_gpu_trace_any_packed(self.ctx, _ptr(rays), len(rays), _ptr(bits)), "trace_any_packed")
         return np.unpackbits(bits.view(np.uint8), bitorder="little")[:len(rays)].astype(bool)
 
+    def trace_primary(self, width=None, height=None, camera=None, seed=None, d_rays_out=None):
+        """Primary rays generated on the device at the pixel centres and traced (miro_gpu_trace_primary): hit records [h * w]."""
+        p = self.render_params(); c = camera or self.camera()
+        w = width or p.width; h = height or p.height
+        hits = np.empty(w * h, HIT_DTYPE)
+        self._gpu_check(self.L.miro_gpu_trace_primary(self.ctx, C.byref(c), w, h, p.seed if seed is None else seed, _ptr(hits), d_rays_out), "trace_primary")
+        return hits
+
     def trace_closest_device(self, d_rays_ptr, n, d_hits_ptr):
         self._gpu_check(self.L.miro_gpu_trace_closest_device(self.ctx, d_rays_ptr, n, d_hits_ptr), "trace_closest_device")
 

@@ -83,7 +83,13 @@ def adjudicate_hard(fx, scene, hits, ref, st, rays, script=None):
     (reference_arm.adjudicate_mismatches).  Returns the class counts; product_missed + unexplained are the true failures."""
     geom = ra.SceneGeometry(script or fx.script, {n: fx.mesh(k) for k, n in enumerate(fx.names)})
     mesh, tri, proxy = scene.resolve_hits(hits)
-    return ra.adjudicate_mismatches(geom, rays, st["hard_idx"], mesh, tri, proxy, ref)
+    adj = ra.adjudicate_mismatches(geom, rays, st["hard_idx"], mesh, tri, proxy, ref)
+    for i in adj["hard_idx"][:8]:      # what a failing assertion needs to show
+        g = geom.intersect(rays[i], int(mesh[i]), int(tri[i]), int(proxy[i])) if mesh[i] >= 0 else None
+        f = geom.intersect(rays[i], int(ref["mesh"][i]), int(ref["tri"][i]), int(ref["proxy"][i])) if ref["mesh"][i] >= 0 else None
+        print("unresolved ray", i, rays[i], "product", (mesh[i], tri[i], proxy[i]), hits[i], "float64 (t, edge distance, reach)", g,
+              "reference", ref[i], "float64", f)
+    return adj
 
 
 def reference_hits(fx, rays, threads=1):

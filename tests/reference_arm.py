@@ -340,8 +340,10 @@ class SceneGeometry:
         return v
 
     def intersect(self, ray, mesh, tri, proxy):
-        """Exact-arithmetic (float64) crossing of `ray` with one triangle: (t, margin) — margin = the smallest barycentric
-        weight (> 0: inside) — or None when the ray is parallel to the plane."""
+        """Exact-arithmetic (float64) crossing of `ray` with one triangle: (t, edge_distance, reach) or None when the ray is
+        parallel to the plane.  edge_distance: how far inside the triangle the crossing lies, measured in the plane
+        perpendicular to the ray (where both sides' triangle tests decide) — negative outside; reach: the largest distance
+        from the ray origin to a vertex, the magnitude at which float32 implementations round the translated vertices."""
         o = ray["o"].astype(np.float64); d = ray["d"].astype(np.float64)
         if proxy >= 0:
             Mi = self.inv[proxy]
@@ -352,26 +354,36 @@ class SceneGeometry:
         if det == 0.0:
             return None
         tv = o - v[0]; a = (tv @ p) / det; q = np.cross(tv, e0); b = (d @ q) / det; t = (e1 @ q) / det
-        return t, min(a, b, 1.0 - a - b)
+        dh = d / np.linalg.norm(d)
+        f0, f1 = e0 - (e0 @ dh) * dh, e1 - (e1 @ dh) * dh              # the triangle's edges projected along the ray
+        area2 = np.linalg.norm(np.cross(f0, f1))
+        dist = min(a * area2 / max(np.linalg.norm(f1), 1e-300), b * area2 / max(np.linalg.norm(f0), 1e-300),
+                   (1.0 - a - b) * area2 / max(np.linalg.norm(f1 - f0), 1e-300))
+        return t, dist, float(np.max(np.linalg.norm(v - o, axis=1)))
 
 
-def adjudicate_mismatches(geom, rays, idx, mesh, tri, proxy, ref, margin_eps=1e-6, t_eps=1e-6):
-    """Every id mismatch in `idx` re-computed in float64 on both sides' triangles.  Classes (first match):
-      reference_missed : the product's triangle is truly crossed, clearly inside (margin > margin_eps), within [tmin, tmax), and
-                         NEARER than what the reference reports (or the reference reports a miss) — the reference's traversal
-                         lost a hit (its slab test is not conservative and its triangle test not watertight);
+def adjudicate_mismatches(geom, rays, idx, mesh, tri, proxy, ref, ulps=16.0, t_eps=1e-6):
+    """Every id mismatch in `idx` re-computed in float64 on both sides' triangles.  A crossing is CLEAR when it lies inside its
+    triangle by more than `ulps` float32 roundings of the translated vertices (edge_distance > ulps * 2^-24 * reach: both the
+    watertight edge test and Moller-Trumbore decide on vertices translated to the ray origin, rounded at that magnitude);
+    nearer than that to an edge it is an edge / vertex tie.  Classes (first match):
+      coincident       : both sides' crossings are real and their distances agree to t_eps: overlapping / touching surfaces;
+      reference_missed : the product's crossing is real, clear, within [tmin, tmax) and NEARER than what the reference reports
+                         (or the reference reports a miss) — the reference's traversal lost a hit (its slab test is not
+                         conservative and its triangle test not watertight);
       product_missed   : the same with the roles swapped — a defect of the product: HARD;
-      coincident       : both crossings are real and their distances agree to t_eps: overlapping / touching surfaces;
-      edge             : the nearer real crossing lies within margin_eps of an edge or vertex of its triangle;
+      edge             : the nearer real crossing is not clear: an edge / vertex tie in float32;
       unexplained      : anything else: HARD."""
     out = dict(reference_missed=0, product_missed=0, coincident=0, edge=0, unexplained=0, hard_idx=[])
+    eps32 = 2.0 ** -24
     for i in idx:
         r = rays[i]
         g = geom.intersect(r, int(mesh[i]), int(tri[i]), int(proxy[i])) if mesh[i] >= 0 else None
         f = geom.intersect(r, int(ref["mesh"][i]), int(ref["tri"][i]), int(ref["proxy"][i])) if ref["mesh"][i] >= 0 else None
-        ok = lambda x: x is not None and r["tmin"] <= x[0] < r["tmax"] and x[1] > -margin_eps
+        tol = lambda x: ulps * eps32 * x[2]
+        ok = lambda x: x is not None and r["tmin"] <= x[0] < r["tmax"] and x[1] > -tol(x)
+        clear = lambda x: x[1] > tol(x)
         gv, fv = ok(g), ok(f)
-        clear = lambda x: x[1] > margin_eps
         if gv and fv and abs(g[0] - f[0]) <= t_eps * abs(f[0]):
             k = "coincident"
         elif gv and clear(g) and (not fv or g[0] < f[0]):

@@ -331,3 +331,34 @@ def test_packed_rays_give_the_hits_of_time_zero(name):
     for n in (0, 1, 33, 1000):
         assert sc.trace_closest_packed(mb.pack_rays(rays[:n])).tobytes() == want[:n].tobytes()
     sc.close()
+
+
+@pytest.mark.parametrize("name", ["c1_cornell", "c2_explosion"])
+def test_device_camera_rays_match_the_references(name):
+    """Camera::eyeRayAdaptive at the pixel centres (src/Camera.cpp:116-174) as k_raygen generates it on the device
+    (miro_gpu_trace_primary), against the camera rays the reference itself generated for the same pixels (the fixtures hold a
+    sample of its --dump-primary output: rays and their pixel indices), and the hits of those rays against the reference's."""
+    import torch
+    fx = helpers.Fixture(helpers.fixture_path(name))
+    sc = fx.scene().attach(0)
+    p = sc.render_params()
+    n = p.width * p.height
+    d_rays = torch.zeros((n, 48), dtype=torch.uint8, device="cuda")
+    hits = sc.trace_primary(d_rays_out=d_rays.data_ptr())
+    rays = d_rays.cpu().numpy().view(mb.RAY_DTYPE).reshape(-1)
+    prim = fx.ray_index < n                     # the fixture's sample: primary rays first (index = pixel), then incoherent ones
+    pix = fx.ray_index[prim]
+    ref_rays = fx.rays[prim]
+    assert prim.sum() > 1000
+    assert np.array_equal(rays["o"][pix], ref_rays["o"])
+    assert np.abs(rays["d"][pix] - ref_rays["d"]).max() < 1e-6      # the reference normalises with rsqrtss + one Newton step (~22 bits)
+    assert (rays["tmin"][pix] == ref_rays["tmin"]).all() and (rays["tmax"][pix] == ref_rays["tmax"]).all()
+    # the two sides' directions differ in their last bits (rsqrtss + Newton vs rsqrtf), so distances are compared at 2e-4 here; the
+    # reference's own rays give 2e-7 (test_closest_hit_matches_reference)
+    st = helpers.compare_hits(sc, hits[pix], fx.hits[prim], rays=ref_rays, t_rel=2e-4)
+    print(name, {k: v for k, v in st.items() if k != "hard_idx"})
+    assert st["id_match"] >= 0.999 and st["hard"] == 0 and st["frac_t_within"] == 1.0, st
+    # the call's hits are those of tracing the rays it generated
+    again = sc.trace_closest(rays)
+    assert again.tobytes() == hits.tobytes()
+    sc.close()

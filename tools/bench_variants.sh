@@ -6,7 +6,7 @@ shopt -s nullglob
 for lib in build/variants/*$filt*.so; do
   for k in warp pool; do
     [ "$which" != both ] && [ "$which" != $k ] && continue
-    case $lib in *pool*) [ $k = warp ] && continue;; esac
+    case $lib in *pool*|*d_s*) [ $k = warp ] && continue;; esac
     MIRO_GPU_LIB=$PWD/$lib MIRO_GPU_TRACE_KERNEL=$k python bench.py --steps 10 --warmup 3 --no-cpu --legs c2 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); r=d['roofline']
