@@ -323,7 +323,8 @@ def roofline_of(leg, hbm_peak, peak_src, traffic_key=None):
     # where the algorithmic bytes are served: a structure that fits L2 leaves DRAM only the ray / hit streams — the SURVEY 8(d)
     # fraction against HBM bandwidth is then an L1/L2-served figure, and the kernel is bound by issue slots and L1 wavefronts
     if traffic is not None:
-        bound = "hbm" if traffic >= 0.5 * alg else "l2/issue (structure L2-resident: ncu DRAM traffic is %.2f x the algorithmic bytes)" % (traffic / alg)
+        bound = "hbm" if traffic >= 0.5 * alg else "l2/issue (ncu DRAM traffic is %.2f x the algorithmic bytes: L1 and L2 serve the rest; %s)" % (
+            traffic / alg, "the structure fits L2" if leg["structure_bytes"] <= L2_BYTES else "the structure exceeds L2, the launch waits on the latency of its L2 misses, not on bandwidth")
     else:
         bound = "hbm" if leg["structure_bytes"] > L2_BYTES else "l2/issue (structure of %.1f MB fits the 126 MB L2)" % (leg["structure_bytes"] * 1e-6)
     return {"bound": bound, "kernel": KERNEL_NAMES[dom], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
@@ -381,7 +382,7 @@ def e2e_legs(sc, leg, args, world, barrier):
     out_hits = [torch.empty((N_BATCH, 20), dtype=torch.uint8).pin_memory() for _ in range(2)]
     out_bits = torch.empty(((N_BATCH + 31) // 32,), dtype=torch.int32).pin_memory()
     d2h = 2 * N_BATCH * 20 + 4 * ((N_BATCH + 31) // 32)
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 40))
 
     def run(fn_c, fn_a, bufs, hits_out, bits_out, ray_bytes, steps):
         def one():
@@ -420,6 +421,18 @@ def e2e_legs(sc, leg, args, world, barrier):
     pageable = run(L.miro_gpu_trace_closest, L.miro_gpu_trace_any, [p.ctypes.data for p in plain], [h.ctypes.data for h in ph], pb.ctypes.data, 48, max(3, e2e_steps // 2))
     pageable["ray_format"] = "miro_gpu_ray, 48 B, PAGEABLE host buffers (what an unmodified Miro caller holds)"
     assert np.array_equal(ph[1]["prim"], inco_hits["prim"])
+    # the same ordinary arrays page-locked in place, once, by the caller (miro_gpu_pin_host_buffer): what the patched Miro does with
+    # the ray / hit arrays it reuses from frame to frame
+    t0 = time.time()
+    for a in plain + ph + [pb]:
+        assert L.miro_gpu_pin_host_buffer(sc.ctx, a.ctypes.data, a.nbytes) == 0
+    pin_ms = (time.time() - t0) * 1e3
+    registered = run(L.miro_gpu_trace_closest, L.miro_gpu_trace_any, [p.ctypes.data for p in plain], [h.ctypes.data for h in ph], pb.ctypes.data, 48, e2e_steps)
+    registered["ray_format"] = "miro_gpu_ray, 48 B, the caller's own (malloc'ed) arrays pinned in place once with miro_gpu_pin_host_buffer"
+    registered["pin_once_ms"] = pin_ms
+    assert np.array_equal(ph[1]["prim"], inco_hits["prim"])
+    for a in plain + ph + [pb]:
+        L.miro_gpu_unpin_host_buffer(sc.ctx, a.ctypes.data)
     # camera rays made on the device (miro_gpu_trace_primary): a renderer's primary batch needs no upload at all; the other two
     # batches as packed rays
     cam = sc.camera()
@@ -443,7 +456,30 @@ def e2e_legs(sc, leg, args, world, barrier):
         s_dc = float(t.item())
     devcam = {"value": 3 * N_BATCH * e2e_steps * world / s_dc * 1e-6, "unit": "Mrays/s", "h2d_bytes_per_step": 2 * N_BATCH * 32, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
               "ray_format": "primary batch: camera rays generated on the device (miro_gpu_trace_primary, hits only travel); incoherent and shadow batches: 32 B packed rays, pinned"}
-    return e2e, packed, pageable, devcam
+    return e2e, packed, pageable, devcam, registered
+
+
+def pcie_probe(world, barrier):
+    """What the host gives this rank when ALL ranks copy at once: plain pinned H2D and D2H of 256 MB, 5 rounds, all ranks between
+    the same barriers — the ceiling of the host-pointer calls (they move 48 + 13 bytes per ray), measured rather than assumed."""
+    import torch
+    import torch.distributed as dist
+    n = 256 << 20
+    h = torch.empty(n, dtype=torch.uint8).pin_memory(); d = torch.empty(n, dtype=torch.uint8, device="cuda")
+    out = {}
+    for name, (src, dst) in (("h2d", (h, d)), ("d2h", (d, h))):
+        dst.copy_(src, non_blocking=True); barrier()
+        t0 = time.time()
+        for _ in range(5):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        s = time.time() - t0
+        if world > 1:
+            t = torch.tensor([s], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); s = float(t.item())
+        out[name + "_GBps_per_rank_all_ranks_concurrent"] = 5 * n / s * 1e-9
+        barrier()
+    out["e2e_ceiling_Mrays_per_s"] = world * 1e3 / (48.0 / out["h2d_GBps_per_rank_all_ranks_concurrent"])      # the upload alone: 48 B per ray
+    return out
 
 
 def render_legs(local, with_reference):
@@ -465,27 +501,40 @@ def render_legs(local, with_reference):
         fx = helpers.Fixture(path)
         script = fx.script if size is None else re.sub(r"image \d+ \d+", "image %d %d" % size, fx.script)
         row = {"config": tag, "workload": label}
+        ref_runs = {}
         if with_reference and ra.have_reference():
             with tempfile.TemporaryDirectory() as tmp:
                 materialise(fx, script, tmp)
-                try:
-                    ev, _ = ra.run_reference(fx, None, threads=threads, scene_dir=tmp, extra_args=["--render-float", os.path.join(tmp, "out.f32")])
-                    rf = [e for e in ev if e.get("event") == "render_float"][0]
-                    row["reference"] = {"rays": rf["rays"], "ms": rf["seconds"] * 1e3, "Mrays_per_s": rf["mrays_per_s"], "cores": rf["threads"],
-                                        "note": "all host threads; with > 1 thread the reference drops ~2 % of its rays (QBVH_Node::boxHit race, DESIGN.md section 4)"}
-                except Exception as e:      # a reference failure must not cost the GPU numbers
-                    row["reference"] = {"error": str(e)[-300:]}
+                for th in (threads, 1):
+                    # all host threads first; ONE thread as well when that is affordable: with several threads the reference's
+                    # traversals corrupt each other (QBVH_Node::boxHit) — on small trees most of them, and
+                    # paths that wrongly miss end early, so the multi-threaded frame is faster than a correct one and wrong
+                    if th == 1 and (threads == 1 or ref_runs[threads].get("ms", 1e9) * threads > 60e3):
+                        continue
+                    try:
+                        ev, _ = ra.run_reference(fx, None, threads=th, scene_dir=tmp, extra_args=["--render-float", os.path.join(tmp, "out.f32")])
+                        rf = [e for e in ev if e.get("event") == "render_float"][0]
+                        ref_runs[th] = {"rays": rf["rays"], "ms": rf["seconds"] * 1e3, "Mrays_per_s": rf["mrays_per_s"], "cores": rf["threads"]}
+                    except Exception as e:      # a reference failure must not cost the GPU numbers
+                        ref_runs[th] = {"error": str(e)[-300:]}
+            row["reference"] = ref_runs[threads]
+            if 1 in ref_runs:
+                row["reference_one_thread"] = ref_runs[1]
         sc = fx.scene(script_override=script).attach(local)
-        sc.render()
+        sc.render_in_place()
         best = 1e30
-        for _ in range(3):
+        for _ in range(5):      # the frame as Scene::raytraceImage leaves it: in the scene's Image (float radiance + 8-bit pixels, on the host)
             sc.reset_counters()
-            t0 = time.time(); img = sc.render(); dt = time.time() - t0
+            t0 = time.time(); img, _img8 = sc.render_in_place(); dt = time.time() - t0
             best = min(best, dt)
         c = sc.counters(); rays = int(c["rays_closest"] + c["rays_any"])
         row["gpu"] = {"rays": rays, "ms": best * 1e3, "Mrays_per_s": rays / best * 1e-6, "kernel_launches": int(c["kernel_launches"]), "frame_mean": float(np.minimum(img, 4).mean())}
         if "reference" in row and "ms" in row["reference"]:
             row["frame_speedup"] = row["reference"]["ms"] / row["gpu"]["ms"]
+            row["reference"]["rays_vs_gpu"] = row["reference"]["rays"] / max(rays, 1)
+        if "reference_one_thread" in row and "ms" in row["reference_one_thread"]:
+            row["frame_speedup_vs_one_correct_thread"] = row["reference_one_thread"]["ms"] / row["gpu"]["ms"]
+            row["reference_one_thread"]["rays_vs_gpu"] = row["reference_one_thread"]["rays"] / max(rays, 1)
         sc.close()
         rows.append(row)
     return rows
@@ -581,9 +630,7 @@ def gpu_main(args, rank, world, local):
         torch.cuda.synchronize()
 
     default_legs = "c2,big,c5,render" if world == 1 else "c2,render_scale"
-    legs = (args.legs or default_legs).split(",")
-    if "c2" not in legs:
-        legs.insert(0, "c2")
+    legs = (args.legs or default_legs).split(",")      # without c2 (profiling runs) there is no headline line: only `workloads` is printed
     do_cpu = world == 1 and not args.no_cpu
     threads = min(os.cpu_count() or 1, 16)
     hbm_peak, peak_src = peaks()
@@ -609,11 +656,12 @@ def gpu_main(args, rank, world, local):
             row["cpu_baseline"] = {"value": ref["n"] / ref["seconds_best"] * 1e-6, "unit": "Mrays/s", "cores": ref["threads"], "kind": "reference",
                                    "sample": ref["sample"] + ", best of 3", "scene_load_and_bvh_build_s": ref["build_s"]}
         if name == "c2":
-            e2e, packed, pageable, devcam = e2e_legs(sc, leg, args, world, barrier)
+            e2e, packed, pageable, devcam, registered = e2e_legs(sc, leg, args, world, barrier)
+            numa.update(pcie_probe(world, barrier))
             line = {"metric": "Mrays/s", "value": leg["value"], "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                     "ms_per_step": leg["total_ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                     "dtype": "f32", "data": "synthetic", "config": bench_config(w), "clocks": clocks, "gpu_launches": 3 * args.steps,
-                    "e2e": e2e, "e2e_packed": packed, "e2e_pageable": pageable, "e2e_device_camera": devcam, "host": numa, "sustained": leg["sustained"], "roofline": roof}
+                    "e2e": e2e, "e2e_packed": packed, "e2e_pageable": pageable, "e2e_registered": registered, "e2e_device_camera": devcam, "host": numa, "sustained": leg["sustained"], "roofline": roof}
             line["roofline"]["frac_abi_node_layout"] = (leg["per_launch"][int(np.argmax(leg["launch_ms"]))]["bytes"] + leg["per_launch"][int(np.argmax(leg["launch_ms"]))]["nodes"] * (128 - NODE_BYTES)) / (max(leg["launch_ms"]) * 1e-3) * 1e-9 / hbm_peak
             line["roofline"]["note"] = ("algorithmic bytes count the SHIPPED 64-byte device node; frac_abi_node_layout counts the 128-byte ABI node as kernel "
                                         "versions <= v4 fetched it (comparable with profiles/bench_r1_v1..v4.json).")
@@ -626,6 +674,8 @@ def gpu_main(args, rank, world, local):
         if parity and rank == 0:
             if parity["hard_total"] > 0 or min(parity["primary"]["id_match"], parity["incoherent"]["id_match"]) < (0.9999 if name != "c5" else 0.999):
                 raise SystemExit("bench.py: parity against the reference FAILED on workload %s: %s" % (name, json.dumps(parity)))
+    if line is None:
+        line = {"note": "no headline workload (c2) among the legs: a tooling run"}
     if rank == 0:
         line["workloads"] = {k: v for k, v in workloads.items() if k != "c2"}
     if "render" in legs and world == 1:

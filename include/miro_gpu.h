@@ -300,6 +300,13 @@ int miro_gpu_trace_any(miro_gpu_ctx* ctx, const miro_gpu_ray* rays, size_t n, ui
 int miro_gpu_trace_closest_device(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, miro_gpu_hit* d_hits);
 int miro_gpu_trace_any_device(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, uint32_t* d_occluded_bits);
 
+/* Host buffers of the calls above may be ordinary (pageable) memory, but then every copy is staged by the driver (measured on
+ * B200: 8 GB/s against 47 GB/s from pinned memory — the host-pointer calls are bound by PCIe either way).  A caller that reuses
+ * its ray / hit arrays (a renderer does) page-locks them once: miro_gpu_pin_host_buffer wraps cudaHostRegister for memory the
+ * caller allocated itself (malloc / new / std::vector), miro_gpu_unpin_host_buffer must be called before that memory is freed. */
+int miro_gpu_pin_host_buffer(miro_gpu_ctx* ctx, void* ptr, size_t bytes);
+int miro_gpu_unpin_host_buffer(miro_gpu_ctx* ctx, void* ptr);
+
 /* The same two queries for packed rays (host pointers; pipelined like miro_gpu_trace_closest / _any).  Results are those of the
  * 48-byte call with time = 0. */
 int miro_gpu_trace_closest_packed(miro_gpu_ctx* ctx, const miro_gpu_ray32* rays, size_t n, miro_gpu_hit* hits);
@@ -315,6 +322,10 @@ int miro_gpu_trace_primary(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, int wi
 /* Scene::raytraceImage.  rgb_out: width*height*3 floats, row 0 = bottom row (src/Image.cpp:150-151),
  * linear radiance before Image::Map.  rgb_out may be a host or a device pointer. */
 int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, const miro_gpu_render_params* params, float* rgb_out);
+/* The same, also (or only) delivering what the reference's Image holds after the frame: rgb8_out = width*height*3 bytes, every
+ * channel through Image::setPixel's Map (src/Image.cpp:71-87: clamp to [0, 1], 32 769-entry 2.2-gamma table) on the device.
+ * Either pointer may be NULL (not both), each may be a host or a device pointer. */
+int miro_gpu_render_image(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, const miro_gpu_render_params* params, float* rgb_out, unsigned char* rgb8_out);
 
 /* Counters.  enable != 0 switches the traversal kernels to their instrumented variant (node / triangle / instance fetch
  * counts, used for the roofline's algorithmic bytes) and brackets the library's launches with timing events; ray counts
@@ -345,7 +356,8 @@ miro_gpu_ctx* miro_gpu_group_ctx(miro_gpu_group* g, int i);          /* member i
 const char* miro_gpu_group_last_error(const miro_gpu_group* g);
 int miro_gpu_group_peer_access(const miro_gpu_group* g, int i);      /* 1: the first member reads member i's frame directly */
 int miro_gpu_group_upload_scene(miro_gpu_group* g, const miro_gpu_scene_desc* desc);
-int miro_gpu_group_render(miro_gpu_group* g, const miro_gpu_camera* cam, const miro_gpu_render_params* params, int sharding, float* rgb_out);
+int miro_gpu_group_render(miro_gpu_group* g, const miro_gpu_camera* cam, const miro_gpu_render_params* params, int sharding, float* rgb_out,
+                          unsigned char* rgb8_out /* NULL, or the 8-bit image as miro_gpu_render_image delivers it (host pointer) */);
 int miro_gpu_group_trace_closest(miro_gpu_group* g, const miro_gpu_ray* rays, size_t n, miro_gpu_hit* hits);
 int miro_gpu_group_trace_any(miro_gpu_group* g, const miro_gpu_ray* rays, size_t n, uint32_t* occluded_bits);
 int miro_gpu_group_get_counters(miro_gpu_group* g, miro_gpu_counters* out);      /* sums over members (times: the slowest member) */

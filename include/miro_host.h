@@ -39,8 +39,11 @@ miro_gpu_group* miro_host_group(miro_host_scene* s);
 int miro_host_trace(miro_host_scene* s, const miro_gpu_ray* rays, size_t n, miro_gpu_hit* hits);
 int miro_host_trace_any(miro_host_scene* s, const miro_gpu_ray* rays, size_t n, uint32_t* occluded_bits);
 miro_gpu_ctx* miro_host_ctx(miro_host_scene* s);
-/* Scene::raytraceImage: rgb = width*height*3 floats (row 0 = bottom); rgb8 (optional) = Image::Map'ed bytes. */
+/* Scene::raytraceImage (src/Scene.h:31): the frame lands in the scene's Image — 8-bit pixels through Image::Map and the float
+ * radiance, both written by the GPU into page-locked buffers — and is copied to rgb (width*height*3 floats, row 0 = bottom) and
+ * rgb8 (bytes) where those are not NULL.  miro_host_image hands out the Image's own buffers (valid until the next resize). */
 int miro_host_raytrace_image(miro_host_scene* s, float* rgb, unsigned char* rgb8, int shard_index, int shard_count);
+int miro_host_image(miro_host_scene* s, const float** rgb, const unsigned char** rgb8, int* width, int* height);
 /* Standalone BVH build over triangle soup (testing the builder): returns node count, fills order (n entries). */
 int miro_host_write_ppm(miro_host_scene* s, const char* path);
 

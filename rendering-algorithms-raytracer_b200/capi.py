@@ -111,7 +111,7 @@ class Counters(C.Structure):
 # every symbol include/miro_gpu.h and include/miro_host.h declare (checked by tests/test_abi.py)
 GPU_SYMBOLS = ["miro_gpu_create", "miro_gpu_destroy", "miro_gpu_last_error", "miro_gpu_abi_version", "miro_gpu_sizeof", "miro_gpu_set_stream", "miro_gpu_set_trace_chaining", "miro_gpu_set_trace_kernel",
                "miro_gpu_upload_scene", "miro_gpu_trace_closest", "miro_gpu_trace_any", "miro_gpu_trace_closest_packed", "miro_gpu_trace_any_packed", "miro_gpu_trace_closest_device",
-               "miro_gpu_trace_any_device", "miro_gpu_trace_primary", "miro_gpu_render", "miro_gpu_enable_counting", "miro_gpu_get_counters",
+               "miro_gpu_trace_any_device", "miro_gpu_trace_primary", "miro_gpu_render", "miro_gpu_render_image", "miro_gpu_pin_host_buffer", "miro_gpu_unpin_host_buffer", "miro_gpu_enable_counting", "miro_gpu_get_counters",
                "miro_gpu_reset_counters",
                "miro_gpu_group_create", "miro_gpu_group_destroy", "miro_gpu_group_size", "miro_gpu_group_ctx", "miro_gpu_group_last_error", "miro_gpu_group_peer_access",
                "miro_gpu_group_upload_scene", "miro_gpu_group_render", "miro_gpu_group_trace_closest", "miro_gpu_group_trace_any", "miro_gpu_group_get_counters",
@@ -119,7 +119,7 @@ GPU_SYMBOLS = ["miro_gpu_create", "miro_gpu_destroy", "miro_gpu_last_error", "mi
 HOST_SYMBOLS = ["miro_host_new", "miro_host_free", "miro_host_error", "miro_host_preload_mesh", "miro_host_preload_image",
                 "miro_host_load_script", "miro_host_get_desc", "miro_host_get_camera", "miro_host_get_render_params",
                 "miro_host_bvh_stats", "miro_host_attach", "miro_host_attach_devices", "miro_host_group", "miro_host_trace", "miro_host_trace_any",
-                "miro_host_ctx", "miro_host_raytrace_image", "miro_host_write_ppm"]
+                "miro_host_ctx", "miro_host_raytrace_image", "miro_host_image", "miro_host_write_ppm"]
 
 _lib = None
 
@@ -173,12 +173,16 @@ def lib():
     L.miro_gpu_group_last_error.argtypes = [vp]; L.miro_gpu_group_last_error.restype = cp
     L.miro_gpu_group_peer_access.argtypes = [vp, i32]; L.miro_gpu_group_peer_access.restype = i32
     L.miro_gpu_group_upload_scene.argtypes = [vp, C.POINTER(SceneDesc)]; L.miro_gpu_group_upload_scene.restype = i32
-    L.miro_gpu_group_render.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), i32, vp]; L.miro_gpu_group_render.restype = i32
+    L.miro_gpu_group_render.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), i32, vp, vp]; L.miro_gpu_group_render.restype = i32
+    L.miro_gpu_pin_host_buffer.argtypes = [vp, vp, sz]; L.miro_gpu_pin_host_buffer.restype = i32
+    L.miro_gpu_unpin_host_buffer.argtypes = [vp, vp]; L.miro_gpu_unpin_host_buffer.restype = i32
+    L.miro_gpu_render_image.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), vp, vp]; L.miro_gpu_render_image.restype = i32
     L.miro_gpu_group_trace_closest.argtypes = [vp, vp, sz, vp]; L.miro_gpu_group_trace_closest.restype = i32
     L.miro_gpu_group_trace_any.argtypes = [vp, vp, sz, vp]; L.miro_gpu_group_trace_any.restype = i32
     L.miro_gpu_group_get_counters.argtypes = [vp, C.POINTER(Counters)]; L.miro_gpu_group_get_counters.restype = i32
     L.miro_gpu_group_reset_counters.argtypes = [vp]; L.miro_gpu_group_reset_counters.restype = i32
     L.miro_host_raytrace_image.argtypes = [vp, vp, vp, i32, i32]; L.miro_host_raytrace_image.restype = i32
+    L.miro_host_image.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(i32)]; L.miro_host_image.restype = i32
     L.miro_host_write_ppm.argtypes = [vp, cp]; L.miro_host_write_ppm.restype = i32
     _lib = L
     return L

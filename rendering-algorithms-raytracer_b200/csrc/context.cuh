@@ -130,6 +130,7 @@ void launch_trace_any_packed(miro_gpu_ctx* ctx, const miro_gpu_ray32* d_rays, si
 void launch_trace_shadow(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, const uint32_t* d_count, const float4* d_E, float4* d_slots);
 
 void render_state_free(miro_gpu_ctx* ctx);
+int map_frame_to_bytes(miro_gpu_ctx* ctx, const float* d_rgb, size_t pixels, unsigned char* d_rgb8, cudaStream_t s);      // render.cu: Image::setPixel on the device
 
 // build.cu: LBVH over static triangles on the device
 int build_lbvh_on_device(miro_gpu_ctx* ctx, const float4* d_tris_in, uint32_t n, const DeviceNode** out_nodes, uint32_t* out_n_nodes,

@@ -739,6 +739,27 @@ int miro_gpu_trace_any_packed(miro_gpu_ctx* ctx, const miro_gpu_ray32* rays, siz
     return trace_host(ctx, rays, n, nullptr, occluded_bits, true);
 }
 
+int miro_gpu_pin_host_buffer(miro_gpu_ctx* ctx, void* ptr, size_t bytes) {
+    if (!ctx) return MIRO_GPU_EINVAL;
+    if (!ptr || !bytes) return set_error(ctx, MIRO_GPU_EINVAL, "miro_gpu_pin_host_buffer: NULL / empty buffer");
+    MIRO_CUDA(ctx, cudaSetDevice(ctx->device));
+    const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return MIRO_GPU_OK; }
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaHostRegister");
+    return MIRO_GPU_OK;
+}
+
+int miro_gpu_unpin_host_buffer(miro_gpu_ctx* ctx, void* ptr) {
+    if (!ctx) return MIRO_GPU_EINVAL;
+    if (!ptr) return set_error(ctx, MIRO_GPU_EINVAL, "miro_gpu_unpin_host_buffer: NULL buffer");
+    MIRO_CUDA(ctx, cudaSetDevice(ctx->device));
+    MIRO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if (e == cudaErrorHostMemoryNotRegistered) { cudaGetLastError(); return set_error(ctx, MIRO_GPU_EINVAL, "miro_gpu_unpin_host_buffer: the buffer is not pinned"); }
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaHostUnregister");
+    return MIRO_GPU_OK;
+}
+
 int miro_gpu_set_trace_kernel(miro_gpu_ctx* ctx, int kind) {
     if (!ctx) return MIRO_GPU_EINVAL;
     if (kind != MIRO_GPU_KERNEL_WARP && kind != MIRO_GPU_KERNEL_POOL) return set_error(ctx, MIRO_GPU_EINVAL, "miro_gpu_set_trace_kernel: unknown kernel");

@@ -26,6 +26,7 @@ struct miro_gpu_group {
     std::vector<float*> staged;         // on member 0's device, for members it cannot read directly
     std::vector<char> peer_ok;          // member 0 can load from member i's memory
     float* combined = nullptr;          // on member 0's device
+    unsigned char* combined8 = nullptr;
     size_t frame_pixels = 0;
     std::string error;
 };
@@ -91,8 +92,10 @@ int ensure_frames(miro_gpu_group* g, size_t pixels) {
         if (!g->peer_ok[i] && cudaMalloc((void**)&g->staged[i], pixels * 3 * sizeof(float)) != cudaSuccess) return group_fail(g, MIRO_GPU_ENOMEM, "group: staging allocation failed");
     }
     if (g->combined) cudaFree(g->combined);
-    g->combined = nullptr;
-    if (cudaMalloc((void**)&g->combined, pixels * 3 * sizeof(float)) != cudaSuccess) return group_fail(g, MIRO_GPU_ENOMEM, "group: frame allocation failed");
+    if (g->combined8) cudaFree(g->combined8);
+    g->combined = nullptr; g->combined8 = nullptr;
+    if (cudaMalloc((void**)&g->combined, pixels * 3 * sizeof(float)) != cudaSuccess || cudaMalloc((void**)&g->combined8, pixels * 3) != cudaSuccess)
+        return group_fail(g, MIRO_GPU_ENOMEM, "group: frame allocation failed");
     g->frame_pixels = pixels;
     return MIRO_GPU_OK;
 }
@@ -134,6 +137,7 @@ void miro_gpu_group_destroy(miro_gpu_group* g) {
     cudaSetDevice(g->device[0]);
     for (float* p : g->staged) if (p) cudaFree(p);
     if (g->combined) cudaFree(g->combined);
+    if (g->combined8) cudaFree(g->combined8);
     for (miro_gpu_ctx* c : g->ctx) miro_gpu_destroy(c);
     delete g;
 }
@@ -148,7 +152,7 @@ int miro_gpu_group_upload_scene(miro_gpu_group* g, const miro_gpu_scene_desc* de
     return for_each_member(g, [&](int i) { return miro_gpu_upload_scene(g->ctx[i], desc); });
 }
 
-int miro_gpu_group_render(miro_gpu_group* g, const miro_gpu_camera* cam, const miro_gpu_render_params* rp, int sharding, float* rgb_out) {
+int miro_gpu_group_render(miro_gpu_group* g, const miro_gpu_camera* cam, const miro_gpu_render_params* rp, int sharding, float* rgb_out, unsigned char* rgb8_out) {
     if (!g || !cam || !rp || !rgb_out) return MIRO_GPU_EINVAL;
     const int n = (int)g->ctx.size();
     if (rp->shard_count > 1 || rp->path_shard_count > 1) return group_fail(g, MIRO_GPU_EINVAL, "miro_gpu_group_render: the group shards the frame itself (pass shard counts of 0 / 1)");
@@ -184,6 +188,11 @@ int miro_gpu_group_render(miro_gpu_group* g, const miro_gpu_camera* cam, const m
     else if (sharding == MIRO_GPU_SHARD_SAMPLES) k_sum_frames<<<grid, 256, 0, s>>>(f, n, pixels * 3, target);
     else k_gather_buckets<<<grid, 256, 0, s>>>(f, n, rp->width, rp->height, target);
     g->ctx[0]->launches++;
+    if (rgb8_out) {      // Image::setPixel over the combined frame, on the device
+        const int mrc = map_frame_to_bytes(g->ctx[0], target, pixels, g->combined8, s);
+        if (mrc) return group_fail(g, mrc, miro_gpu_last_error(g->ctx[0]));
+        if (cudaMemcpyAsync(rgb8_out, g->combined8, pixels * 3, cudaMemcpyDeviceToHost, s) != cudaSuccess) return group_fail(g, MIRO_GPU_ECUDA, "group: frame download failed");
+    }
     if (!out_is_device && cudaMemcpyAsync(rgb_out, g->combined, pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, s) != cudaSuccess) return group_fail(g, MIRO_GPU_ECUDA, "group: frame download failed");
     const cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return group_fail(g, MIRO_GPU_ECUDA, std::string("group: combine failed: ") + cudaGetErrorString(e));

@@ -38,6 +38,9 @@
 namespace miro {
 
 constexpr int SHADE_BLOCK = 128;
+#ifndef MIRO_SHADE_MIN_BLOCKS
+#define MIRO_SHADE_MIN_BLOCKS 4
+#endif
 // ray.flags of a queued continuation ray: path 0-15 | giBounces 16-23 | bounces 24-26 | FLAG_SECONDARY | FLAG_SAMPLE_ENV
 constexpr uint32_t FLAG_SAMPLE_ENV = 0x80000000u;      // the environment / background is added when the ray leaves the scene
 constexpr uint32_t FLAG_SECONDARY = 0x08000000u;       // shade(..., isSecondary = true): reached through calculatePathTracing
@@ -93,7 +96,7 @@ struct RenderState {
     size_t key_paths = 0, key_shadow_per_path = 0, key_slots_per_path = 0, key_next_mult = 1; bool key_ior = false, key_walk = false;
     // frame buffers
     float4* level_sum = nullptr; float4* result = nullptr; uint32_t* active[2] = {nullptr, nullptr};
-    float* rgb_dev = nullptr; size_t frame_pixels = 0;
+    float* rgb_dev = nullptr; unsigned char* rgb8_dev = nullptr; size_t frame_pixels = 0;
     float* gamma_lut = nullptr;
     uint32_t* h_count = nullptr;       // pinned
     uint32_t* bucket_first = nullptr;  // per owned bucket: its first position in the shard's pixel list (+ the total at the end)
@@ -171,7 +174,7 @@ __device__ __forceinline__ bool light_walks(const miro_gpu_light& l) {
 }
 
 template <bool PRIMARY>
-__global__ void __launch_bounds__(SHADE_BLOCK)
+__global__ void __launch_bounds__(SHADE_BLOCK, MIRO_SHADE_MIN_BLOCKS)
 k_shade(DeviceScene sc, DeviceShading sh, RenderParamsDev P, Queues q, int in_q, uint32_t n_static, const uint32_t* __restrict__ d_count,
         float4* __restrict__ level_sum, uint32_t shadow_cap, uint32_t slot_cap) {
     const uint32_t n = PRIMARY ? n_static : min(*d_count, P.next_cap);
@@ -534,12 +537,27 @@ k_level_resolve(const uint32_t* __restrict__ active, uint32_t n_active, int leve
     }
 }
 
-__global__ void k_write_rgb(const uint32_t* __restrict__ pixels, uint32_t n, const float4* __restrict__ result, float* __restrict__ rgb) {
+// Image::setPixel's tone mapping (Map, src/Image.cpp:71-76): clamp, index the 32 769-entry 2.2-gamma table, truncate to a byte.
+__device__ __forceinline__ unsigned char map_byte(const float* __restrict__ lut, float r) {
+    const float m = 32768.0f * r;
+    const int linear = (m > 32768.0f) ? 32768 : (int)(m > 0.f ? m : 0.f);
+    return (unsigned char)(int)__ldg(lut + linear);
+}
+
+// The shard's pixels leave the accumulation buffer: float radiance (rgb, may be NULL) and / or the 8-bit image the reference's
+// Image holds (rgb8, may be NULL) — mapping 2 M pixels through Image::setPixel on the host cost more than rendering them.
+__global__ void k_write_rgb(const uint32_t* __restrict__ pixels, uint32_t n, const float4* __restrict__ result, float* __restrict__ rgb,
+                            unsigned char* __restrict__ rgb8, const float* __restrict__ lut) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t p = pixels[i];
     const float4 r = result[p];
-    rgb[(size_t)p * 3 + 0] = r.x; rgb[(size_t)p * 3 + 1] = r.y; rgb[(size_t)p * 3 + 2] = r.z;
+    if (rgb) { rgb[(size_t)p * 3 + 0] = r.x; rgb[(size_t)p * 3 + 1] = r.y; rgb[(size_t)p * 3 + 2] = r.z; }
+    if (rgb8) { rgb8[(size_t)p * 3 + 0] = map_byte(lut, r.x); rgb8[(size_t)p * 3 + 1] = map_byte(lut, r.y); rgb8[(size_t)p * 3 + 2] = map_byte(lut, r.z); }
+}
+
+__global__ void k_map_frame(const float* __restrict__ rgb, size_t n, unsigned char* __restrict__ rgb8, const float* __restrict__ lut) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) rgb8[i] = map_byte(lut, rgb[i]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -559,7 +577,7 @@ void render_state_free(miro_gpu_ctx* ctx) {
     if (!ctx->render_state) return;
     RenderState* st = static_cast<RenderState*>(ctx->render_state);
     free_queues(st);
-    cudaFree(st->level_sum); cudaFree(st->result); cudaFree(st->active[0]); cudaFree(st->active[1]); cudaFree(st->rgb_dev); cudaFree(st->gamma_lut); cudaFree(st->bucket_first);
+    cudaFree(st->level_sum); cudaFree(st->result); cudaFree(st->active[0]); cudaFree(st->active[1]); cudaFree(st->rgb_dev); cudaFree(st->rgb8_dev); cudaFree(st->gamma_lut); cudaFree(st->bucket_first);
     if (st->h_count) cudaFreeHost(st->h_count);
     if (st->aux) cudaStreamDestroy(st->aux);
     if (st->ev_fork) cudaEventDestroy(st->ev_fork);
@@ -614,13 +632,14 @@ static int ensure_frame(miro_gpu_ctx* ctx, RenderState* st, size_t pixels) {
         MIRO_CUDA(ctx, cudaEventCreateWithFlags(&st->ev_join, cudaEventDisableTiming));
     }
     if (st->frame_pixels >= pixels) return MIRO_GPU_OK;
-    cudaFree(st->level_sum); cudaFree(st->result); cudaFree(st->active[0]); cudaFree(st->active[1]); cudaFree(st->rgb_dev);
-    st->level_sum = st->result = nullptr; st->active[0] = st->active[1] = nullptr; st->rgb_dev = nullptr; st->frame_pixels = 0;
+    cudaFree(st->level_sum); cudaFree(st->result); cudaFree(st->active[0]); cudaFree(st->active[1]); cudaFree(st->rgb_dev); cudaFree(st->rgb8_dev);
+    st->level_sum = st->result = nullptr; st->active[0] = st->active[1] = nullptr; st->rgb_dev = nullptr; st->rgb8_dev = nullptr; st->frame_pixels = 0;
     MIRO_CUDA(ctx, cudaMalloc((void**)&st->level_sum, pixels * sizeof(float4)));
     MIRO_CUDA(ctx, cudaMalloc((void**)&st->result, pixels * sizeof(float4)));
     MIRO_CUDA(ctx, cudaMalloc((void**)&st->active[0], pixels * sizeof(uint32_t)));
     MIRO_CUDA(ctx, cudaMalloc((void**)&st->active[1], pixels * sizeof(uint32_t)));
     MIRO_CUDA(ctx, cudaMalloc((void**)&st->rgb_dev, pixels * 3 * sizeof(float)));
+    MIRO_CUDA(ctx, cudaMalloc((void**)&st->rgb8_dev, pixels * 3));
     st->frame_pixels = pixels;
     return MIRO_GPU_OK;
 }
@@ -696,9 +715,26 @@ extern "C" int miro_gpu_trace_primary(miro_gpu_ctx* ctx, const miro_gpu_camera* 
     return MIRO_GPU_OK;
 }
 
+namespace miro {
+// Image::setPixel over a whole frame that already lies in device memory of ctx's GPU (the combined frame of a group)
+int map_frame_to_bytes(miro_gpu_ctx* ctx, const float* d_rgb, size_t pixels, unsigned char* d_rgb8, cudaStream_t s) {
+    RenderState* st = state_of(ctx);
+    int rc;
+    if ((rc = ensure_frame(ctx, st, 1))) return rc;      // the gamma table
+    k_map_frame<<<ctx->sm_count * 8, 256, 0, s>>>(d_rgb, pixels * 3, d_rgb8, st->gamma_lut);
+    ctx->launches++;
+    return MIRO_GPU_OK;
+}
+}  // namespace miro
+
 extern "C" int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, const miro_gpu_render_params* rp, float* rgb_out) {
+    if (ctx && !rgb_out) return set_error(ctx, MIRO_GPU_EINVAL, "miro_gpu_render: NULL argument");
+    return miro_gpu_render_image(ctx, cam, rp, rgb_out, nullptr);
+}
+
+extern "C" int miro_gpu_render_image(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, const miro_gpu_render_params* rp, float* rgb_out, unsigned char* rgb8_out) {
     if (!ctx) return MIRO_GPU_EINVAL;
-    if (!cam || !rp || !rgb_out) return set_error(ctx, MIRO_GPU_EINVAL, "miro_gpu_render: NULL argument");
+    if (!cam || !rp || (!rgb_out && !rgb8_out)) return set_error(ctx, MIRO_GPU_EINVAL, "miro_gpu_render: NULL argument");
     if (!ctx->has_scene) return set_error(ctx, MIRO_GPU_ENOSCENE, "render before upload_scene");
     if (rp->width <= 0 || rp->height <= 0 || (size_t)rp->width * rp->height > 0x7fffffffu) return set_error(ctx, MIRO_GPU_EINVAL, "bad image size");
     if (rp->num_paths < 1 || rp->num_paths > 0xffff) return set_error(ctx, MIRO_GPU_EINVAL, "num_paths must be in 1..65535");
@@ -841,32 +877,34 @@ extern "C" int miro_gpu_render(miro_gpu_ctx* ctx, const miro_gpu_camera* cam, co
         }
     }
     // ---- hand the shard's pixels back (row 0 = bottom); pixels of other shards are left untouched
-    cudaPointerAttributes attr;
-    const bool out_is_device = cudaPointerGetAttributes(&attr, rgb_out) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
-    cudaGetLastError();
-    float* target = out_is_device ? rgb_out : st->rgb_dev;
+    auto is_device = [](const void* p) { cudaPointerAttributes a; const bool d = p && cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeDevice; cudaGetLastError(); return d; };
+    const bool f_dev = is_device(rgb_out), b_dev = is_device(rgb8_out);
+    float* target = rgb_out ? (f_dev ? rgb_out : st->rgb_dev) : nullptr;
+    unsigned char* target8 = rgb8_out ? (b_dev ? rgb8_out : st->rgb8_dev) : nullptr;
     if (n_own) {
         k_own_pixels<<<n_owned, 1024, 0, s>>>(st->bucket_first, shard_i, shard_n, nbx, W, H, st->active[cur]);
-        k_write_rgb<<<grid_for(n_own, 256), 256, 0, s>>>(st->active[cur], n_own, st->result, target);
+        k_write_rgb<<<grid_for(n_own, 256), 256, 0, s>>>(st->active[cur], n_own, st->result, target, target8, st->gamma_lut);
         ctx->launches += 2;
     }
     MIRO_CUDA(ctx, cudaGetLastError());
-    if (!out_is_device) {
-        const bool whole = n_own == pixels;
-        if (whole) MIRO_CUDA(ctx, cudaMemcpyAsync(rgb_out, st->rgb_dev, pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
-        else {
-            std::vector<float> tmp(pixels * 3);
-            MIRO_CUDA(ctx, cudaMemcpyAsync(tmp.data(), st->rgb_dev, pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
-            MIRO_CUDA(ctx, cudaStreamSynchronize(s));
-            for (int b = shard_i; b < nbx * nby; b += shard_n) {      // only this shard's pixels reach the caller's frame
-                const int bx = b % nbx, by = b / nbx;
-                for (int y = by * 32; y < std::min((by + 1) * 32, H); ++y) {
-                    const size_t a = ((size_t)y * W + bx * 32) * 3, n = (size_t)(std::min((bx + 1) * 32, W) - bx * 32) * 3;
-                    memcpy(rgb_out + a, tmp.data() + a, n * sizeof(float));
-                }
+    // host destinations: the whole frame in one copy, or — a shard of it — through a staging copy from which only the shard's
+    // bucket rows reach the caller's frame
+    auto download = [&](void* host, const void* dev, size_t bytes_per_pixel) -> int {
+        if (n_own == pixels) { MIRO_CUDA(ctx, cudaMemcpyAsync(host, dev, pixels * bytes_per_pixel, cudaMemcpyDeviceToHost, s)); return MIRO_GPU_OK; }
+        std::vector<unsigned char> tmp(pixels * bytes_per_pixel);
+        MIRO_CUDA(ctx, cudaMemcpyAsync(tmp.data(), dev, tmp.size(), cudaMemcpyDeviceToHost, s));
+        MIRO_CUDA(ctx, cudaStreamSynchronize(s));
+        for (int b = shard_i; b < nbx * nby; b += shard_n) {
+            const int bx = b % nbx, by = b / nbx;
+            for (int y = by * 32; y < std::min((by + 1) * 32, H); ++y) {
+                const size_t a = ((size_t)y * W + bx * 32) * bytes_per_pixel, n = (size_t)(std::min((bx + 1) * 32, W) - bx * 32) * bytes_per_pixel;
+                memcpy(static_cast<unsigned char*>(host) + a, tmp.data() + a, n);
             }
         }
-    }
+        return MIRO_GPU_OK;
+    };
+    if (rgb_out && !f_dev && (rc = download(rgb_out, st->rgb_dev, 3 * sizeof(float)))) return rc;
+    if (rgb8_out && !b_dev && (rc = download(rgb8_out, st->rgb8_dev, 3))) return rc;
     if (any_disperse) {
         MIRO_CUDA(ctx, cudaMemcpyAsync(st->h_count + 1, st->q[0].counts + 5, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         MIRO_CUDA(ctx, cudaMemcpyAsync(st->h_count + 2, st->q[1].counts + 5, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));

@@ -8,6 +8,7 @@
 #include <chrono>
 #include <map>
 #include <xmmintrin.h>
+#include <cuda_runtime.h>
 
 namespace miro {
 
@@ -263,7 +264,20 @@ bool RawImage::loadImage(const char* filename) {
 }
 
 Image::Image() { initGamma(); }
+Image::~Image() { unpin(); }
+void Image::pin() {
+    if (m_pinned || m_radiance.empty()) return;
+    if (cudaHostRegister(m_radiance.data(), m_radiance.size() * sizeof(float), cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return; }
+    if (cudaHostRegister(m_pixels.data(), m_pixels.size(), cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); cudaHostUnregister(m_radiance.data()); return; }
+    m_pinned = true;
+}
+void Image::unpin() {
+    if (!m_pinned) return;
+    cudaHostUnregister(m_radiance.data()); cudaHostUnregister(m_pixels.data()); cudaGetLastError();
+    m_pinned = false;
+}
 void Image::resize(int width, int height) {
+    unpin();
     m_width = width; m_height = height;
     m_pixels.assign((size_t)width * height * 3, 0);
     m_radiance.assign((size_t)width * height * 3, 0.f);
@@ -700,19 +714,17 @@ bool Scene::raytraceImage(const Camera* cam, Image* img, int shard_index, int sh
     if (!m_ctx && !m_group) { m_error = "raytraceImage: scene is not attached to a GPU (there is no CPU renderer)"; return false; }
     miro_gpu_camera c; cam->fill(c);
     miro_gpu_render_params p; renderParams(img, p);
+    img->pin();
+    // the frame arrives as the reference's Image holds it — 8-bit pixels through Image::setPixel's mapping, applied on the device —
+    // together with the float radiance
     if (m_group) {
         if (shard_count > 1) { m_error = "raytraceImage: a scene attached to several devices shards the frame itself"; return false; }
-        int rc = miro_gpu_group_render(m_group, &c, &p, m_sampleSharding ? MIRO_GPU_SHARD_SAMPLES : MIRO_GPU_SHARD_BUCKETS, img->m_radiance.data());
+        int rc = miro_gpu_group_render(m_group, &c, &p, m_sampleSharding ? MIRO_GPU_SHARD_SAMPLES : MIRO_GPU_SHARD_BUCKETS, img->m_radiance.data(), img->charPixels());
         if (rc) { m_error = std::string("miro_gpu_group_render: ") + miro_gpu_group_last_error(m_group); return false; }
     } else {
         p.shard_index = shard_index; p.shard_count = shard_count;
-        int rc = miro_gpu_render(m_ctx, &c, &p, img->m_radiance.data());
+        int rc = miro_gpu_render_image(m_ctx, &c, &p, img->m_radiance.data(), img->charPixels());
         if (rc) { m_error = std::string("miro_gpu_render: ") + miro_gpu_last_error(m_ctx); return false; }
-    }
-    const int w = img->width(), h = img->height();
-    for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) {
-        const float* q = &img->m_radiance[((size_t)y * w + x) * 3];
-        img->setPixel(x, y, Vector3(q[0], q[1], q[2]));
     }
     return true;
 }

@@ -75,18 +75,27 @@ public:
 class Image {   // frame buffer: 8-bit gamma-mapped pixels (as the reference) + the float radiance the GPU returned
 public:
     Image();
+    ~Image();
+    Image(const Image&) = delete;
+    Image& operator=(const Image&) = delete;
     void resize(int width, int height);
+    // page-lock the frame buffers (once per size) so that the frame comes down at PCIe speed: a 1080p float frame is 25 MB, and
+    // into ordinary memory the driver stages it at ~8 GB/s — longer than the frame takes to render
+    void pin();
     void setPixel(int x, int y, const Vector3& p);     // src/Image.cpp:71-87 (Map: clamp, 2.2 gamma LUT)
     void writePPM(const char* file) const;             // bottom-up flip, src/Image.cpp:132-154
     int width() const { return m_width; }
     int height() const { return m_height; }
     const unsigned char* getCharPixels() const { return m_pixels.data(); }
+    unsigned char* charPixels() { return m_pixels.data(); }      // filled by the GPU (Image::setPixel's mapping runs on the device)
     std::vector<float> m_radiance;                     // width*height*3, row 0 = bottom
     static unsigned char Map(float r);
     static const float* linearToGammaF();              // 32769-entry table used by the adaptive cut-off
 private:
+    void unpin();
     std::vector<unsigned char> m_pixels;
     int m_width = 1, m_height = 1;
+    bool m_pinned = false;
 };
 
 // ---- materials -------------------------------------------------------------------------------

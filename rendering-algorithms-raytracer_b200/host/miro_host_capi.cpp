@@ -101,11 +101,20 @@ int miro_host_trace_any(miro_host_scene* s, const miro_gpu_ray* rays, size_t n, 
 miro_gpu_ctx* miro_host_ctx(miro_host_scene* s) { return (s && s->ready) ? s->loaded.scene->context() : nullptr; }
 
 int miro_host_raytrace_image(miro_host_scene* s, float* rgb, unsigned char* rgb8, int shard_index, int shard_count) {
-    if (!s || !s->ready || !rgb) return MIRO_GPU_EINVAL;
+    if (!s || !s->ready) return MIRO_GPU_EINVAL;
     Image* img = s->loaded.image.get();
     if (!s->loaded.scene->raytraceImage(s->loaded.camera.get(), img, shard_index, shard_count)) { s->error = s->loaded.scene->lastError(); return MIRO_GPU_ECUDA; }
-    memcpy(rgb, img->m_radiance.data(), img->m_radiance.size() * sizeof(float));
+    if (rgb) memcpy(rgb, img->m_radiance.data(), img->m_radiance.size() * sizeof(float));
     if (rgb8) memcpy(rgb8, img->getCharPixels(), (size_t)img->width() * img->height() * 3);
+    return MIRO_GPU_OK;
+}
+int miro_host_image(miro_host_scene* s, const float** rgb, const unsigned char** rgb8, int* width, int* height) {
+    if (!s || !s->ready) return MIRO_GPU_EINVAL;
+    Image* img = s->loaded.image.get();
+    if (rgb) *rgb = img->m_radiance.data();
+    if (rgb8) *rgb8 = img->getCharPixels();
+    if (width) *width = img->width();
+    if (height) *height = img->height();
     return MIRO_GPU_OK;
 }
 int miro_host_write_ppm(miro_host_scene* s, const char* path) {

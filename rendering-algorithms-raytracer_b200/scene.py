@@ -216,12 +216,27 @@ class MiroScene:
     def set_stream(self, cuda_stream_ptr):
         self._gpu_check(self.L.miro_gpu_set_stream(self.ctx, cuda_stream_ptr), "set_stream")
 
-    def render(self, shard_index=0, shard_count=1, want_bytes=False):
+    def render(self, shard_index=0, shard_count=1, want_bytes=False, out=None):
+        """Scene::raytraceImage through the host layer.  out = (rgb float32 [h, w, 3], rgb8 uint8 [h, w, 3] or None): buffers to
+        reuse from frame to frame (fresh arrays cost a page fault per 4 KB, which at 1080p is as long as the frame itself)."""
         p = self.render_params()
-        rgb = np.zeros((p.height, p.width, 3), np.float32)
-        rgb8 = np.zeros((p.height, p.width, 3), np.uint8) if want_bytes else None
+        if out is not None:
+            rgb, rgb8 = out
+        else:
+            rgb = np.zeros((p.height, p.width, 3), np.float32)
+            rgb8 = np.zeros((p.height, p.width, 3), np.uint8) if want_bytes else None
         self._check(self.L.miro_host_raytrace_image(self.h, _ptr(rgb), _ptr(rgb8), shard_index, shard_count), "raytrace_image")
         return (rgb, rgb8) if want_bytes else rgb
+
+    def render_in_place(self, shard_index=0, shard_count=1):
+        """Scene::raytraceImage with the frame left in the scene's Image (no copies out): returns views (rgb float32 [h, w, 3],
+        rgb8 uint8 [h, w, 3]) of the Image's own page-locked buffers, valid until the next render / resize."""
+        self._check(self.L.miro_host_raytrace_image(self.h, None, None, shard_index, shard_count), "raytrace_image")
+        f, b, w, h = C.c_void_p(), C.c_void_p(), C.c_int(), C.c_int()
+        self._check(self.L.miro_host_image(self.h, C.byref(f), C.byref(b), C.byref(w), C.byref(h)), "image")
+        rgb = np.ctypeslib.as_array(C.cast(f, C.POINTER(C.c_float)), shape=(h.value, w.value, 3))
+        rgb8 = np.ctypeslib.as_array(C.cast(b, C.POINTER(C.c_ubyte)), shape=(h.value, w.value, 3))
+        return rgb, rgb8
 
     def render_device(self, d_rgb_ptr, params=None, camera=None):
         p = params or self.render_params(); c = camera or self.camera()

@@ -115,7 +115,7 @@ def write_obj_scene(fx, tmp, script=None):
         for line in script.splitlines():
             tok = line.split()
             if len(tok) >= 3 and tok[0] == "mesh" and tok[1] == name:
-                line = "mesh %s %s" % (name, path) + ("" if len(tok) == 3 else " " + " ".join(tok[3:]))
+                line = "mesh %s %s" % (name, path)      # without the script's `ctm`: the fixture holds the vertices AFTER the reference's load, transform applied
             lines.append(line)
         script = "\n".join(lines) + "\n"
     sp = os.path.join(tmp, "scene.miro")

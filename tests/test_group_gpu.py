@@ -81,7 +81,7 @@ def test_group_errors():
     p = sc.render_params(); cam = sc.camera()
     p.shard_count = 2
     out = np.zeros((p.height, p.width, 3), np.float32)
-    assert L.miro_gpu_group_render(sc.group, C.byref(cam), C.byref(p), 0, out.ctypes.data) == capi.EINVAL
+    assert L.miro_gpu_group_render(sc.group, C.byref(cam), C.byref(p), 0, out.ctypes.data, None) == capi.EINVAL
     assert b"shards the frame itself" in L.miro_gpu_group_last_error(sc.group)
     sc.close()
 

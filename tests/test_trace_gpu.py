@@ -357,8 +357,28 @@ def test_device_camera_rays_match_the_references(name):
     # reference's own rays give 2e-7 (test_closest_hit_matches_reference)
     st = helpers.compare_hits(sc, hits[pix], fx.hits[prim], rays=ref_rays, t_rel=2e-4)
     print(name, {k: v for k, v in st.items() if k != "hard_idx"})
-    assert st["id_match"] >= 0.999 and st["hard"] == 0 and st["frac_t_within"] == 1.0, st
+    # (c1: the camera's symmetry puts a pixel diagonal exactly on the back wall's shared diagonal — all ties)
+    assert st["id_match"] >= (0.998 if name == "c1_cornell" else 0.9995) and st["hard"] == 0 and st["frac_t_within"] == 1.0, st
     # the call's hits are those of tracing the rays it generated
     again = sc.trace_closest(rays)
     assert again.tobytes() == hits.tobytes()
+    sc.close()
+
+
+def test_pinning_the_callers_buffers():
+    """miro_gpu_pin_host_buffer page-locks ordinary arrays in place: same hits, and unpinning something unknown is an error."""
+    fx = helpers.Fixture(helpers.fixture_path("c2_explosion"))
+    sc = fx.scene().attach(0)
+    rays = np.ascontiguousarray(fx.rays); hits = np.empty(len(rays), mb.HIT_DTYPE)
+    want = sc.trace_closest(rays)
+    L = sc.L
+    assert L.miro_gpu_pin_host_buffer(sc.ctx, rays.ctypes.data, rays.nbytes) == 0
+    assert L.miro_gpu_pin_host_buffer(sc.ctx, rays.ctypes.data, rays.nbytes) == 0      # twice is not an error
+    assert L.miro_gpu_pin_host_buffer(sc.ctx, hits.ctypes.data, hits.nbytes) == 0
+    assert L.miro_gpu_trace_closest(sc.ctx, rays.ctypes.data, len(rays), hits.ctypes.data) == 0
+    assert hits.tobytes() == want.tobytes()
+    assert L.miro_gpu_unpin_host_buffer(sc.ctx, rays.ctypes.data) == 0
+    assert L.miro_gpu_unpin_host_buffer(sc.ctx, hits.ctypes.data) == 0
+    assert L.miro_gpu_unpin_host_buffer(sc.ctx, hits.ctypes.data) != 0
+    assert L.miro_gpu_pin_host_buffer(sc.ctx, None, 16) != 0
     sc.close()
