@@ -47,6 +47,17 @@ SEED = 0x5EED
 L2_BYTES = 126e6
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -154,7 +165,7 @@ def reference_main(args, rank):
     if "c2" not in legs:
         legs.insert(0, "c2")
     if not ra.have_reference():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/miro_ref is not built (run __graft_entry__.build() where /root/reference exists)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/miro_ref is not built (run __graft_entry__.build() where /root/reference exists)"})
         return
     rows = {}
     for name in legs:
@@ -171,7 +182,7 @@ def reference_main(args, rank):
             "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": c2["cores"], "kind": "reference", "sample": c2["sample"]},
             "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "workloads": rows}
-    print(json.dumps(line))
+    emit(line)
 
 
 def bench_config(w):
@@ -685,7 +696,7 @@ def gpu_main(args, rank, world, local):
         if rank == 0:
             line["render_scaling"] = rs
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -700,6 +711,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the reference legs (kernel tuning runs): no cpu_baseline, no parity")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: whatever a library prints to file descriptor 1 meanwhile (NCCL's version banner, build
+    # output) is sent to stderr, and the line is written to the real stdout at the end
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         reference_main(args, rank)
     else:

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Strong scaling of ONE frame through miro_gpu_group_* (one caller, N GPUs of one box): the C4 and C3 stand-ins at 2048x2048, bucket
 sharding (and sample sharding for C4), N = 1, 2, 4, 8 as far as the box has devices.  Frame time = wall time of
-miro_host_raytrace_image (render on every device + combine over peer memory + download of the float and the 8-bit frame), best of 3.
+miro_host_raytrace_image with the frame left in the scene's Image (render on every device + combine over peer memory + download of
+the float and the 8-bit frame into page-locked host memory), best of 3.
 usage: tools/group_scale.py [--size 2048] [scene ...]"""
 import argparse
 import json
@@ -32,11 +33,12 @@ def main():
                 continue
             for n in [k for k in (1, 2, 4, 8) if k <= n_dev]:
                 sc = fx.scene(script_override=script).attach_devices(list(range(n)), sample_sharding=(mode == "samples"))
-                img = sc.render()
+                img, _ = sc.render_in_place()
                 best = 1e30
-                for _ in range(3):
-                    self_rc = sc.L.miro_gpu_group_reset_counters(sc.group)
-                    t0 = time.time(); img = sc.render(); best = min(best, time.time() - t0)
+                for _ in range(3):      # the frame as Scene::raytraceImage leaves it: in the scene's (page-locked) Image, float + 8-bit
+                    sc.L.miro_gpu_group_reset_counters(sc.group)
+                    t0 = time.time(); img, _ = sc.render_in_place(); best = min(best, time.time() - t0)
+                img = img.copy()
                 c = sc.group_counters(); rays = int(c["rays_closest"] + c["rays_any"])
                 peers = [int(sc.L.miro_gpu_group_peer_access(sc.group, i)) for i in range(n)]
                 if n == 1:

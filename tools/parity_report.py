@@ -27,7 +27,12 @@ def trace_stats(fx, sc, rays, ref):
     sc.set_trace_kernel("warp"); hits = sc.trace_closest(rays)
     sc.set_trace_kernel("pool"); pool = sc.trace_closest(rays)
     sc.set_trace_kernel("warp")
-    st = clean(helpers.compare_hits(sc, hits, ref, t_rel=1e-5, rays=rays))
+    raw = helpers.compare_hits(sc, hits, ref, t_rel=1e-5, rays=rays)
+    adj = helpers.adjudicate_hard(fx, sc, hits, ref, raw, rays)
+    st = clean(raw)
+    st["unclassed_by_the_barycentric_heuristic"] = st.pop("hard")
+    st["unclassed_in_float64"] = {k: v for k, v in adj.items() if k != "hard_idx"}
+    st["hard"] = adj["product_missed"] + adj["unexplained"]
     st["pool_kernel_identical"] = bool(hits.tobytes() == pool.tobytes())
     occ = sc.trace_any(rays)
     st["any_hit_agrees_with_reference"] = float((occ == (ref["mesh"] >= 0)).mean())
