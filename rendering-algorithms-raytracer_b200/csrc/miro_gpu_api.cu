@@ -65,6 +65,11 @@ void drain_timing(miro_gpu_ctx* ctx) {
 enum { TRACE_CLOSEST = 0, TRACE_ANY_BITS = 1, TRACE_ANY_ACCUM = 2 };
 constexpr int WORK_RING = 32;     // pairs of work counters per lane; launch k of a lane uses pair k % WORK_RING and re-arms it when its last block leaves
 constexpr int WORK_LANES = 4;     // lanes = streams a caller may spread traversal launches over (miro_gpu_ctx::work_lane)
+// The pool kernel keeps the deep end of its traversal stacks in a scratch in global memory.  Chained launches overlap, so
+// consecutive launches of a lane must not share it: SCRATCH_COPIES regions used round-robin, and the chain is broken every
+// SCRATCH_COPIES-th launch (that launch waits for the complete end of everything before it), so the launches that can be live
+// together always hold different regions.
+constexpr int SCRATCH_COPIES = 3;
 
 // PACKED: rays are miro_gpu_ray32 records (two 16-byte words: o, tmin | d, tmax; time = 0) instead of miro_gpu_ray (three).
 template <int MODE, bool COUNT, bool ALPHA, bool PACKED>
@@ -220,7 +225,7 @@ static int trace_grid(miro_gpu_ctx* ctx, size_t n) {
 // depth of the uploaded trees and allocated on first use.
 template <int MODE, bool PACKED>
 static cudaError_t launch_trace_pool(miro_gpu_ctx* ctx, const cudaLaunchConfig_t& base_cfg, const float4* r, size_t n, const uint32_t* d_count, uint32_t chunk,
-                                     miro_gpu_hit* d_hits, uint32_t* d_bits, const float4* d_E, float4* d_slots, uint32_t* work) {
+                                     miro_gpu_hit* d_hits, uint32_t* d_bits, const float4* d_E, float4* d_slots, uint32_t* work, uint64_t scratch_copy) {
     static int per_sm[4] = {0, 0, 0, 0};
     int& v = per_sm[(ctx->counting ? 1 : 0) + (ctx->has_alpha ? 2 : 0)];
 #define MIRO_POOL_KERNEL(COUNT, ALPHA) k_trace_pool<MODE, COUNT, ALPHA, PACKED>
@@ -242,16 +247,17 @@ static cudaError_t launch_trace_pool(miro_gpu_ctx* ctx, const cudaLaunchConfig_t
     const int cap = std::max(0, ctx->stack_need - POOL_STACK);
     const size_t need = (size_t)full_grid * POOL_WARPS * POOL_SLOTS * (size_t)cap;
     PoolScratch& sc = ctx->pool_ovf[ctx->work_lane];
-    if (need > sc.entries) {
+    if (need * SCRATCH_COPIES > sc.entries) {
         if (sc.ptr) { cudaStreamSynchronize(ctx->stream); cudaFree(sc.ptr); sc.ptr = nullptr; sc.entries = 0; }
-        cudaError_t e = cudaMalloc((void**)&sc.ptr, need * sizeof(unsigned long long));
+        cudaError_t e = cudaMalloc((void**)&sc.ptr, need * SCRATCH_COPIES * sizeof(unsigned long long));
         if (e != cudaSuccess) return e;
-        sc.entries = need;
+        sc.entries = need * SCRATCH_COPIES;
     }
+    unsigned long long* const scratch = sc.ptr ? sc.ptr + need * (size_t)(scratch_copy % SCRATCH_COPIES) : nullptr;
     cudaLaunchConfig_t cfg = base_cfg;
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(POOL_BLOCK); cfg.dynamicSmemBytes = POOL_SMEM_BYTES;
     cudaError_t e = cudaSuccess;
-#define MIRO_POOL_LAUNCH(COUNT, ALPHA) e = cudaLaunchKernelEx(&cfg, MIRO_POOL_KERNEL(COUNT, ALPHA), ctx->scene, r, (uint32_t)n, d_count, chunk, d_hits, d_bits, d_E, d_slots, ctx->d_counters, work, sc.ptr, cap)
+#define MIRO_POOL_LAUNCH(COUNT, ALPHA) e = cudaLaunchKernelEx(&cfg, MIRO_POOL_KERNEL(COUNT, ALPHA), ctx->scene, r, (uint32_t)n, d_count, chunk, d_hits, d_bits, d_E, d_slots, ctx->d_counters, work, scratch, cap)
     MIRO_POOL_DISPATCH(MIRO_POOL_LAUNCH)
 #undef MIRO_POOL_LAUNCH
 #undef MIRO_POOL_DISPATCH
@@ -288,12 +294,13 @@ static void launch_trace(miro_gpu_ctx* ctx, const void* d_rays, size_t n, const 
     // griddepcontrol.wait while still resident, so without the break any number of them could be live behind one long launch
     // and launch k + WORK_RING would claim rays from the not yet re-armed counter pair of launch k.  With the break at most
     // WORK_RING - 1 consecutive launches of a lane are ever live together.
-    const bool chained = ctx->chain_traces && ctx->in_api_trace && (slot % (WORK_RING - 1)) != 0;
+    const bool scratch_kernel = ctx->trace_kernel != MIRO_GPU_KERNEL_WARP;      // see SCRATCH_COPIES
+    const bool chained = ctx->chain_traces && ctx->in_api_trace && (slot % (WORK_RING - 1)) != 0 && !(scratch_kernel && slot % SCRATCH_COPIES == 0);
     cfg.attrs = attr; cfg.numAttrs = chained ? 1 : 0;
     ctx->launches++;
     if (ctx->trace_kernel == MIRO_GPU_KERNEL_POOL) {
         static_assert((int)TRACE_CLOSEST == (int)POOL_TRACE_CLOSEST && (int)TRACE_ANY_BITS == (int)POOL_TRACE_ANY_BITS && (int)TRACE_ANY_ACCUM == (int)POOL_TRACE_ANY_ACCUM, "mode numbering");
-        const cudaError_t e = launch_trace_pool<MODE, PACKED>(ctx, cfg, r, n, d_count, chunk, d_hits, d_bits, d_E, d_slots, work);
+        const cudaError_t e = launch_trace_pool<MODE, PACKED>(ctx, cfg, r, n, d_count, chunk, d_hits, d_bits, d_E, d_slots, work, slot);
         if (e != cudaSuccess) ctx->error = std::string("pool traversal launch: ") + cudaGetErrorString(e);      // surfaces through the caller's cudaGetLastError check
         return;
     }
