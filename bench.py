@@ -652,7 +652,9 @@ def gpu_main(args, rank, world, local):
         ref = None
         if do_cpu and ra.have_reference():
             ref = reference_workload(w, threads, 3, 0, want_meshes=True)      # first: the product traces the geometry the reference holds
+        t_build = time.time()
         sc = product_scene(w, ref["meshes"] if ref else None, local)
+        t_build = time.time() - t_build
         sampler = None
         if name == "c2":
             sampler = ClockSampler(local); sampler.start()
@@ -662,6 +664,7 @@ def gpu_main(args, rank, world, local):
         parity = parity_of(w, sc, ref) if ref else None
         row = {"workload": w.label, "triangles": w.triangles(), "device_nodes": leg["n_nodes"], "device_triangle_slots": leg["n_tris_device"],
                "device_instances": leg["n_instances_device"], "structure_MB_on_device": leg["structure_bytes"] * 1e-6,
+               "host_bvh_build_flatten_and_upload_s": t_build,
                "Mrays_per_s": leg["value"], "ms_per_step": leg["total_ms"] / args.steps, "roofline": roof, "parity": parity}
         if ref:
             row["cpu_baseline"] = {"value": ref["n"] / ref["seconds_best"] * 1e-6, "unit": "Mrays/s", "cores": ref["threads"], "kind": "reference",

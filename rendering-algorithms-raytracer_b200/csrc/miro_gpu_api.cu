@@ -63,6 +63,9 @@ void drain_timing(miro_gpu_ctx* ctx) {
 // MODE: 0 closest hit -> hit records; 1 any hit -> one bit per ray; 2 any hit -> the unoccluded ray's light sample
 // (sample_E[i] = E.rgb, specular input) is added to the accumulator of its light loop (slot index in ray.user0).
 enum { TRACE_CLOSEST = 0, TRACE_ANY_BITS = 1, TRACE_ANY_ACCUM = 2 };
+// rays are claimed from a 32-bit work counter that every warp keeps advancing by 32 after the batch is exhausted (a few million
+// past n at full occupancy): n stays 2^24 below the wrap
+constexpr unsigned long long MAX_RAYS_PER_CALL = 0xff000000ull;
 constexpr int WORK_RING = 32;     // pairs of work counters per lane; launch k of a lane uses pair k % WORK_RING and re-arms it when its last block leaves
 constexpr int WORK_LANES = 4;     // lanes = streams a caller may spread traversal launches over (miro_gpu_ctx::work_lane)
 // The pool kernel keeps the deep end of its traversal stacks in a scratch in global memory.  Chained launches overlap, so
@@ -272,11 +275,7 @@ static void launch_trace(miro_gpu_ctx* ctx, const void* d_rays, size_t n, const 
     const int grid = trace_grid<MODE>(ctx, n);
     // rays are claimed one warp-load (32) at a time: measured on the coherent 1080p batch, 64-ray chunks left a tail worth 15 %
     // of the launch (a warp stuck with two heavy chunks while the rest of the GPU had drained); 16 is no better than 32
-#ifdef MIRO_TRACE_CHUNK
-    const uint32_t chunk = MIRO_TRACE_CHUNK;
-#else
-    const uint32_t chunk = 32u;
-#endif
+    const uint32_t chunk = 32u;      // exactly one any-hit result word per claim: the claiming warp clears it in-kernel
     static_assert(MODE != TRACE_ANY_BITS || true, "");
     const float4* r = reinterpret_cast<const float4*>(d_rays);
     // Every launch has its own pair of work counters out of a ring, so consecutive traversal launches can overlap.  When the
@@ -604,7 +603,7 @@ int miro_gpu_upload_scene(miro_gpu_ctx* ctx, const miro_gpu_scene_desc* d) {
 int miro_gpu_trace_closest_device(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, miro_gpu_hit* d_hits) {
     if (!ctx) return MIRO_GPU_EINVAL;
     if (!ctx->has_scene) return set_error(ctx, MIRO_GPU_ENOSCENE, "trace before upload_scene");
-    if (n > 0xffffffffull) return set_error(ctx, MIRO_GPU_EINVAL, "more than 2^32-1 rays in one call");
+    if (n > MAX_RAYS_PER_CALL) return set_error(ctx, MIRO_GPU_EINVAL, "more than 2^32 - 2^24 rays in one call");
     if (n == 0) return MIRO_GPU_OK;
     if (!d_rays || !d_hits) return set_error(ctx, MIRO_GPU_EINVAL, "NULL ray/hit buffer");
     MIRO_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -621,7 +620,7 @@ int miro_gpu_trace_closest_device(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays,
 int miro_gpu_trace_any_device(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, uint32_t* d_bits) {
     if (!ctx) return MIRO_GPU_EINVAL;
     if (!ctx->has_scene) return set_error(ctx, MIRO_GPU_ENOSCENE, "trace before upload_scene");
-    if (n > 0xffffffffull) return set_error(ctx, MIRO_GPU_EINVAL, "more than 2^32-1 rays in one call");
+    if (n > MAX_RAYS_PER_CALL) return set_error(ctx, MIRO_GPU_EINVAL, "more than 2^32 - 2^24 rays in one call");
     if (n == 0) return MIRO_GPU_OK;
     if (!d_rays || !d_bits) return set_error(ctx, MIRO_GPU_EINVAL, "NULL ray/bit buffer");
     MIRO_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -642,7 +641,7 @@ static int trace_host(miro_gpu_ctx* ctx, const void* rays_v, size_t n, miro_gpu_
     const size_t ray_bytes = packed ? sizeof(miro_gpu_ray32) : sizeof(miro_gpu_ray);
     if (!ctx) return MIRO_GPU_EINVAL;
     if (!ctx->has_scene) return set_error(ctx, MIRO_GPU_ENOSCENE, "trace before upload_scene");
-    if (n > 0xffffffffull) return set_error(ctx, MIRO_GPU_EINVAL, "more than 2^32-1 rays in one call");
+    if (n > MAX_RAYS_PER_CALL) return set_error(ctx, MIRO_GPU_EINVAL, "more than 2^32 - 2^24 rays in one call");
     if (n == 0) return MIRO_GPU_OK;
     if (!rays || (!hits && !bits)) return set_error(ctx, MIRO_GPU_EINVAL, "NULL ray/result buffer");
     MIRO_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -95,6 +95,7 @@ struct Builder {
 
     int32_t make_leaf(int32_t me, const std::vector<Ref>& refs) {
         const uint32_t first = leaf_next.fetch_add((uint32_t)refs.size(), std::memory_order_relaxed);
+        if ((size_t)first + refs.size() > leaf_prims.size()) { fprintf(stderr, "miro_bvh: leaf storage exhausted (%u + %zu > %zu)\n", first, refs.size(), leaf_prims.size()); abort(); }
         bn[me].first = first; bn[me].count = (uint32_t)refs.size();
         for (size_t i = 0; i < refs.size(); ++i) leaf_prims[first + i] = refs[i].prim;
         return me;
@@ -241,7 +242,11 @@ struct Builder {
                     }
                 }
                 have_split = !left.empty() && !right.empty() && left.size() < count && right.size() < count;
-                if (have_split) { const size_t used = left.size() + right.size() - count; extra_refs.fetch_add(used, std::memory_order_relaxed); budget -= std::min(budget, used); }
+                // the bins predicted sp_nl + sp_nr references; the partition compares the boxes with sp_pos directly and can find a
+                // few more straddlers — a split that would overdraw the allowance is dropped for the object split (the storage
+                // is sized from the allowance)
+                if (have_split && left.size() + right.size() - count > budget) have_split = false;
+                if (have_split) { const size_t used = left.size() + right.size() - count; extra_refs.fetch_add(used, std::memory_order_relaxed); budget -= used; }
                 else { left.clear(); right.clear(); }
             }
             if (!have_split && best_axis >= 0 && depth < 40) {   // beyond 40 levels fall through to balanced median splits

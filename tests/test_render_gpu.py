@@ -330,3 +330,54 @@ def test_reference_binding_renders_motion_blur_and_instances_on_the_gpu(tmp_path
     print("reference binding c5: means", img.mean(), ref.mean(), "block diff", np.abs(blk(img) - blk(ref)).mean())
     assert abs(img.mean() - ref.mean()) <= 0.02 * ref.mean()
     assert np.abs(blk(img) - blk(ref)).mean() < 0.01
+
+
+def test_render_image_delivers_the_8_bit_frame():
+    """miro_gpu_render_image: rgb8 = every channel of the float frame through Image::setPixel's Map (src/Image.cpp:71-87: clamp,
+    32 769-entry 2.2-gamma table), applied on the device; host and device destinations, either output alone, shards."""
+    import ctypes as C
+    import torch
+    fx, sc = load("c4_cornell_pt")
+    p = sc.render_params(); cam = sc.camera()
+    L = sc.L
+    n = p.width * p.height * 3
+    rgb = np.zeros(n, np.float32); rgb8 = np.zeros(n, np.uint8)
+    assert L.miro_gpu_render_image(sc.ctx, C.byref(cam), C.byref(p), rgb.ctypes.data, rgb8.ctypes.data) == 0
+    # the table as Image::generateGammaTables builds it (float arithmetic), indexed as Map indexes it
+    lut = (np.power(np.arange(32769, dtype=np.float32) / np.float32(32768.0), np.float32(1 / 2.2)) * np.float32(255.0) + np.float32(0.5)).astype(np.int32)
+    idx = np.where(rgb * np.float32(32768.0) > 32768.0, 32768, np.maximum(rgb * np.float32(32768.0), 0).astype(np.int32))
+    want = lut[idx].astype(np.uint8)
+    diff = np.abs(want.astype(int) - rgb8.astype(int))
+    assert diff.max() <= 1 and (diff != 0).mean() < 1e-3, (diff.max(), (diff != 0).mean())      # powf vs numpy's float32 power at a table entry or two
+    assert rgb8.max() == 255 and rgb8.min() == 0
+    # bytes only; bytes into device memory; nothing at all is an error
+    only8 = np.zeros(n, np.uint8)
+    assert L.miro_gpu_render_image(sc.ctx, C.byref(cam), C.byref(p), None, only8.ctypes.data) == 0
+    d8 = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    assert L.miro_gpu_render_image(sc.ctx, C.byref(cam), C.byref(p), None, d8.data_ptr()) == 0
+    torch.cuda.synchronize()
+    for other in (only8, d8.cpu().numpy()):      # path-traced frames differ between renders in the last bits (float atomics): a byte step here and there
+        assert (np.abs(other.astype(int) - rgb8.astype(int)) > 1).mean() == 0 and (other != rgb8).mean() < 0.02
+    assert L.miro_gpu_render_image(sc.ctx, C.byref(cam), C.byref(p), None, None) != 0
+    # a shard touches its own pixels only, in both outputs
+    p.shard_index, p.shard_count = 1, 3
+    part = np.full(n, 7, np.uint8); partf = np.full(n, -1.0, np.float32)
+    assert L.miro_gpu_render_image(sc.ctx, C.byref(cam), C.byref(p), partf.ctypes.data, part.ctypes.data) == 0
+    ys, xs = np.mgrid[0:p.height, 0:p.width]
+    own = ((ys // 32) * ((p.width + 31) // 32) + xs // 32) % 3 == 1
+    part = part.reshape(p.height, p.width, 3); partf = partf.reshape(p.height, p.width, 3)
+    assert (part[~own] == 7).all() and (partf[~own] == -1.0).all()
+    assert (np.abs(part[own].astype(int) - rgb8.reshape(p.height, p.width, 3)[own].astype(int)) <= 1).all()
+    sc.close()
+
+
+def test_frame_lands_in_the_scenes_image():
+    """miro_host_raytrace_image without copies: the frame is in the scene's Image (float radiance + 8-bit pixels), as
+    Scene::raytraceImage leaves it in the reference; the copying variant returns the same frame."""
+    fx, sc = load("c1_cornell")
+    rgb, rgb8 = sc.render_in_place()
+    rgb = rgb.copy(); rgb8 = rgb8.copy()
+    again, again8 = sc.render(want_bytes=True)
+    assert np.array_equal(rgb, again) and np.array_equal(rgb8, again8)
+    assert rgb8.max() > 100
+    sc.close()

@@ -387,3 +387,59 @@ def test_pinning_the_callers_buffers():
     assert L.miro_gpu_unpin_host_buffer(sc.ctx, hits.ctypes.data) != 0
     assert L.miro_gpu_pin_host_buffer(sc.ctx, None, 16) != 0
     sc.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_many_short_chained_launches_behind_a_long_one(kernel):
+    """One long launch followed by 40 short chained ones into distinct buffers: the short ones pass their launch_dependents point
+    during the long one's tail, so without a bound on the chain depth launch k + WORK_RING would claim rays from the not yet
+    re-armed counter pair of launch k and write nothing (the ring has 32 pairs; the chain is broken before it can wrap)."""
+    import torch
+    fx = helpers.Fixture(helpers.fixture_path("c2_explosion"))
+    sc = fx.scene().attach(0)
+    sc.set_trace_kernel(kernel)
+    long_rays = np.concatenate([fx.rays] * 32)      # 1 M rays
+    short = fx.rays[:1000]
+    want_long = sc.trace_closest(long_rays); want_short = sc.trace_closest(short)
+    want_occ = sc.trace_any(short)
+    d_long = torch.from_numpy(long_rays.view(np.uint8).reshape(len(long_rays), -1)).cuda()
+    d_short = torch.from_numpy(short.view(np.uint8).reshape(len(short), -1)).cuda()
+    stream = torch.cuda.Stream(); sc.set_stream(stream.cuda_stream)
+    h_long = torch.full((len(long_rays), 20), 0xff, dtype=torch.uint8, device="cuda")
+    h_short = [torch.full((len(short), 20), 0xff, dtype=torch.uint8, device="cuda") for _ in range(40)]
+    b_short = [torch.full(((len(short) + 31) // 32,), -1, dtype=torch.int32, device="cuda") for _ in range(40)]
+    torch.cuda.synchronize()
+    sc.set_trace_chaining(True)
+    sc.trace_closest_device(d_long.data_ptr(), len(long_rays), h_long.data_ptr())
+    for k in range(40):
+        sc.trace_closest_device(d_short.data_ptr(), len(short), h_short[k].data_ptr())
+        sc.trace_any_device(d_short.data_ptr(), len(short), b_short[k].data_ptr())
+    stream.synchronize()
+    sc.set_trace_chaining(False); sc.set_stream(None)
+    assert h_long.cpu().numpy().view(mb.HIT_DTYPE).reshape(-1).tobytes() == want_long.tobytes()
+    for k in range(40):
+        assert h_short[k].cpu().numpy().view(mb.HIT_DTYPE).reshape(-1).tobytes() == want_short.tobytes(), k
+        occ = np.unpackbits(b_short[k].cpu().numpy().view(np.uint8), bitorder="little")[:len(short)].astype(bool)
+        assert np.array_equal(occ, want_occ), k
+    sc.close()
+
+
+def test_trace_primary_shapes_and_errors():
+    """miro_gpu_trace_primary on frames that are not a multiple of its chunk, into device memory, and its error returns."""
+    import ctypes as C
+    import torch
+    fx = helpers.Fixture(helpers.fixture_path("c2_explosion"))
+    sc = fx.scene().attach(0)
+    cam = sc.camera()
+    full = sc.trace_primary(width=1920, height=1080)                  # 7.9 chunks of 2^18 rays
+    small = sc.trace_primary(width=333, height=77)
+    assert (full["prim"] >= 0).mean() > 0.05 and (small["prim"] >= 0).mean() > 0.05
+    d_hits = torch.zeros((1920 * 1080, 20), dtype=torch.uint8, device="cuda")
+    assert sc.L.miro_gpu_trace_primary(sc.ctx, C.byref(cam), 1920, 1080, sc.render_params().seed, d_hits.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    assert d_hits.cpu().numpy().view(mb.HIT_DTYPE).reshape(-1).tobytes() == full.tobytes()
+    out = np.zeros(16, mb.HIT_DTYPE)
+    assert sc.L.miro_gpu_trace_primary(sc.ctx, None, 4, 4, 0, out.ctypes.data, None) != 0
+    assert sc.L.miro_gpu_trace_primary(sc.ctx, C.byref(cam), 0, 4, 0, out.ctypes.data, None) != 0
+    assert sc.L.miro_gpu_trace_primary(sc.ctx, C.byref(cam), 4, 4, 0, None, None) != 0
+    sc.close()
