@@ -425,6 +425,24 @@ void dumpMeshes(const std::string& dir) {
     }
 }
 
+// --dump-instances FILE: per ProxyObject, in ordinal order, the 16 floats of its ProxyMatrix::m_inverse (row-major) and what
+// multiplyAndDivideByW multiplies a transformed point by for an affine matrix, recipps(m44) — the numbers the product's host layer
+// must reproduce bit for bit (host/miro_math.h invertedAsReference, referenceRecip).
+void dumpInstances(const std::string& path) {
+    std::vector<const ProxyObject*> byOrdinal(g_proxyOrdinal.size(), (const ProxyObject*)0);
+    for (std::map<const ProxyObject*, int>::iterator it = g_proxyOrdinal.begin(); it != g_proxyOrdinal.end(); ++it) byOrdinal[it->second] = it->first;
+    std::vector<float> out;
+    for (size_t i = 0; i < byOrdinal.size(); i++) {
+        const Matrix4x4& I = byOrdinal[i]->getMatrix().m_inverse;
+        const float m[16] = {I.m11, I.m12, I.m13, I.m14, I.m21, I.m22, I.m23, I.m24, I.m31, I.m32, I.m33, I.m34, I.m41, I.m42, I.m43, I.m44};
+        out.insert(out.end(), m, m + 16);
+        __attribute__((aligned(16))) float w[4] = {I.m44, I.m44, I.m44, I.m44}; __attribute__((aligned(16))) float r[4];
+        storeps(recipps(loadps(w)), r);
+        out.push_back(r[0]);
+    }
+    writeVec(path, out);
+}
+
 // --dump-textures DIR: every texture as the reference's loaders left it (RawImage.cpp / hdrloader.cpp): float texels.
 void dumpTextures(const std::string& dir) {
     for (std::map<std::string, Texture*>::iterator it = g_textures.begin(); it != g_textures.end(); ++it) {
@@ -705,7 +723,7 @@ double renderGPU(const std::string& out, const std::string& libPath) {
 }  // namespace
 
 int main(int argc, char** argv) {
-    std::string scene, dumpPrim, traceIn, traceOut, floatOut, ppmOut, meshDir, qbvhOut, texDir, gpuOut, gpuLib, gpuPpm, shadowRaysOut, shadowHitsOut;
+    std::string scene, dumpPrim, traceIn, traceOut, floatOut, ppmOut, meshDir, qbvhOut, texDir, gpuOut, gpuLib, gpuPpm, shadowRaysOut, shadowHitsOut, instOut;
     int threads = 1, repeat = 1, warmup = 0; bool stock = false, doFloat = false, doShadow = false;
     float shadowLight[3] = {0, 0, 0}; size_t shadowFirst = 0, shadowCount = 0;
     for (int i = 1; i < argc; i++) {
@@ -728,6 +746,7 @@ int main(int argc, char** argv) {
         else if (a == "--dump-meshes") meshDir = NEXT();
         else if (a == "--dump-qbvh") qbvhOut = NEXT();
         else if (a == "--dump-textures") texDir = NEXT();
+        else if (a == "--dump-instances") instOut = NEXT();
         else if (a == "--render-gpu") gpuOut = NEXT();
         else if (a == "--gpu-lib") gpuLib = NEXT();
         else if (a == "--gpu-ppm") gpuPpm = NEXT();
@@ -746,6 +765,7 @@ int main(int argc, char** argv) {
     if (!meshDir.empty()) dumpMeshes(meshDir);
     if (!qbvhOut.empty()) dumpQBVH(qbvhOut);
     if (!texDir.empty()) dumpTextures(texDir);
+    if (!instOut.empty()) dumpInstances(instOut);
     if (!dumpPrim.empty()) dumpPrimary(dumpPrim);
     if (!gpuOut.empty()) {
         if (gpuLib.empty()) die("--render-gpu needs --gpu-lib path/to/libmiro_gpu.so");
