@@ -40,7 +40,7 @@ import bench_workloads as bw        # noqa: E402
 
 N_BATCH = bw.N_BATCH
 NODE_BYTES = 64      # device node (csrc/traverse.cuh DeviceNode)
-TRI_BYTES = 48       # bytes a triangle test reads (the device record is padded to 64 for alignment; 48 are loaded)
+TRI_BYTES = 48       # bytes a triangle test reads = the device record
 MBTRI_BYTES = 96
 INST_BYTES = 64
 SEED = 0x5EED
@@ -312,7 +312,7 @@ def trace_leg(w, sc, args, rank, world, local, barrier, sampler=None, sustain_s=
     value = 3 * N_BATCH * args.steps * world / total_ms * 1e-3
     sc.set_stream(None)
     return {"value": value, "total_ms": total_ms, "launch_ms": launch_ms, "per_launch": per_launch, "batches": batches, "inco_hits": inco_hits,
-            "sustained": sustained, "wall": (t_wall0, t_wall1), "structure_bytes": int(d.n_nodes) * NODE_BYTES + int(d.n_tris) * 64 + int(d.n_mbtris) * 96 + int(d.n_instances) * 64,
+            "sustained": sustained, "wall": (t_wall0, t_wall1), "structure_bytes": int(d.n_nodes) * NODE_BYTES + int(d.n_tris) * TRI_BYTES + int(d.n_mbtris) * 96 + int(d.n_instances) * 64,
             "n_nodes": int(d.n_nodes), "n_tris_device": int(d.n_tris), "n_instances_device": int(d.n_instances)}
 
 

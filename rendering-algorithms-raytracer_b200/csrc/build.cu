@@ -153,7 +153,7 @@ __global__ void k_gather_tris(const float4* __restrict__ in, const uint32_t* __r
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const size_t s = (size_t)perm[i] * 3;
-    float4* o = out + TRI_F4 * (size_t)i;       // 64-byte device records (traverse.cuh)
+    float4* o = out + TRI_F4 * (size_t)i;       // device triangle records (traverse.cuh, TRI_F4)
     o[0] = in[s]; o[1] = in[s + 1]; o[2] = in[s + 2]; o[3] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 __global__ void k_gather_prims(const miro_gpu_prim* __restrict__ in, const uint32_t* __restrict__ perm, uint32_t n, miro_gpu_prim* __restrict__ out) {
@@ -236,7 +236,7 @@ int build_lbvh_on_device(miro_gpu_ctx* ctx, const float4* d_tris_in, uint32_t n,
     auto grid = [&](size_t k) { return (unsigned)((k + B - 1) / B); };
     if (n <= MIRO_GPU_MAX_LEAF) {        // the whole scene is one leaf (cf. src/BVH.cpp:118-132)
         MIRO_CUDA(ctx, cudaMemsetAsync(tris_sorted, 0, (size_t)std::max<uint32_t>(n, 1) * TRI_F4 * sizeof(float4), s));
-        if (n) MIRO_CUDA(ctx, cudaMemcpy2DAsync(tris_sorted, TRI_F4 * sizeof(float4), d_tris_in, 48, 48, n, cudaMemcpyDeviceToDevice, s));      // 48-byte ABI records -> 64-byte device records
+        if (n) MIRO_CUDA(ctx, cudaMemcpy2DAsync(tris_sorted, TRI_F4 * sizeof(float4), d_tris_in, 48, 48, n, cudaMemcpyDeviceToDevice, s));      // 48-byte ABI records -> device records
         std::vector<uint32_t> id(n); for (uint32_t i = 0; i < n; ++i) id[i] = i;
         MIRO_CUDA(ctx, cudaMemcpyAsync(perm, id.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
         MIRO_CUDA(ctx, cudaStreamSynchronize(s));

@@ -522,13 +522,18 @@ int miro_gpu_upload_scene(miro_gpu_ctx* ctx, const miro_gpu_scene_desc* d) {
         std::vector<DeviceNode> cnodes(d->n_nodes);          // 128-byte ABI nodes -> 64-byte device nodes (traverse.cuh)
         for (uint32_t i = 0; i < d->n_nodes; ++i) cnodes[i] = compress_node(d->nodes[i]);
         if ((rc = upload_array(ctx, cnodes.data(), cnodes.size(), &dn))) return rc;
-        // 48-byte ABI triangles -> 64-byte aligned device records (traverse.cuh, TRI_F4)
+        // triangles: as they are, or (TRI_F4 == 4) as 64-byte aligned device records (traverse.cuh)
+#if MIRO_TRI_F4 == 4
         struct Tri64 { miro_gpu_tri t; uint32_t pad[4]; };
         static_assert(sizeof(Tri64) == TRI_F4 * sizeof(float4), "device triangle record");
         std::vector<Tri64> ctris(d->n_tris);
         for (uint32_t i = 0; i < d->n_tris; ++i) { ctris[i].t = d->tris[i]; ctris[i].pad[0] = ctris[i].pad[1] = ctris[i].pad[2] = ctris[i].pad[3] = 0; }
         const Tri64* dt64;
         if ((rc = upload_array(ctx, ctris.data(), ctris.size(), &dt64))) return rc;
+#else
+        const miro_gpu_tri* dt64;
+        if ((rc = upload_array(ctx, d->tris, d->n_tris, &dt64))) return rc;
+#endif
         MIRO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the staging vectors go out of scope
         dt = reinterpret_cast<const miro_gpu_tri*>(dt64);
     }

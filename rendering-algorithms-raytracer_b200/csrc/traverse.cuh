@@ -96,7 +96,7 @@ struct AlphaData {
 struct DeviceScene {
     AlphaData alpha;
     const float4* nodes;     // DeviceNode: 4 x float4 per node (the 64-byte compressed form, see compress_node)
-    const float4* tris;      // TRI_F4 x float4 per triangle (64-byte records: v0, v1, v2, pad), leaf order
+    const float4* tris;      // TRI_F4 x float4 per triangle (v0, v1, v2 [, pad]), leaf order
     const float4* mbtris;    // 6 x float4 per motion-blur triangle (96 bytes: three 32-byte loads)
     const float4* insts;     // 4 x float4 per instance
     int32_t root;
@@ -111,14 +111,23 @@ __device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
                  : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
 }
 
-// Device triangle record: the 48-byte ABI triangle (three float4 vertices) padded to 64 bytes and 64-byte aligned, so a test
-// fetches it with ONE 32-byte and ONE 16-byte load out of one 128-byte line and exactly two 32-byte sectors (the 48-byte stride
-// needed three 16-byte loads — L1 wavefronts are per lane and per load for divergent addresses — and every fourth triangle
-// straddled two lines; ncu: L1 sector traffic 1.23 x algorithmic).  The kernel still reads 48 bytes per test.
-constexpr int TRI_F4 = 4;
+// Device triangle record.  3 (default): the 48-byte ABI triangle (three float4 vertices) as it is, three 16-byte loads.
+// 4: padded to 64 bytes and 64-byte aligned — one 32-byte + one 16-byte load out of one 128-byte line and exactly two 32-byte
+// sectors (the 48-byte stride straddles a line with every fourth triangle; ncu: L1 sector traffic 1.23 x algorithmic).  Built in
+// round 2 and measured against each other: the padded record is 0.6 % slower on the 87 k-triangle scene and 2.2 % slower on
+// the 1.74 M-triangle one (a third more footprint for the same data: 237 MB against 187 MB) — the sectors it saves were never
+// the limit.  Either way a test reads 48 bytes.
+#ifndef MIRO_TRI_F4
+#define MIRO_TRI_F4 3
+#endif
+constexpr int TRI_F4 = MIRO_TRI_F4;
 __device__ __forceinline__ void load_tri(const float4* __restrict__ t, float4& p0, float4& p1, float4& p2) {
+#if MIRO_TRI_F4 == 4
     ldg256(t, p0, p1);
     p2 = __ldg(t + 2);
+#else
+    p0 = __ldg(t); p1 = __ldg(t + 1); p2 = __ldg(t + 2);
+#endif
 }
 
 struct TraceCounters {
