@@ -154,7 +154,8 @@ __global__ void k_gather_tris(const float4* __restrict__ in, const uint32_t* __r
     if (i >= n) return;
     const size_t s = (size_t)perm[i] * 3;
     float4* o = out + TRI_F4 * (size_t)i;       // device triangle records (traverse.cuh, TRI_F4)
-    o[0] = in[s]; o[1] = in[s + 1]; o[2] = in[s + 2]; o[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+    o[0] = in[s]; o[1] = in[s + 1]; o[2] = in[s + 2];
+    if (TRI_F4 == 4) o[TRI_F4 - 1] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 __global__ void k_gather_prims(const miro_gpu_prim* __restrict__ in, const uint32_t* __restrict__ perm, uint32_t n, miro_gpu_prim* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -207,7 +207,7 @@ __global__ void k_translate_hits(miro_gpu_hit* __restrict__ hits, uint32_t n, co
 template <int MODE>
 static int trace_grid(miro_gpu_ctx* ctx, size_t n) {
     // persistent grid: every SM holds as many blocks as fit (asked of the occupancy calculator once per kernel)
-    static int per_sm[4] = {0, 0, 0, 0};
+    static int per_sm[4] = {0, 0, 0, 0};      // (group worker threads may fill an entry concurrently: with the same value)
     int& v = per_sm[(ctx->counting ? 1 : 0) + (ctx->has_alpha ? 2 : 0)];
     if (v == 0) {
         if (ctx->has_alpha) {
