@@ -504,13 +504,15 @@ def render_legs(local, with_reference):
                ("C2", "c2_explosion", None, "explosion01.obj (stand-in), Lambert + PointLight, 1920x1080, 1 spp primary + shadow"),
                ("C3", "c3_dome_pt", (512, 512), "teapot + floor (stand-in), Blinn path tracing, DomeLight (Arches_E_PineTree.hdr) importance sampling, 64 paths, 512x512"),
                ("C4", "c4_cornell_pt", (512, 512), "Cornell box (Sponza stand-in), Blinn, RectangleLight x4 soft-shadow samples + emitter, 16 paths, 4 indirect segments, 512x512"),
-               ("C5", "c5_mb_instances", (512, 512), "motion-blur bullets + 961 ProxyObject instances of testGrass.obj, 2 subdivision levels (5 camera samples), 512x512")]
+               ("C5", "c5_mb_instances", (512, 512), "motion-blur bullets + 961 ProxyObject instances of testGrass.obj, 2 subdivision levels (5 camera samples), 512x512"),
+               ("C5 at makeProxyGrid scale", "c5_mb_instances", (512, 512), "motion-blur bullets + 201 x 201 = 40401 ProxyObject instances (src/main.cpp:37-52), 2 subdivision levels (5 camera samples), 512x512")]
     for tag, name, size, label in configs:
         path = helpers.fixture_path(name)
         if path is None:
             continue
         fx = helpers.Fixture(path)
-        script = fx.script if size is None else re.sub(r"image \d+ \d+", "image %d %d" % size, fx.script)
+        base_script = bw.Workload("c5").script if tag == "C5 at makeProxyGrid scale" else fx.script
+        script = base_script if size is None else re.sub(r"image \d+ \d+", "image %d %d" % size, base_script)
         row = {"config": tag, "workload": label}
         ref_runs = {}
         if with_reference and ra.have_reference():

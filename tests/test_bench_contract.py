@@ -36,3 +36,24 @@ def test_product_arm_has_no_cpu_path():
     assert p.returncode != 0
     assert "no CUDA device" in (p.stderr + p.stdout)
     assert not any(l.startswith("{") for l in p.stdout.splitlines())
+
+
+def test_bench_workloads_are_deterministic_and_named():
+    """Both arms of bench.py build their scenes and ray batches from tests/bench_workloads.py: the same script text and the same
+    seeded rays on every call (the reference arm and the product arm run in different processes)."""
+    import numpy as np
+    import bench_workloads as bw
+    for name, tris in (("c2", 86914), ("big", 20 * 86914)):
+        a, b = bw.Workload(name).load(), bw.Workload(name).load()
+        assert a.script == b.script and a.triangles() == tris, name
+        assert np.array_equal(a.primary(), b.primary()) and len(a.primary()) == 1920 * 1080
+        assert a.incoherent(7).tobytes() == b.incoherent(7).tobytes() and a.incoherent(7).tobytes() != a.incoherent(8).tobytes()
+        p, q = a.sample(a.primary(), a.incoherent(7))
+        assert len(p) == len(q) == 1920 * 1080 // 8
+    c5 = bw.Workload("c5").load()
+    assert c5.script.count("\ninstance ") == 201 * 201 and c5.times
+    assert (c5.incoherent(1)["time"] > 0).any()
+    big = bw.Workload("big").load()
+    assert len(big.mesh_names()) == 20 and big.label.startswith("C2 at dragon scale")
+    lo, hi = big.bounds()
+    assert (hi - lo > np.array([4.0, 0.9, 2.0])).all()
