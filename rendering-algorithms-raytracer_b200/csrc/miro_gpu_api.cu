@@ -11,6 +11,7 @@
 #include "context.cuh"
 #include "dome.cuh"
 #include "trace_pool.cuh"
+#include "trace_flat.cuh"
 
 using namespace miro;
 
@@ -207,8 +208,19 @@ __global__ void k_translate_hits(miro_gpu_hit* __restrict__ hits, uint32_t n, co
 template <int MODE>
 static int trace_grid(miro_gpu_ctx* ctx, size_t n) {
     // persistent grid: every SM holds as many blocks as fit (asked of the occupancy calculator once per kernel)
-    static int per_sm[4] = {0, 0, 0, 0};      // (group worker threads may fill an entry concurrently: with the same value)
-    int& v = per_sm[(ctx->counting ? 1 : 0) + (ctx->has_alpha ? 2 : 0)];
+    static int per_sm[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // (group worker threads may fill an entry concurrently: with the same value)
+    const bool flat = ctx->trace_kernel == MIRO_GPU_KERNEL_FLAT;
+    int& v = per_sm[(ctx->counting ? 1 : 0) + (ctx->has_alpha ? 2 : 0) + (flat ? 4 : 0)];
+    if (v == 0 && flat) {
+        if (ctx->has_alpha) {
+            if (ctx->counting) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace_flat<MODE, true, true, false>, TRACE_BLOCK, 0);
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace_flat<MODE, false, true, false>, TRACE_BLOCK, 0);
+        } else {
+            if (ctx->counting) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace_flat<MODE, true, false, false>, TRACE_BLOCK, 0);
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace_flat<MODE, false, false, false>, TRACE_BLOCK, 0);
+        }
+        if (v <= 0) v = 1;
+    }
     if (v == 0) {
         if (ctx->has_alpha) {
             if (ctx->counting) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace<MODE, true, true, false>, TRACE_BLOCK, 0);
@@ -293,7 +305,7 @@ static void launch_trace(miro_gpu_ctx* ctx, const void* d_rays, size_t n, const 
     // griddepcontrol.wait while still resident, so without the break any number of them could be live behind one long launch
     // and launch k + WORK_RING would claim rays from the not yet re-armed counter pair of launch k.  With the break at most
     // WORK_RING - 1 consecutive launches of a lane are ever live together.
-    const bool scratch_kernel = ctx->trace_kernel != MIRO_GPU_KERNEL_WARP;      // see SCRATCH_COPIES
+    const bool scratch_kernel = ctx->trace_kernel == MIRO_GPU_KERNEL_POOL;      // see SCRATCH_COPIES
     const bool chained = ctx->chain_traces && ctx->in_api_trace && (slot % (WORK_RING - 1)) != 0 && !(scratch_kernel && slot % SCRATCH_COPIES == 0);
     cfg.attrs = attr; cfg.numAttrs = chained ? 1 : 0;
     ctx->launches++;
@@ -303,7 +315,9 @@ static void launch_trace(miro_gpu_ctx* ctx, const void* d_rays, size_t n, const 
         if (e != cudaSuccess) ctx->error = std::string("pool traversal launch: ") + cudaGetErrorString(e);      // surfaces through the caller's cudaGetLastError check
         return;
     }
-#define MIRO_LAUNCH(COUNT, ALPHA) cudaLaunchKernelEx(&cfg, k_trace<MODE, COUNT, ALPHA, PACKED>, ctx->scene, r, (uint32_t)n, d_count, chunk, d_hits, d_bits, d_E, d_slots, ctx->d_counters, work)
+#define MIRO_LAUNCH(COUNT, ALPHA) do { if (ctx->trace_kernel == MIRO_GPU_KERNEL_FLAT) \
+        cudaLaunchKernelEx(&cfg, k_trace_flat<MODE, COUNT, ALPHA, PACKED>, ctx->scene, r, (uint32_t)n, d_count, chunk, d_hits, d_bits, d_E, d_slots, ctx->d_counters, work); \
+    else cudaLaunchKernelEx(&cfg, k_trace<MODE, COUNT, ALPHA, PACKED>, ctx->scene, r, (uint32_t)n, d_count, chunk, d_hits, d_bits, d_E, d_slots, ctx->d_counters, work); } while (0)
     if (ctx->has_alpha) { if (ctx->counting) MIRO_LAUNCH(true, true); else MIRO_LAUNCH(false, true); }
     else { if (ctx->counting) MIRO_LAUNCH(true, false); else MIRO_LAUNCH(false, false); }
 #undef MIRO_LAUNCH
@@ -369,7 +383,7 @@ int miro_gpu_create(miro_gpu_ctx** out, int device_id) {
     if ((e = cudaMalloc((void**)&ctx->d_work, 2 * WORK_RING * WORK_LANES * sizeof(uint32_t))) != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaMalloc(work counter)"); }
     cudaMemset(ctx->d_work, 0, 2 * WORK_RING * WORK_LANES * sizeof(uint32_t));
     ctx->sm_count = prop.multiProcessorCount;
-    if (const char* k = getenv("MIRO_GPU_TRACE_KERNEL")) ctx->trace_kernel = strcmp(k, "pool") == 0 ? MIRO_GPU_KERNEL_POOL : MIRO_GPU_KERNEL_WARP;
+    if (const char* k = getenv("MIRO_GPU_TRACE_KERNEL")) ctx->trace_kernel = strcmp(k, "pool") == 0 ? MIRO_GPU_KERNEL_POOL : strcmp(k, "flat") == 0 ? MIRO_GPU_KERNEL_FLAT : MIRO_GPU_KERNEL_WARP;
     // the traversal kernels keep their stacks in shared memory and want the rest of the 256 KB as L1
     *out = ctx;
     return MIRO_GPU_OK;
@@ -773,7 +787,7 @@ int miro_gpu_unpin_host_buffer(miro_gpu_ctx* ctx, void* ptr) {
 
 int miro_gpu_set_trace_kernel(miro_gpu_ctx* ctx, int kind) {
     if (!ctx) return MIRO_GPU_EINVAL;
-    if (kind != MIRO_GPU_KERNEL_WARP && kind != MIRO_GPU_KERNEL_POOL) return set_error(ctx, MIRO_GPU_EINVAL, "miro_gpu_set_trace_kernel: unknown kernel");
+    if (kind != MIRO_GPU_KERNEL_WARP && kind != MIRO_GPU_KERNEL_POOL && kind != MIRO_GPU_KERNEL_FLAT) return set_error(ctx, MIRO_GPU_EINVAL, "miro_gpu_set_trace_kernel: unknown kernel");
     MIRO_CUDA(ctx, cudaSetDevice(ctx->device));
     MIRO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->trace_kernel = kind;

@@ -334,11 +334,12 @@ struct Lane {
     __device__ __forceinline__ void set_ray(float ox, float oy, float oz, float dx, float dy, float dz) {
         r.set(ox, oy, oz, dx, dy, dz);
     }
+    __device__ __forceinline__ const RaySpace& ray_space() const { return r; }      // (the flat kernel's lane keeps part of it in shared memory, trace_flat.cuh)
 };
 
 // Pops the next candidate that can still beat the current hit; `cur` = MIRO_GPU_CHILD_EMPTY when the stack runs dry.
-template <class ST>
-__device__ __forceinline__ void pop_next(Lane& L, ST& st) {
+template <class LN, class ST>
+__device__ __forceinline__ void pop_next(LN& L, ST& st) {
     L.cur = MIRO_GPU_CHILD_EMPTY;
     const int limit = float_key(L.hit.t);
     while (st.sp > 0) {
@@ -425,8 +426,8 @@ __device__ __forceinline__ void node_fetch(const DeviceScene& s, int32_t cur, No
     ldg256(n + 0, d.h0, d.chf); ldg256(n + 2, d.q0, d.q1);
 }
 
-template <class ST>
-__device__ __forceinline__ void node_test(const NodeData& d, Lane& L, ST& st) {
+template <class LN, class ST>
+__device__ __forceinline__ void node_test(const NodeData& d, LN& L, ST& st) {
     const float4 h0 = d.h0, chf = d.chf, q0 = d.q0, q1 = d.q1;
     const uint32_t ex = __float_as_uint(h0.w);
     // per axis: t(q) = q * (step / d) + (p - o) / d   (the subtraction first, so the error of the second term is relative to it)
@@ -492,8 +493,8 @@ __device__ __forceinline__ void node_test(const NodeData& d, Lane& L, ST& st) {
     else pop_next(L, st);
 }
 
-template <bool COUNT, class ST>
-__device__ __forceinline__ void node_step(const DeviceScene& s, Lane& L, ST& st, uint32_t& n_nodes) {
+template <bool COUNT, class LN, class ST>
+__device__ __forceinline__ void node_step(const DeviceScene& s, LN& L, ST& st, uint32_t& n_nodes) {
     NodeData d;
     node_fetch(s, L.cur, d);
     if (COUNT) ++n_nodes;
@@ -530,8 +531,8 @@ __device__ __forceinline__ float hit_alpha(const AlphaData& A, uint32_t prim, fl
 
 // Instance leaf {first, count}: the lane enters instance `first` with the world-space ray (wo, wd) moved into its object space and
 // defers the others; a marker on the stack restores the world-space ray when the instance's sub-tree is exhausted.
-template <class ST>
-__device__ __forceinline__ void enter_instance(const DeviceScene& s, Lane& L, ST& st, uint32_t first, uint32_t count,
+template <class LN, class ST>
+__device__ __forceinline__ void enter_instance(const DeviceScene& s, LN& L, ST& st, uint32_t first, uint32_t count,
                                                float wox, float woy, float woz, float wdx, float wdy, float wdz) {
     const int ninf = (int)0x80000000;
     if (count > 1u) st.push(MIRO_GPU_LEAF(MIRO_GPU_KIND_INST, first + 1u, count - 1u), ninf);
@@ -555,20 +556,21 @@ __device__ __forceinline__ void enter_instance(const DeviceScene& s, Lane& L, ST
 }
 
 // Leaf phase.  Returns true when an ANY query has found its occluder.
-template <bool ANY, bool COUNT, bool ALPHA, class ST>
-__device__ __forceinline__ bool intersect_leaf(const DeviceScene& s, Lane& L, ST& st, const float4* __restrict__ rays, const uint32_t ray_f4,
+template <bool ANY, bool COUNT, bool ALPHA, class LN, class ST>
+__device__ __forceinline__ bool intersect_leaf(const DeviceScene& s, LN& L, ST& st, const float4* __restrict__ rays, const uint32_t ray_f4,
                                                uint32_t& n_tris, uint32_t& n_insts) {
     const uint32_t u = (uint32_t)L.cur;
     const uint32_t kind = (u >> 29) & 3u;
     const uint32_t count = ((u >> MIRO_GPU_LEAF_INDEX_BITS) & 7u) + 1u;
     const uint32_t first = u & ((1u << MIRO_GPU_LEAF_INDEX_BITS) - 1u);
     if (kind == MIRO_GPU_KIND_TRI) {
+        const auto& rs = L.ray_space();
         for (uint32_t i = 0; i < count; ++i) {
             float4 p0, p1, p2;
             load_tri(s.tris + (size_t)(first + i) * TRI_F4, p0, p1, p2);
             if (COUNT) ++n_tris;
             float ht, ha, hb;
-            if (intersect_tri<ANY && !ALPHA>(L.r, L.tmin, L.hit.t, p0, p1, p2, ht, ha, hb) && (!ALPHA || hit_alpha(s.alpha, first + i, ha, hb) >= 0.5f)) {
+            if (intersect_tri<ANY && !ALPHA>(rs, L.tmin, L.hit.t, p0, p1, p2, ht, ha, hb) && (!ALPHA || hit_alpha(s.alpha, first + i, ha, hb) >= 0.5f)) {
                 L.hit.t = ht; L.hit.a = ha; L.hit.b = hb;
                 L.hit.prim = (int32_t)(first + i); L.hit.inst = L.cur_inst;
                 if (ANY) return true;
@@ -576,6 +578,7 @@ __device__ __forceinline__ bool intersect_leaf(const DeviceScene& s, Lane& L, ST
         }
     } else if (kind == MIRO_GPU_KIND_MBTRI) {
         const float w1 = L.time, w0 = __fsub_rn(1.0f, L.time);    // src/BVH.cpp:1320-1321
+        const auto& rs = L.ray_space();
         for (uint32_t i = 0; i < count; ++i) {
             const float4* t = s.mbtris + (size_t)(first + i) * 6;
             float4 a0, a1, a2, b0, b1, b2;
@@ -589,7 +592,7 @@ __device__ __forceinline__ bool intersect_leaf(const DeviceScene& s, Lane& L, ST
             p2.x = MIRO_LERP(b2.x, a2.x); p2.y = MIRO_LERP(b2.y, a2.y); p2.z = MIRO_LERP(b2.z, a2.z);
 #undef MIRO_LERP
             float ht, ha, hb;
-            if (intersect_tri<ANY && !ALPHA>(L.r, L.tmin, L.hit.t, p0, p1, p2, ht, ha, hb) && (!ALPHA || hit_alpha(s.alpha, s.n_tris + first + i, ha, hb) >= 0.5f)) {
+            if (intersect_tri<ANY && !ALPHA>(rs, L.tmin, L.hit.t, p0, p1, p2, ht, ha, hb) && (!ALPHA || hit_alpha(s.alpha, s.n_tris + first + i, ha, hb) >= 0.5f)) {
                 L.hit.t = ht; L.hit.a = ha; L.hit.b = hb;
                 L.hit.prim = (int32_t)(s.n_tris + first + i); L.hit.inst = L.cur_inst;
                 if (ANY) return true;

@@ -248,7 +248,7 @@ class MiroScene:
 
     def set_trace_kernel(self, kind):
         """'warp' (persistent warps, one ray per lane) or 'pool' (64-ray pool per warp, csrc/trace_pool.cuh)."""
-        self._gpu_check(self.L.miro_gpu_set_trace_kernel(self.ctx, {"warp": 0, "pool": 1}[kind]), "set_trace_kernel")
+        self._gpu_check(self.L.miro_gpu_set_trace_kernel(self.ctx, {"warp": 0, "pool": 1, "flat": 2}[kind]), "set_trace_kernel")
 
     def enable_counting(self, on=True):
         self._gpu_check(self.L.miro_gpu_enable_counting(self.ctx, 1 if on else 0), "enable_counting")

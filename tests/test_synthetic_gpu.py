@@ -75,7 +75,7 @@ def test_soup_matches_oracle(n, clustered, size):
     sc.close()
 
 
-@pytest.mark.parametrize("kernel", ["warp", "pool"])
+@pytest.mark.parametrize("kernel", ["warp", "pool", "flat"])
 def test_deep_tree_uses_the_stack_overflow_path(kernel):
     """A chain of nested shells: every ray crosses dozens of overlapping boxes, so the per-ray stack grows past its
     shared-memory entries (16 / 12) into the overflow (local memory of the lane / the pool kernel's per-slot scratch in global

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 SCENES = ["c1_cornell", "c2_explosion", "c5_mb_instances", "c7_foliage"]      # c7: alpha cut-outs inside Scene::trace
 
 
-KERNELS = ["warp", "pool"]      # miro_gpu_set_trace_kernel: both traversal kernels must give the reference's hits
+KERNELS = ["warp", "pool", "flat"]      # miro_gpu_set_trace_kernel: every traversal kernel must give the reference's hits
 
 
 @pytest.fixture(scope="module", params=[(s, k) for s in SCENES for k in KERNELS], ids=lambda p: "%s-%s" % p)
@@ -32,7 +32,7 @@ def test_pool_kernel_gives_the_warp_kernels_hits():
         fx = helpers.Fixture(helpers.fixture_path(name))
         sc = fx.scene().attach(0)
         sc.set_trace_kernel("warp"); a = sc.trace_closest(fx.rays); oa = sc.trace_any(fx.rays)
-        for kernel in ("pool",):
+        for kernel in ("pool", "flat"):
             sc.set_trace_kernel(kernel); b = sc.trace_closest(fx.rays); ob = sc.trace_any(fx.rays)
             assert a.tobytes() == b.tobytes(), (name, kernel)
             assert (oa == ob).all(), (name, kernel)
@@ -148,6 +148,8 @@ def test_full_size_batches_against_reference(name):
     sc = fx.scene().attach(0)
     sc.set_trace_kernel("pool")
     pool_hits = sc.trace_closest(fx.rays)
+    sc.set_trace_kernel("flat")
+    assert sc.trace_closest(fx.rays).tobytes() == pool_hits.tobytes()
     sc.set_trace_kernel("warp")
     assert sc.trace_closest(fx.rays).tobytes() == pool_hits.tobytes()
     hits = sc.trace_closest(fx.rays)
