@@ -24,6 +24,20 @@
 namespace miro {
 
 constexpr int FLAT_MAX_LEAF = 4;                                 // leaves of up to this many triangles are dealt out
+// A leaf round is run when  n_leaf * NUM > n_node * DEN: dealt leaf rounds are cheap at any number of waiting leaves and return
+// their lanes to the node phase, so they are favoured (measured on the C2 step: 1:1 7 107, 3:2 7 489, 2:1 7 604, 5:2 7 587,
+// 3:1 7 529 Mrays/s).
+#ifndef MIRO_FLAT_BIAS_NUM
+#define MIRO_FLAT_BIAS_NUM 2
+#endif
+#ifndef MIRO_FLAT_BIAS_DEN
+#define MIRO_FLAT_BIAS_DEN 1
+#endif
+// With more than this many pairs waiting (a coherent batch: most lanes of the warp reach their leaves together) the leaves take
+// the sequential per-lane loop of traverse.cuh, which is efficient exactly then; dealing serves 32 pairs per round.
+#ifndef MIRO_FLAT_SEQ_PAIRS
+#define MIRO_FLAT_SEQ_PAIRS 48
+#endif
 // Shared memory of a thread = one 8-byte COLUMN of [row][thread of the block] (the traversal stack's layout, TraversalStack::STRIDE
 // between rows): rows 0 .. SMEM_STACK-1 the stack, then three rows of ray constants and one row for the pair table, so every
 // address is st.base + a compile-time offset (+ 8 x lane distance for another lane's column) and costs no register.
@@ -193,7 +207,7 @@ k_trace_flat(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, 
         const bool at_leaf = !at_node && L.cur != MIRO_GPU_CHILD_EMPTY;
         const int n_node = __popc(__ballot_sync(0xffffffffu, at_node)), n_leaf = 32 - n_idle - n_node;
         bool finished = false;
-        if (n_node * TRACE_NODE_BIAS_DEN >= n_leaf * TRACE_NODE_BIAS_NUM || (TRACE_LEAF_MIN > 0 && n_node > 0 && n_leaf < TRACE_LEAF_MIN)) {
+        if (n_node * MIRO_FLAT_BIAS_DEN >= n_leaf * MIRO_FLAT_BIAS_NUM) {
             if (at_node) { node_step<COUNT>(s, L, st, c_nodes); finished = L.cur == MIRO_GPU_CHILD_EMPTY; }
         } else {
             // ---- leaf round: every lane of the warp takes part as a worker
@@ -202,28 +216,29 @@ k_trace_flat(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, 
             // with count - 1 < 4 (larger leaves: sequential path below)
             const bool tri_leaf = DEAL && (u >> 28) == 8u;
             const uint32_t cnt = tri_leaf ? ((u >> MIRO_GPU_LEAF_INDEX_BITS) & 3u) + 1u : 0u;
-            bool dealt = false;
+            const bool c0 = tri_leaf && (u & (1u << MIRO_GPU_LEAF_INDEX_BITS)) != 0u, c1 = tri_leaf && (u & (2u << MIRO_GPU_LEAF_INDEX_BITS)) != 0u;      // bits of count - 1
+            bool dealt = false, sequential = !DEAL;
             if (DEAL) {
-                // pair numbering, owner-major: S = pairs of the lanes below, from ballots over the three bits of the count
-                const uint32_t B0 = __ballot_sync(0xffffffffu, (cnt & 1u) != 0u), B1 = __ballot_sync(0xffffffffu, (cnt & 2u) != 0u), B2 = __ballot_sync(0xffffffffu, (cnt & 4u) != 0u);
-                if ((B0 | B1 | B2) != 0u) {                     // (a round of instance entries / exits / motion-blur leaves only: nothing to deal)
-                    const uint32_t S = __popc(B0 & lt_mask) + 2u * __popc(B1 & lt_mask) + 4u * __popc(B2 & lt_mask);
-                    const uint32_t total = __popc(B0) + 2u * __popc(B1) + 4u * __popc(B2);
+                // pair numbering, owner-major: S = pairs of the lanes below = sum of 1 + (count - 1) over them, from three ballots
+                const uint32_t BT = __ballot_sync(0xffffffffu, tri_leaf), B0 = __ballot_sync(0xffffffffu, c0), B1 = __ballot_sync(0xffffffffu, c1);
+                const uint32_t total = __popc(BT) + __popc(B0) + 2u * __popc(B1);
+                if (total > (uint32_t)MIRO_FLAT_SEQ_PAIRS) sequential = true;
+                else if (total != 0u) {                         // (0: a round of instance entries / exits / motion-blur leaves only, nothing to deal)
+                    const uint32_t S = __popc(BT & lt_mask) + __popc(B0 & lt_mask) + 2u * __popc(B1 & lt_mask);
                     // ONE pass of 32 pairs per round: an owner whose pairs do not all fit keeps waiting at its leaf (the lowest
                     // waiting lane always fits, so every leaf is served)
                     dealt = tri_leaf && S + cnt <= 32u;
                     // pair table: entry p (in the column of lane p) = triangle index | owner lane << 26
                     const uint32_t word = (u & ((1u << MIRO_GPU_LEAF_INDEX_BITS) - 1u)) | (lane << MIRO_GPU_LEAF_INDEX_BITS);
                     const uint32_t ent = st.base + FLAT_ROW_PAIR + (S - lane) * 8u;      // entry S, relative to this lane's own column
-                    sts32_if(dealt, ent, word);
-                    sts32_if(dealt && cnt >= 2u, ent + 8u, word + 1u);
-                    sts32_if(dealt && cnt >= 3u, ent + 16u, word + 2u);
-                    sts32_if(dealt && cnt >= 4u, ent + 24u, word + 3u);
+                    // (the one owner that straddles entry 32 writes its first pairs too: tested for nothing, which is cheaper than
+                    // finding out where the served pairs end)
+                    sts32_if(tri_leaf && S < 32u, ent, word);
+                    sts32_if(cnt >= 2u && S + 1u < 32u, ent + 8u, word + 1u);
+                    sts32_if(cnt >= 3u && S + 2u < 32u, ent + 16u, word + 2u);
+                    sts32_if(cnt >= 4u && S + 3u < 32u, ent + 24u, word + 3u);
                     __syncwarp();
-                    // the pairs of owners that did not fit start at the first such owner's S: everything below is served
-                    const uint32_t unfit = __ballot_sync(0xffffffffu, tri_leaf && !dealt);
-                    const uint32_t served = unfit ? __shfl_sync(0xffffffffu, S, __ffs(unfit) - 1) : total;
-                    const bool valid = lane < served;
+                    const bool valid = lane < total;
                     const uint32_t pw = valid ? lds32(st.base + FLAT_ROW_PAIR) : 0u;
                     const uint32_t owner = pw >> MIRO_GPU_LEAF_INDEX_BITS;
                     const float wox = __shfl_sync(0xffffffffu, L.r.ox, owner), woy = __shfl_sync(0xffffffffu, L.r.oy, owner), woz = __shfl_sync(0xffffffffu, L.r.oz, owner);
@@ -262,7 +277,7 @@ k_trace_flat(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, 
                 if (COUNT) c_tris += cnt;
                 L.cur = MIRO_GPU_CHILD_EMPTY;
                 finished = ANY && L.hit.prim >= 0;
-            } else if (at_leaf && !tri_leaf) {
+            } else if (at_leaf && (!tri_leaf || sequential)) {
                 if (L.cur == STACK_SENTINEL) {            // leaving an instance: back to the world-space ray
                     const float4 w0 = __ldg(rays + (size_t)L.ray_idx * RAY_F4), w1 = __ldg(rays + (size_t)L.ray_idx * RAY_F4 + 1);
                     L.set_ray(w0.x, w0.y, w0.z, w1.x, w1.y, w1.z);
