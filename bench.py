@@ -664,7 +664,7 @@ def gpu_main(args, rank, world, local):
         clocks = sampler.finish(*leg["wall"]) if sampler else None
         roof = roofline_of(leg, hbm_peak, peak_src, traffic_key=name)
         parity = parity_of(w, sc, ref) if ref else None
-        row = {"workload": w.label, "triangles": w.triangles(), "device_nodes": leg["n_nodes"], "device_triangle_slots": leg["n_tris_device"],
+        row = {"workload": w.label, "traversal_kernel": sc.trace_kernel(), "triangles": w.triangles(), "device_nodes": leg["n_nodes"], "device_triangle_slots": leg["n_tris_device"],
                "device_instances": leg["n_instances_device"], "structure_MB_on_device": leg["structure_bytes"] * 1e-6,
                "host_bvh_build_flatten_and_upload_s": t_build,
                "Mrays_per_s": leg["value"], "ms_per_step": leg["total_ms"] / args.steps, "roofline": roof, "parity": parity}
@@ -676,7 +676,7 @@ def gpu_main(args, rank, world, local):
             numa.update(pcie_probe(world, barrier))
             line = {"metric": "Mrays/s", "value": leg["value"], "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                     "ms_per_step": leg["total_ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                    "dtype": "f32", "data": "synthetic", "config": bench_config(w), "clocks": clocks, "gpu_launches": 3 * args.steps,
+                    "dtype": "f32", "data": "synthetic", "config": bench_config(w), "traversal_kernel": sc.trace_kernel(), "clocks": clocks, "gpu_launches": 3 * args.steps,
                     "e2e": e2e, "e2e_packed": packed, "e2e_pageable": pageable, "e2e_registered": registered, "e2e_device_camera": devcam, "host": numa, "sustained": leg["sustained"], "roofline": roof}
             line["roofline"]["frac_abi_node_layout"] = (leg["per_launch"][int(np.argmax(leg["launch_ms"]))]["bytes"] + leg["per_launch"][int(np.argmax(leg["launch_ms"]))]["nodes"] * (128 - NODE_BYTES)) / (max(leg["launch_ms"]) * 1e-3) * 1e-9 / hbm_peak
             line["roofline"]["note"] = ("algorithmic bytes count the SHIPPED 64-byte device node; frac_abi_node_layout counts the 128-byte ABI node as kernel "

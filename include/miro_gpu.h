@@ -278,18 +278,22 @@ int miro_gpu_set_stream(miro_gpu_ctx* ctx, void* cuda_stream);
  * miro_gpu_render never chains its own launches.  Timing events (enable_counting) break the chain. */
 int miro_gpu_set_trace_chaining(miro_gpu_ctx* ctx, int on);
 
-/* Which traversal kernel serves Scene::trace on this context (all give the same hits; tests run all of them):
+/* Which traversal kernel serves Scene::trace on this context (all give the same hits, byte for byte; tests run all of them):
  *   MIRO_GPU_KERNEL_WARP  persistent warps, one ray per lane in registers, majority vote per round between a node and a leaf step
  *   MIRO_GPU_KERNEL_POOL  a warp owns a pool of 64 rays in shared memory and advances, per round, up to 32 of them that wait for
  *                         the same kind of step (csrc/trace_pool.cuh)
  *   MIRO_GPU_KERNEL_FLAT  the persistent-warp kernel with the triangle tests of a leaf round dealt out over all 32 lanes of the warp
  *                         (csrc/trace_flat.cuh)
- * The default is the faster one on the benchmark step; the environment variable MIRO_GPU_TRACE_KERNEL
- * (warp | pool | flat), read at miro_gpu_create, overrides it. */
+ * The default, MIRO_GPU_KERNEL_AUTO, picks per uploaded scene the kernel measured faster on that kind of scene (DESIGN.md section
+ * 3.1): FLAT for static and motion-blur triangles, WARP when the scene has instances or alpha cut-outs.  The environment variable
+ * MIRO_GPU_TRACE_KERNEL (auto | warp | pool | flat), read at miro_gpu_create, overrides the default;
+ * miro_gpu_get_trace_kernel returns the kernel in effect (never AUTO once a scene is uploaded). */
+#define MIRO_GPU_KERNEL_AUTO (-1)
 #define MIRO_GPU_KERNEL_WARP 0
 #define MIRO_GPU_KERNEL_POOL 1
 #define MIRO_GPU_KERNEL_FLAT 2
 int miro_gpu_set_trace_kernel(miro_gpu_ctx* ctx, int kind);
+int miro_gpu_get_trace_kernel(const miro_gpu_ctx* ctx);
 
 /* Copy a flattened scene to the device (replaces any previous scene of this context). */
 int miro_gpu_upload_scene(miro_gpu_ctx* ctx, const miro_gpu_scene_desc* desc);

@@ -109,7 +109,7 @@ class Counters(C.Structure):
 
 
 # every symbol include/miro_gpu.h and include/miro_host.h declare (checked by tests/test_abi.py)
-GPU_SYMBOLS = ["miro_gpu_create", "miro_gpu_destroy", "miro_gpu_last_error", "miro_gpu_abi_version", "miro_gpu_sizeof", "miro_gpu_set_stream", "miro_gpu_set_trace_chaining", "miro_gpu_set_trace_kernel",
+GPU_SYMBOLS = ["miro_gpu_create", "miro_gpu_destroy", "miro_gpu_last_error", "miro_gpu_abi_version", "miro_gpu_sizeof", "miro_gpu_set_stream", "miro_gpu_set_trace_chaining", "miro_gpu_set_trace_kernel", "miro_gpu_get_trace_kernel",
                "miro_gpu_upload_scene", "miro_gpu_trace_closest", "miro_gpu_trace_any", "miro_gpu_trace_closest_packed", "miro_gpu_trace_any_packed", "miro_gpu_trace_closest_device",
                "miro_gpu_trace_any_device", "miro_gpu_trace_primary", "miro_gpu_render", "miro_gpu_render_image", "miro_gpu_pin_host_buffer", "miro_gpu_unpin_host_buffer", "miro_gpu_enable_counting", "miro_gpu_get_counters",
                "miro_gpu_reset_counters",
@@ -148,6 +148,7 @@ def lib():
     L.miro_gpu_enable_counting.argtypes = [vp, i32]; L.miro_gpu_enable_counting.restype = i32
     L.miro_gpu_set_trace_chaining.argtypes = [vp, i32]; L.miro_gpu_set_trace_chaining.restype = i32
     L.miro_gpu_set_trace_kernel.argtypes = [vp, i32]; L.miro_gpu_set_trace_kernel.restype = i32
+    L.miro_gpu_get_trace_kernel.argtypes = [vp]; L.miro_gpu_get_trace_kernel.restype = i32
     L.miro_gpu_get_counters.argtypes = [vp, C.POINTER(Counters)]; L.miro_gpu_get_counters.restype = i32
     L.miro_gpu_reset_counters.argtypes = [vp]; L.miro_gpu_reset_counters.restype = i32
     L.miro_host_new.argtypes = []; L.miro_host_new.restype = vp

@@ -90,7 +90,8 @@ struct miro_gpu_ctx {
                                                 // stream-ordered or PDL-chained, so a ring never wraps onto a live launch)
     int build_levels = 0;                       // depth of the last device-built wide tree
     int stack_need = 0;                         // deepest traversal stack the uploaded trees can ask for (entries)
-    int trace_kernel = MIRO_GPU_KERNEL_WARP;    // miro_gpu_set_trace_kernel
+    int trace_kernel_request = MIRO_GPU_KERNEL_AUTO;   // miro_gpu_set_trace_kernel / MIRO_GPU_TRACE_KERNEL
+    int trace_kernel = MIRO_GPU_KERNEL_FLAT;    // the kernel in effect (resolve_trace_kernel: the request, or per scene when it is AUTO)
     miro::PoolScratch pool_ovf[4];              // per work lane
     std::vector<miro::EventPair> events;        // pending (not yet summed) timing pairs
     std::vector<miro::EventPair> event_pool;
@@ -129,6 +130,7 @@ void launch_trace_any_packed(miro_gpu_ctx* ctx, const miro_gpu_ray32* d_rays, si
 // any-hit traversal of shadow rays; an unoccluded ray adds d_E[i] to d_slots[4 * ray.user0] (see render.cu)
 void launch_trace_shadow(miro_gpu_ctx* ctx, const miro_gpu_ray* d_rays, size_t n, const uint32_t* d_count, const float4* d_E, float4* d_slots);
 
+void resolve_trace_kernel(miro_gpu_ctx* ctx);
 void render_state_free(miro_gpu_ctx* ctx);
 int map_frame_to_bytes(miro_gpu_ctx* ctx, const float* d_rgb, size_t pixels, unsigned char* d_rgb8, cudaStream_t s);      // render.cu: Image::setPixel on the device
 

@@ -116,7 +116,7 @@ k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const
         // ---- refill: idle slots write their results, then take the next rays of the warp's chunk
         const uint32_t idle = __ballot_sync(0xffffffffu, L.cur == MIRO_GPU_CHILD_EMPTY);
         int n_idle = __popc(idle);
-        if (n_idle >= TRACE_REFILL || (exhausted && idle == 0xffffffffu)) {
+        if (n_idle >= TRACE_REFILL) {      // (all 32 idle included)
             if (pending && L.cur == MIRO_GPU_CHILD_EMPTY) { write_result(); pending = false; }
             if (exhausted) { if (idle == 0xffffffffu) break; }
             else {
@@ -197,6 +197,15 @@ k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const
         __threadfence();
         if (atomicAdd(work + 1, 1u) == gridDim.x - 1) { work[0] = 0; work[1] = 0; __threadfence(); }      // this launch's own pair (ring of pairs)
     }
+}
+
+// MIRO_GPU_KERNEL_AUTO: the kernel measured faster on the kind of scene that is uploaded (profiles/r2_ncu_summary.md section 4).  The
+// flat kernel deals out the tests of static-triangle leaves: +10 % on the 87 k-triangle C2 step, +12 % on 1.74 M triangles; on the
+// 40 401-instance field, where instance entries / exits and the nodes of the bottom-level trees dominate, it is 2 - 6 % behind the
+// warp kernel, and with alpha cut-outs its leaves take the sequential path anyway.
+void resolve_trace_kernel(miro_gpu_ctx* ctx) {
+    if (ctx->trace_kernel_request != MIRO_GPU_KERNEL_AUTO) ctx->trace_kernel = ctx->trace_kernel_request;
+    else ctx->trace_kernel = (ctx->n_insts > 0 || ctx->has_alpha) ? MIRO_GPU_KERNEL_WARP : MIRO_GPU_KERNEL_FLAT;
 }
 
 // Device-built trees: hit records leave the library in the CALLER's triangle numbering.
@@ -383,7 +392,9 @@ int miro_gpu_create(miro_gpu_ctx** out, int device_id) {
     if ((e = cudaMalloc((void**)&ctx->d_work, 2 * WORK_RING * WORK_LANES * sizeof(uint32_t))) != cudaSuccess) { delete ctx; return cuda_fail(nullptr, e, "cudaMalloc(work counter)"); }
     cudaMemset(ctx->d_work, 0, 2 * WORK_RING * WORK_LANES * sizeof(uint32_t));
     ctx->sm_count = prop.multiProcessorCount;
-    if (const char* k = getenv("MIRO_GPU_TRACE_KERNEL")) ctx->trace_kernel = strcmp(k, "pool") == 0 ? MIRO_GPU_KERNEL_POOL : strcmp(k, "flat") == 0 ? MIRO_GPU_KERNEL_FLAT : MIRO_GPU_KERNEL_WARP;
+    if (const char* k = getenv("MIRO_GPU_TRACE_KERNEL"))
+        ctx->trace_kernel_request = strcmp(k, "pool") == 0 ? MIRO_GPU_KERNEL_POOL : strcmp(k, "flat") == 0 ? MIRO_GPU_KERNEL_FLAT : strcmp(k, "warp") == 0 ? MIRO_GPU_KERNEL_WARP : MIRO_GPU_KERNEL_AUTO;
+    resolve_trace_kernel(ctx);
     // the traversal kernels keep their stacks in shared memory and want the rest of the 256 KB as L1
     *out = ctx;
     return MIRO_GPU_OK;
@@ -603,6 +614,7 @@ int miro_gpu_upload_scene(miro_gpu_ctx* ctx, const miro_gpu_scene_desc* d) {
     static_assert(sizeof(AlphaTexture) == sizeof(DeviceTexture), "AlphaTexture mirrors DeviceTexture");
     ctx->scene.alpha = AlphaData{sh.prims, sh.uvs, sh.materials, reinterpret_cast<const AlphaTexture*>(sh.textures)};
     if (ctx->has_alpha && !d->prims) return set_error(ctx, MIRO_GPU_EINVAL, "alpha-mapped materials need the prims table");
+    resolve_trace_kernel(ctx);
     // dome lights: importance tables (DomeLight::setTexture, src/DomeLight.cpp:8-78)
     std::vector<DeviceDome> domes(std::max<uint32_t>(d->n_lights, 1));
     memset(domes.data(), 0, domes.size() * sizeof(DeviceDome));
@@ -787,12 +799,16 @@ int miro_gpu_unpin_host_buffer(miro_gpu_ctx* ctx, void* ptr) {
 
 int miro_gpu_set_trace_kernel(miro_gpu_ctx* ctx, int kind) {
     if (!ctx) return MIRO_GPU_EINVAL;
-    if (kind != MIRO_GPU_KERNEL_WARP && kind != MIRO_GPU_KERNEL_POOL && kind != MIRO_GPU_KERNEL_FLAT) return set_error(ctx, MIRO_GPU_EINVAL, "miro_gpu_set_trace_kernel: unknown kernel");
+    if (kind != MIRO_GPU_KERNEL_AUTO && kind != MIRO_GPU_KERNEL_WARP && kind != MIRO_GPU_KERNEL_POOL && kind != MIRO_GPU_KERNEL_FLAT)
+        return set_error(ctx, MIRO_GPU_EINVAL, "miro_gpu_set_trace_kernel: unknown kernel");
     MIRO_CUDA(ctx, cudaSetDevice(ctx->device));
     MIRO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->trace_kernel = kind;
+    ctx->trace_kernel_request = kind;
+    miro::resolve_trace_kernel(ctx);
     return MIRO_GPU_OK;
 }
+
+int miro_gpu_get_trace_kernel(const miro_gpu_ctx* ctx) { return ctx ? ctx->trace_kernel : MIRO_GPU_KERNEL_AUTO; }
 
 int miro_gpu_set_trace_chaining(miro_gpu_ctx* ctx, int on) {
     if (!ctx) return MIRO_GPU_EINVAL;

@@ -35,6 +35,9 @@ constexpr int FLAT_MAX_LEAF = 4;                                 // leaves of up
 #endif
 // With more than this many pairs waiting (a coherent batch: most lanes of the warp reach their leaves together) the leaves take
 // the sequential per-lane loop of traverse.cuh, which is efficient exactly then; dealing serves 32 pairs per round.
+#ifndef MIRO_FLAT_KIND_VOTE
+#define MIRO_FLAT_KIND_VOTE 0
+#endif
 #ifndef MIRO_FLAT_SEQ_PAIRS
 #define MIRO_FLAT_SEQ_PAIRS 48
 #endif
@@ -169,7 +172,7 @@ k_trace_flat(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, 
         // ---- refill (as k_trace)
         const uint32_t idle = __ballot_sync(0xffffffffu, L.cur == MIRO_GPU_CHILD_EMPTY);
         int n_idle = __popc(idle);
-        if (n_idle >= TRACE_REFILL || (exhausted && idle == 0xffffffffu)) {
+        if (n_idle >= TRACE_REFILL) {      // (all 32 idle included)
             if (pending && L.cur == MIRO_GPU_CHILD_EMPTY) { write_result(); pending = false; }
             if (exhausted) { if (idle == 0xffffffffu) break; }
             else {
@@ -207,7 +210,14 @@ k_trace_flat(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, 
         const bool at_leaf = !at_node && L.cur != MIRO_GPU_CHILD_EMPTY;
         const int n_node = __popc(__ballot_sync(0xffffffffu, at_node)), n_leaf = 32 - n_idle - n_node;
         bool finished = false;
+#if MIRO_FLAT_KIND_VOTE
+        // only the leaves that are dealt (static triangles) get the bias; instance entries / exits and motion-blur leaves run at the
+        // lane count they have, like a node step, and weigh 1:1
+        const int n_tri = __popc(__ballot_sync(0xffffffffu, DEAL && ((uint32_t)L.cur >> 28) == 8u));
+        if (n_node * MIRO_FLAT_BIAS_DEN >= n_tri * MIRO_FLAT_BIAS_NUM + (n_leaf - n_tri) * MIRO_FLAT_BIAS_DEN) {
+#else
         if (n_node * MIRO_FLAT_BIAS_DEN >= n_leaf * MIRO_FLAT_BIAS_NUM) {
+#endif
             if (at_node) { node_step<COUNT>(s, L, st, c_nodes); finished = L.cur == MIRO_GPU_CHILD_EMPTY; }
         } else {
             // ---- leaf round: every lane of the warp takes part as a worker

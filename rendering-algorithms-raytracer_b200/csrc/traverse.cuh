@@ -60,6 +60,7 @@ constexpr int TRACE_MIN_BLOCKS = MIRO_TRACE_MIN_BLOCKS;  // resident blocks per 
 #define MIRO_TRACE_REFILL 8
 #endif
 constexpr int TRACE_REFILL = MIRO_TRACE_REFILL;
+static_assert(TRACE_REFILL >= 1 && TRACE_REFILL <= 32, "a warp whose 32 slots are idle must reach the refill block (that is where it leaves)");
 // a node round is run when  n_node * DEN >= n_leaf * NUM  (NUM/DEN < 1 favours node rounds: leaf rounds cost more and fill up while waiting)
 #ifndef MIRO_NODE_BIAS_NUM
 #define MIRO_NODE_BIAS_NUM 1

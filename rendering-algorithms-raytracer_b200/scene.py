@@ -247,8 +247,13 @@ class MiroScene:
         self._gpu_check(self.L.miro_gpu_set_trace_chaining(self.ctx, 1 if on else 0), "set_trace_chaining")
 
     def set_trace_kernel(self, kind):
-        """'warp' (persistent warps, one ray per lane) or 'pool' (64-ray pool per warp, csrc/trace_pool.cuh)."""
-        self._gpu_check(self.L.miro_gpu_set_trace_kernel(self.ctx, {"warp": 0, "pool": 1, "flat": 2}[kind]), "set_trace_kernel")
+        """'auto' (the default: per scene), 'warp' (persistent warps, one ray per lane), 'pool' (64-ray pool per warp,
+        csrc/trace_pool.cuh) or 'flat' (the warp kernel with leaf rounds dealt out over the warp, csrc/trace_flat.cuh)."""
+        self._gpu_check(self.L.miro_gpu_set_trace_kernel(self.ctx, {"auto": -1, "warp": 0, "pool": 1, "flat": 2}[kind]), "set_trace_kernel")
+
+    def trace_kernel(self):
+        """The traversal kernel in effect on this context."""
+        return {-1: "auto", 0: "warp", 1: "pool", 2: "flat"}[self.L.miro_gpu_get_trace_kernel(self.ctx)]
 
     def enable_counting(self, on=True):
         self._gpu_check(self.L.miro_gpu_enable_counting(self.ctx, 1 if on else 0), "enable_counting")

@@ -24,6 +24,20 @@ def loaded(request):
     sc.close()
 
 
+def test_default_kernel_is_chosen_per_scene():
+    """MIRO_GPU_KERNEL_AUTO (the default): the flat kernel for static triangles, the warp kernel when the scene has instances or
+    alpha cut-outs (include/miro_gpu.h); an explicit choice sticks across uploads, 'auto' gives the choice back."""
+    import os
+    if os.environ.get("MIRO_GPU_TRACE_KERNEL", "auto") != "auto":
+        pytest.skip("MIRO_GPU_TRACE_KERNEL overrides the default")
+    for name, want in (("c2_explosion", "flat"), ("c5_mb_instances", "warp"), ("c7_foliage", "warp")):
+        sc = helpers.Fixture(helpers.fixture_path(name)).scene().attach(0)
+        assert sc.trace_kernel() == want, (name, sc.trace_kernel())
+        sc.set_trace_kernel("pool"); assert sc.trace_kernel() == "pool"
+        sc.set_trace_kernel("auto"); assert sc.trace_kernel() == want
+        sc.close()
+
+
 def test_pool_kernel_gives_the_warp_kernels_hits():
     """The two traversal kernels visit nodes in the same per-ray order, so their hit records are byte-identical (closest hits;
     occlusion bits likewise), on a static scene and on motion blur + instances; the pool kernel's stack overflow scratch
