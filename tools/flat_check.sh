@@ -6,7 +6,7 @@ if [ "$1" = tests ]; then shift
   python -m pytest tests/test_trace_gpu.py tests/test_synthetic_gpu.py -m gpu -x -q -k "flat or gives_the_warp or full_size" 2>&1 | tail -6
 fi
 for k in ${*:-warp flat}; do
-  MIRO_GPU_TRACE_KERNEL=$k python bench.py --steps 20 --warmup 3 --no-cpu --legs c2,big,c5 2>gpurun_out/flat_$k.err | python -c "
+  MIRO_GPU_TRACE_KERNEL=$k python bench.py --steps 20 --warmup 3 --no-cpu --legs ${LEGS:-c2,big,c5} 2>gpurun_out/flat_$k.err | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
 rows=[('c2', d.get('value'), d.get('roofline'))]+[(k, v['Mrays_per_s'], v['roofline']) for k, v in d.get('workloads', {}).items()]
