@@ -285,7 +285,8 @@ int miro_gpu_set_trace_chaining(miro_gpu_ctx* ctx, int on);
  *   MIRO_GPU_KERNEL_FLAT  the persistent-warp kernel with the triangle tests of a leaf round dealt out over all 32 lanes of the warp
  *                         (csrc/trace_flat.cuh)
  * The default, MIRO_GPU_KERNEL_AUTO, picks per uploaded scene the kernel measured faster on that kind of scene (DESIGN.md section
- * 3.1): FLAT for static and motion-blur triangles, WARP when the scene has instances or alpha cut-outs.  The environment variable
+ * 3.1): FLAT for scenes of static and motion-blur triangles from 16 384 triangles up, WARP for smaller ones and when the scene has
+ * instances or alpha cut-outs.  The environment variable
  * MIRO_GPU_TRACE_KERNEL (auto | warp | pool | flat), read at miro_gpu_create, overrides the default;
  * miro_gpu_get_trace_kernel returns the kernel in effect (never AUTO once a scene is uploaded). */
 #define MIRO_GPU_KERNEL_AUTO (-1)

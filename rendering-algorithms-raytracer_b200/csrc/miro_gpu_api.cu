@@ -202,10 +202,12 @@ k_trace(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const
 // MIRO_GPU_KERNEL_AUTO: the kernel measured faster on the kind of scene that is uploaded (profiles/r2_ncu_summary.md section 4).  The
 // flat kernel deals out the tests of static-triangle leaves: +10 % on the 87 k-triangle C2 step, +12 % on 1.74 M triangles; on the
 // 40 401-instance field, where instance entries / exits and the nodes of the bottom-level trees dominate, it is 2 - 6 % behind the
-// warp kernel, and with alpha cut-outs its leaves take the sequential path anyway.
+// warp kernel, and with alpha cut-outs its leaves take the sequential path anyway.  Scenes of a few thousand triangles (the Cornell
+// box and teapot frames: leaves of one or two triangles, everything in L1) are 2 % faster on the warp kernel.
+constexpr uint32_t FLAT_MIN_TRIANGLES = 16384;
 void resolve_trace_kernel(miro_gpu_ctx* ctx) {
     if (ctx->trace_kernel_request != MIRO_GPU_KERNEL_AUTO) ctx->trace_kernel = ctx->trace_kernel_request;
-    else ctx->trace_kernel = (ctx->n_insts > 0 || ctx->has_alpha) ? MIRO_GPU_KERNEL_WARP : MIRO_GPU_KERNEL_FLAT;
+    else ctx->trace_kernel = (ctx->n_insts > 0 || ctx->has_alpha || ctx->n_tris + ctx->n_mbtris < FLAT_MIN_TRIANGLES) ? MIRO_GPU_KERNEL_WARP : MIRO_GPU_KERNEL_FLAT;
 }
 
 // Device-built trees: hit records leave the library in the CALLER's triangle numbering.

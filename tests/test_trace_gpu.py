@@ -25,12 +25,12 @@ def loaded(request):
 
 
 def test_default_kernel_is_chosen_per_scene():
-    """MIRO_GPU_KERNEL_AUTO (the default): the flat kernel for static triangles, the warp kernel when the scene has instances or
-    alpha cut-outs (include/miro_gpu.h); an explicit choice sticks across uploads, 'auto' gives the choice back."""
+    """MIRO_GPU_KERNEL_AUTO (the default): the flat kernel for static triangles (from 16 384 up), the warp kernel for small scenes
+    and when the scene has instances or alpha cut-outs (include/miro_gpu.h); an explicit choice sticks across uploads, 'auto' gives the choice back."""
     import os
     if os.environ.get("MIRO_GPU_TRACE_KERNEL", "auto") != "auto":
         pytest.skip("MIRO_GPU_TRACE_KERNEL overrides the default")
-    for name, want in (("c2_explosion", "flat"), ("c5_mb_instances", "warp"), ("c7_foliage", "warp")):
+    for name, want in (("c2_explosion", "flat"), ("c1_cornell", "warp"), ("c5_mb_instances", "warp"), ("c7_foliage", "warp")):
         sc = helpers.Fixture(helpers.fixture_path(name)).scene().attach(0)
         assert sc.trace_kernel() == want, (name, sc.trace_kernel())
         sc.set_trace_kernel("pool"); assert sc.trace_kernel() == "pool"
