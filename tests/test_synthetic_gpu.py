@@ -106,6 +106,37 @@ def test_deep_tree_uses_the_stack_overflow_path(kernel):
     sc.close()
 
 
+def test_flat_kernel_on_leaves_of_up_to_eight_triangles():
+    """The flat kernel deals out leaves of up to four triangles and walks larger ones (the ABI's leaf reference holds up to 8)
+    sequentially: a tree built with MIRO_BVH_MAX_LEAF=8 (read once per process, hence the child process) must give the warp
+    kernel's hits byte for byte, closest and any-hit."""
+    import subprocess
+    import sys
+    code = """
+import os, sys, ctypes as C
+import numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+import test_synthetic_gpu as T
+v, f = T.soup(60000, 5, 0.004, True)
+sc = T.scene_of(v, f)
+d = sc.desc()
+ch = np.ctypeslib.as_array(C.cast(d.nodes, C.POINTER(C.c_uint32)), shape=(d.n_nodes, 32))[:, 24:28]
+leaf = ch[(ch >> 31) == 1]
+counts = ((leaf >> 26) & 7) + 1
+assert counts.max() > 4 and (counts <= 4).any(), np.bincount(counts)
+sc.attach(0)
+rays = T.rays_for(v, 200000, 3)
+sc.set_trace_kernel("warp"); a = sc.trace_closest(rays); oa = sc.trace_any(rays)
+sc.set_trace_kernel("flat"); b = sc.trace_closest(rays); ob = sc.trace_any(rays)
+assert (a["prim"] >= 0).mean() > 0.05
+assert a.tobytes() == b.tobytes() and (oa == ob).all() and (oa == (a["prim"] >= 0)).all()
+print("leaf sizes", np.bincount(counts).tolist())
+""" % (helpers.ROOT, helpers.ROOT)
+    p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, MIRO_BVH_MAX_LEAF="8"), capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, (p.stdout[-1000:], p.stderr[-3000:])
+    print(p.stdout.strip())
+
+
 def devicebuild_scene(fx, extra=""):
     script = fx.script.replace("scene ", "scene devicebuild 1 " + extra, 1)
     assert "devicebuild 1" in script

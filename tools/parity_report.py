@@ -16,7 +16,7 @@ import helpers
 import test_trace_gpu as T
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r2"
-out = {"what": "GPU (libmiro_gpu.so, warp kernel; pool kernel asserted byte-identical) vs the unmodified reference", "trace": {}, "render": {}}
+out = {"what": "GPU (libmiro_gpu.so, warp kernel; flat and pool kernels asserted byte-identical; the kernel MIRO_GPU_KERNEL_AUTO picks is named per config) vs the unmodified reference", "trace": {}, "render": {}}
 
 
 def clean(st):
@@ -24,8 +24,10 @@ def clean(st):
 
 
 def trace_stats(fx, sc, rays, ref):
+    sc.set_trace_kernel("auto"); auto_kernel = sc.trace_kernel()
     sc.set_trace_kernel("warp"); hits = sc.trace_closest(rays)
     sc.set_trace_kernel("pool"); pool = sc.trace_closest(rays)
+    sc.set_trace_kernel("flat"); flat = sc.trace_closest(rays); flat_occ = sc.trace_any(rays)
     sc.set_trace_kernel("warp")
     raw = helpers.compare_hits(sc, hits, ref, t_rel=1e-5, rays=rays)
     adj = helpers.adjudicate_hard(fx, sc, hits, ref, raw, rays)
@@ -34,7 +36,10 @@ def trace_stats(fx, sc, rays, ref):
     st["unclassed_in_float64"] = {k: v for k, v in adj.items() if k != "hard_idx"}
     st["hard"] = adj["product_missed"] + adj["unexplained"]
     st["pool_kernel_identical"] = bool(hits.tobytes() == pool.tobytes())
+    st["flat_kernel_identical"] = bool(hits.tobytes() == flat.tobytes())
+    st["default_kernel"] = auto_kernel
     occ = sc.trace_any(rays)
+    st["flat_kernel_any_hit_identical"] = bool((occ == flat_occ).all())
     st["any_hit_agrees_with_reference"] = float((occ == (ref["mesh"] >= 0)).mean())
     st["any_hit_agrees_with_own_closest"] = float((occ == (hits["prim"] >= 0)).mean())
     return st
