@@ -23,6 +23,10 @@
 
 namespace miro {
 
+// Leaves of up to 4 triangles are dealt out (the host builder's MAX_LEAF_SIZE).  Dealing leaves of up to 8 (the ABI's limit: a
+// fourth ballot over bit 2 of count - 1, eight table entries, an eight-step gather) was built and measured on trees with larger
+// leaves — MIRO_BVH_MAX_LEAF 4 / 5 / 6 / 8: 7 543 / 7 603 / 7 599 / 7 459 Mrays/s on the C2 step against 7 792 for this build on
+// leaves of <= 4 (smaller leaves lose as well: <= 3: 7 303, <= 2: 6 487) — and removed.
 constexpr int FLAT_MAX_LEAF = 4;                                 // leaves of up to this many triangles are dealt out
 // A leaf round is run when  n_leaf * NUM > n_node * DEN: dealt leaf rounds are cheap at any number of waiting leaves and return
 // their lanes to the node phase, so they are favoured (measured on the C2 step: 1:1 7 107, 3:2 7 489, 2:1 7 604, 5:2 7 587,
