@@ -224,11 +224,11 @@ static int trace_grid(miro_gpu_ctx* ctx, size_t n) {
     int& v = per_sm[(ctx->counting ? 1 : 0) + (ctx->has_alpha ? 2 : 0) + (flat ? 4 : 0)];
     if (v == 0 && flat) {
         if (ctx->has_alpha) {
-            if (ctx->counting) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace_flat<MODE, true, true, false>, TRACE_BLOCK, 0);
-            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace_flat<MODE, false, true, false>, TRACE_BLOCK, 0);
+            if (ctx->counting) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace_flat<MODE, true, true, false, false>, TRACE_BLOCK, 0);
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace_flat<MODE, false, true, false, false>, TRACE_BLOCK, 0);
         } else {
-            if (ctx->counting) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace_flat<MODE, true, false, false>, TRACE_BLOCK, 0);
-            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace_flat<MODE, false, false, false>, TRACE_BLOCK, 0);
+            if (ctx->counting) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace_flat<MODE, true, false, false, false>, TRACE_BLOCK, 0);
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace_flat<MODE, false, false, false, false>, TRACE_BLOCK, 0);
         }
         if (v <= 0) v = 1;
     }
@@ -327,7 +327,8 @@ static void launch_trace(miro_gpu_ctx* ctx, const void* d_rays, size_t n, const 
         return;
     }
 #define MIRO_LAUNCH(COUNT, ALPHA) do { if (ctx->trace_kernel == MIRO_GPU_KERNEL_FLAT) \
-        cudaLaunchKernelEx(&cfg, k_trace_flat<MODE, COUNT, ALPHA, PACKED>, ctx->scene, r, (uint32_t)n, d_count, chunk, d_hits, d_bits, d_E, d_slots, ctx->d_counters, work); \
+        { if (ctx->n_mbtris) cudaLaunchKernelEx(&cfg, k_trace_flat<MODE, COUNT, ALPHA, PACKED, true>, ctx->scene, r, (uint32_t)n, d_count, chunk, d_hits, d_bits, d_E, d_slots, ctx->d_counters, work); \
+          else cudaLaunchKernelEx(&cfg, k_trace_flat<MODE, COUNT, ALPHA, PACKED, false>, ctx->scene, r, (uint32_t)n, d_count, chunk, d_hits, d_bits, d_E, d_slots, ctx->d_counters, work); } \
     else cudaLaunchKernelEx(&cfg, k_trace<MODE, COUNT, ALPHA, PACKED>, ctx->scene, r, (uint32_t)n, d_count, chunk, d_hits, d_bits, d_E, d_slots, ctx->d_counters, work); } while (0)
     if (ctx->has_alpha) { if (ctx->counting) MIRO_LAUNCH(true, true); else MIRO_LAUNCH(false, true); }
     else { if (ctx->counting) MIRO_LAUNCH(true, false); else MIRO_LAUNCH(false, false); }

@@ -39,6 +39,12 @@ constexpr int FLAT_MAX_LEAF = 4;                                 // leaves of up
 #endif
 // With more than this many pairs waiting (a coherent batch: most lanes of the warp reach their leaves together) the leaves take
 // the sequential per-lane loop of traverse.cuh, which is efficient exactly then; dealing serves 32 pairs per round.
+#ifndef MIRO_FLAT_OTHER_NUM
+#define MIRO_FLAT_OTHER_NUM 1
+#endif
+#ifndef MIRO_FLAT_OTHER_DEN
+#define MIRO_FLAT_OTHER_DEN 1
+#endif
 #ifndef MIRO_FLAT_KIND_VOTE
 #define MIRO_FLAT_KIND_VOTE 0
 #endif
@@ -136,7 +142,9 @@ __device__ __forceinline__ float flat_pair_test(uint32_t ocol, float ox, float o
 enum { FLAT_TRACE_CLOSEST = 0, FLAT_TRACE_ANY_BITS = 1, FLAT_TRACE_ANY_ACCUM = 2 };
 
 // Same contract, parameters, work claiming, result writing and launch chaining as k_trace (miro_gpu_api.cu); the rounds differ.
-template <int MODE, bool COUNT, bool ALPHA, bool PACKED>
+// MB: the scene holds motion-blur triangles (their leaves are dealt as well; a separate instantiation, so that scenes without
+// them do not carry the registers of the two-pose fetch).
+template <int MODE, bool COUNT, bool ALPHA, bool PACKED, bool MB>
 __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS)
 k_trace_flat(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, const uint32_t* __restrict__ d_count, uint32_t chunk,
              miro_gpu_hit* __restrict__ hits, uint32_t* __restrict__ bits, const float4* __restrict__ sample_E, float4* __restrict__ slots,
@@ -146,6 +154,7 @@ k_trace_flat(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, 
     constexpr uint32_t RAY_F4 = PACKED ? 2u : 3u;
     __shared__ unsigned long long stack[FLAT_ROWS * TRACE_BLOCK];      // [row][thread]: stack entries, ray constants, pair table (see FLAT_ROW_*)
     const uint32_t n = d_count ? min(*d_count, n_static) : n_static;
+    constexpr bool has_mb = MB;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t c_nodes = 0, c_tris = 0, c_insts = 0, c_rays = 0;
@@ -217,8 +226,8 @@ k_trace_flat(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, 
 #if MIRO_FLAT_KIND_VOTE
         // only the leaves that are dealt (static triangles) get the bias; instance entries / exits and motion-blur leaves run at the
         // lane count they have, like a node step, and weigh 1:1
-        const int n_tri = __popc(__ballot_sync(0xffffffffu, DEAL && ((uint32_t)L.cur >> 28) == 8u));
-        if (n_node * MIRO_FLAT_BIAS_DEN >= n_tri * MIRO_FLAT_BIAS_NUM + (n_leaf - n_tri) * MIRO_FLAT_BIAS_DEN) {
+        const int n_tri = __popc(__ballot_sync(0xffffffffu, DEAL && (((uint32_t)L.cur >> 28) == 8u || (has_mb && ((uint32_t)L.cur >> 28) == 10u))));
+        if (n_node * (MIRO_FLAT_BIAS_DEN * MIRO_FLAT_OTHER_DEN) >= n_tri * (MIRO_FLAT_BIAS_NUM * MIRO_FLAT_OTHER_DEN) + (n_leaf - n_tri) * (MIRO_FLAT_OTHER_NUM * MIRO_FLAT_BIAS_DEN)) {
 #else
         if (n_node * MIRO_FLAT_BIAS_DEN >= n_leaf * MIRO_FLAT_BIAS_NUM) {
 #endif
@@ -228,7 +237,10 @@ k_trace_flat(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, 
             const uint32_t u = (uint32_t)L.cur;
             // bits 31..28 == 1000: a leaf reference (bit 31; the instance-exit marker and EMPTY lack it) of static triangles (kind 0)
             // with count - 1 < 4 (larger leaves: sequential path below)
-            const bool tri_leaf = DEAL && (u >> 28) == 8u;
+            // ... or of motion-blur triangles (kind 1: bits 31..28 == 1010), dealt the same way: the worker lerps the two poses at the
+            // owner's time first (src/BVH.cpp:1320-1335)
+            const bool mb_leaf = DEAL && has_mb && (u >> 28) == 10u;
+            const bool tri_leaf = (DEAL && (u >> 28) == 8u) || mb_leaf;
             const uint32_t cnt = tri_leaf ? ((u >> MIRO_GPU_LEAF_INDEX_BITS) & 3u) + 1u : 0u;
             const bool c0 = tri_leaf && (u & (1u << MIRO_GPU_LEAF_INDEX_BITS)) != 0u, c1 = tri_leaf && (u & (2u << MIRO_GPU_LEAF_INDEX_BITS)) != 0u;      // bits of count - 1
             bool dealt = false, sequential = !DEAL;
@@ -243,7 +255,7 @@ k_trace_flat(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, 
                     // waiting lane always fits, so every leaf is served)
                     dealt = tri_leaf && S + cnt <= 32u;
                     // pair table: entry p (in the column of lane p) = triangle index | owner lane << 26
-                    const uint32_t word = (u & ((1u << MIRO_GPU_LEAF_INDEX_BITS) - 1u)) | (lane << MIRO_GPU_LEAF_INDEX_BITS);
+                    const uint32_t word = (u & ((1u << MIRO_GPU_LEAF_INDEX_BITS) - 1u)) | (lane << MIRO_GPU_LEAF_INDEX_BITS) | (mb_leaf ? 0x80000000u : 0u);
                     const uint32_t ent = st.base + FLAT_ROW_PAIR + (S - lane) * 8u;      // entry S, relative to this lane's own column
                     // (the one owner that straddles entry 32 writes its first pairs too: tested for nothing, which is cheaper than
                     // finding out where the served pairs end)
@@ -254,13 +266,24 @@ k_trace_flat(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, 
                     __syncwarp();
                     const bool valid = lane < total;
                     const uint32_t pw = valid ? lds32(st.base + FLAT_ROW_PAIR) : 0u;
-                    const uint32_t owner = pw >> MIRO_GPU_LEAF_INDEX_BITS;
+                    const uint32_t owner = (pw >> MIRO_GPU_LEAF_INDEX_BITS) & 31u;
                     const float wox = __shfl_sync(0xffffffffu, L.r.ox, owner), woy = __shfl_sync(0xffffffffu, L.r.oy, owner), woz = __shfl_sync(0xffffffffu, L.r.oz, owner);
                     const float wtmin = __shfl_sync(0xffffffffu, L.tmin, owner), wtmax = __shfl_sync(0xffffffffu, L.hit.t, owner);
                     float ht = __int_as_float(0x7f800000), ha = 0.f, hb = 0.f;
+                    const float wtime = has_mb ? __shfl_sync(0xffffffffu, L.time, owner) : 0.f;
                     if (valid) {
                         float4 p0, p1, p2;
-                        load_tri(s.tris + (size_t)(pw & ((1u << MIRO_GPU_LEAF_INDEX_BITS) - 1u)) * TRI_F4, p0, p1, p2);
+                        const uint32_t idx = pw & ((1u << MIRO_GPU_LEAF_INDEX_BITS) - 1u);
+                        if (has_mb && (int32_t)pw < 0) {
+                            // time * pose2 + (1 - time) * pose1 with both products rounded, as intersect_leaf has it
+                            const float4* t = s.mbtris + (size_t)idx * 6;
+                            const float w1 = wtime, w0 = __fsub_rn(1.0f, wtime);
+#define MIRO_LERP(B, A) __fadd_rn(__fmul_rn(w1, B), __fmul_rn(w0, A))
+                            { const float4 a = __ldg(t), b = __ldg(t + 3); p0.x = MIRO_LERP(b.x, a.x); p0.y = MIRO_LERP(b.y, a.y); p0.z = MIRO_LERP(b.z, a.z); }
+                            { const float4 a = __ldg(t + 1), b = __ldg(t + 4); p1.x = MIRO_LERP(b.x, a.x); p1.y = MIRO_LERP(b.y, a.y); p1.z = MIRO_LERP(b.z, a.z); }
+                            { const float4 a = __ldg(t + 2), b = __ldg(t + 5); p2.x = MIRO_LERP(b.x, a.x); p2.y = MIRO_LERP(b.y, a.y); p2.z = MIRO_LERP(b.z, a.z); }
+#undef MIRO_LERP
+                        } else load_tri(s.tris + (size_t)idx * TRI_F4, p0, p1, p2);
                         ht = flat_pair_test<ANY>(st.base + (owner - lane) * 8u, wox, woy, woz, wtmin, wtmax, p0, p1, p2, ha, hb);
                     }
                     const uint32_t hitmask = __ballot_sync(0xffffffffu, ht != __int_as_float(0x7f800000));
@@ -281,7 +304,7 @@ k_trace_flat(DeviceScene s, const float4* __restrict__ rays, uint32_t n_static, 
                         const float fa = __shfl_sync(0xffffffffu, ha, bsrc), fb = __shfl_sync(0xffffffffu, hb, bsrc);
                         if (dealt && best < L.hit.t) {
                             L.hit.t = best; L.hit.a = fa; L.hit.b = fb;
-                            L.hit.prim = (int32_t)((u & ((1u << MIRO_GPU_LEAF_INDEX_BITS) - 1u)) + (bsrc - S)); L.hit.inst = L.cur_inst;
+                            L.hit.prim = (int32_t)((mb_leaf ? s.n_tris : 0u) + (u & ((1u << MIRO_GPU_LEAF_INDEX_BITS) - 1u)) + (bsrc - S)); L.hit.inst = L.cur_inst;
                         }
                     }
                     __syncwarp();      // the pair table is rewritten by the next leaf round
