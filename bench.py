@@ -65,6 +65,23 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def l2_copy_bandwidth():
+    """Measured on the spot: device-to-device copies of a 32 MB buffer into another one (64 MB in all: L2-resident on the 126 MB
+    L2), read + written bytes per second, CUDA events around 200 copies.  The denominator of roofline.frac_l2 — the launch whose
+    DRAM traffic is a twelfth of its algorithmic bytes is served by L1 and L2, so the HBM figure alone says little about it."""
+    import torch
+    n = 8 << 20
+    x = torch.ones(n, dtype=torch.float32, device="cuda"); y = torch.empty_like(x)
+    for _ in range(20):
+        y.copy_(x)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); a.record()
+    for _ in range(200):
+        y.copy_(x)
+    b.record(); torch.cuda.synchronize()
+    return 2.0 * x.numel() * 4 * 200 / (a.elapsed_time(b) * 1e-3) * 1e-9
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
@@ -319,7 +336,12 @@ def trace_leg(w, sc, args, rank, world, local, barrier, sampler=None, sustain_s=
 KERNEL_NAMES = ["k_trace<closest> primary", "k_trace<closest> incoherent", "k_trace<any> shadow"]
 
 
+_L2_PEAK = []
+
+
 def roofline_of(leg, hbm_peak, peak_src, traffic_key=None):
+    if not _L2_PEAK:
+        _L2_PEAK.append(l2_copy_bandwidth())
     launch_ms, per_launch = leg["launch_ms"], leg["per_launch"]
     dom = int(np.argmax(launch_ms))
     achieved = per_launch[dom]["bytes"] / (launch_ms[dom] * 1e-3) * 1e-9
@@ -340,6 +362,11 @@ def roofline_of(leg, hbm_peak, peak_src, traffic_key=None):
         bound = "hbm" if leg["structure_bytes"] > L2_BYTES else "l2/issue (structure of %.1f MB fits the 126 MB L2)" % (leg["structure_bytes"] * 1e-6)
     return {"bound": bound, "kernel": KERNEL_NAMES[dom], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
             "peak_source": peak_src, "traffic": traffic, "l2_traffic": l2_bytes, "l1_global_load_traffic": l1_bytes,
+            "l2_copy_bandwidth_measured_GBps": _L2_PEAK[0],
+            "frac_l2": (l2_bytes / (launch_ms[dom] * 1e-3) * 1e-9 / _L2_PEAK[0]) if l2_bytes else None,
+            "frac_l2_note": "L2 sector traffic of the launch (committed ncu capture, lts__t_sectors x 32 B) / its live duration / the L2-resident copy "
+                            "bandwidth measured in this run: how much of the L2 the launch uses — it is bound by issue slots and dependent-fetch "
+                            "latency (profiles/r2_ncu_summary.md), not by L2 bandwidth either",
             "algorithmic_bytes_per_launch": alg, "structure_bytes_on_device": leg["structure_bytes"],
             "nodes_per_ray": per_launch[dom]["nodes"] / N_BATCH, "tris_per_ray": per_launch[dom]["tris"] / N_BATCH, "insts_per_ray": per_launch[dom]["insts"] / N_BATCH,
             "launch_ms": launch_ms[dom], "share_of_step": launch_ms[dom] / sum(launch_ms),
