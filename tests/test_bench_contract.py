@@ -57,3 +57,22 @@ def test_bench_workloads_are_deterministic_and_named():
     assert len(big.mesh_names()) == 20 and big.label.startswith("C2 at dragon scale")
     lo, hi = big.bounds()
     assert (hi - lo > np.array([4.0, 0.9, 2.0])).all()
+
+
+def test_committed_traffic_figures_come_from_the_committed_ncu_pages():
+    """profiles/traffic.json (read by bench.py for roofline.traffic / l2_traffic / l1_global_load_traffic) is what
+    tools/traffic_from_ncu.py derives from the committed `ncu --set full --page raw` captures of the shipped kernels."""
+    import json
+    ROOT = helpers.ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import traffic_from_ncu as T
+    tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    for key, page in (("c2", "r2_c2_flat_ncu_raw.csv"), ("big", "r2_big_flat_ncu_raw.csv")):
+        kernels, dram, l2, l1 = T.traffic_of(os.path.join(ROOT, "profiles", page))
+        assert all("k_trace_flat" in k for k in kernels), kernels
+        assert tj[key]["captured_kernels"] == kernels
+        for name in T.NAMES:
+            assert abs(tj[key]["per_launch_dram_bytes"][name] - dram[name]) < 1.0
+            assert abs(tj[key]["per_launch_l2_bytes"][name] - l2[name]) < 1.0
+            assert abs(tj[key]["per_launch_l1_global_load_bytes"][name] - l1[name]) < 1.0
+            assert dram[name] < l2[name]      # L2-resident structures: DRAM carries the ray / hit streams only
